@@ -1,0 +1,189 @@
+/* lseg_b200 — C ABI of the B200-native LSeg forward path (liblseg_b200.so).
+ *
+ * Drop-in boundary for the hot path of isl-org/lang-seg: LSegNet.forward
+ * (modules/models/lseg_net.py:160-205) and its zero-shot twin (modules/models/lseg_net_zs.py:177-214).
+ * The reference has no FFI (it is pure Python over torch); the binding a maintainer adds is the ctypes
+ * shim shown in INTEGRATION.md, which replaces `self.net = LSegNet(...)` in modules/lseg_module.py:76-84.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer below is a DEVICE pointer unless it says "host";
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises
+ *     except where stated;
+ *   - every function returns 0 on success, non-zero on failure; lseg_last_error() returns a
+ *     thread-local message. There is NO CPU fallback: without a CUDA device of compute capability
+ *     10.0 every compute entry point fails.
+ *   - fp16 tensors are IEEE binary16 ("half"); int64 tokens match clip.tokenize's LongTensor [K,77].
+ */
+#ifndef LSEG_B200_H_
+#define LSEG_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LSEG_B200_ABI_VERSION 1
+
+/* ---- error / info ------------------------------------------------------------------------------ */
+const char* lseg_last_error(void);
+int lseg_abi_version(void);
+/* Reads and clears the device-side barrier watchdog: out[0] != 0 means a kernel timed out on an
+ * mbarrier (out[0] = wait tag, out[1] = block, out[2] = thread, out[3] = parity). Synchronises stream. */
+int lseg_read_watchdog(int out[4], void* stream);
+
+/* ---- stage ops (each one is parity-tested on its own; SURVEY.md section 2b numbering) ------------ */
+
+/* activation applied in the GEMM epilogue */
+enum { LSEG_ACT_NONE = 0, LSEG_ACT_GELU = 1, LSEG_ACT_QUICKGELU = 2, LSEG_ACT_RELU = 3 };
+/* output addressing of the GEMM epilogue */
+enum { LSEG_STORE_ROWMAJOR = 0, LSEG_STORE_D2S = 1, LSEG_STORE_NCHW_T = 2 };
+
+/* One dense contraction  C[M,N] = epi(A[M,K] * W[N,K]^T)  on tcgen05 (k1,k4,k6-k8,k10-k17,k19).
+ * Replaces the torch Linear / Conv2d(1x1, 3x3 s1 p1) / ConvTranspose2d(k==s) calls listed in
+ * timm Block linears (lseg_vit.py:196-197), ProjectReadout (lseg_vit.py:79-90),
+ * act_postprocess convs (lseg_vit.py:450-522), scratch.layerN_rn (lseg_blocks.py:73-108),
+ * ResidualConvUnit_custom convs (lseg_blocks.py:265-288), out_conv (lseg_blocks.py:356),
+ * head1 and the pixel x text matmul (lseg_net.py:185,194). */
+typedef struct lseg_gemm_args {
+  const void* a;        /* plain: fp16 [a_rows >= M, lda]; conv: fp16 NHWC [B,H,W,K] */
+  long long lda;        /* plain only, elements */
+  int a_rows;           /* allocated rows of a (>= M) */
+  const void* w;        /* fp16 [w_rows >= N, ksize*ksize*K] row-major, tap-major for conv */
+  int w_rows;
+  int M, N, K;          /* conv: M = B*H*W, K = input channels */
+  int conv;             /* 0 plain, 1 = ksize x ksize stride-1 conv with zero padding `pad` */
+  int B, H, W, ksize, pad;
+  const float* bias;    /* [N] or [groups, N]; nullable */
+  int bias_group_rows;  /* >0: row r uses bias row r / bias_group_rows */
+  const float* scale;   /* [N], applied before bias; nullable */
+  int act;
+  const float* res_f32; /* nullable, row-major ldc */
+  const float* res2_f32;/* nullable, second fp32 residual (fusion skip add, lseg_blocks.py:345-347) */
+  const void* res_f16;  /* nullable, fp16 residual added in fp16 after rounding (CLIP text stream) */
+  float* out_f32;       /* nullable */
+  void* out_f16;        /* nullable */
+  void* out_f16_relu;   /* nullable: fp16 relu(result) */
+  long long ldc;
+  int store;
+  int d2s_s, d2s_cout, d2s_h, d2s_w;
+  int nchw_p, nchw_k;
+} lseg_gemm_args;
+int lseg_gemm(const lseg_gemm_args* args, void* stream);
+
+/* Fused MHSA, head_dim 64 (k5; timm Attention restated at lseg_vit.py:26-39; CLIP text MHA).
+ * qkv fp16 [B, N, 3*heads*64] (q|k|v thirds) -> out fp16 [B*N, heads*64]. */
+int lseg_mhsa(const void* qkv, void* out, int B, int N, int heads, int causal, void* stream);
+
+/* LayerNorm over the last dim (k3): x fp32 (in_f16=0) or fp16 (in_f16=1) [M,C] -> y fp16. */
+int lseg_layernorm(const void* x, int in_f16, const float* gamma, const float* beta, void* y, long long M, int C,
+                   float eps, void* stream);
+
+/* x fp32 NCHW [B,3,H,W] -> fp16 [B*(H/16)*(W/16), 768] patch rows (k1 operand). */
+int lseg_patchify(const float* x, void* a, int B, int H, int W, void* stream);
+/* bilinear (align_corners=False) resize of pos_embed [1+g0*g0, D] -> [1+gh*gw, D] (k2; lseg_vit.py:149-163). */
+int lseg_pos_resize(const float* pos, float* out, int g0, int gh, int gw, int D, void* stream);
+/* x[b] = cat(cls, patch[b]) + pos (lseg_vit.py:188-193); fp32. */
+int lseg_assemble_tokens(const float* patch, const float* cls, const float* pos, float* x, int B, int T, int D,
+                         void* stream);
+/* tap fp32 [B,1+T,D] -> tok fp16 [B*T,D], cls fp16 [B,D] (k10 operands; lseg_vit.py:79-90). */
+int lseg_readout_split(const float* tap, void* tok, void* cls, int B, int T, int D, void* stream);
+/* NHWC fp16 [B,H,W,C] -> im2col rows for the 3x3 stride-2 pad-1 conv (k13; lseg_vit.py:516-522). */
+int lseg_im2col_3x3_s2(const void* x, void* a, int B, int H, int W, int C, void* stream);
+/* bilinear x2 align_corners=True, NHWC fp16 (k16; lseg_blocks.py:352-354). */
+int lseg_upsample2x_nhwc(const void* x, void* y, int B, int H, int W, int C, void* stream);
+/* rows fp32 [M,C] -> half(row/||row||) * logit_scale in fp16 (k19 prologue; lseg_net.py:191,194). */
+int lseg_l2norm_scale(const float* x, void* y, long long M, int C, float logit_scale, void* stream);
+/* text rows fp16 [M,C] -> row/||row|| in fp16 (lseg_net.py:192). */
+int lseg_l2norm_f16(const void* x, void* y, int M, int C, void* stream);
+/* fp16 logits [planes,H,W] -> fp32 [planes,2H,2W], bilinear align_corners=True (k20; lseg_net.py:203). */
+int lseg_upsample2x_nchw(const void* x, float* y, long long planes, int H, int W, void* stream);
+/* CLIP text glue (k18). tokens int64 [K,L]. */
+int lseg_text_embed(const int64_t* tokens, const float* tok_emb, const float* pos_emb, void* x, int K, int L, int Wd,
+                    void* stream);
+int lseg_text_eot_gather(const int64_t* tokens, const void* x, void* out, int K, int L, int Wd, void* stream);
+
+/* ---- whole-model engine -------------------------------------------------------------------------- */
+
+typedef struct lseg_linear_w {
+  const void* w;       /* fp16 [rows>=out, in] row-major, rows padded to a multiple of 128 */
+  const float* b;      /* fp32 [out] or NULL */
+  int out, in, rows;
+} lseg_linear_w;
+
+typedef struct lseg_vit_block_w {          /* timm Block (Appendix A.1) */
+  const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  lseg_linear_w qkv, proj, fc1, fc2;
+} lseg_vit_block_w;
+
+typedef struct lseg_rcu_w {                /* ResidualConvUnit_custom, BN folded to scale/shift */
+  lseg_linear_w conv1, conv2;              /* [256, 9*256] tap-major */
+  const float *bn1_scale, *bn1_shift, *bn2_scale, *bn2_shift;
+} lseg_rcu_w;
+
+typedef struct lseg_text_block_w {         /* CLIP ResidualAttentionBlock (Appendix A.2) */
+  const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  lseg_linear_w in_proj, out_proj, c_fc, c_proj;
+} lseg_text_block_w;
+
+#define LSEG_VIT_DEPTH 24
+#define LSEG_TEXT_DEPTH 12
+
+typedef struct lseg_weights {
+  /* image trunk: timm vit_large_patch16_384 driven by forward_flex (lseg_vit.py:166-201) */
+  lseg_linear_w patch;                     /* [1024, 768] */
+  const float* cls_token;                  /* [1024] */
+  const float* pos_embed;                  /* [1+pos_grid^2, 1024] */
+  int pos_grid;                            /* 24 */
+  lseg_vit_block_w blocks[LSEG_VIT_DEPTH];
+  int hooks[4];                            /* 5, 11, 17, 23 (lseg_net.py:119-123) */
+  /* reassemble (lseg_vit.py:442-522) */
+  lseg_linear_w readout_tok[4];            /* W[:, :1024]  */
+  lseg_linear_w readout_cls[4];            /* W[:, 1024:] with the bias */
+  lseg_linear_w post_conv1x1[4];           /* 1024 -> {256,512,1024,1024} */
+  lseg_linear_w post1_deconv;              /* ConvT k4 s4: [(i*4+j)*256+co, ci], bias expanded [4096] */
+  lseg_linear_w post2_deconv;              /* ConvT k2 s2: [(i*2+j)*512+co, ci], bias expanded [2048] */
+  lseg_linear_w post4_conv;                /* 3x3 s2: [1024, 9*1024] tap-major */
+  /* decoder (lseg_blocks.py:60-110, 222-358) */
+  lseg_linear_w layer_rn[4];               /* [256, 9*Cin] tap-major, no bias */
+  lseg_rcu_w rcu1[4], rcu2[4];             /* index i = refinenet(i+1); rcu1[3] is dead (lseg_net.py:176) */
+  lseg_linear_w out_conv[4];               /* [256,256] + bias */
+  lseg_linear_w head1;                     /* [512,256] + bias */
+  float logit_scale;                       /* exp(log(1/0.07)) (lseg_net.py:141) */
+  /* CLIP ViT-B/32 text tower */
+  const float* tok_emb;                    /* [49408, 512] fp32 */
+  const float* text_pos;                   /* [77, 512] fp32 */
+  lseg_text_block_w text_blocks[LSEG_TEXT_DEPTH];
+  const float *lnf_g, *lnf_b;
+  lseg_linear_w text_proj;                 /* text_projection^T as [512(out), 512(in)], no bias */
+} lseg_weights;
+
+typedef struct lseg_engine lseg_engine;
+
+/* Copies the descriptor (pointers are borrowed; the caller keeps the device buffers alive). */
+int lseg_create(const lseg_weights* w, int device, lseg_engine** out);
+void lseg_destroy(lseg_engine* e);
+
+/* clip_pretrained.encode_text + L2 normalisation (lseg_net.py:183,192).
+ * tokens int64 [K,77] -> text fp16 [rows_padded(K), 512], rows >= K zeroed; rows_padded = ceil(K/128)*128. */
+int lseg_encode_text(lseg_engine* e, const int64_t* tokens, int K, void* text_out, void* stream);
+
+/* LSeg.forward after tokenisation (lseg_net.py:166-205).
+ * x fp32 NCHW [B,3,H,W] (H, W multiples of 32) -> out fp32 NCHW [B,K,H,W].
+ * text fp16 [rows_padded(K),512] shared by all images (text_image_stride = 0), or one such block per
+ * image at text + b*text_image_stride*512 halves (zero-shot path, lseg_net_zs.py:196-210). */
+int lseg_forward(lseg_engine* e, const float* x, int B, int H, int W, const void* text, int K,
+                 long long text_image_stride, float* out, void* stream);
+
+/* Introspection for tests: copies of intermediate activations of the last forward (device pointers
+ * into the workspace, valid until the next forward). name: "tap0".."tap3" fp32 [B,N,1024];
+ * "path1" fp16 NHWC [B,H/2,W/2,256]; "logits_lr" fp16 [B,K,H/2,W/2]. Returns NULL if unknown. */
+const void* lseg_debug_buffer(lseg_engine* e, const char* name);
+
+/* Number of kernel launches issued by the last lseg_forward / lseg_encode_text call. */
+int lseg_last_launch_count(lseg_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSEG_B200_H_ */

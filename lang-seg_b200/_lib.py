@@ -1,0 +1,134 @@
+"""ctypes binding of liblseg_b200.so (the C ABI declared in include/lseg_b200.h).
+
+This is the reference-side FFI stub: plain pointers and sizes, no torch types cross the boundary
+(torch only provides device memory and the current stream). There is no CPU fallback: if the
+shared library is missing it is built with nvcc; if that fails, importing fails loudly.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblseg_b200.so")
+
+VIT_DEPTH = 24
+TEXT_DEPTH = 12
+
+ACT_NONE, ACT_GELU, ACT_QUICKGELU, ACT_RELU = 0, 1, 2, 3
+STORE_ROWMAJOR, STORE_D2S, STORE_NCHW_T = 0, 1, 2
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("lda", C.c_longlong), ("a_rows", C.c_int),
+        ("w", C.c_void_p), ("w_rows", C.c_int),
+        ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
+        ("conv", C.c_int), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("ksize", C.c_int), ("pad", C.c_int),
+        ("bias", C.c_void_p), ("bias_group_rows", C.c_int), ("scale", C.c_void_p), ("act", C.c_int),
+        ("res_f32", C.c_void_p), ("res2_f32", C.c_void_p), ("res_f16", C.c_void_p),
+        ("out_f32", C.c_void_p), ("out_f16", C.c_void_p), ("out_f16_relu", C.c_void_p),
+        ("ldc", C.c_longlong), ("store", C.c_int),
+        ("d2s_s", C.c_int), ("d2s_cout", C.c_int), ("d2s_h", C.c_int), ("d2s_w", C.c_int),
+        ("nchw_p", C.c_int), ("nchw_k", C.c_int),
+    ]
+
+
+class LinearW(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("b", C.c_void_p), ("out", C.c_int), ("in_", C.c_int), ("rows", C.c_int)]
+
+
+class VitBlockW(C.Structure):
+    _fields_ = [("ln1_g", C.c_void_p), ("ln1_b", C.c_void_p), ("ln2_g", C.c_void_p), ("ln2_b", C.c_void_p),
+                ("qkv", LinearW), ("proj", LinearW), ("fc1", LinearW), ("fc2", LinearW)]
+
+
+class RcuW(C.Structure):
+    _fields_ = [("conv1", LinearW), ("conv2", LinearW),
+                ("bn1_scale", C.c_void_p), ("bn1_shift", C.c_void_p),
+                ("bn2_scale", C.c_void_p), ("bn2_shift", C.c_void_p)]
+
+
+class TextBlockW(C.Structure):
+    _fields_ = [("ln1_g", C.c_void_p), ("ln1_b", C.c_void_p), ("ln2_g", C.c_void_p), ("ln2_b", C.c_void_p),
+                ("in_proj", LinearW), ("out_proj", LinearW), ("c_fc", LinearW), ("c_proj", LinearW)]
+
+
+class Weights(C.Structure):
+    _fields_ = [
+        ("patch", LinearW), ("cls_token", C.c_void_p), ("pos_embed", C.c_void_p), ("pos_grid", C.c_int),
+        ("blocks", VitBlockW * VIT_DEPTH), ("hooks", C.c_int * 4),
+        ("readout_tok", LinearW * 4), ("readout_cls", LinearW * 4), ("post_conv1x1", LinearW * 4),
+        ("post1_deconv", LinearW), ("post2_deconv", LinearW), ("post4_conv", LinearW),
+        ("layer_rn", LinearW * 4), ("rcu1", RcuW * 4), ("rcu2", RcuW * 4), ("out_conv", LinearW * 4),
+        ("head1", LinearW), ("logit_scale", C.c_float),
+        ("tok_emb", C.c_void_p), ("text_pos", C.c_void_p), ("text_blocks", TextBlockW * TEXT_DEPTH),
+        ("lnf_g", C.c_void_p), ("lnf_b", C.c_void_p), ("text_proj", LinearW),
+    ]
+
+
+# every symbol include/lseg_b200.h declares (checked by tests/test_abi.py)
+SYMBOLS = [
+    "lseg_last_error", "lseg_abi_version", "lseg_read_watchdog",
+    "lseg_gemm", "lseg_mhsa", "lseg_layernorm", "lseg_patchify", "lseg_pos_resize", "lseg_assemble_tokens",
+    "lseg_readout_split", "lseg_im2col_3x3_s2", "lseg_upsample2x_nhwc", "lseg_l2norm_scale", "lseg_l2norm_f16",
+    "lseg_upsample2x_nchw", "lseg_text_embed", "lseg_text_eot_gather",
+    "lseg_create", "lseg_destroy", "lseg_encode_text", "lseg_forward", "lseg_debug_buffer",
+    "lseg_last_launch_count",
+]
+
+_lib = None
+
+
+def load(build_if_missing=True):
+    """dlopen the in-tree library, building it first if needed. Raises on failure (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if build_if_missing:
+        from . import build as _build
+        try:
+            _build.build()
+        except Exception:
+            if not os.path.exists(LIB_PATH):
+                raise
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("liblseg_b200.so is missing and could not be built; lseg_b200 has no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    lib.lseg_last_error.restype = C.c_char_p
+    lib.lseg_debug_buffer.restype = C.c_void_p
+    lib.lseg_debug_buffer.argtypes = [C.c_void_p, C.c_char_p]
+    lib.lseg_gemm.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
+    lib.lseg_mhsa.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.lseg_layernorm.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int,
+                                   C.c_float, C.c_void_p]
+    lib.lseg_patchify.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.lseg_pos_resize.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.lseg_assemble_tokens.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                         C.c_void_p]
+    lib.lseg_readout_split.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.lseg_im2col_3x3_s2.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.lseg_upsample2x_nhwc.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.lseg_l2norm_scale.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_void_p]
+    lib.lseg_l2norm_f16.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.lseg_upsample2x_nchw.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p]
+    lib.lseg_text_embed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                    C.c_void_p]
+    lib.lseg_text_eot_gather.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.lseg_read_watchdog.argtypes = [C.POINTER(C.c_int * 4), C.c_void_p]
+    lib.lseg_create.argtypes = [C.POINTER(Weights), C.c_int, C.POINTER(C.c_void_p)]
+    lib.lseg_destroy.argtypes = [C.c_void_p]
+    lib.lseg_destroy.restype = None
+    lib.lseg_encode_text.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.lseg_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                 C.c_longlong, C.c_void_p, C.c_void_p]
+    lib.lseg_last_launch_count.argtypes = [C.c_void_p]
+    _lib = lib
+    return lib
+
+
+class LsegError(RuntimeError):
+    pass
+
+
+def check(status):
+    if status != 0:
+        raise LsegError(load().lseg_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,712 @@
+// lseg_b200 — whole-model orchestration: LSeg.forward (modules/models/lseg_net.py:160-205) and
+// CLIP encode_text as a static list of kernel launches over a bump-allocated
+// HBM workspace. Plans (TMA descriptors, grids) are built once per input shape and replayed; nothing
+// here touches the host between launches, so a forward is ~290 back-to-back async launches on one stream.
+//
+// Data layout in HBM (all activations stay resident for the whole forward):
+//   residual stream      fp32 [B*N, 1024]   (taps of blocks 5/11/17/23 are separate fp32 buffers)
+//   GEMM operands        fp16 row-major, K contiguous (tokens) / NHWC (decoder feature maps)
+//   decoder residuals    fp32 NHWC
+//   low-res logits       fp16 [B, K, H/2, W/2]; final logits fp32 NCHW [B, K, H, W]
+#pragma once
+#include <functional>
+#include <map>
+#include <memory>
+
+namespace lseg {
+
+struct CallCtx {
+  const float* x;
+  const __half* text;
+  int K;
+  long long text_image_stride;
+  float* out;
+};
+using Step = std::function<int(const CallCtx&, cudaStream_t)>;
+
+struct Arena {
+  uint8_t* base = nullptr;
+  size_t cap = 0;
+  size_t off = 0;
+  std::vector<void*> owned;
+  // Simple bump allocator over cudaMalloc'd slabs (256-byte aligned blocks).
+  void* alloc(size_t bytes) {
+    bytes = (bytes + 1023) & ~size_t(1023);
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+    owned.push_back(p);
+    return p;
+  }
+  void release() {
+    for (void* p : owned) cudaFree(p);
+    owned.clear();
+  }
+};
+
+struct ImagePlan {
+  int B = 0, H = 0, W = 0;
+  Arena arena;
+  std::vector<Step> steps;
+  std::map<std::string, const void*> debug;
+  // head buffers needed by the per-call tail
+  __half* featn = nullptr;
+  __half* logits_lr = nullptr;
+  size_t logits_cap_k = 0;
+  ~ImagePlan() { arena.release(); }
+};
+
+struct TextPlan {
+  int K = 0;
+  Arena arena;
+  std::vector<std::function<int(const long long*, __half*, cudaStream_t)>> steps;
+  ~TextPlan() { arena.release(); }
+};
+
+}  // namespace lseg
+
+struct lseg_engine {
+  lseg_weights w;
+  int device = 0;
+  std::unique_ptr<lseg::ImagePlan> img;
+  std::unique_ptr<lseg::TextPlan> txt;
+  std::map<std::pair<int, int>, float*> pos_cache;
+  int last_launches = 0;
+};
+
+namespace lseg {
+
+#define LSEG_ALLOC(var, type, count)                                                        \
+  type* var = static_cast<type*>(arena.alloc(sizeof(type) * static_cast<size_t>(count)));   \
+  if (!var) {                                                                               \
+    set_error("workspace allocation of %zu bytes failed", sizeof(type) * (size_t)(count));  \
+    return -1;                                                                              \
+  }
+
+static GemmEpi epi_none() {
+  GemmEpi e;
+  memset(&e, 0, sizeof(e));
+  return e;
+}
+
+// Build a plain GEMM step: A [M,K] (lda) x lin.w -> epilogue e.
+static int add_gemm(std::vector<Step>& steps, const __half* a, long long lda, int a_rows, int M,
+                    const lseg_linear_w& lin, const GemmEpi& e) {
+  GemmDesc d;
+  memset(&d, 0, sizeof(d));
+  d.a = a;
+  d.lda = lda;
+  d.a_rows = a_rows;
+  d.w = static_cast<const __half*>(lin.w);
+  d.w_rows = lin.rows;
+  d.M = M;
+  d.N = lin.out;
+  d.K = lin.in;
+  d.e = e;
+  GemmPlan plan;
+  if (gemm_plan(d, &plan)) return -1;
+  steps.push_back([plan](const CallCtx&, cudaStream_t s) { return gemm_run(plan, s); });
+  return 0;
+}
+
+// 3x3 stride-1 pad-1 conv over NHWC fp16 [B,H,W,C] with tap-major weights [N, 9*C].
+static int add_conv3x3(std::vector<Step>& steps, const __half* a, int B, int H, int W, int C,
+                       const lseg_linear_w& lin, const GemmEpi& e) {
+  GemmDesc d;
+  memset(&d, 0, sizeof(d));
+  d.a = a;
+  d.w = static_cast<const __half*>(lin.w);
+  d.w_rows = lin.rows;
+  d.M = B * H * W;
+  d.N = lin.out;
+  d.K = C;
+  d.conv = 1;
+  d.B = B;
+  d.H = H;
+  d.W = W;
+  d.kh = d.kw = 3;
+  d.pad = 1;
+  d.e = e;
+  GemmPlan plan;
+  if (gemm_plan(d, &plan)) return -1;
+  steps.push_back([plan](const CallCtx&, cudaStream_t s) { return gemm_run(plan, s); });
+  return 0;
+}
+
+static int add_layernorm(std::vector<Step>& steps, const void* x, int in_f16, const float* g, const float* b,
+                         __half* y, long long M, int C, float eps) {
+  steps.push_back(
+      [=](const CallCtx&, cudaStream_t s) { return run_layernorm(x, in_f16, g, b, y, M, C, eps, s); });
+  return 0;
+}
+
+// ResidualConvUnit_custom (modules/models/lseg_blocks.py:265-288) on NHWC [B,h,w,256]:
+//   in_relu = relu(x) fp16, x_f32 = x;   out = bn2(conv2(relu(bn1(conv1(in_relu))))) + x (+ skip)
+static int add_rcu(std::vector<Step>& steps, const lseg_rcu_w& rw, const __half* in_relu, const float* x_f32,
+                   const float* skip_f32, __half* tmp, int B, int h, int w, float* out_f32, __half* out_f16,
+                   __half* out_f16_relu) {
+  GemmEpi e1 = epi_none();
+  e1.scale = rw.bn1_scale;
+  e1.bias = rw.bn1_shift;
+  e1.act = ACT_RELU;
+  e1.out_f16 = tmp;
+  e1.ldc = 256;
+  if (add_conv3x3(steps, in_relu, B, h, w, 256, rw.conv1, e1)) return -1;
+  GemmEpi e2 = epi_none();
+  e2.scale = rw.bn2_scale;
+  e2.bias = rw.bn2_shift;
+  e2.res_f32 = x_f32;
+  e2.res2_f32 = skip_f32;
+  e2.out_f32 = out_f32;
+  e2.out_f16 = out_f16;
+  e2.out_f16_relu = out_f16_relu;
+  e2.ldc = 256;
+  return add_conv3x3(steps, tmp, B, h, w, 256, rw.conv2, e2);
+}
+
+static int get_pos_embed(lseg_engine* eng, int gh, int gw, cudaStream_t stream, const float** out) {
+  auto key = std::make_pair(gh, gw);
+  auto it = eng->pos_cache.find(key);
+  if (it != eng->pos_cache.end()) {
+    *out = it->second;
+    return 0;
+  }
+  float* buf = nullptr;
+  LSEG_CHECK_CUDA(cudaMalloc(&buf, sizeof(float) * (1 + (size_t)gh * gw) * 1024));
+  pos_resize_kernel<<<1 + gh * gw, 256, 0, stream>>>(eng->w.pos_embed, buf, eng->w.pos_grid, gh, gw, 1024);
+  LSEG_CHECK_CUDA(cudaGetLastError());
+  eng->pos_cache[key] = buf;
+  *out = buf;
+  return 0;
+}
+
+static int build_image_plan(lseg_engine* eng, int B, int H, int W, cudaStream_t stream) {
+  const lseg_weights& w = eng->w;
+  std::unique_ptr<ImagePlan> plan(new ImagePlan());
+  plan->B = B;
+  plan->H = H;
+  plan->W = W;
+  Arena& arena = plan->arena;
+  std::vector<Step>& steps = plan->steps;
+  const int gh = H / 16, gw = W / 16, T = gh * gw, N = T + 1;
+  const int D = 1024;
+  const long long M = static_cast<long long>(B) * N;
+  const long long BT = static_cast<long long>(B) * T;
+
+  const float* pos = nullptr;
+  if (get_pos_embed(eng, gh, gw, stream, &pos)) return -1;
+
+  // ---- ViT trunk (modules/models/lseg_vit.py:166-201) ----
+  LSEG_ALLOC(patch_a, __half, BT * 768);
+  LSEG_ALLOC(patch_out, float, BT * D);
+  LSEG_ALLOC(xbuf, float, M * D);
+  LSEG_ALLOC(xn, __half, M * D);
+  LSEG_ALLOC(qkv, __half, M * 3 * D);
+  LSEG_ALLOC(attn, __half, M * D);
+  LSEG_ALLOC(hbuf, __half, M * 4 * D);
+  float* taps[4];
+  for (int k = 0; k < 4; ++k) {
+    LSEG_ALLOC(t, float, M * D);
+    taps[k] = t;
+    char name[8];
+    snprintf(name, sizeof(name), "tap%d", k);
+    plan->debug[name] = t;
+  }
+
+  steps.push_back([=](const CallCtx& c, cudaStream_t s) {
+    const long long total = BT * 3 * 16 * 4;
+    patchify_kernel<<<ew_grid(total, 256), 256, 0, s>>>(c.x, patch_a, B, H, W);
+    LSEG_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  });
+  {
+    GemmEpi e = epi_none();
+    e.bias = w.patch.b;
+    e.out_f32 = patch_out;
+    e.ldc = D;
+    if (add_gemm(steps, patch_a, 768, (int)BT, (int)BT, w.patch, e)) return -1;
+  }
+  {
+    const float* cls = w.cls_token;
+    steps.push_back([=](const CallCtx&, cudaStream_t s) {
+      const long long total = M * (D / 4);
+      assemble_tokens_kernel<<<ew_grid(total, 256), 256, 0, s>>>(patch_out, cls, pos, xbuf, B, T, D);
+      LSEG_CHECK_CUDA(cudaGetLastError());
+      return 0;
+    });
+  }
+  float* xin = xbuf;
+  for (int i = 0; i < LSEG_VIT_DEPTH; ++i) {
+    const lseg_vit_block_w& bw = w.blocks[i];
+    float* xout = xin;
+    for (int k = 0; k < 4; ++k)
+      if (w.hooks[k] == i) xout = taps[k];
+    add_layernorm(steps, xin, 0, bw.ln1_g, bw.ln1_b, xn, M, D, 1e-6f);
+    {
+      GemmEpi e = epi_none();
+      e.bias = bw.qkv.b;
+      e.out_f16 = qkv;
+      e.ldc = 3 * D;
+      if (add_gemm(steps, xn, D, (int)M, (int)M, bw.qkv, e)) return -1;
+    }
+    {
+      MhsaDesc md;
+      md.qkv = qkv;
+      md.out = attn;
+      md.B = B;
+      md.N = N;
+      md.heads = 16;
+      md.causal = 0;
+      MhsaPlan mp;
+      if (mhsa_plan(md, &mp)) return -1;
+      steps.push_back([mp](const CallCtx&, cudaStream_t s) { return mhsa_run(mp, s); });
+    }
+    {
+      GemmEpi e = epi_none();
+      e.bias = bw.proj.b;
+      e.res_f32 = xin;
+      e.out_f32 = xin;
+      e.ldc = D;
+      if (add_gemm(steps, attn, D, (int)M, (int)M, bw.proj, e)) return -1;
+    }
+    add_layernorm(steps, xin, 0, bw.ln2_g, bw.ln2_b, xn, M, D, 1e-6f);
+    {
+      GemmEpi e = epi_none();
+      e.bias = bw.fc1.b;
+      e.act = ACT_GELU;
+      e.out_f16 = hbuf;
+      e.ldc = 4 * D;
+      if (add_gemm(steps, xn, D, (int)M, (int)M, bw.fc1, e)) return -1;
+    }
+    {
+      GemmEpi e = epi_none();
+      e.bias = bw.fc2.b;
+      e.res_f32 = xin;
+      e.out_f32 = xout;
+      e.ldc = D;
+      if (add_gemm(steps, hbuf, 4 * D, (int)M, (int)M, bw.fc2, e)) return -1;
+    }
+    xin = xout;
+  }
+  // final self.norm is dead code in the reference (glob unused, lseg_vit.py:108,199) -> skipped.
+
+  // ---- readout + reassemble (lseg_vit.py:79-90, 104-146, 442-522) ----
+  const int c_post[4] = {256, 512, 1024, 1024};
+  LSEG_ALLOC(tok, __half, BT * D);
+  const int cls_rows = ((B + 127) / 128) * 128;
+  LSEG_ALLOC(cls16, __half, (size_t)cls_rows * D);
+  LSEG_CHECK_CUDA(cudaMemsetAsync(cls16, 0, sizeof(__half) * (size_t)cls_rows * D, stream));
+  LSEG_ALLOC(clsb, float, (size_t)B * D);
+  LSEG_ALLOC(ro, __half, BT * D);
+  __half* layer_in[4];  // NHWC fp16 inputs of scratch.layerN_rn
+  const int lh[4] = {4 * gh, 2 * gh, gh, gh / 2};
+  const int lw[4] = {4 * gw, 2 * gw, gw, gw / 2};
+  for (int k = 0; k < 4; ++k) {
+    const float* tap = taps[k];
+    steps.push_back([=](const CallCtx&, cudaStream_t s) {
+      const long long total = M * (D / 4);
+      readout_split_kernel<<<ew_grid(total, 256), 256, 0, s>>>(tap, tok, cls16, B, T, D);
+      LSEG_CHECK_CUDA(cudaGetLastError());
+      return 0;
+    });
+    {  // per-image half of the readout projection: cls * W[:,1024:]^T + b
+      GemmEpi e = epi_none();
+      e.bias = w.readout_cls[k].b;
+      e.out_f32 = clsb;
+      e.ldc = D;
+      if (add_gemm(steps, cls16, D, cls_rows, B, w.readout_cls[k], e)) return -1;
+    }
+    {  // tok * W[:,:1024]^T + (per-image row) -> GELU
+      GemmEpi e = epi_none();
+      e.bias = clsb;
+      e.bias_group_rows = T;
+      e.act = ACT_GELU;
+      e.out_f16 = ro;
+      e.ldc = D;
+      if (add_gemm(steps, tok, D, (int)BT, (int)BT, w.readout_tok[k], e)) return -1;
+    }
+    LSEG_ALLOC(pk, __half, BT * c_post[k]);
+    {
+      GemmEpi e = epi_none();
+      e.bias = w.post_conv1x1[k].b;
+      e.out_f16 = pk;
+      e.ldc = c_post[k];
+      if (add_gemm(steps, ro, D, (int)BT, (int)BT, w.post_conv1x1[k], e)) return -1;
+    }
+    if (k == 0 || k == 1) {
+      const int s_up = (k == 0) ? 4 : 2;
+      const lseg_linear_w& dw = (k == 0) ? w.post1_deconv : w.post2_deconv;
+      LSEG_ALLOC(lk, __half, BT * s_up * s_up * c_post[k]);
+      GemmEpi e = epi_none();
+      e.bias = dw.b;
+      e.out_f16 = lk;
+      e.store = STORE_D2S;
+      e.d2s_s = s_up;
+      e.d2s_cout = c_post[k];
+      e.d2s_h = gh;
+      e.d2s_w = gw;
+      if (add_gemm(steps, pk, c_post[k], (int)BT, (int)BT, dw, e)) return -1;
+      layer_in[k] = lk;
+    } else if (k == 2) {
+      layer_in[k] = pk;
+    } else {
+      const long long rows4 = static_cast<long long>(B) * lh[3] * lw[3];
+      LSEG_ALLOC(a4, __half, rows4 * 9 * 1024);
+      LSEG_ALLOC(l4, __half, rows4 * 1024);
+      steps.push_back([=](const CallCtx&, cudaStream_t s) {
+        const long long total = rows4 * 9 * (1024 / 8);
+        im2col_3x3_s2_kernel<<<ew_grid(total, 256), 256, 0, s>>>(pk, a4, B, gh, gw, 1024);
+        LSEG_CHECK_CUDA(cudaGetLastError());
+        return 0;
+      });
+      GemmEpi e = epi_none();
+      e.bias = w.post4_conv.b;
+      e.out_f16 = l4;
+      e.ldc = 1024;
+      if (add_gemm(steps, a4, 9 * 1024, (int)rows4, (int)rows4, w.post4_conv, e)) return -1;
+      layer_in[k] = l4;
+    }
+  }
+
+  // ---- scratch.layerN_rn (lseg_blocks.py:73-108; lseg_net.py:171-174) ----
+  float* rn_f32[4];
+  __half* rn_relu[4];
+  for (int k = 0; k < 4; ++k) {
+    const long long px = static_cast<long long>(B) * lh[k] * lw[k];
+    LSEG_ALLOC(f, float, px * 256);
+    LSEG_ALLOC(r, __half, px * 256);
+    rn_f32[k] = f;
+    rn_relu[k] = r;
+    GemmEpi e = epi_none();
+    e.out_f32 = f;
+    e.out_f16_relu = r;
+    e.ldc = 256;
+    if (add_conv3x3(steps, layer_in[k], B, lh[k], lw[k], c_post[k], w.layer_rn[k], e)) return -1;
+  }
+
+  // ---- fusion decoder (lseg_blocks.py:337-358; lseg_net.py:176-179) ----
+  const float* path_prev = nullptr;  // fp32 NHWC output of the previous refinenet (same res as rn[k])
+  __half* path1_f16 = nullptr;
+  for (int k = 3; k >= 0; --k) {
+    const int h = lh[k], ww = lw[k];
+    const long long px = static_cast<long long>(B) * h * ww;
+    LSEG_ALLOC(tmp, __half, px * 256);
+    LSEG_ALLOC(r2, __half, px * 256);
+    const __half* rcu2_in_relu = rn_relu[k];
+    const float* rcu2_in_f32 = rn_f32[k];
+    if (path_prev) {  // output = xs[0] + resConfUnit1(xs[1])
+      LSEG_ALLOC(sum_f32, float, px * 256);
+      LSEG_ALLOC(sum_relu, __half, px * 256);
+      if (add_rcu(steps, w.rcu1[k], rn_relu[k], rn_f32[k], path_prev, tmp, B, h, ww, sum_f32, nullptr, sum_relu))
+        return -1;
+      rcu2_in_relu = sum_relu;
+      rcu2_in_f32 = sum_f32;
+    }
+    if (add_rcu(steps, w.rcu2[k], rcu2_in_relu, rcu2_in_f32, nullptr, tmp, B, h, ww, nullptr, r2, nullptr)) return -1;
+    LSEG_ALLOC(up, __half, px * 4 * 256);
+    steps.push_back([=](const CallCtx&, cudaStream_t s) {
+      const long long total = px * 4 * (256 / 8);
+      upsample2x_nhwc_kernel<<<ew_grid(total, 256), 256, 0, s>>>(r2, up, B, h, ww, 256);
+      LSEG_CHECK_CUDA(cudaGetLastError());
+      return 0;
+    });
+    GemmEpi e = epi_none();
+    e.bias = w.out_conv[k].b;
+    e.ldc = 256;
+    if (k > 0) {
+      LSEG_ALLOC(pth, float, px * 4 * 256);
+      e.out_f32 = pth;
+      path_prev = pth;
+    } else {
+      LSEG_ALLOC(pth16, __half, px * 4 * 256);
+      e.out_f16 = pth16;
+      path1_f16 = pth16;
+    }
+    if (add_gemm(steps, up, 256, (int)(px * 4), (int)(px * 4), w.out_conv[k], e)) return -1;
+  }
+  plan->debug["path1"] = path1_f16;
+
+  // ---- head1 + pixel normalisation (lseg_net.py:185-191) ----
+  const long long BP = static_cast<long long>(B) * (H / 2) * (W / 2);
+  LSEG_ALLOC(feat, float, BP * 512);
+  LSEG_ALLOC(featn, __half, BP * 512);
+  {
+    GemmEpi e = epi_none();
+    e.bias = w.head1.b;
+    e.out_f32 = feat;
+    e.ldc = 512;
+    if (add_gemm(steps, path1_f16, 256, (int)BP, (int)BP, w.head1, e)) return -1;
+  }
+  {
+    const float ls = w.logit_scale;
+    steps.push_back([=](const CallCtx&, cudaStream_t s) {
+      l2norm_scale_kernel<<<static_cast<int>((BP + 7) / 8), 256, 0, s>>>(feat, featn, BP, 512, ls);
+      LSEG_CHECK_CUDA(cudaGetLastError());
+      return 0;
+    });
+  }
+  plan->featn = featn;
+  eng->img = std::move(plan);
+  return 0;
+}
+
+static int run_forward(lseg_engine* eng, const CallCtx& ctx, int B, int H, int W, cudaStream_t stream) {
+  if (ensure_init()) return -1;
+  if (H % 32 != 0 || W % 32 != 0 || H <= 0 || W <= 0) {
+    // the reference fails deep inside skip_add.add (lseg_blocks.py:347) for odd token grids
+    set_error("lseg_forward: H=%d, W=%d must be positive multiples of 32", H, W);
+    return -1;
+  }
+  if (ctx.K <= 0) {
+    set_error("lseg_forward: K=%d labels", ctx.K);
+    return -1;
+  }
+  LSEG_CHECK_CUDA(cudaSetDevice(eng->device));
+  if (!eng->img || eng->img->B != B || eng->img->H != H || eng->img->W != W) {
+    eng->img.reset();
+    if (build_image_plan(eng, B, H, W, stream)) return -1;
+  }
+  ImagePlan& plan = *eng->img;
+  const int h2 = H / 2, w2 = W / 2;
+  const long long P = static_cast<long long>(h2) * w2;
+  if (!plan.logits_lr || plan.logits_cap_k < (size_t)ctx.K) {
+    void* p = plan.arena.alloc(sizeof(__half) * (size_t)B * ctx.K * P);
+    if (!p) {
+      set_error("logits workspace allocation failed");
+      return -1;
+    }
+    plan.logits_lr = static_cast<__half*>(p);
+    plan.logits_cap_k = ctx.K;
+    plan.debug["logits_lr"] = p;
+  }
+  int launches = 0;
+  for (auto& st : plan.steps) {
+    if (st(ctx, stream)) return -1;
+    ++launches;
+  }
+  // ---- pixel x text correlation (lseg_net.py:194-196): fp16 GEMM, fp16 result, NCHW store ----
+  const int kpad = ((ctx.K + 127) / 128) * 128;
+  const int groups = ctx.text_image_stride > 0 ? B : 1;
+  for (int g = 0; g < groups; ++g) {
+    GemmDesc d;
+    memset(&d, 0, sizeof(d));
+    const long long rows = (groups == 1) ? static_cast<long long>(B) * P : P;
+    d.a = plan.featn + static_cast<long long>(g) * P * 512;
+    d.lda = 512;
+    d.a_rows = (int)rows;
+    d.w = ctx.text + static_cast<long long>(g) * ctx.text_image_stride * 512;
+    d.w_rows = kpad;
+    d.M = (int)rows;
+    d.N = ctx.K;
+    d.K = 512;
+    d.e = epi_none();
+    d.e.out_f16 = plan.logits_lr + static_cast<long long>(g) * ctx.K * P;
+    d.e.store = STORE_NCHW_T;
+    d.e.nchw_p = (int)P;
+    d.e.nchw_k = ctx.K;
+    GemmPlan gp;
+    if (gemm_plan(d, &gp)) return -1;
+    if (gemm_run(gp, stream)) return -1;
+    ++launches;
+  }
+  // ---- scratch.output_conv: bilinear x2, align_corners=True (lseg_net.py:203) ----
+  {
+    const long long planes = static_cast<long long>(B) * ctx.K;
+    const long long total = planes * H * (W / 4);
+    upsample2x_nchw_kernel<<<ew_grid(total, 256), 256, 0, stream>>>(plan.logits_lr, ctx.out, planes, h2, w2);
+    LSEG_CHECK_CUDA(cudaGetLastError());
+    ++launches;
+  }
+  eng->last_launches = launches;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// CLIP text tower: fp16 residual stream, fp32 LayerNorm statistics
+// ------------------------------------------------------------------------------------------
+static int build_text_plan(lseg_engine* eng, int K) {
+  const lseg_weights& w = eng->w;
+  std::unique_ptr<TextPlan> plan(new TextPlan());
+  plan->K = K;
+  Arena& arena = plan->arena;
+  const int L = 77, Wd = 512;
+  const long long M = static_cast<long long>(K) * L;
+  const int kpad = ((K + 127) / 128) * 128;
+  LSEG_ALLOC(tx, __half, M * Wd);
+  LSEG_ALLOC(txn, __half, M * Wd);
+  LSEG_ALLOC(tqkv, __half, M * 3 * Wd);
+  LSEG_ALLOC(tattn, __half, M * Wd);
+  LSEG_ALLOC(th, __half, M * 4 * Wd);
+  LSEG_ALLOC(teot, __half, (size_t)kpad * Wd);
+  LSEG_ALLOC(tfeat, __half, (size_t)kpad * Wd);
+  LSEG_CHECK_CUDA(cudaMemset(teot, 0, sizeof(__half) * (size_t)kpad * Wd));
+
+  std::vector<Step> gsteps;  // reuse the image-side builders, then adapt
+  auto& steps = plan->steps;
+  auto wrap = [&steps](std::vector<Step>& src) {
+    for (auto& st : src) {
+      Step s = st;
+      steps.push_back([s](const long long*, __half*, cudaStream_t stream) {
+        CallCtx c;
+        memset(&c, 0, sizeof(c));
+        return s(c, stream);
+      });
+    }
+    src.clear();
+  };
+  const float* tok_emb = w.tok_emb;
+  const float* text_pos = w.text_pos;
+  steps.push_back([=](const long long* tokens, __half*, cudaStream_t s) {
+    const long long total = M * Wd;
+    text_embed_kernel<<<ew_grid(total, 256), 256, 0, s>>>(tokens, tok_emb, text_pos, tx, K, L, Wd);
+    LSEG_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  });
+  for (int i = 0; i < LSEG_TEXT_DEPTH; ++i) {
+    const lseg_text_block_w& bw = w.text_blocks[i];
+    add_layernorm(gsteps, tx, 1, bw.ln1_g, bw.ln1_b, txn, M, Wd, 1e-5f);
+    {
+      GemmEpi e = epi_none();
+      e.bias = bw.in_proj.b;
+      e.out_f16 = tqkv;
+      e.ldc = 3 * Wd;
+      if (add_gemm(gsteps, txn, Wd, (int)M, (int)M, bw.in_proj, e)) return -1;
+    }
+    {
+      MhsaDesc md;
+      md.qkv = tqkv;
+      md.out = tattn;
+      md.B = K;
+      md.N = L;
+      md.heads = 8;
+      md.causal = 1;
+      MhsaPlan mp;
+      if (mhsa_plan(md, &mp)) return -1;
+      gsteps.push_back([mp](const CallCtx&, cudaStream_t s) { return mhsa_run(mp, s); });
+    }
+    {
+      GemmEpi e = epi_none();
+      e.bias = bw.out_proj.b;
+      e.res_f16 = tx;
+      e.out_f16 = tx;
+      e.ldc = Wd;
+      if (add_gemm(gsteps, tattn, Wd, (int)M, (int)M, bw.out_proj, e)) return -1;
+    }
+    add_layernorm(gsteps, tx, 1, bw.ln2_g, bw.ln2_b, txn, M, Wd, 1e-5f);
+    {
+      GemmEpi e = epi_none();
+      e.bias = bw.c_fc.b;
+      e.act = ACT_QUICKGELU;
+      e.out_f16 = th;
+      e.ldc = 4 * Wd;
+      if (add_gemm(gsteps, txn, Wd, (int)M, (int)M, bw.c_fc, e)) return -1;
+    }
+    {
+      GemmEpi e = epi_none();
+      e.bias = bw.c_proj.b;
+      e.res_f16 = tx;
+      e.out_f16 = tx;
+      e.ldc = Wd;
+      if (add_gemm(gsteps, th, 4 * Wd, (int)M, (int)M, bw.c_proj, e)) return -1;
+    }
+    wrap(gsteps);
+  }
+  add_layernorm(gsteps, tx, 1, w.lnf_g, w.lnf_b, txn, M, Wd, 1e-5f);
+  wrap(gsteps);
+  steps.push_back([=](const long long* tokens, __half*, cudaStream_t s) {
+    text_eot_gather_kernel<<<K, 128, 0, s>>>(tokens, txn, teot, K, L, Wd);
+    LSEG_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  });
+  {
+    GemmEpi e = epi_none();
+    e.out_f16 = tfeat;
+    e.ldc = Wd;
+    if (add_gemm(gsteps, teot, Wd, kpad, K, w.text_proj, e)) return -1;
+    wrap(gsteps);
+  }
+  steps.push_back([=](const long long*, __half* out, cudaStream_t s) {
+    LSEG_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(__half) * (size_t)kpad * Wd, s));
+    l2norm_f16_kernel<<<(K + 7) / 8, 256, 0, s>>>(tfeat, out, K, Wd);
+    LSEG_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  });
+  eng->txt = std::move(plan);
+  return 0;
+}
+
+}  // namespace lseg
+
+extern "C" {
+
+int lseg_create(const lseg_weights* w, int device, lseg_engine** out) {
+  using namespace lseg;
+  if (!w || !out) {
+    set_error("lseg_create: null argument");
+    return -1;
+  }
+  LSEG_CHECK_CUDA(cudaSetDevice(device));
+  if (ensure_init()) return -1;
+  lseg_engine* e = new lseg_engine();
+  e->w = *w;
+  e->device = device;
+  *out = e;
+  return 0;
+}
+
+void lseg_destroy(lseg_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  e->img.reset();
+  e->txt.reset();
+  for (auto& kv : e->pos_cache) cudaFree(kv.second);
+  delete e;
+}
+
+int lseg_encode_text(lseg_engine* e, const int64_t* tokens, int K, void* text_out, void* stream) {
+  using namespace lseg;
+  if (!e || !tokens || !text_out || K <= 0) {
+    set_error("lseg_encode_text: bad argument");
+    return -1;
+  }
+  if (ensure_init()) return -1;
+  LSEG_CHECK_CUDA(cudaSetDevice(e->device));
+  if (!e->txt || e->txt->K != K) {
+    e->txt.reset();
+    if (build_text_plan(e, K)) return -1;
+  }
+  int launches = 0;
+  for (auto& st : e->txt->steps) {
+    if (st(reinterpret_cast<const long long*>(tokens), static_cast<__half*>(text_out),
+           static_cast<cudaStream_t>(stream)))
+      return -1;
+    ++launches;
+  }
+  e->last_launches = launches;
+  return 0;
+}
+
+int lseg_forward(lseg_engine* e, const float* x, int B, int H, int W, const void* text, int K,
+                 long long text_image_stride, float* out, void* stream) {
+  using namespace lseg;
+  if (!e || !x || !text || !out || B <= 0) {
+    set_error("lseg_forward: bad argument");
+    return -1;
+  }
+  CallCtx ctx;
+  ctx.x = x;
+  ctx.text = static_cast<const __half*>(text);
+  ctx.K = K;
+  ctx.text_image_stride = text_image_stride;
+  ctx.out = out;
+  return run_forward(e, ctx, B, H, W, static_cast<cudaStream_t>(stream));
+}
+
+const void* lseg_debug_buffer(lseg_engine* e, const char* name) {
+  if (!e || !e->img || !name) return nullptr;
+  auto it = e->img->debug.find(name);
+  return it == e->img->debug.end() ? nullptr : it->second;
+}
+
+int lseg_last_launch_count(lseg_engine* e) { return e ? e->last_launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,363 @@
+// lseg_b200 — persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   C[M,N] = epilogue( A[M,K] * W[N,K]^T )       fp16 operands, fp32 accumulate in TMEM
+//
+// One kernel covers every dense contraction of the LSeg forward path (SURVEY.md §2b k1,k4,k6-k8,
+// k10-k17,k19): linear layers, 1x1 convs, kernel==stride transposed convs (depth-to-space store),
+// and 3x3 stride-1 convs as implicit GEMM (the A tile of tap (dy,dx) is a shifted 4-D TMA box of
+// the NHWC activation; TMA zero-fills the padding halo).
+//
+// Roles (one CTA per SM, persistent over a static round-robin tile list):
+//   warp 0   TMA producer       : fills the A/B smem ring (128B-swizzled, K-major)
+//   warp 1   MMA issuer         : one thread issues tcgen05.mma 128 x BN x 16, commits to mbarriers
+//   warp 2   TMEM allocator
+//   warps 4+ epilogue           : tcgen05.ld accumulator -> regs -> bias/scale/act/residual -> global
+// The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
+// the main loop of tile i+1.
+#pragma once
+#include "common.cuh"
+
+namespace lseg {
+
+constexpr int kGemmBM = 128;
+constexpr int kGemmBK = 64;
+constexpr int kConvTH = 8;   // conv M tile = 8 x 16 output pixels
+constexpr int kConvTW = 16;
+constexpr int kGemmEpiWarps = 8;
+constexpr int kGemmThreads = 128 + 32 * kGemmEpiWarps;
+
+enum GemmAct { ACT_NONE = 0, ACT_GELU = 1, ACT_QUICKGELU = 2, ACT_RELU = 3 };
+enum GemmStore { STORE_ROWMAJOR = 0, STORE_D2S = 1, STORE_NCHW_T = 2 };
+
+struct GemmEpi {
+  const float* bias;       // [N] (or [groups, N] when bias_group_rows > 0); nullable
+  int bias_group_rows;     // rows sharing one bias row (per-image broadcast bias, readout k10)
+  const float* scale;      // [N] per-column scale applied before bias (folded BatchNorm); nullable
+  int act;                 // GemmAct
+  const float* res_f32;    // fp32 residual, same row-major layout as the output; nullable
+  const float* res2_f32;   // second fp32 residual (fusion-block skip add); nullable
+  const __half* res_f16;   // fp16 residual (CLIP text tower: fp16 residual stream); nullable
+  float* out_f32;          // nullable
+  __half* out_f16;         // nullable
+  __half* out_f16_relu;    // nullable: relu(result) copy in fp16 (input of the next RCU conv)
+  long long ldc;           // row stride in elements (row-major store + residual)
+  int store;               // GemmStore
+  int d2s_s, d2s_cout, d2s_h, d2s_w;  // depth-to-space: input grid h x w, upscale s, cout channels
+  int nchw_p, nchw_k;      // STORE_NCHW_T: pixels per image, channel count (n < nchw_k stored)
+};
+
+struct GemmParams {
+  CUtensorMap tma_a;  // plain: 2-D {K, M}; conv: 4-D {C, W, H, B}
+  CUtensorMap tma_b;  // 2-D {Ktot, N}, Ktot = taps * C, tap-major
+  int M, N;
+  int k_iters;   // total K chunks of 64 (taps * C/64)
+  int k_chunks;  // chunks per tap (C/64); == k_iters for plain
+  int conv;      // 0 plain, 1 implicit-GEMM conv
+  int H, W, kw, pad;
+  int tiles_h, tiles_w;
+  int num_m_tiles, num_n_tiles;
+  GemmEpi e;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kABytes = kGemmBM * kGemmBK * 2;
+  static constexpr int kBBytes = BN * kGemmBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;                          // [kStages]
+  uint64_t* empty_bar = bars + Cfg::kStages;          // [kStages]
+  uint64_t* tmem_full = bars + 2 * Cfg::kStages;      // [2]
+  uint64_t* tmem_empty = bars + 2 * Cfg::kStages + 2; // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tma_a);
+    tma_prefetch_desc(&p.tma_b);
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 32 * kGemmEpiWarps);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_base_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile % p.num_m_tiles;
+        const int n_tile = tile / p.num_m_tiles;
+        const int n0 = n_tile * BN;
+        int cb = 0, ch0 = 0, cw0 = 0;
+        if (p.conv) {
+          const int per_img = p.tiles_h * p.tiles_w;
+          cb = m_tile / per_img;
+          const int t = m_tile % per_img;
+          ch0 = (t / p.tiles_w) * kConvTH;
+          cw0 = (t % p.tiles_w) * kConvTW;
+        }
+        for (int kit = 0; kit < p.k_iters; ++kit) {
+          mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          if (p.conv) {
+            const int tap = kit / p.k_chunks;
+            const int c = kit - tap * p.k_chunks;
+            const int dy = tap / p.kw, dx = tap - dy * p.kw;
+            tma_load_4d(sa, &p.tma_a, &full_bar[stage], c * kGemmBK, cw0 + dx - p.pad, ch0 + dy - p.pad, cb);
+          } else {
+            tma_load_2d(sa, &p.tma_a, &full_bar[stage], kit * kGemmBK, m_tile * kGemmBM);
+          }
+          tma_load_2d(sb, &p.tma_b, &full_bar[stage], kit * kGemmBK, n0);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(kGemmBM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 2);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kit = 0; kit < p.k_iters; ++kit) {
+          mbar_wait(&full_bar[stage], phase, 3);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t b_base = a_base + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < kGemmBK / 16; ++k) {
+            const uint64_t da = umma_desc_sw128(a_base + k * 32, 1024, 0);
+            const uint64_t db = umma_desc_sw128(b_base + k * 32, 1024, 0);
+            umma_f16_ss(d_tmem, da, db, idesc, (kit | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== Epilogue =====================
+    const int ew = warp - 4;
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = ew >> 2;                     // column half handled by this warp
+    constexpr int kColsPerWarp = BN / (kGemmEpiWarps / 4);
+    const int r = quarter * 32 + lane;            // row inside the 128-row tile
+    const GemmEpi& e = p.e;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_tile = tile % p.num_m_tiles;
+      const int n_tile = tile / p.num_m_tiles;
+      long long grow;
+      bool valid;
+      if (p.conv) {
+        const int per_img = p.tiles_h * p.tiles_w;
+        const int b = m_tile / per_img;
+        const int t = m_tile % per_img;
+        const int h = (t / p.tiles_w) * kConvTH + r / kConvTW;
+        const int w = (t % p.tiles_w) * kConvTW + r % kConvTW;
+        valid = (h < p.H) && (w < p.W);
+        grow = (static_cast<long long>(b) * p.H + h) * p.W + w;
+      } else {
+        grow = static_cast<long long>(m_tile) * kGemmBM + r;
+        valid = grow < p.M;
+      }
+      mbar_wait(&tmem_full[acc], acc_phase, 4);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * kColsPerWarp;
+      const long long bias_off =
+          (e.bias_group_rows > 0) ? (grow / e.bias_group_rows) * static_cast<long long>(p.N) : 0;
+#pragma unroll 1
+      for (int c = 0; c < kColsPerWarp / 32; ++c) {
+        const int n0 = n_tile * BN + half * kColsPerWarp + c * 32;
+        if (n0 >= p.N) break;  // warp-uniform
+        uint32_t v[32];
+        __syncwarp();
+        tmem_ld32(t_row + c * 32, v);
+        tmem_ld_wait();
+        if (!valid) continue;
+        const int nvalid = min(32, p.N - n0);
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+        if (e.scale) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] *= (i < nvalid) ? __ldg(e.scale + n0 + i) : 0.f;
+        }
+        if (e.bias) {
+          const float* bp = e.bias + ((e.bias_group_rows > 0 && valid) ? bias_off : 0) + n0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] += (i < nvalid) ? __ldg(bp + i) : 0.f;
+        }
+        if (e.act == ACT_GELU) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
+        } else if (e.act == ACT_QUICKGELU) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = quick_gelu(f[i]);
+        } else if (e.act == ACT_RELU) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+        }
+        if (e.store == STORE_ROWMAJOR) {
+          const long long off = grow * e.ldc + n0;
+          if (nvalid == 32) {
+            if (e.res_f32) {
+              const float4* rp = reinterpret_cast<const float4*>(e.res_f32 + off);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 q = rp[i];
+                f[4 * i + 0] += q.x; f[4 * i + 1] += q.y; f[4 * i + 2] += q.z; f[4 * i + 3] += q.w;
+              }
+            }
+            if (e.res2_f32) {
+              const float4* rp = reinterpret_cast<const float4*>(e.res2_f32 + off);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 q = rp[i];
+                f[4 * i + 0] += q.x; f[4 * i + 1] += q.y; f[4 * i + 2] += q.z; f[4 * i + 3] += q.w;
+              }
+            }
+            if (e.out_f32) {
+              float4* op = reinterpret_cast<float4*>(e.out_f32 + off);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+            }
+            if (e.out_f16) {
+              __half2 h[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+              if (e.res_f16) {  // fp16 residual stream: round the branch output first, then add in fp16
+                const uint4* rp = reinterpret_cast<const uint4*>(e.res_f16 + off);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const uint4 q = rp[i];
+                  const __half2* qh = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) h[4 * i + j] = __hadd2(qh[j], h[4 * i + j]);
+                }
+              }
+              uint4* op = reinterpret_cast<uint4*>(e.out_f16 + off);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) op[i] = *reinterpret_cast<uint4*>(&h[4 * i]);
+            }
+            if (e.out_f16_relu) {
+              __half2 h[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) h[i] = __floats2half2_rn(fmaxf(f[2 * i], 0.f), fmaxf(f[2 * i + 1], 0.f));
+              uint4* op = reinterpret_cast<uint4*>(e.out_f16_relu + off);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) op[i] = *reinterpret_cast<uint4*>(&h[4 * i]);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (i < nvalid) {
+                float x = f[i];
+                if (e.res_f32) x += e.res_f32[off + i];
+                if (e.res2_f32) x += e.res2_f32[off + i];
+                if (e.out_f32) e.out_f32[off + i] = x;
+                if (e.out_f16) {
+                  __half hx = __float2half_rn(x);
+                  if (e.res_f16) hx = __hadd(e.res_f16[off + i], hx);
+                  e.out_f16[off + i] = hx;
+                }
+                if (e.out_f16_relu) e.out_f16_relu[off + i] = __float2half_rn(fmaxf(x, 0.f));
+              }
+            }
+          }
+        } else if (e.store == STORE_D2S) {
+          // column n = (i*s + j)*cout + co ; row grow = (b*h + y)*w + x  ->  NHWC [B, h*s, w*s, cout]
+          const int ij = n0 / e.d2s_cout;
+          const int co0 = n0 - ij * e.d2s_cout;
+          const int di = ij / e.d2s_s, dj = ij - di * e.d2s_s;
+          const int hw = e.d2s_h * e.d2s_w;
+          const int b = static_cast<int>(grow / hw);
+          const int yx = static_cast<int>(grow - static_cast<long long>(b) * hw);
+          const int y = yx / e.d2s_w, x = yx - y * e.d2s_w;
+          const long long orow =
+              (static_cast<long long>(b) * (e.d2s_h * e.d2s_s) + (y * e.d2s_s + di)) * (e.d2s_w * e.d2s_s) +
+              (x * e.d2s_s + dj);
+          __half2 h[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+          uint4* op = reinterpret_cast<uint4*>(e.out_f16 + orow * e.d2s_cout + co0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) op[i] = *reinterpret_cast<uint4*>(&h[4 * i]);
+        } else {  // STORE_NCHW_T : out[(b*K + n)*P + p], fp16
+          const int b = static_cast<int>(grow / e.nchw_p);
+          const int pix = static_cast<int>(grow - static_cast<long long>(b) * e.nchw_p);
+          __half* op = e.out_f16 + (static_cast<long long>(b) * e.nchw_k + n0) * e.nchw_p + pix;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (n0 + i < e.nchw_k) op[static_cast<long long>(i) * e.nchw_p] = __float2half_rn(f[i]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Host launchers
+// ------------------------------------------------------------------------------------------
+struct GemmDesc {
+  // A operand
+  const __half* a;      // plain: [a_rows >= M, lda] ; conv: NHWC [B, H, W, C]
+  long long lda;        // plain only (elements)
+  int a_rows;           // plain only: allocated rows (tensor-map extent)
+  // B operand (weights) [N, Ktot] row-major fp16, rows padded to a multiple of 128
+  const __half* w;
+  int w_rows;           // allocated rows of w (>= N)
+  int M, N, K;          // plain: K ; conv: K = C (per tap)
+  int conv, B, H, W, kh, kw, pad;
+  GemmEpi e;
+};
+
+}  // namespace lseg

@@ -1,0 +1,449 @@
+// lseg_b200 — single translation unit of liblseg_b200.so: host launchers, the C ABI declared in
+// include/lseg_b200.h, and (engine.cuh) the whole-model forward. Compiled for sm_100a only.
+#include "../../include/lseg_b200.h"
+
+#include <stdarg.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "elementwise.cuh"
+#include "gemm_tc.cuh"
+#include "mhsa.cuh"
+
+namespace lseg {
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local char t_error[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_error, sizeof(t_error), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return t_error; }
+
+// ------------------------------------------------------------------------------------------
+// device / driver entry points
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+static int g_num_sms = 0;
+static std::once_flag g_init_flag;
+static int g_init_status = -1;
+
+static void init_once() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    set_error("lseg_b200: no CUDA device available (there is no CPU fallback)");
+    return;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+    set_error("lseg_b200: cudaGetDeviceProperties failed");
+    return;
+  }
+  if (prop.major != 10) {
+    set_error("lseg_b200: device '%s' is sm_%d%d; this library contains sm_100a code only", prop.name, prop.major,
+              prop.minor);
+    return;
+  }
+  g_num_sms = prop.multiProcessorCount;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+    set_error("lseg_b200: cuTensorMapEncodeTiled not available from the driver");
+    return;
+  }
+  g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256>::kSmemBytes);
+  cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::kSmemBytes);
+  cudaFuncSetAttribute(mhsa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMhsaSmemBytes);
+  cudaFuncSetAttribute(mhsa_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  g_init_status = 0;
+}
+static int ensure_init() {
+  std::call_once(g_init_flag, init_once);
+  return g_init_status;
+}
+
+int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box) {
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[5];
+  cuuint32_t bdim[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    if (i + 1 < rank) gstr[i] = strides_bytes[i];
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) {
+    set_error("tensor map base %p is not 16-byte aligned", base);
+    return -1;
+  }
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with %d (rank %d dims %llu,%llu,%llu,%llu box %u,%u,%u,%u)", (int)r, rank,
+              (unsigned long long)gdim[0], (unsigned long long)(rank > 1 ? gdim[1] : 0),
+              (unsigned long long)(rank > 2 ? gdim[2] : 0), (unsigned long long)(rank > 3 ? gdim[3] : 0), bdim[0],
+              rank > 1 ? bdim[1] : 0, rank > 2 ? bdim[2] : 0, rank > 3 ? bdim[3] : 0);
+    return -1;
+  }
+  return 0;
+}
+
+int read_watchdog(int out[4], cudaStream_t stream) {
+  LSEG_CHECK_CUDA(cudaStreamSynchronize(stream));
+  LSEG_CHECK_CUDA(cudaMemcpyFromSymbol(out, g_watchdog, sizeof(int) * 4));
+  int zero[4] = {0, 0, 0, 0};
+  LSEG_CHECK_CUDA(cudaMemcpyToSymbol(g_watchdog, zero, sizeof(zero)));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// GEMM planning / launch
+// ------------------------------------------------------------------------------------------
+struct GemmPlan {
+  GemmParams p;
+  int bn;
+  int grid;
+};
+
+static int gemm_plan(const GemmDesc& d, GemmPlan* plan) {
+  if (ensure_init()) return -1;
+  GemmParams& p = plan->p;
+  memset(&p, 0, sizeof(p));
+  if (d.K % kGemmBK != 0) {
+    set_error("gemm: K=%d must be a multiple of %d", d.K, kGemmBK);
+    return -1;
+  }
+  const int bn = (d.N > 128) ? 256 : 128;
+  plan->bn = bn;
+  const int taps = d.conv ? d.kh * d.kw : 1;
+  const long long ktot = static_cast<long long>(taps) * d.K;
+  if (d.w_rows < bn && d.w_rows < d.N) {
+    set_error("gemm: weight rows %d < N %d", d.w_rows, d.N);
+    return -1;
+  }
+  p.M = d.M;
+  p.N = d.N;
+  p.k_chunks = d.K / kGemmBK;
+  p.k_iters = p.k_chunks * taps;
+  p.conv = d.conv;
+  p.e = d.e;
+  if (d.conv) {
+    p.H = d.H;
+    p.W = d.W;
+    p.kw = d.kw;
+    p.pad = d.pad;
+    p.tiles_h = (d.H + kConvTH - 1) / kConvTH;
+    p.tiles_w = (d.W + kConvTW - 1) / kConvTW;
+    p.num_m_tiles = d.B * p.tiles_h * p.tiles_w;
+    const uint64_t dims[4] = {(uint64_t)d.K, (uint64_t)d.W, (uint64_t)d.H, (uint64_t)d.B};
+    const uint64_t str[3] = {(uint64_t)d.K * 2, (uint64_t)d.K * d.W * 2, (uint64_t)d.K * d.W * d.H * 2};
+    const uint32_t box[4] = {kGemmBK, kConvTW, kConvTH, 1};
+    if (make_tmap_f16(&p.tma_a, d.a, 4, dims, str, box)) return -1;
+  } else {
+    p.num_m_tiles = (d.M + kGemmBM - 1) / kGemmBM;
+    const uint64_t dims[2] = {(uint64_t)d.K, (uint64_t)d.a_rows};
+    const uint64_t str[1] = {(uint64_t)d.lda * 2};
+    const uint32_t box[2] = {kGemmBK, kGemmBM};
+    if (make_tmap_f16(&p.tma_a, d.a, 2, dims, str, box)) return -1;
+  }
+  p.num_n_tiles = (d.N + bn - 1) / bn;
+  {
+    const uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)d.w_rows};
+    const uint64_t str[1] = {(uint64_t)ktot * 2};
+    const uint32_t box[2] = {kGemmBK, (uint32_t)bn};
+    if (make_tmap_f16(&p.tma_b, d.w, 2, dims, str, box)) return -1;
+  }
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  plan->grid = tiles < g_num_sms ? tiles : g_num_sms;
+  if (p.e.store == STORE_D2S && (p.e.d2s_cout % 32 != 0 || !p.e.out_f16)) {
+    set_error("gemm: depth-to-space store needs cout %% 32 == 0 and an fp16 output");
+    return -1;
+  }
+  if (p.e.store == STORE_ROWMAJOR && (p.e.ldc % 8 != 0)) {
+    set_error("gemm: ldc must be a multiple of 8");
+    return -1;
+  }
+  return 0;
+}
+
+static int gemm_run(const GemmPlan& plan, cudaStream_t stream) {
+  if (plan.grid <= 0) return 0;
+  if (plan.bn == 256)
+    gemm_tc_kernel<256><<<plan.grid, kGemmThreads, GemmCfg<256>::kSmemBytes, stream>>>(plan.p);
+  else
+    gemm_tc_kernel<128><<<plan.grid, kGemmThreads, GemmCfg<128>::kSmemBytes, stream>>>(plan.p);
+  LSEG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// MHSA planning / launch
+// ------------------------------------------------------------------------------------------
+struct MhsaPlan {
+  MhsaParams p;
+  dim3 grid;
+};
+static int mhsa_plan(const MhsaDesc& d, MhsaPlan* plan) {
+  if (ensure_init()) return -1;
+  MhsaParams& p = plan->p;
+  memset(&p, 0, sizeof(p));
+  const int D = d.heads * kMhsaDh;
+  const uint64_t dims[3] = {(uint64_t)3 * D, (uint64_t)d.N, (uint64_t)d.B};
+  const uint64_t str[2] = {(uint64_t)3 * D * 2, (uint64_t)3 * D * d.N * 2};
+  const uint32_t box[3] = {kMhsaDh, kMhsaTile, 1};
+  if (make_tmap_f16(&p.tma_qkv, d.qkv, 3, dims, str, box)) return -1;
+  p.out = d.out;
+  p.n_tokens = d.N;
+  p.heads = d.heads;
+  p.D = D;
+  p.causal = d.causal;
+  p.scale_log2e = 0.125f * 1.44269504088896340736f;
+  plan->grid = dim3((d.N + kMhsaTile - 1) / kMhsaTile, d.B * d.heads, 1);
+  return 0;
+}
+static int mhsa_run(const MhsaPlan& plan, cudaStream_t stream) {
+  mhsa_kernel<<<plan.grid, kMhsaThreads, kMhsaSmemBytes, stream>>>(plan.p);
+  LSEG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// elementwise launch helpers
+// ------------------------------------------------------------------------------------------
+static inline int ew_grid(long long total, int threads) {
+  long long blocks = (total + threads - 1) / threads;
+  const long long cap = static_cast<long long>(g_num_sms > 0 ? g_num_sms : 148) * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+static int run_layernorm(const void* x, int in_f16, const float* g, const float* b, __half* y, long long M, int C,
+                         float eps, cudaStream_t s) {
+  if (C % 128 != 0 || C > 1024) {
+    set_error("layernorm: C=%d must be a multiple of 128 and <= 1024", C);
+    return -1;
+  }
+  const int rows_per_block = 8;
+  const int grid = static_cast<int>((M + rows_per_block - 1) / rows_per_block);
+  if (in_f16)
+    layernorm_kernel<__half><<<grid, rows_per_block * 32, 0, s>>>(static_cast<const __half*>(x), g, b, y, M, C, eps);
+  else
+    layernorm_kernel<float><<<grid, rows_per_block * 32, 0, s>>>(static_cast<const float*>(x), g, b, y, M, C, eps);
+  LSEG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace lseg
+
+#include "engine.cuh"
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+using namespace lseg;
+
+extern "C" {
+
+const char* lseg_last_error(void) { return get_error(); }
+int lseg_abi_version(void) { return LSEG_B200_ABI_VERSION; }
+
+int lseg_read_watchdog(int out[4], void* stream) {
+  if (ensure_init()) return -1;
+  return read_watchdog(out, static_cast<cudaStream_t>(stream));
+}
+
+static void fill_epi(const lseg_gemm_args* a, GemmEpi* e) {
+  memset(e, 0, sizeof(*e));
+  e->bias = a->bias;
+  e->bias_group_rows = a->bias_group_rows;
+  e->scale = a->scale;
+  e->act = a->act;
+  e->res_f32 = a->res_f32;
+  e->res2_f32 = a->res2_f32;
+  e->res_f16 = static_cast<const __half*>(a->res_f16);
+  e->out_f32 = a->out_f32;
+  e->out_f16 = static_cast<__half*>(a->out_f16);
+  e->out_f16_relu = static_cast<__half*>(a->out_f16_relu);
+  e->ldc = a->ldc;
+  e->store = a->store;
+  e->d2s_s = a->d2s_s;
+  e->d2s_cout = a->d2s_cout;
+  e->d2s_h = a->d2s_h;
+  e->d2s_w = a->d2s_w;
+  e->nchw_p = a->nchw_p;
+  e->nchw_k = a->nchw_k;
+}
+
+int lseg_gemm(const lseg_gemm_args* a, void* stream) {
+  if (!a) {
+    set_error("lseg_gemm: null args");
+    return -1;
+  }
+  GemmDesc d;
+  memset(&d, 0, sizeof(d));
+  d.a = static_cast<const __half*>(a->a);
+  d.lda = a->lda;
+  d.a_rows = a->a_rows > 0 ? a->a_rows : a->M;
+  d.w = static_cast<const __half*>(a->w);
+  d.w_rows = a->w_rows > 0 ? a->w_rows : a->N;
+  d.M = a->M;
+  d.N = a->N;
+  d.K = a->K;
+  d.conv = a->conv;
+  d.B = a->B;
+  d.H = a->H;
+  d.W = a->W;
+  d.kh = d.kw = a->ksize;
+  d.pad = a->pad;
+  fill_epi(a, &d.e);
+  GemmPlan plan;
+  if (gemm_plan(d, &plan)) return -1;
+  return gemm_run(plan, static_cast<cudaStream_t>(stream));
+}
+
+int lseg_mhsa(const void* qkv, void* out, int B, int N, int heads, int causal, void* stream) {
+  MhsaDesc d;
+  d.qkv = static_cast<const __half*>(qkv);
+  d.out = static_cast<__half*>(out);
+  d.B = B;
+  d.N = N;
+  d.heads = heads;
+  d.causal = causal;
+  MhsaPlan plan;
+  if (mhsa_plan(d, &plan)) return -1;
+  return mhsa_run(plan, static_cast<cudaStream_t>(stream));
+}
+
+int lseg_layernorm(const void* x, int in_f16, const float* gamma, const float* beta, void* y, long long M, int C,
+                   float eps, void* stream) {
+  if (ensure_init()) return -1;
+  return run_layernorm(x, in_f16, gamma, beta, static_cast<__half*>(y), M, C, eps, static_cast<cudaStream_t>(stream));
+}
+
+int lseg_patchify(const float* x, void* a, int B, int H, int W, void* stream) {
+  if (ensure_init()) return -1;
+  if (H % 16 || W % 16) {
+    set_error("patchify: H, W must be multiples of 16");
+    return -1;
+  }
+  const long long total = static_cast<long long>(B) * (H / 16) * (W / 16) * 3 * 16 * 4;
+  patchify_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<__half*>(a), B, H,
+                                                                                      W);
+  LSEG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int lseg_pos_resize(const float* pos, float* out, int g0, int gh, int gw, int D, void* stream) {
+  if (ensure_init()) return -1;
+  pos_resize_kernel<<<1 + gh * gw, 256, 0, static_cast<cudaStream_t>(stream)>>>(pos, out, g0, gh, gw, D);
+  LSEG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int lseg_assemble_tokens(const float* patch, const float* cls, const float* pos, float* x, int B, int T, int D,
+                         void* stream) {
+  if (ensure_init()) return -1;
+  const long long total = static_cast<long long>(B) * (T + 1) * (D / 4);
+  assemble_tokens_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(patch, cls, pos, x, B, T,
+                                                                                             D);
+  LSEG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int lseg_readout_split(const float* tap, void* tok, void* cls, int B, int T, int D, void* stream) {
+  if (ensure_init()) return -1;
+  const long long total = static_cast<long long>(B) * (T + 1) * (D / 4);
+  readout_split_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      tap, static_cast<__half*>(tok), static_cast<__half*>(cls), B, T, D);
+  LSEG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int lseg_im2col_3x3_s2(const void* x, void* a, int B, int H, int W, int C, void* stream) {
+  if (ensure_init()) return -1;
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const long long total = static_cast<long long>(B) * Ho * Wo * 9 * (C / 8);
+  im2col_3x3_s2_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(x), static_cast<__half*>(a), B, H, W, C);
+  LSEG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int lseg_upsample2x_nhwc(const void* x, void* y, int B, int H, int W, int C, void* stream) {
+  if (ensure_init()) return -1;
+  const long long total = static_cast<long long>(B) * 4 * H * W * (C / 8);
+  upsample2x_nhwc_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(x), static_cast<__half*>(y), B, H, W, C);
+  LSEG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int lseg_l2norm_scale(const float* x, void* y, long long M, int C, float logit_scale, void* stream) {
+  if (ensure_init()) return -1;
+  if (C % 128 != 0 || C > 512) {
+    set_error("l2norm_scale: C=%d must be a multiple of 128 and <= 512", C);
+    return -1;
+  }
+  const int grid = static_cast<int>((M + 7) / 8);
+  l2norm_scale_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<__half*>(y), M, C,
+                                                                           logit_scale);
+  LSEG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int lseg_l2norm_f16(const void* x, void* y, int M, int C, void* stream) {
+  if (ensure_init()) return -1;
+  l2norm_f16_kernel<<<(M + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(x),
+                                                                               static_cast<__half*>(y), M, C);
+  LSEG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int lseg_upsample2x_nchw(const void* x, float* y, long long planes, int H, int W, void* stream) {
+  if (ensure_init()) return -1;
+  if ((2 * W) % 4 != 0) {
+    set_error("upsample2x_nchw: output width must be a multiple of 4");
+    return -1;
+  }
+  const long long total = planes * 2 * H * (2 * W / 4);
+  upsample2x_nchw_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(x), y, planes, H, W);
+  LSEG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int lseg_text_embed(const int64_t* tokens, const float* tok_emb, const float* pos_emb, void* x, int K, int L, int Wd,
+                    void* stream) {
+  if (ensure_init()) return -1;
+  const long long total = static_cast<long long>(K) * L * Wd;
+  text_embed_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(tokens), tok_emb, pos_emb, static_cast<__half*>(x), K, L, Wd);
+  LSEG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int lseg_text_eot_gather(const int64_t* tokens, const void* x, void* out, int K, int L, int Wd, void* stream) {
+  if (ensure_init()) return -1;
+  text_eot_gather_kernel<<<K, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(tokens), static_cast<const __half*>(x), static_cast<__half*>(out), K, L, Wd);
+  LSEG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,220 @@
+"""GPU parity tests of the stage ops (C ABI) against plain torch fp32 references of the same op.
+
+Tolerances: operands are fp16 (inputs are pre-rounded so the reference sees identical values),
+accumulation is fp32 on both sides -> differences come only from summation order (<= 1e-3 relative
+to the output scale) plus one fp16 rounding where the output is fp16 (2^-11 relative).
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import lseg_b200  # noqa: F401
+    from lseg_b200 import ops as _ops
+    return _ops
+
+
+@pytest.fixture(autouse=True)
+def _watchdog(ops):
+    yield
+    torch.cuda.synchronize()
+    wd = ops.read_watchdog()
+    assert wd[0] == 0, f"device barrier watchdog fired: tag={wd[0]} block={wd[1]} thread={wd[2]} parity={wd[3]}"
+
+
+def _rand(shape, seed, scale=1.0, dtype=torch.float16):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dtype).cuda()
+
+
+def _close(got, ref, tol, what):
+    got = got.float()
+    ref = ref.float()
+    assert torch.isfinite(got).all(), f"{what}: non-finite values"
+    denom = ref.abs().max().item() + 1e-12
+    err = (got - ref).abs().max().item() / denom
+    assert err <= tol, f"{what}: max rel err {err:.3e} > {tol:.1e} (scale {denom:.3e})"
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 256, 128), (7208, 3072, 1024), (500, 128, 512), (1000, 512, 4096),
+                                   (8, 1024, 1024), (154, 1536, 512)])
+def test_gemm_bias_f32_f16(ops, M, N, K):
+    a = _rand((M, K), 1)
+    w = _rand((N, K), 2, 0.05)
+    bias = _rand((N,), 3, 1.0, torch.float32)
+    ref = a.float() @ w.float().t() + bias
+    out32 = torch.zeros((M, N), dtype=torch.float32, device="cuda")
+    out16 = torch.zeros((M, N), dtype=torch.float16, device="cuda")
+    a_pad = ops.pad_rows(a)  # rows >= 128 so the TMA box never exceeds the tensor
+    ops.gemm(a_pad, ops.pad_rows(w), N, M=M, bias=bias, out_f32=out32, out_f16=out16)
+    _close(out32, ref, 2e-4, "fp32 out")
+    _close(out16, ref, 1e-3, "fp16 out")
+
+
+def test_gemm_gelu_residual_relu(ops):
+    M, N, K = 901 * 2, 1024, 1024
+    a = _rand((M, K), 4)
+    w = _rand((N, K), 5, 0.03)
+    bias = _rand((N,), 6, 0.5, torch.float32)
+    res = _rand((M, N), 7, 1.0, torch.float32)
+    res2 = _rand((M, N), 8, 1.0, torch.float32)
+    scale = _rand((N,), 9, 1.0, torch.float32).abs() + 0.5
+    wp = ops.pad_rows(w)
+    # GELU(erf) epilogue, fp16 out
+    out16 = torch.zeros((M, N), dtype=torch.float16, device="cuda")
+    ops.gemm(a, wp, N, bias=bias, act=ops.ACT_GELU, out_f16=out16)
+    _close(out16, F.gelu(a.float() @ w.float().t() + bias), 1e-3, "gelu")
+    # scale + bias + two fp32 residuals, in-place on res, plus relu copy
+    acc = (a.float() @ w.float().t()) * scale + bias + res + res2
+    x = res.clone()
+    relu16 = torch.zeros((M, N), dtype=torch.float16, device="cuda")
+    ops.gemm(a, wp, N, bias=bias, scale=scale, res_f32=x, res2_f32=res2, out_f32=x, out_f16_relu=relu16)
+    _close(x, acc, 2e-4, "scale/bias/res in-place")
+    _close(relu16, acc.clamp_min(0), 1e-3, "relu copy")
+    # grouped (per-image) bias rows
+    gb = _rand((2, N), 10, 1.0, torch.float32)
+    out32 = torch.zeros((M, N), dtype=torch.float32, device="cuda")
+    ops.gemm(a, wp, N, bias=gb, bias_group_rows=901, out_f32=out32)
+    ref = a.float() @ w.float().t() + gb.repeat_interleave(901, dim=0)
+    _close(out32, ref, 2e-4, "grouped bias")
+    # QuickGELU + fp16 residual stream (CLIP text tower semantics)
+    r16 = _rand((M, N), 11)
+    out16 = torch.zeros((M, N), dtype=torch.float16, device="cuda")
+    ops.gemm(a, wp, N, bias=bias, res_f16=r16, out_f16=out16)
+    ref = (r16 + (a.float() @ w.float().t() + bias).half()).float()
+    _close(out16, ref, 1.5e-3, "fp16 residual")
+    ops.gemm(a, wp, N, bias=bias, act=ops.ACT_QUICKGELU, out_f16=out16)
+    h = (a.float() @ w.float().t() + bias).half()
+    _close(out16, (h * torch.sigmoid(1.702 * h)).float(), 2e-3, "quickgelu")
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 30, 30, 128, 256), (1, 15, 15, 1024, 256), (2, 120, 120, 256, 256),
+                                            (3, 60, 60, 512, 256)])
+def test_conv3x3(ops, B, H, W, Cin, Cout):
+    x = _rand((B, H, W, Cin), 12)
+    wt = _rand((Cout, Cin, 3, 3), 13, 0.03)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), padding=1).permute(0, 2, 3, 1)
+    wp = ops.pad_rows(wt.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous())  # tap-major [N, (ky,kx,c)]
+    out32 = torch.zeros((B, H, W, Cout), dtype=torch.float32, device="cuda")
+    relu16 = torch.zeros((B, H, W, Cout), dtype=torch.float16, device="cuda")
+    ops.gemm(x, wp, Cout, conv=(3, 1), out_f32=out32, out_f16_relu=relu16, ldc=Cout)
+    _close(out32, ref, 3e-4, "conv3x3")
+    _close(relu16, ref.clamp_min(0), 1e-3, "conv3x3 relu copy")
+
+
+@pytest.mark.parametrize("s,cin,cout,g", [(4, 256, 256, 30), (2, 512, 512, 6)])
+def test_deconv_depth_to_space(ops, s, cin, cout, g):
+    B = 2
+    x = _rand((B * g * g, cin), 14)
+    wt = _rand((cin, cout, s, s), 15, 0.05)  # ConvTranspose2d weight layout [Cin, Cout, kH, kW]
+    bias = _rand((cout,), 16, 1.0, torch.float32)
+    xin = x.float().view(B, g, g, cin).permute(0, 3, 1, 2)
+    ref = F.conv_transpose2d(xin, wt.float(), bias, stride=s).permute(0, 2, 3, 1)  # NHWC
+    wp = ops.pad_rows(wt.permute(2, 3, 1, 0).reshape(s * s * cout, cin).contiguous())  # [(i,j,co), ci]
+    bexp = bias.repeat(s * s).contiguous()
+    out = torch.zeros((B, g * s, g * s, cout), dtype=torch.float16, device="cuda")
+    ops.gemm(x, wp, s * s * cout, bias=bexp, out_f16=out, store=ops.STORE_D2S, d2s=(s, cout, g, g))
+    _close(out, ref, 1e-3, "deconv d2s")
+
+
+@pytest.mark.parametrize("K", [2, 150, 512])
+def test_gemm_nchw_store(ops, K):
+    B, P = 2, 57600 // 16
+    a = _rand((B * P, 512), 17)
+    t = _rand((K, 512), 18, 0.05)
+    out = torch.zeros((B, K, P), dtype=torch.float16, device="cuda")
+    ops.gemm(a, ops.pad_rows(t), K, out_f16=out, store=ops.STORE_NCHW_T, nchw=(P, K))
+    ref = (a.float() @ t.float().t()).view(B, P, K).permute(0, 2, 1)
+    _close(out, ref, 1e-3, "nchw store")
+
+
+@pytest.mark.parametrize("B,N,heads,causal", [(2, 901, 16, False), (3, 77, 8, True), (1, 37, 16, False),
+                                              (1, 300, 2, True)])
+def test_mhsa(ops, B, N, heads, causal):
+    D = heads * 64
+    qkv = _rand((B, N, 3 * D), 19, 1.0)
+    out = ops.mhsa(qkv, B, N, heads, causal)
+    q, k, v = qkv.float().view(B, N, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-1, -2)) * 0.125
+    if causal:
+        s = s + torch.full((N, N), float("-inf"), device="cuda").triu_(1)
+    ref = (s.softmax(-1) @ v).transpose(1, 2).reshape(B * N, D)
+    _close(out, ref, 2e-3, "mhsa")
+
+
+def test_layernorm(ops):
+    for dtype, C, eps in [(torch.float32, 1024, 1e-6), (torch.float16, 512, 1e-5)]:
+        x = _rand((777, C), 20, 3.0, dtype) + 0.5
+        g = _rand((C,), 21, 1.0, torch.float32)
+        b = _rand((C,), 22, 1.0, torch.float32)
+        y = ops.layernorm(x, g, b, eps)
+        _close(y, F.layer_norm(x.float(), (C,), g, b, eps), 1e-3, f"layernorm {dtype}")
+
+
+def test_patch_tokens_pos(ops):
+    B, H, W = 2, 64, 96
+    x = _rand((B, 3, H, W), 23, 1.0, torch.float32).clamp(-1, 1)
+    a = ops.patchify(x)
+    ref = F.unfold(x, 16, stride=16).transpose(1, 2).reshape(B * 24, 768)
+    _close(a, ref, 1e-3, "patchify")
+    pos = _rand((1 + 24 * 24, 1024), 24, 0.02, torch.float32)
+    pr = ops.pos_resize(pos, 24, 4, 6)
+    grid = pos[1:].view(1, 24, 24, 1024).permute(0, 3, 1, 2)
+    refp = F.interpolate(grid, size=(4, 6), mode="bilinear").permute(0, 2, 3, 1).reshape(24, 1024)
+    _close(pr[1:], refp, 1e-5, "pos resize")
+    _close(pr[:1], pos[:1], 0, "pos cls")
+    patch = _rand((B * 24, 1024), 25, 1.0, torch.float32)
+    cls = _rand((1024,), 26, 1.0, torch.float32)
+    xt = ops.assemble_tokens(patch, cls, pr, B, 24)
+    reft = torch.cat([cls.view(1, 1, -1).expand(B, -1, -1), patch.view(B, 24, 1024)], 1) + pr
+    _close(xt, reft, 1e-6, "assemble")
+    tok, c16 = ops.readout_split(xt)
+    _close(tok, xt[:, 1:].reshape(B * 24, 1024), 1e-3, "readout tok")
+    _close(c16[:B], xt[:, 0], 1e-3, "readout cls")
+
+
+def test_im2col_upsample_norms(ops):
+    x = _rand((2, 30, 30, 64), 27)
+    a = ops.im2col_3x3_s2(x)
+    cols = F.unfold(x.float().permute(0, 3, 1, 2), 3, padding=1, stride=2)  # [B, C*9, L], index c*9+tap
+    ref = cols.view(2, 64, 9, 225).permute(0, 3, 2, 1).reshape(2 * 225, 9 * 64)
+    _close(a, ref, 0, "im2col s2")
+    y = ops.upsample2x_nhwc(x)
+    refu = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="bilinear", align_corners=True)
+    _close(y, refu.permute(0, 2, 3, 1), 1e-3, "upsample nhwc")
+    lg = _rand((2, 5, 24, 40), 28, 3.0)
+    up = ops.upsample2x_nchw(lg)
+    _close(up, F.interpolate(lg.float(), scale_factor=2, mode="bilinear", align_corners=True), 1e-6, "upsample nchw")
+    f = _rand((1000, 512), 29, 2.0, torch.float32)
+    ls = math.exp(math.log(1 / 0.07))
+    n16 = ops.l2norm_scale(f, ls)
+    refn = (torch.tensor(ls) * (f / f.norm(dim=-1, keepdim=True)).half()).float()
+    _close(n16, refn, 1e-3, "l2norm_scale")
+    t = _rand((150, 512), 30, 0.3)
+    tn = ops.l2norm_f16(t)
+    _close(tn, (t / t.norm(dim=-1, keepdim=True)).float(), 1e-3, "l2norm f16")
+
+
+def test_text_glue(ops):
+    K, L, Wd = 5, 77, 512
+    g = torch.Generator().manual_seed(31)
+    tokens = torch.zeros((K, L), dtype=torch.int64)
+    for k in range(K):
+        n = 1 + k
+        tokens[k, 0] = 49406
+        tokens[k, 1:1 + n] = torch.randint(1000, 40000, (n,), generator=g)
+        tokens[k, 1 + n] = 49407
+    tokens = tokens.cuda()
+    emb = _rand((49408, Wd), 32, 0.02, torch.float32)
+    pos = _rand((L, Wd), 33, 0.01, torch.float32)
+    x = ops.text_embed(tokens, emb, pos)
+    ref = (emb[tokens].half() + pos.half()).view(K * L, Wd)
+    _close(x, ref.float(), 0, "text embed")
+    eot = ops.text_eot_gather(tokens, x)
+    _close(eot[:K], x.view(K, L, Wd)[torch.arange(K), tokens.argmax(-1)].float(), 0, "eot gather")
