@@ -1,0 +1,275 @@
+"""Drop-in `LSegNet` / `LSegNetZS` whose forward runs on the sm_100a engine.
+
+Mirrors the reference interface for the hot path:
+  * constructor signatures of modules/models/lseg_net.py:208-226 and lseg_net_zs.py:219-239;
+  * `forward(x, labelset='')` (lseg_net.py:160) / `forward(x, class_info)` (lseg_net_zs.py:177);
+  * attributes the callers touch: `.pretrained.model.patch_embed.img_size` (lseg_module.py:86-89),
+    `.scratch`, `.clip_pretrained` (with `.encode_text`), `.labels`, `.text`, `.crop_size`, `.out_c`,
+    `.arch_option`, `.logit_scale`;
+  * state-dict key names and shapes of SURVEY.md Appendix C, so `BaseModel.load` / Lightning's
+    `load_from_checkpoint` (prefix `net.`) keep working; the unused `clip_pretrained.visual.*` and timm
+    `head.*` entries of real checkpoints are accepted and ignored.
+The torch sub-modules below are parameter holders only (they give the reference's names, shapes and
+default inits); no torch op runs in forward. There is no CPU path: a non-CUDA input raises.
+"""
+import threading
+import weakref
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+
+from .packing import reference_logit_scale
+from .tokenizer import tokenize
+
+
+# ---------------------------------------------------------------------------------------------
+# parameter holders (names == reference / timm / CLIP module names)
+# ---------------------------------------------------------------------------------------------
+def _vit_large_holder():
+    m = nn.Module()
+    m.patch_embed = nn.Module()
+    m.patch_embed.proj = nn.Conv2d(3, 1024, kernel_size=16, stride=16)
+    m.patch_embed.img_size = (384, 384)
+    m.cls_token = nn.Parameter(torch.zeros(1, 1, 1024))
+    m.pos_embed = nn.Parameter(torch.zeros(1, 577, 1024))
+    nn.init.normal_(m.cls_token, std=0.02)
+    nn.init.normal_(m.pos_embed, std=0.02)
+    blocks = []
+    for _ in range(24):
+        b = nn.Module()
+        b.norm1 = nn.LayerNorm(1024, eps=1e-6)
+        b.attn = nn.Module()
+        b.attn.qkv = nn.Linear(1024, 3072)
+        b.attn.proj = nn.Linear(1024, 1024)
+        b.attn.num_heads = 16
+        b.norm2 = nn.LayerNorm(1024, eps=1e-6)
+        b.mlp = nn.Module()
+        b.mlp.fc1 = nn.Linear(1024, 4096)
+        b.mlp.fc2 = nn.Linear(4096, 1024)
+        blocks.append(b)
+    m.blocks = nn.ModuleList(blocks)
+    m.norm = nn.LayerNorm(1024, eps=1e-6)  # present in checkpoints; dead in forward (lseg_vit.py:108,199)
+    m.patch_size = [16, 16]
+    m.start_index = 1
+    return m
+
+
+def _readout_holder():
+    r = nn.Module()
+    r.project = nn.Sequential(nn.Linear(2048, 1024), nn.GELU())
+    return r
+
+
+def _pretrained_holder():
+    p = nn.Module()
+    p.model = _vit_large_holder()
+    p.act_postprocess1 = nn.Sequential(_readout_holder(), nn.Identity(), nn.Identity(), nn.Conv2d(1024, 256, 1),
+                                       nn.ConvTranspose2d(256, 256, 4, stride=4))
+    p.act_postprocess2 = nn.Sequential(_readout_holder(), nn.Identity(), nn.Identity(), nn.Conv2d(1024, 512, 1),
+                                       nn.ConvTranspose2d(512, 512, 2, stride=2))
+    p.act_postprocess3 = nn.Sequential(_readout_holder(), nn.Identity(), nn.Identity(), nn.Conv2d(1024, 1024, 1))
+    p.act_postprocess4 = nn.Sequential(_readout_holder(), nn.Identity(), nn.Identity(), nn.Conv2d(1024, 1024, 1),
+                                       nn.Conv2d(1024, 1024, 3, stride=2, padding=1))
+    return p
+
+
+def _rcu_holder():
+    u = nn.Module()
+    u.conv1 = nn.Conv2d(256, 256, 3, padding=1, bias=False)
+    u.conv2 = nn.Conv2d(256, 256, 3, padding=1, bias=False)
+    u.bn1 = nn.BatchNorm2d(256)
+    u.bn2 = nn.BatchNorm2d(256)
+    return u
+
+
+def _scratch_holder(out_c):
+    s = nn.Module()
+    for k, cin in enumerate((256, 512, 1024, 1024)):
+        setattr(s, f"layer{k + 1}_rn", nn.Conv2d(cin, 256, 3, padding=1, bias=False))
+    for k in range(1, 5):
+        f = nn.Module()
+        f.out_conv = nn.Conv2d(256, 256, 1)
+        f.resConfUnit1 = _rcu_holder()
+        f.resConfUnit2 = _rcu_holder()
+        setattr(s, f"refinenet{k}", f)
+    s.head1 = nn.Conv2d(256, out_c, 1)
+    s.output_conv = nn.Sequential()  # Interpolate(x2, bilinear, align_corners=True): no parameters
+    return s
+
+
+class _ClipTextHolder(nn.Module):
+    """CLIP ViT-B/32 text tower parameters; `encode_text` runs on the engine of the owning net."""
+
+    def __init__(self):
+        super().__init__()
+        self.positional_embedding = nn.Parameter(torch.empty(77, 512).normal_(std=0.01))
+        self.text_projection = nn.Parameter(torch.empty(512, 512).normal_(std=512 ** -0.5))
+        self.logit_scale = nn.Parameter(torch.ones([]) * 2.6592600)
+        self.token_embedding = nn.Embedding(49408, 512)
+        nn.init.normal_(self.token_embedding.weight, std=0.02)
+        blocks = []
+        for _ in range(12):
+            b = nn.Module()
+            b.attn = nn.MultiheadAttention(512, 8)
+            b.ln_1 = nn.LayerNorm(512)
+            b.mlp = nn.Sequential(OrderedDict([("c_fc", nn.Linear(512, 2048)), ("gelu", nn.Identity()),
+                                               ("c_proj", nn.Linear(2048, 512))]))
+            b.ln_2 = nn.LayerNorm(512)
+            blocks.append(b)
+        self.transformer = nn.Module()
+        self.transformer.resblocks = nn.Sequential(*blocks)
+        self.ln_final = nn.LayerNorm(512)
+        self._owner = None
+
+    def encode_text(self, text):
+        owner = self._owner() if self._owner is not None else None
+        if owner is None:
+            raise RuntimeError("clip_pretrained is detached from its LSegNet")
+        feats = owner._engine_for(text.device).encode_text(text)
+        # un-normalised features are not kept by the engine; callers on this path (lseg_net.py:183-192)
+        # normalise immediately, and normalisation is idempotent.
+        return feats[: text.shape[0]]
+
+
+_IGNORED_PREFIXES = ("clip_pretrained.visual.", "pretrained.model.head.", "pretrained.model.pre_logits.")
+
+
+class _LSegBase(nn.Module):
+    def _init_common(self, **kwargs):
+        backbone = kwargs.get("backbone", "clip_vitl16_384")
+        if backbone != "clip_vitl16_384":
+            # same failure mode as lseg_blocks.py:53-55; other backbones are out of scope
+            print(f"Backbone '{backbone}' not implemented")
+            assert False
+        self.arch_option = kwargs.get("arch_option", 0)
+        if self.arch_option not in (0, None):
+            raise NotImplementedError("arch_option 1/2 head blocks are not part of the B200 hot path yet")
+        self.channels_last = False
+        self.out_c = 512
+        self.clip_pretrained = _ClipTextHolder()
+        self.pretrained = _pretrained_holder()
+        self.scratch = _scratch_holder(self.out_c)
+        self.logit_scale = torch.tensor(reference_logit_scale())
+        self.clip_pretrained._owner = weakref.ref(self)
+        self._shared = {"engines": {}, "text_cache": {}, "lock": threading.Lock(), "master": weakref.ref(self)}
+
+    # -- weight management -------------------------------------------------------------------
+    def _invalidate(self):
+        if hasattr(self, "_shared"):
+            with self._shared["lock"]:
+                self._shared["engines"].clear()
+                self._shared["text_cache"].clear()
+
+    def refresh(self):
+        """Re-pack weights after in-place parameter edits."""
+        self._invalidate()
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self._invalidate()
+        return out
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        filtered = OrderedDict((k, v) for k, v in state_dict.items() if not k.startswith(_IGNORED_PREFIXES))
+        out = super().load_state_dict(filtered, strict=strict, **kw)
+        self._invalidate()
+        return out
+
+    def load(self, path):
+        """BaseModel.load (modules/models/lseg_net.py:81-92)."""
+        parameters = torch.load(path, map_location=torch.device("cpu"))
+        if "optimizer" in parameters:
+            parameters = parameters["model"]
+        self.load_state_dict(parameters)
+
+    def _engine_for(self, device):
+        from .engine import Engine
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("lseg_b200.LSegNet runs on CUDA (B200, sm_100a) only; there is no CPU fallback")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        shared = self._shared
+        with shared["lock"]:
+            eng = shared["engines"].get(device)
+            if eng is None:
+                sd = self.state_dict()
+                if not sd:  # DataParallel replica: parameters live on the master copy
+                    master = shared["master"]()
+                    sd = master.state_dict() if master is not None else sd
+                eng = Engine(sd, device)
+                shared["engines"][device] = eng
+            return eng
+
+    def _text_features(self, engine, tokens):
+        key = (engine.device, tokens.shape[0], tokens.cpu().numpy().tobytes())
+        cache = self._shared["text_cache"]
+        feats = cache.get(key)
+        if feats is None:
+            feats = engine.encode_text(tokens)
+            if len(cache) > 64:
+                cache.clear()
+            cache[key] = feats
+        return feats
+
+    def _check_eval(self):
+        if self.training:
+            raise NotImplementedError("lseg_b200.LSegNet is inference-only (BatchNorm running stats, no autograd); "
+                                      "call .eval() first")
+
+
+class LSegNet(_LSegBase):
+    """Network for semantic segmentation — B200-native forward (reference: lseg_net.py:208-226)."""
+
+    def __init__(self, labels, path=None, scale_factor=0.5, crop_size=480, **kwargs):
+        super().__init__()
+        self.crop_size = crop_size
+        self.scale_factor = scale_factor
+        self.labels = labels
+        self._init_common(**kwargs)
+        self.text = tokenize(self.labels)
+        if path is not None:
+            self.load(path)
+
+    @torch.no_grad()
+    def forward(self, x, labelset=""):
+        self._check_eval()
+        if isinstance(labelset, torch.Tensor):
+            text = labelset
+        elif isinstance(labelset, str) and labelset == "":
+            text = self.text
+        else:
+            text = tokenize(labelset)
+        engine = self._engine_for(x.device)
+        feats = self._text_features(engine, text)
+        return engine.forward(x.float(), feats, text.shape[0])
+
+
+class LSegNetZS(_LSegBase):
+    """Zero-shot variant (reference: lseg_net_zs.py:219-239; forward :177-214): one ['others', name]
+    prompt pair per image, selected by class_info."""
+
+    def __init__(self, label_list, path=None, scale_factor=0.5, aux=False, use_relabeled=False, use_pretrained=True,
+                 **kwargs):
+        super().__init__()
+        self.scale_factor = scale_factor
+        self.aux = aux
+        self.use_relabeled = use_relabeled
+        self.label_list = label_list
+        self.use_pretrained = use_pretrained
+        self._init_common(**kwargs)
+        self.texts = [tokenize(["others", name]) for name in self.label_list]  # lseg_net_zs.py:169-175
+        if path is not None:
+            self.load(path)
+
+    @torch.no_grad()
+    def forward(self, x, class_info):
+        self._check_eval()
+        engine = self._engine_for(x.device)
+        ids = [int(c) for c in class_info]
+        stride = engine.padded_rows(2)
+        text = torch.zeros((len(ids) * stride, 512), dtype=torch.float16, device=x.device)
+        for i, c in enumerate(ids):
+            text[i * stride:(i + 1) * stride] = self._text_features(engine, self.texts[c])
+        return engine.forward(x.float(), text, 2, text_image_stride=stride)

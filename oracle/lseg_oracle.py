@@ -1,0 +1,258 @@
+"""TEST INFRASTRUCTURE — CPU oracle: restatement of the reference LSeg forward path in plain torch.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module; the product path (lang-seg_b200/) never does.
+
+Parity status: the reference ships NO golden vectors or known-answer tests for this path
+(SURVEY.md section 4), so the oracle is pinned against the reference itself: oracle/make_golden.py
+imports /root/reference/modules/models/lseg_net.py unchanged (with stand-ins for the absent third-party
+packages timm / clip, oracle/ref_standins.py), runs it on the seeded inputs of oracle/synth.py, checks
+that this restatement reproduces it, and commits the outputs as fixtures under tests/golden/.
+The timm-0.4.12 ViT block and the CLIP@04f4dc2 text tower are third-party code that is absent from
+/root/reference; they are restated from their published algorithm and
+cross-checked against transformers' CLIPTextModelWithProjection / ViTLayer in tests/test_oracle.py.
+
+dtype pipeline = the reference's on CUDA: fp32 image trunk; fp16 text tower (clip.load(device='cuda')
+converts Linear/MHA/text_projection weights to fp16, lseg_vit.py:224); fp16 pixel x text matmul
+(lseg_net.py:194).
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+VIT_HOOKS = (5, 11, 17, 23)  # modules/models/lseg_net.py:119-123
+
+
+# ------------------------------------------------------------------------------------------------
+# image trunk
+# ------------------------------------------------------------------------------------------------
+def resize_pos_embed(posemb, gs_h, gs_w, start_index=1):
+    """modules/models/lseg_vit.py:149-163 (bilinear, align_corners default False)."""
+    posemb_tok, posemb_grid = posemb[:, :start_index], posemb[0, start_index:]
+    gs_old = int(math.sqrt(len(posemb_grid)))
+    posemb_grid = posemb_grid.reshape(1, gs_old, gs_old, -1).permute(0, 3, 1, 2)
+    posemb_grid = F.interpolate(posemb_grid, size=(gs_h, gs_w), mode="bilinear")
+    posemb_grid = posemb_grid.permute(0, 2, 3, 1).reshape(1, gs_h * gs_w, -1)
+    return torch.cat([posemb_tok, posemb_grid], dim=1)
+
+
+def vit_attention(x, sd, prefix, num_heads=16):
+    """timm 0.4.12 Attention.forward (same math as lseg_vit.py:26-39)."""
+    B, N, C = x.shape
+    qkv = F.linear(x, sd[prefix + "qkv.weight"], sd[prefix + "qkv.bias"])
+    qkv = qkv.reshape(B, N, 3, num_heads, C // num_heads).permute(2, 0, 3, 1, 4)
+    q, k, v = qkv[0], qkv[1], qkv[2]
+    attn = (q @ k.transpose(-2, -1)) * ((C // num_heads) ** -0.5)
+    attn = attn.softmax(dim=-1)
+    x = (attn @ v).transpose(1, 2).reshape(B, N, C)
+    return F.linear(x, sd[prefix + "proj.weight"], sd[prefix + "proj.bias"])
+
+
+def vit_block(x, sd, prefix):
+    """timm 0.4.12 Block.forward: x + Attn(LN1(x)); x + Mlp(LN2(x)); LN eps 1e-6, exact-erf GELU."""
+    h = F.layer_norm(x, (x.shape[-1],), sd[prefix + "norm1.weight"], sd[prefix + "norm1.bias"], 1e-6)
+    x = x + vit_attention(h, sd, prefix + "attn.")
+    h = F.layer_norm(x, (x.shape[-1],), sd[prefix + "norm2.weight"], sd[prefix + "norm2.bias"], 1e-6)
+    h = F.linear(h, sd[prefix + "mlp.fc1.weight"], sd[prefix + "mlp.fc1.bias"])
+    h = F.gelu(h)
+    h = F.linear(h, sd[prefix + "mlp.fc2.weight"], sd[prefix + "mlp.fc2.bias"])
+    return x + h
+
+
+def vit_forward_flex(x, sd, hooks=VIT_HOOKS, depth=24):
+    """modules/models/lseg_vit.py:166-201 + the forward hooks of :421-426. Returns the four taps
+    (outputs of blocks `hooks`, i.e. the un-normed residual stream). The final self.norm (:199) only
+    feeds `glob`, which forward_vit discards (:108), so it is not computed."""
+    p = "pretrained.model."
+    b, c, h, w = x.shape
+    pos_embed = resize_pos_embed(sd[p + "pos_embed"], h // 16, w // 16)
+    x = F.conv2d(x, sd[p + "patch_embed.proj.weight"], sd[p + "patch_embed.proj.bias"], stride=16)
+    x = x.flatten(2).transpose(1, 2)
+    cls_tokens = sd[p + "cls_token"].expand(b, -1, -1)
+    x = torch.cat((cls_tokens, x), dim=1)
+    x = x + pos_embed
+    taps = []
+    for i in range(depth):
+        x = vit_block(x, sd, f"{p}blocks.{i}.")
+        if i in hooks:
+            taps.append(x)
+        if i == max(hooks):
+            break
+    return taps
+
+
+def project_readout(x, sd, prefix):
+    """modules/models/lseg_vit.py:79-90: GELU(Linear(cat(tok, cls)))."""
+    readout = x[:, 0].unsqueeze(1).expand_as(x[:, 1:])
+    features = torch.cat((x[:, 1:], readout), -1)
+    return F.gelu(F.linear(features, sd[prefix + "project.0.weight"], sd[prefix + "project.0.bias"]))
+
+
+def forward_vit(x, sd):
+    """modules/models/lseg_vit.py:104-146 with the act_postprocess stacks of :442-522."""
+    b, c, h, w = x.shape
+    taps = vit_forward_flex(x, sd)
+    layers = []
+    for k, tap in enumerate(taps):
+        q = f"pretrained.act_postprocess{k + 1}."
+        y = project_readout(tap, sd, q + "0.").transpose(1, 2)
+        y = y.unflatten(2, (h // 16, w // 16))
+        y = F.conv2d(y, sd[q + "3.weight"], sd[q + "3.bias"])
+        if k == 0:
+            y = F.conv_transpose2d(y, sd[q + "4.weight"], sd[q + "4.bias"], stride=4)
+        elif k == 1:
+            y = F.conv_transpose2d(y, sd[q + "4.weight"], sd[q + "4.bias"], stride=2)
+        elif k == 3:
+            y = F.conv2d(y, sd[q + "4.weight"], sd[q + "4.bias"], stride=2, padding=1)
+        layers.append(y)
+    return layers
+
+
+# ------------------------------------------------------------------------------------------------
+# decoder
+# ------------------------------------------------------------------------------------------------
+def _bn(x, sd, prefix):
+    return F.batch_norm(x, sd[prefix + "running_mean"], sd[prefix + "running_var"], sd[prefix + "weight"],
+                        sd[prefix + "bias"], False, 0.0, 1e-5)
+
+
+def residual_conv_unit(x, sd, prefix):
+    """modules/models/lseg_blocks.py:265-288 (bn=True, activation = ReLU(inplace=False))."""
+    out = F.relu(x)
+    out = _bn(F.conv2d(out, sd[prefix + "conv1.weight"], None, padding=1), sd, prefix + "bn1.")
+    out = F.relu(out)
+    out = _bn(F.conv2d(out, sd[prefix + "conv2.weight"], None, padding=1), sd, prefix + "bn2.")
+    return out + x
+
+
+def feature_fusion_block(sd, prefix, *xs):
+    """modules/models/lseg_blocks.py:337-358."""
+    output = xs[0]
+    if len(xs) == 2:
+        output = output + residual_conv_unit(xs[1], sd, prefix + "resConfUnit1.")
+    output = residual_conv_unit(output, sd, prefix + "resConfUnit2.")
+    output = F.interpolate(output, scale_factor=2, mode="bilinear", align_corners=True)
+    return F.conv2d(output, sd[prefix + "out_conv.weight"], sd[prefix + "out_conv.bias"])
+
+
+def decoder(layers, sd):
+    """modules/models/lseg_net.py:171-179."""
+    rn = [F.conv2d(layers[k], sd[f"scratch.layer{k + 1}_rn.weight"], None, padding=1) for k in range(4)]
+    path_4 = feature_fusion_block(sd, "scratch.refinenet4.", rn[3])
+    path_3 = feature_fusion_block(sd, "scratch.refinenet3.", path_4, rn[2])
+    path_2 = feature_fusion_block(sd, "scratch.refinenet2.", path_3, rn[1])
+    path_1 = feature_fusion_block(sd, "scratch.refinenet1.", path_2, rn[0])
+    return path_1
+
+
+# ------------------------------------------------------------------------------------------------
+# CLIP text tower (fp16, as loaded on CUDA)
+# ------------------------------------------------------------------------------------------------
+def _ln_fp32(x, w, b, eps=1e-5):
+    """CLIP's LayerNorm subclass: computed in fp32, cast back to the input dtype."""
+    return F.layer_norm(x.float(), (x.shape[-1],), w.float(), b.float(), eps).to(x.dtype)
+
+
+def clip_text_weights_fp16(sd):
+    """clip.model.convert_weights: Linear / MultiheadAttention / text_projection -> fp16; LayerNorm,
+    embeddings stay fp32."""
+    c = "clip_pretrained."
+    out = {}
+    for k, v in sd.items():
+        if not k.startswith(c) or k.startswith(c + "visual."):
+            continue
+        name = k[len(c):]
+        if ("ln_" in name) or name in ("positional_embedding", "token_embedding.weight", "logit_scale"):
+            out[name] = v.float()
+        else:
+            out[name] = v.half()
+    return out
+
+
+def clip_encode_text(text, tw, heads=8, layers=12):
+    """CLIP.encode_text. text int64 [K,77] -> fp16 [K,512]."""
+    dtype = torch.float16
+    x = tw["token_embedding.weight"][text].to(dtype)
+    x = x + tw["positional_embedding"].to(dtype)
+    K, L, Wd = x.shape
+    mask = torch.full((L, L), float("-inf")).triu_(1).to(dtype)
+    x = x.permute(1, 0, 2)  # LND
+    for i in range(layers):
+        b = f"transformer.resblocks.{i}."
+        h = _ln_fp32(x, tw[b + "ln_1.weight"], tw[b + "ln_1.bias"])
+        # nn.MultiheadAttention (torch 1.9 multi_head_attention_forward)
+        qkv = F.linear(h, tw[b + "attn.in_proj_weight"], tw[b + "attn.in_proj_bias"])
+        q, k, v = qkv.chunk(3, dim=-1)
+        hd = Wd // heads
+        q = q * (float(hd) ** -0.5)
+        q = q.contiguous().view(L, K * heads, hd).transpose(0, 1)
+        k = k.contiguous().view(L, K * heads, hd).transpose(0, 1)
+        v = v.contiguous().view(L, K * heads, hd).transpose(0, 1)
+        attn = torch.bmm(q, k.transpose(1, 2)) + mask
+        attn = F.softmax(attn, dim=-1)
+        o = torch.bmm(attn, v).transpose(0, 1).contiguous().view(L, K, Wd)
+        o = F.linear(o, tw[b + "attn.out_proj.weight"], tw[b + "attn.out_proj.bias"])
+        x = x + o
+        h = _ln_fp32(x, tw[b + "ln_2.weight"], tw[b + "ln_2.bias"])
+        h = F.linear(h, tw[b + "mlp.c_fc.weight"], tw[b + "mlp.c_fc.bias"])
+        h = h * torch.sigmoid(1.702 * h)  # QuickGELU
+        h = F.linear(h, tw[b + "mlp.c_proj.weight"], tw[b + "mlp.c_proj.bias"])
+        x = x + h
+    x = x.permute(1, 0, 2)
+    x = _ln_fp32(x, tw["ln_final.weight"], tw["ln_final.bias"]).to(dtype)
+    x = x[torch.arange(x.shape[0]), text.argmax(dim=-1)] @ tw["text_projection"]
+    return x
+
+
+# ------------------------------------------------------------------------------------------------
+# head
+# ------------------------------------------------------------------------------------------------
+LOGIT_SCALE = torch.tensor(math.log(1 / 0.07)).exp()  # modules/models/lseg_net.py:141
+
+
+def correlation_head(path_1, text_features, sd):
+    """modules/models/lseg_net.py:185-196: head1, L2 norms, fp16 scale-then-matmul, NCHW fp32 view."""
+    image_features = F.conv2d(path_1, sd["scratch.head1.weight"], sd["scratch.head1.bias"])
+    imshape = image_features.shape
+    image_features = image_features.permute(0, 2, 3, 1).reshape(-1, imshape[1])
+    image_features = image_features / image_features.norm(dim=-1, keepdim=True)
+    text_features = text_features / text_features.norm(dim=-1, keepdim=True)
+    logits_per_image = LOGIT_SCALE * image_features.half() @ text_features.t()
+    return logits_per_image.float().view(imshape[0], imshape[2], imshape[3], -1).permute(0, 3, 1, 2)
+
+
+def output_conv(out):
+    """scratch.output_conv = Interpolate(x2, bilinear, align_corners=True) (lseg_net.py:203,219-221)."""
+    return F.interpolate(out, scale_factor=2, mode="bilinear", align_corners=True)
+
+
+@torch.no_grad()
+def lseg_forward(x, tokens, sd, text_weights=None, return_stages=False):
+    """LSeg.forward (modules/models/lseg_net.py:160-205, arch_option 0). x fp32 [B,3,H,W], tokens int64 [K,77]."""
+    if x.shape[2] % 32 or x.shape[3] % 32:
+        raise ValueError("H and W must be multiples of 32 (even token grid)")
+    tw = text_weights if text_weights is not None else clip_text_weights_fp16(sd)
+    layers = forward_vit(x, sd)
+    path_1 = decoder(layers, sd)
+    text_features = clip_encode_text(tokens, tw)
+    low = correlation_head(path_1, text_features, sd)
+    out = output_conv(low)
+    if return_stages:
+        tf = text_features / text_features.norm(dim=-1, keepdim=True)
+        return out, {"layers": layers, "path_1": path_1, "text_features": tf, "logits_lr": low}
+    return out
+
+
+@torch.no_grad()
+def lseg_forward_zs(x, class_info, label_tokens, sd, text_weights=None):
+    """Zero-shot LSeg.forward (modules/models/lseg_net_zs.py:177-214): per-image ['others', name] pair.
+    label_tokens: list of int64 [2,77] tensors (self.texts, :169-175); class_info int64 [B]."""
+    tw = text_weights if text_weights is not None else clip_text_weights_fp16(sd)
+    layers = forward_vit(x, sd)
+    path_1 = decoder(layers, sd)
+    outs = []
+    for i in range(x.shape[0]):
+        tf = clip_encode_text(label_tokens[int(class_info[i])], tw)
+        outs.append(correlation_head(path_1[i:i + 1], tf, sd))
+    return output_conv(torch.cat(outs, dim=0))
