@@ -175,6 +175,13 @@ int lseg_encode_text(lseg_engine* e, const int64_t* tokens, int K, void* text_ou
 int lseg_forward(lseg_engine* e, const float* x, int B, int H, int W, const void* text, int K,
                  long long text_image_stride, float* out, void* stream);
 
+/* Same as lseg_forward, but brackets every kernel launch with CUDA events on `stream`, synchronises,
+ * and returns per-launch device time (ms), kernel class (0 elementwise, 1 tcgen05 GEMM, 2 MHSA,
+ * 3 LayerNorm) and ALGORITHMIC flops of the launch. Used by bench.py for the roofline block. */
+int lseg_forward_profiled(lseg_engine* e, const float* x, int B, int H, int W, const void* text, int K,
+                          long long text_image_stride, float* out, void* stream, float* step_ms, int* step_kind,
+                          double* step_flops, int cap, int* count);
+
 /* Introspection for tests: copies of intermediate activations of the last forward (device pointers
  * into the workspace, valid until the next forward). name: "tap0".."tap3" fp32 [B,N,1024];
  * "path1" fp16 NHWC [B,H/2,W/2,256]; "logits_lr" fp16 [B,K,H/2,W/2]. Returns NULL if unknown. */

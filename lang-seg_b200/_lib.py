@@ -72,7 +72,7 @@ SYMBOLS = [
     "lseg_readout_split", "lseg_im2col_3x3_s2", "lseg_upsample2x_nhwc", "lseg_l2norm_scale", "lseg_l2norm_f16",
     "lseg_upsample2x_nchw", "lseg_text_embed", "lseg_text_eot_gather",
     "lseg_create", "lseg_destroy", "lseg_encode_text", "lseg_forward", "lseg_debug_buffer",
-    "lseg_last_launch_count",
+    "lseg_last_launch_count", "lseg_forward_profiled",
 ]
 
 _lib = None
@@ -121,6 +121,9 @@ def load(build_if_missing=True):
     lib.lseg_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                  C.c_longlong, C.c_void_p, C.c_void_p]
     lib.lseg_last_launch_count.argtypes = [C.c_void_p]
+    lib.lseg_forward_profiled.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                          C.c_longlong, C.c_void_p, C.c_void_p, C.POINTER(C.c_float),
+                                          C.POINTER(C.c_int), C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int)]
     _lib = lib
     return lib
 

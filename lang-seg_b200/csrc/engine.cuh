@@ -22,7 +22,19 @@ struct CallCtx {
   long long text_image_stride;
   float* out;
 };
-using Step = std::function<int(const CallCtx&, cudaStream_t)>;
+using StepFn = std::function<int(const CallCtx&, cudaStream_t)>;
+enum StepKind { KIND_EW = 0, KIND_GEMM = 1, KIND_MHSA = 2, KIND_LN = 3 };
+// One launch of the forward: the closure plus what bench.py's roofline needs (kernel class and
+// the ALGORITHMIC flops of this launch, 2*M*N*K for GEMMs, 4*N^2*dh per head for attention).
+struct Step {
+  StepFn fn;
+  int kind = KIND_EW;
+  double flops = 0.0;
+  Step() {}
+  template <class F, class = typename std::enable_if<!std::is_same<typename std::decay<F>::type, Step>::value>::type>
+  Step(F&& f, int kind_ = KIND_EW, double flops_ = 0.0) : fn(std::forward<F>(f)), kind(kind_), flops(flops_) {}
+  int operator()(const CallCtx& c, cudaStream_t s) const { return fn(c, s); }
+};
 
 struct Arena {
   uint8_t* base = nullptr;
@@ -104,7 +116,8 @@ static int add_gemm(std::vector<Step>& steps, const __half* a, long long lda, in
   d.e = e;
   GemmPlan plan;
   if (gemm_plan(d, &plan)) return -1;
-  steps.push_back([plan](const CallCtx&, cudaStream_t s) { return gemm_run(plan, s); });
+  steps.emplace_back([plan](const CallCtx&, cudaStream_t s) { return gemm_run(plan, s); }, KIND_GEMM,
+                     2.0 * M * lin.out * lin.in);
   return 0;
 }
 
@@ -128,14 +141,15 @@ static int add_conv3x3(std::vector<Step>& steps, const __half* a, int B, int H, 
   d.e = e;
   GemmPlan plan;
   if (gemm_plan(d, &plan)) return -1;
-  steps.push_back([plan](const CallCtx&, cudaStream_t s) { return gemm_run(plan, s); });
+  steps.emplace_back([plan](const CallCtx&, cudaStream_t s) { return gemm_run(plan, s); }, KIND_GEMM,
+                     2.0 * B * H * W * lin.out * 9.0 * C);
   return 0;
 }
 
 static int add_layernorm(std::vector<Step>& steps, const void* x, int in_f16, const float* g, const float* b,
                          __half* y, long long M, int C, float eps) {
-  steps.push_back(
-      [=](const CallCtx&, cudaStream_t s) { return run_layernorm(x, in_f16, g, b, y, M, C, eps, s); });
+  steps.emplace_back([=](const CallCtx&, cudaStream_t s) { return run_layernorm(x, in_f16, g, b, y, M, C, eps, s); },
+                     KIND_LN, 0.0);
   return 0;
 }
 
@@ -258,7 +272,8 @@ static int build_image_plan(lseg_engine* eng, int B, int H, int W, cudaStream_t 
       md.causal = 0;
       MhsaPlan mp;
       if (mhsa_plan(md, &mp)) return -1;
-      steps.push_back([mp](const CallCtx&, cudaStream_t s) { return mhsa_run(mp, s); });
+      steps.emplace_back([mp](const CallCtx&, cudaStream_t s) { return mhsa_run(mp, s); }, KIND_MHSA,
+                         4.0 * B * 16 * static_cast<double>(N) * N * 64);
     }
     {
       GemmEpi e = epi_none();
@@ -449,7 +464,23 @@ static int build_image_plan(lseg_engine* eng, int B, int H, int W, cudaStream_t 
   return 0;
 }
 
-static int run_forward(lseg_engine* eng, const CallCtx& ctx, int B, int H, int W, cudaStream_t stream) {
+// Optional per-launch timing (bench.py roofline): CUDA events recorded on the launching stream
+// around every launch of one forward.
+struct Profile {
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> kind;
+  std::vector<double> flops;
+  int mark(cudaStream_t s) {
+    cudaEvent_t e;
+    LSEG_CHECK_CUDA(cudaEventCreate(&e));
+    LSEG_CHECK_CUDA(cudaEventRecord(e, s));
+    ev.push_back(e);
+    return 0;
+  }
+};
+
+static int run_forward(lseg_engine* eng, const CallCtx& ctx, int B, int H, int W, cudaStream_t stream,
+                       Profile* prof = nullptr) {
   if (ensure_init()) return -1;
   if (H % 32 != 0 || W % 32 != 0 || H <= 0 || W <= 0) {
     // the reference fails deep inside skip_add.add (lseg_blocks.py:347) for odd token grids
@@ -479,9 +510,15 @@ static int run_forward(lseg_engine* eng, const CallCtx& ctx, int B, int H, int W
     plan.debug["logits_lr"] = p;
   }
   int launches = 0;
+  if (prof && prof->mark(stream)) return -1;
   for (auto& st : plan.steps) {
     if (st(ctx, stream)) return -1;
     ++launches;
+    if (prof) {
+      if (prof->mark(stream)) return -1;
+      prof->kind.push_back(st.kind);
+      prof->flops.push_back(st.flops);
+    }
   }
   // ---- pixel x text correlation (lseg_net.py:194-196): fp16 GEMM, fp16 result, NCHW store ----
   const int kpad = ((ctx.K + 127) / 128) * 128;
@@ -507,6 +544,11 @@ static int run_forward(lseg_engine* eng, const CallCtx& ctx, int B, int H, int W
     if (gemm_plan(d, &gp)) return -1;
     if (gemm_run(gp, stream)) return -1;
     ++launches;
+    if (prof) {
+      if (prof->mark(stream)) return -1;
+      prof->kind.push_back(KIND_GEMM);
+      prof->flops.push_back(2.0 * rows * ctx.K * 512.0);
+    }
   }
   // ---- scratch.output_conv: bilinear x2, align_corners=True (lseg_net.py:203) ----
   {
@@ -515,6 +557,11 @@ static int run_forward(lseg_engine* eng, const CallCtx& ctx, int B, int H, int W
     upsample2x_nchw_kernel<<<ew_grid(total, 256), 256, 0, stream>>>(plan.logits_lr, ctx.out, planes, h2, w2);
     LSEG_CHECK_CUDA(cudaGetLastError());
     ++launches;
+    if (prof) {
+      if (prof->mark(stream)) return -1;
+      prof->kind.push_back(KIND_EW);
+      prof->flops.push_back(0.0);
+    }
   }
   eng->last_launches = launches;
   return 0;
@@ -699,6 +746,43 @@ int lseg_forward(lseg_engine* e, const float* x, int B, int H, int W, const void
   ctx.text_image_stride = text_image_stride;
   ctx.out = out;
   return run_forward(e, ctx, B, H, W, static_cast<cudaStream_t>(stream));
+}
+
+int lseg_forward_profiled(lseg_engine* e, const float* x, int B, int H, int W, const void* text, int K,
+                          long long text_image_stride, float* out, void* stream, float* step_ms, int* step_kind,
+                          double* step_flops, int cap, int* count) {
+  using namespace lseg;
+  if (!e || !x || !text || !out || B <= 0 || !step_ms || !step_kind || !step_flops || !count) {
+    set_error("lseg_forward_profiled: bad argument");
+    return -1;
+  }
+  CallCtx ctx;
+  ctx.x = x;
+  ctx.text = static_cast<const __half*>(text);
+  ctx.K = K;
+  ctx.text_image_stride = text_image_stride;
+  ctx.out = out;
+  Profile prof;
+  int rc = run_forward(e, ctx, B, H, W, static_cast<cudaStream_t>(stream), &prof);
+  if (rc == 0 && cudaStreamSynchronize(static_cast<cudaStream_t>(stream)) != cudaSuccess) {
+    set_error("lseg_forward_profiled: stream sync failed");
+    rc = -1;
+  }
+  int n = 0;
+  if (rc == 0) {
+    n = static_cast<int>(prof.kind.size());
+    if (n > cap) n = cap;
+    for (int i = 0; i < n; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, prof.ev[i], prof.ev[i + 1]);
+      step_ms[i] = ms;
+      step_kind[i] = prof.kind[i];
+      step_flops[i] = prof.flops[i];
+    }
+  }
+  for (cudaEvent_t ev : prof.ev) cudaEventDestroy(ev);
+  *count = n;
+  return rc;
 }
 
 const void* lseg_debug_buffer(lseg_engine* e, const char* name) {

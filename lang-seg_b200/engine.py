@@ -70,6 +70,24 @@ class Engine:
                                              C.c_void_p(out.data_ptr()), _stream()))
         return out
 
+    def forward_profiled(self, x, text, k, text_image_stride=0, out=None):
+        """One forward with CUDA events around every launch. Returns (out, [(ms, kind, flops), ...])."""
+        x = x.contiguous()
+        b, _, h, w = x.shape
+        if out is None:
+            out = torch.empty((b, k, h, w), dtype=torch.float32, device=self.device)
+        cap = 2048
+        ms = (C.c_float * cap)()
+        kind = (C.c_int * cap)()
+        flops = (C.c_double * cap)()
+        n = C.c_int(0)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.lseg_forward_profiled(self.handle, C.c_void_p(x.data_ptr()), b, h, w,
+                                                      C.c_void_p(text.data_ptr()), k, text_image_stride,
+                                                      C.c_void_p(out.data_ptr()), _stream(), ms, kind, flops, cap,
+                                                      C.byref(n)))
+        return out, [(ms[i], kind[i], flops[i]) for i in range(n.value)]
+
     def last_launch_count(self):
         return int(self.lib.lseg_last_launch_count(self.handle))
 

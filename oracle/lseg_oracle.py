@@ -89,10 +89,12 @@ def project_readout(x, sd, prefix):
     return F.gelu(F.linear(features, sd[prefix + "project.0.weight"], sd[prefix + "project.0.bias"]))
 
 
-def forward_vit(x, sd):
+def forward_vit(x, sd, taps_out=None):
     """modules/models/lseg_vit.py:104-146 with the act_postprocess stacks of :442-522."""
     b, c, h, w = x.shape
     taps = vit_forward_flex(x, sd)
+    if taps_out is not None:
+        taps_out.extend(taps)
     layers = []
     for k, tap in enumerate(taps):
         q = f"pretrained.act_postprocess{k + 1}."
@@ -233,14 +235,15 @@ def lseg_forward(x, tokens, sd, text_weights=None, return_stages=False):
     if x.shape[2] % 32 or x.shape[3] % 32:
         raise ValueError("H and W must be multiples of 32 (even token grid)")
     tw = text_weights if text_weights is not None else clip_text_weights_fp16(sd)
-    layers = forward_vit(x, sd)
+    taps = []
+    layers = forward_vit(x, sd, taps)
     path_1 = decoder(layers, sd)
     text_features = clip_encode_text(tokens, tw)
     low = correlation_head(path_1, text_features, sd)
     out = output_conv(low)
     if return_stages:
         tf = text_features / text_features.norm(dim=-1, keepdim=True)
-        return out, {"layers": layers, "path_1": path_1, "text_features": tf, "logits_lr": low}
+        return out, {"taps": taps, "layers": layers, "path_1": path_1, "text_features": tf, "logits_lr": low}
     return out
 
 
