@@ -50,8 +50,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, int tag) {
+  // try_wait suspends the thread in hardware for a bounded time, so this loop is not a hot spin.
+  // The watchdog bookkeeping (a global-memory flag read, ~1 us) runs only every 256 failed polls so
+  // that it never sits on the critical path of a healthy pipeline.
   const long long t0 = clock64();
+  uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if ((++polls & 0xFFu) != 0) continue;
     if (*reinterpret_cast<volatile int*>(&g_watchdog[0]) != 0) return;
     if (clock64() - t0 > kWatchdogCycles) {
       if (atomicCAS(&g_watchdog[0], 0, tag) == 0) {

@@ -251,7 +251,10 @@ static int build_image_plan(lseg_engine* eng, int B, int H, int W, cudaStream_t 
   float* xin = xbuf;
   for (int i = 0; i < LSEG_VIT_DEPTH; ++i) {
     const lseg_vit_block_w& bw = w.blocks[i];
-    float* xout = xin;
+    // The block reads its input from `xin` (xbuf, or the tap buffer written by a hooked block, which
+    // must stay intact for the readout) and always works in xbuf; a hooked block writes its OUTPUT
+    // to its tap buffer instead (lseg_vit.py:421-426: the hook captures the block's return value).
+    float* xout = xbuf;
     for (int k = 0; k < 4; ++k)
       if (w.hooks[k] == i) xout = taps[k];
     add_layernorm(steps, xin, 0, bw.ln1_g, bw.ln1_b, xn, M, D, 1e-6f);
@@ -279,11 +282,11 @@ static int build_image_plan(lseg_engine* eng, int B, int H, int W, cudaStream_t 
       GemmEpi e = epi_none();
       e.bias = bw.proj.b;
       e.res_f32 = xin;
-      e.out_f32 = xin;
+      e.out_f32 = xbuf;
       e.ldc = D;
       if (add_gemm(steps, attn, D, (int)M, (int)M, bw.proj, e)) return -1;
     }
-    add_layernorm(steps, xin, 0, bw.ln2_g, bw.ln2_b, xn, M, D, 1e-6f);
+    add_layernorm(steps, xbuf, 0, bw.ln2_g, bw.ln2_b, xn, M, D, 1e-6f);
     {
       GemmEpi e = epi_none();
       e.bias = bw.fc1.b;
@@ -295,7 +298,7 @@ static int build_image_plan(lseg_engine* eng, int B, int H, int W, cudaStream_t 
     {
       GemmEpi e = epi_none();
       e.bias = bw.fc2.b;
-      e.res_f32 = xin;
+      e.res_f32 = xbuf;
       e.out_f32 = xout;
       e.ldc = D;
       if (add_gemm(steps, hbuf, 4 * D, (int)M, (int)M, bw.fc2, e)) return -1;

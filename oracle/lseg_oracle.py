@@ -156,9 +156,9 @@ def _ln_fp32(x, w, b, eps=1e-5):
     return F.layer_norm(x.float(), (x.shape[-1],), w.float(), b.float(), eps).to(x.dtype)
 
 
-def clip_text_weights_fp16(sd):
+def clip_text_weights_fp16(sd, dtype=torch.float16):
     """clip.model.convert_weights: Linear / MultiheadAttention / text_projection -> fp16; LayerNorm,
-    embeddings stay fp32."""
+    embeddings stay fp32. dtype=float32 gives the un-converted tower (tests)."""
     c = "clip_pretrained."
     out = {}
     for k, v in sd.items():
@@ -168,13 +168,12 @@ def clip_text_weights_fp16(sd):
         if ("ln_" in name) or name in ("positional_embedding", "token_embedding.weight", "logit_scale"):
             out[name] = v.float()
         else:
-            out[name] = v.half()
+            out[name] = v.to(dtype)
     return out
 
 
-def clip_encode_text(text, tw, heads=8, layers=12):
+def clip_encode_text(text, tw, heads=8, layers=12, dtype=torch.float16):
     """CLIP.encode_text. text int64 [K,77] -> fp16 [K,512]."""
-    dtype = torch.float16
     x = tw["token_embedding.weight"][text].to(dtype)
     x = x + tw["positional_embedding"].to(dtype)
     K, L, Wd = x.shape

@@ -1,0 +1,88 @@
+"""CPU-side checks of the C-ABI boundary: the library builds/loads without a GPU, exports every symbol
+include/lseg_b200.h declares, and fails LOUDLY (no CPU fallback) when no CUDA device is present."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import lseg_b200  # noqa: F401
+    from lseg_b200 import _lib
+    return _lib.load()
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "lseg_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lseg_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported(lib):
+    from lseg_b200 import _lib
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, f"declared in include/lseg_b200.h but not exported: {missing}"
+    assert sorted(_lib.SYMBOLS) == declared, "ctypes binding list out of sync with the header"
+    assert lib.lseg_abi_version() == 1
+
+
+def test_no_torch_types_in_signatures():
+    text = open(os.path.join(ROOT, "include", "lseg_b200.h")).read()
+    assert "torch" not in text.lower().replace("pytorch-encoding", "") or "at::" not in text
+    assert "at::Tensor" not in text and "#include <torch" not in text
+
+
+def test_library_has_no_libcuda_or_torch_dependency():
+    import subprocess
+    from lseg_b200 import _lib
+    out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "libtorch" not in out and "libcuda.so" not in out and "libc10" not in out
+
+
+def test_struct_layout_matches_header():
+    """The ctypes mirrors must have the C layout of the header structs (spot-check sizes/offsets)."""
+    from lseg_b200 import _lib
+    assert C.sizeof(_lib.LinearW) == 32
+    assert C.sizeof(_lib.VitBlockW) == 4 * 8 + 4 * 32
+    assert C.sizeof(_lib.RcuW) == 2 * 32 + 4 * 8
+    assert _lib.GemmArgs.lda.offset == 8 and _lib.GemmArgs.w.offset == 24
+    # lseg_weights: first member patch (32 B), then two pointers, int pos_grid (+pad), 24 blocks ...
+    assert _lib.Weights.blocks.offset == 32 + 8 + 8 + 8
+    assert _lib.Weights.hooks.offset == _lib.Weights.blocks.offset + 24 * 160
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_compute_entry_points_fail_loudly_without_gpu(lib):
+    from lseg_b200 import _lib
+    args = _lib.GemmArgs()
+    rc = lib.lseg_gemm(C.byref(args), None)
+    assert rc != 0
+    msg = lib.lseg_last_error().decode()
+    assert "no CUDA device" in msg or "CUDA" in msg
+    with pytest.raises(RuntimeError):
+        from lseg_b200.engine import Engine
+        Engine({}, "cpu")
+
+
+def test_lsegnet_refuses_cpu_and_train_mode():
+    from lseg_b200.lseg_net import _LSegBase
+    assert hasattr(_LSegBase, "_engine_for")
+    import inspect
+    src = inspect.getsource(_LSegBase._engine_for)
+    assert "no CPU fallback" in src
+
+
+def test_product_path_never_imports_oracle():
+    pkg = os.path.join(ROOT, "lang-seg_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
