@@ -69,6 +69,132 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+// ------------------------------------------------------------------------------------------
+// Epilogue of one 32-column chunk of one output row (shared by the 1-CTA and 2-CTA kernels):
+// v = 32 fp32 accumulators of row `grow`, columns [n0, n0+32).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void gemm_epilogue_chunk(const GemmEpi& e, int N, const uint32_t (&v)[32], long long grow,
+                                                    int n0, long long bias_off) {
+  const bool valid = true;
+  const int nvalid = min(32, N - n0);
+  
+  float f[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+  if (e.scale) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] *= (i < nvalid) ? __ldg(e.scale + n0 + i) : 0.f;
+  }
+  if (e.bias) {
+    const float* bp = e.bias + ((e.bias_group_rows > 0 && valid) ? bias_off : 0) + n0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] += (i < nvalid) ? __ldg(bp + i) : 0.f;
+  }
+  if (e.act == ACT_GELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
+  } else if (e.act == ACT_QUICKGELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = quick_gelu(f[i]);
+  } else if (e.act == ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+  }
+  if (e.store == STORE_ROWMAJOR) {
+    const long long off = grow * e.ldc + n0;
+    if (nvalid == 32) {
+      if (e.res_f32) {
+        const float4* rp = reinterpret_cast<const float4*>(e.res_f32 + off);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 q = rp[i];
+          f[4 * i + 0] += q.x; f[4 * i + 1] += q.y; f[4 * i + 2] += q.z; f[4 * i + 3] += q.w;
+        }
+      }
+      if (e.res2_f32) {
+        const float4* rp = reinterpret_cast<const float4*>(e.res2_f32 + off);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 q = rp[i];
+          f[4 * i + 0] += q.x; f[4 * i + 1] += q.y; f[4 * i + 2] += q.z; f[4 * i + 3] += q.w;
+        }
+      }
+      if (e.out_f32) {
+        float4* op = reinterpret_cast<float4*>(e.out_f32 + off);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+      }
+      if (e.out_f16) {
+        __half2 h[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+        if (e.res_f16) {  // fp16 residual stream: round the branch output first, then add in fp16
+          const uint4* rp = reinterpret_cast<const uint4*>(e.res_f16 + off);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 q = rp[i];
+            const __half2* qh = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) h[4 * i + j] = __hadd2(qh[j], h[4 * i + j]);
+          }
+        }
+        uint4* op = reinterpret_cast<uint4*>(e.out_f16 + off);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) op[i] = *reinterpret_cast<uint4*>(&h[4 * i]);
+      }
+      if (e.out_f16_relu) {
+        __half2 h[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) h[i] = __floats2half2_rn(fmaxf(f[2 * i], 0.f), fmaxf(f[2 * i + 1], 0.f));
+        uint4* op = reinterpret_cast<uint4*>(e.out_f16_relu + off);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) op[i] = *reinterpret_cast<uint4*>(&h[4 * i]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (i < nvalid) {
+          float x = f[i];
+          if (e.res_f32) x += e.res_f32[off + i];
+          if (e.res2_f32) x += e.res2_f32[off + i];
+          if (e.out_f32) e.out_f32[off + i] = x;
+          if (e.out_f16) {
+            __half hx = __float2half_rn(x);
+            if (e.res_f16) hx = __hadd(e.res_f16[off + i], hx);
+            e.out_f16[off + i] = hx;
+          }
+          if (e.out_f16_relu) e.out_f16_relu[off + i] = __float2half_rn(fmaxf(x, 0.f));
+        }
+      }
+    }
+  } else if (e.store == STORE_D2S) {
+    // column n = (i*s + j)*cout + co ; row grow = (b*h + y)*w + x  ->  NHWC [B, h*s, w*s, cout]
+    const int ij = n0 / e.d2s_cout;
+    const int co0 = n0 - ij * e.d2s_cout;
+    const int di = ij / e.d2s_s, dj = ij - di * e.d2s_s;
+    const int hw = e.d2s_h * e.d2s_w;
+    const int b = static_cast<int>(grow / hw);
+    const int yx = static_cast<int>(grow - static_cast<long long>(b) * hw);
+    const int y = yx / e.d2s_w, x = yx - y * e.d2s_w;
+    const long long orow =
+        (static_cast<long long>(b) * (e.d2s_h * e.d2s_s) + (y * e.d2s_s + di)) * (e.d2s_w * e.d2s_s) +
+        (x * e.d2s_s + dj);
+    __half2 h[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+    uint4* op = reinterpret_cast<uint4*>(e.out_f16 + orow * e.d2s_cout + co0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) op[i] = *reinterpret_cast<uint4*>(&h[4 * i]);
+  } else {  // STORE_NCHW_T : out[(b*K + n)*P + p], fp16
+    const int b = static_cast<int>(grow / e.nchw_p);
+    const int pix = static_cast<int>(grow - static_cast<long long>(b) * e.nchw_p);
+    __half* op = e.out_f16 + (static_cast<long long>(b) * e.nchw_k + n0) * e.nchw_p + pix;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (n0 + i < e.nchw_k) op[static_cast<long long>(i) * e.nchw_p] = __float2half_rn(f[i]);
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BN>;
@@ -212,122 +338,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         tmem_ld32(t_row + c * 32, v);
         tmem_ld_wait();
         if (!valid) continue;
-        const int nvalid = min(32, p.N - n0);
-        float f[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-        if (e.scale) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] *= (i < nvalid) ? __ldg(e.scale + n0 + i) : 0.f;
-        }
-        if (e.bias) {
-          const float* bp = e.bias + ((e.bias_group_rows > 0 && valid) ? bias_off : 0) + n0;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] += (i < nvalid) ? __ldg(bp + i) : 0.f;
-        }
-        if (e.act == ACT_GELU) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
-        } else if (e.act == ACT_QUICKGELU) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = quick_gelu(f[i]);
-        } else if (e.act == ACT_RELU) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
-        }
-        if (e.store == STORE_ROWMAJOR) {
-          const long long off = grow * e.ldc + n0;
-          if (nvalid == 32) {
-            if (e.res_f32) {
-              const float4* rp = reinterpret_cast<const float4*>(e.res_f32 + off);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 q = rp[i];
-                f[4 * i + 0] += q.x; f[4 * i + 1] += q.y; f[4 * i + 2] += q.z; f[4 * i + 3] += q.w;
-              }
-            }
-            if (e.res2_f32) {
-              const float4* rp = reinterpret_cast<const float4*>(e.res2_f32 + off);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 q = rp[i];
-                f[4 * i + 0] += q.x; f[4 * i + 1] += q.y; f[4 * i + 2] += q.z; f[4 * i + 3] += q.w;
-              }
-            }
-            if (e.out_f32) {
-              float4* op = reinterpret_cast<float4*>(e.out_f32 + off);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-            }
-            if (e.out_f16) {
-              __half2 h[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
-              if (e.res_f16) {  // fp16 residual stream: round the branch output first, then add in fp16
-                const uint4* rp = reinterpret_cast<const uint4*>(e.res_f16 + off);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const uint4 q = rp[i];
-                  const __half2* qh = reinterpret_cast<const __half2*>(&q);
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) h[4 * i + j] = __hadd2(qh[j], h[4 * i + j]);
-                }
-              }
-              uint4* op = reinterpret_cast<uint4*>(e.out_f16 + off);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) op[i] = *reinterpret_cast<uint4*>(&h[4 * i]);
-            }
-            if (e.out_f16_relu) {
-              __half2 h[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) h[i] = __floats2half2_rn(fmaxf(f[2 * i], 0.f), fmaxf(f[2 * i + 1], 0.f));
-              uint4* op = reinterpret_cast<uint4*>(e.out_f16_relu + off);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) op[i] = *reinterpret_cast<uint4*>(&h[4 * i]);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              if (i < nvalid) {
-                float x = f[i];
-                if (e.res_f32) x += e.res_f32[off + i];
-                if (e.res2_f32) x += e.res2_f32[off + i];
-                if (e.out_f32) e.out_f32[off + i] = x;
-                if (e.out_f16) {
-                  __half hx = __float2half_rn(x);
-                  if (e.res_f16) hx = __hadd(e.res_f16[off + i], hx);
-                  e.out_f16[off + i] = hx;
-                }
-                if (e.out_f16_relu) e.out_f16_relu[off + i] = __float2half_rn(fmaxf(x, 0.f));
-              }
-            }
-          }
-        } else if (e.store == STORE_D2S) {
-          // column n = (i*s + j)*cout + co ; row grow = (b*h + y)*w + x  ->  NHWC [B, h*s, w*s, cout]
-          const int ij = n0 / e.d2s_cout;
-          const int co0 = n0 - ij * e.d2s_cout;
-          const int di = ij / e.d2s_s, dj = ij - di * e.d2s_s;
-          const int hw = e.d2s_h * e.d2s_w;
-          const int b = static_cast<int>(grow / hw);
-          const int yx = static_cast<int>(grow - static_cast<long long>(b) * hw);
-          const int y = yx / e.d2s_w, x = yx - y * e.d2s_w;
-          const long long orow =
-              (static_cast<long long>(b) * (e.d2s_h * e.d2s_s) + (y * e.d2s_s + di)) * (e.d2s_w * e.d2s_s) +
-              (x * e.d2s_s + dj);
-          __half2 h[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
-          uint4* op = reinterpret_cast<uint4*>(e.out_f16 + orow * e.d2s_cout + co0);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) op[i] = *reinterpret_cast<uint4*>(&h[4 * i]);
-        } else {  // STORE_NCHW_T : out[(b*K + n)*P + p], fp16
-          const int b = static_cast<int>(grow / e.nchw_p);
-          const int pix = static_cast<int>(grow - static_cast<long long>(b) * e.nchw_p);
-          __half* op = e.out_f16 + (static_cast<long long>(b) * e.nchw_k + n0) * e.nchw_p + pix;
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (n0 + i < e.nchw_k) op[static_cast<long long>(i) * e.nchw_p] = __float2half_rn(f[i]);
-        }
+        gemm_epilogue_chunk(e, p.N, v, grow, n0, bias_off);
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
@@ -341,6 +352,191 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ==========================================================================================
+// CTA-pair variant (tcgen05 cta_group::2): a cluster of two CTAs (one TPC) computes a 256 x BN tile.
+// Each CTA stages its own 128 A rows and HALF of the weight tile, so the bytes pulled from L2 per MMA
+// drop by a third (A 16 KB + B 16 KB instead of 16 + 32 per 128x256x64 step) — the 1-CTA kernel is
+// L2->SM bandwidth bound at ~85 flop/B. The even CTA issues tcgen05.mma.cta_group::2 (M = 256) for
+// the pair; both CTAs run a TMA producer and 8 epilogue warps over their own 128 TMEM lanes.
+//   full barrier   : in the leader, armed with the pair's byte count; both CTAs' TMA credit it
+//   empty barrier  : per CTA, released by a multicast tcgen05.commit
+//   tmem full      : per CTA (multicast commit);  tmem empty: in the leader, 2 x 8 warp arrivals
+// ==========================================================================================
+template <int BN>
+struct Gemm2Cfg {
+  static constexpr int kABytes = kGemmBM * kGemmBK * 2;
+  static constexpr int kBBytes = (BN / 2) * kGemmBK * 2;  // this CTA's half of the weight tile
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN == 256) ? 6 : 8;
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+    gemm_tc2_kernel(const __grid_constant__ GemmParams p) {
+  using Cfg = Gemm2Cfg<BN>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::kStages;
+  uint64_t* tmem_full = bars + 2 * Cfg::kStages;
+  uint64_t* tmem_empty = bars + 2 * Cfg::kStages + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tma_a);
+    tma_prefetch_desc(&p.tma_b);
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 2 * kGemmEpiWarps);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc_2cta(tmem_base_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  cluster_sync_all();  // barriers + TMEM of BOTH CTAs exist before any cross-CTA traffic
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  const int m_pairs = (p.num_m_tiles + 1) >> 1;
+  const int num_tiles = m_pairs * p.num_n_tiles;  // pair tiles (256 x BN)
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int m_tile = (tile % m_pairs) * 2 + static_cast<int>(rank);
+        const int n_tile = tile / m_pairs;
+        const int n0 = n_tile * BN + static_cast<int>(rank) * (BN / 2);
+        int cb = 0, ch0 = 0, cw0 = 0;
+        if (p.conv) {
+          const int per_img = p.tiles_h * p.tiles_w;
+          cb = m_tile / per_img;  // == B for the phantom tile of an odd count -> TMA zero-fills
+          const int t = m_tile % per_img;
+          ch0 = (t / p.tiles_w) * kConvTH;
+          cw0 = (t % p.tiles_w) * kConvTW;
+        }
+        for (int kit = 0; kit < p.k_iters; ++kit) {
+          mbar_wait(&empty_bar[stage], phase ^ 1, 21);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+          if (p.conv) {
+            const int tap = kit / p.k_chunks;
+            const int c = kit - tap * p.k_chunks;
+            const int dy = tap / p.kw, dx = tap - dy * p.kw;
+            tma_load_4d_2sm(sa, &p.tma_a, &full_bar[stage], c * kGemmBK, cw0 + dx - p.pad, ch0 + dy - p.pad, cb);
+          } else {
+            tma_load_2d_2sm(sa, &p.tma_a, &full_bar[stage], kit * kGemmBK, m_tile * kGemmBM);
+          }
+          tma_load_2d_2sm(sb, &p.tma_b, &full_bar[stage], kit * kGemmBK, n0);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(2 * kGemmBM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 22);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kit = 0; kit < p.k_iters; ++kit) {
+          mbar_wait(&full_bar[stage], phase, 23);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t b_base = a_base + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < kGemmBK / 16; ++k) {
+            const uint64_t da = umma_desc_sw128(a_base + k * 32, 1024, 0);
+            const uint64_t db = umma_desc_sw128(b_base + k * 32, 1024, 0);
+            umma_f16_ss_2cta(d_tmem, da, db, idesc, (kit | k) != 0);
+          }
+          umma_commit_2cta(&empty_bar[stage], 0x3);  // both CTAs' smem slots
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2cta(&tmem_full[acc], 0x3);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== Epilogue (both CTAs, own 128 TMEM lanes) =====================
+    const int ew = warp - 4;
+    const int quarter = warp & 3;
+    const int half = ew >> 2;
+    constexpr int kColsPerWarp = BN / (kGemmEpiWarps / 4);
+    const int r = quarter * 32 + lane;
+    const GemmEpi& e = p.e;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int m_tile = (tile % m_pairs) * 2 + static_cast<int>(rank);
+      const int n_tile = tile / m_pairs;
+      long long grow;
+      bool valid = m_tile < p.num_m_tiles;
+      if (p.conv) {
+        const int per_img = p.tiles_h * p.tiles_w;
+        const int b = m_tile / per_img;
+        const int t = m_tile % per_img;
+        const int h = (t / p.tiles_w) * kConvTH + r / kConvTW;
+        const int w = (t % p.tiles_w) * kConvTW + r % kConvTW;
+        valid = valid && (h < p.H) && (w < p.W);
+        grow = (static_cast<long long>(b) * p.H + h) * p.W + w;
+      } else {
+        grow = static_cast<long long>(m_tile) * kGemmBM + r;
+        valid = valid && (grow < p.M);
+      }
+      mbar_wait(&tmem_full[acc], acc_phase, 24);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * kColsPerWarp;
+      const long long bias_off =
+          (e.bias_group_rows > 0 && valid) ? (grow / e.bias_group_rows) * static_cast<long long>(p.N) : 0;
+#pragma unroll 1
+      for (int c = 0; c < kColsPerWarp / 32; ++c) {
+        const int n0 = n_tile * BN + half * kColsPerWarp + c * 32;
+        if (n0 >= p.N) break;  // warp-uniform
+        uint32_t v[32];
+        __syncwarp();
+        tmem_ld32(t_row + c * 32, v);
+        tmem_ld_wait();
+        if (valid) gemm_epilogue_chunk(e, p.N, v, grow, n0, bias_off);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);  // leader's barrier: 2 CTAs x 8 warps
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // no CTA may exit (or free TMEM) while its peer can still touch it
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, Cfg::kTmemCols);
   }
 }
 

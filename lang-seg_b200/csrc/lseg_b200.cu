@@ -3,6 +3,7 @@
 #include "../../include/lseg_b200.h"
 
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -36,6 +37,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static PFN_encodeTiled g_encode = nullptr;
 static int g_num_sms = 0;
+static int g_gemm_two_cta = 1;
 static std::once_flag g_init_flag;
 static int g_init_status = -1;
 
@@ -65,6 +67,12 @@ static void init_once() {
   g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
   cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256>::kSmemBytes);
   cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::kSmemBytes);
+  cudaFuncSetAttribute(gemm_tc2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg<256>::kSmemBytes);
+  cudaFuncSetAttribute(gemm_tc2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg<128>::kSmemBytes);
+  {  // LSEG_GEMM_1CTA=1 selects the single-CTA GEMM (A/B comparisons, debugging)
+    const char* env = getenv("LSEG_GEMM_1CTA");
+    g_gemm_two_cta = (env && env[0] == '1') ? 0 : 1;
+  }
   cudaFuncSetAttribute(mhsa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMhsaSmemBytes);
   cudaFuncSetAttribute(mhsa_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   g_init_status = 0;
@@ -118,6 +126,7 @@ struct GemmPlan {
   GemmParams p;
   int bn;
   int grid;
+  int two_cta;  // 1: CTA-pair kernel (tcgen05 cta_group::2), 0: single-CTA kernel
 };
 
 static int gemm_plan(const GemmDesc& d, GemmPlan* plan) {
@@ -130,6 +139,7 @@ static int gemm_plan(const GemmDesc& d, GemmPlan* plan) {
   }
   const int bn = (d.N > 128) ? 256 : 128;
   plan->bn = bn;
+  plan->two_cta = g_gemm_two_cta;
   const int taps = d.conv ? d.kh * d.kw : 1;
   const long long ktot = static_cast<long long>(taps) * d.K;
   if (d.w_rows < bn && d.w_rows < d.N) {
@@ -165,11 +175,18 @@ static int gemm_plan(const GemmDesc& d, GemmPlan* plan) {
   {
     const uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)d.w_rows};
     const uint64_t str[1] = {(uint64_t)ktot * 2};
-    const uint32_t box[2] = {kGemmBK, (uint32_t)bn};
+    // CTA-pair kernel: each CTA of the pair loads half of the weight tile
+    const uint32_t box[2] = {kGemmBK, (uint32_t)(plan->two_cta ? bn / 2 : bn)};
     if (make_tmap_f16(&p.tma_b, d.w, 2, dims, str, box)) return -1;
   }
-  const int tiles = p.num_m_tiles * p.num_n_tiles;
-  plan->grid = tiles < g_num_sms ? tiles : g_num_sms;
+  if (plan->two_cta) {
+    const int pair_tiles = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
+    const int max_pairs = g_num_sms / 2;
+    plan->grid = 2 * (pair_tiles < max_pairs ? pair_tiles : max_pairs);
+  } else {
+    const int tiles = p.num_m_tiles * p.num_n_tiles;
+    plan->grid = tiles < g_num_sms ? tiles : g_num_sms;
+  }
   if (p.e.store == STORE_D2S && (p.e.d2s_cout % 32 != 0 || !p.e.out_f16)) {
     set_error("gemm: depth-to-space store needs cout %% 32 == 0 and an fp16 output");
     return -1;
@@ -183,6 +200,14 @@ static int gemm_plan(const GemmDesc& d, GemmPlan* plan) {
 
 static int gemm_run(const GemmPlan& plan, cudaStream_t stream) {
   if (plan.grid <= 0) return 0;
+  if (plan.two_cta) {
+    if (plan.bn == 256)
+      gemm_tc2_kernel<256><<<plan.grid, kGemmThreads, Gemm2Cfg<256>::kSmemBytes, stream>>>(plan.p);
+    else
+      gemm_tc2_kernel<128><<<plan.grid, kGemmThreads, Gemm2Cfg<128>::kSmemBytes, stream>>>(plan.p);
+    LSEG_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   if (plan.bn == 256)
     gemm_tc_kernel<256><<<plan.grid, kGemmThreads, GemmCfg<256>::kSmemBytes, stream>>>(plan.p);
   else

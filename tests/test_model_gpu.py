@@ -136,7 +136,9 @@ def test_argmax_planted_prototypes(net):
     feat = feat.permute(0, 2, 3, 1).reshape(-1, 512)
     g = torch.Generator().manual_seed(11)
     idx = torch.randperm(feat.shape[0], generator=g)[:K]
-    protos = feat[idx]
+    # random-weight pixel embeddings share one dominant direction (cos to the mean ~0.99), so the prototypes
+    # are centred: classes are then separated by the per-pixel deviation (oracle margins > 0.5 for 99% of pixels)
+    protos = feat[idx] - feat.mean(dim=0, keepdim=True)
     protos = (protos / protos.norm(dim=-1, keepdim=True)).half()
     ref = O.output_conv(O.correlation_head(path_1, protos, sd))
     eng = net._engine_for(torch.device("cuda"))
@@ -147,7 +149,7 @@ def test_argmax_planted_prototypes(net):
     d.update(argmax_report(got, ref, margin_eps(ref)))
     _report("planted_prototypes_480_K150", d)
     assert d["logits"] < LOGIT_TOL, d
-    assert d["ok"] and d["agree_frac"] > 0.995, d
+    assert d["ok"] and d["agree_frac"] > 0.999, d
 
 
 def test_batch_consistency(net):
