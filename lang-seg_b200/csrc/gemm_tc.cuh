@@ -64,9 +64,11 @@ struct GemmCfg {
   static constexpr int kABytes = kGemmBM * kGemmBK * 2;
   static constexpr int kBBytes = BN * kGemmBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kStages = (BN == 256) ? 3 : 5;
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  // stages | 256 B of mbarriers | per-warp epilogue transpose tiles
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + 1024 /*align slack*/ + 256 + kGemmEpiWarps * 32 * 36 * 4;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -195,6 +197,138 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmEpi& e, int N, con
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Coalesced epilogue (row-major and depth-to-space stores).
+// tcgen05.ld hands every thread one ROW of the accumulator, so storing straight from registers makes
+// each warp-level access touch 32 different 128 B lines (ncu: the L1TEX wavefront queue, not HBM, bounded
+// the fp32 residual epilogues: proj GEMM at 369 TFLOP/s). Each epilogue warp therefore transposes its
+// 32 x 32 fp32 chunk through a private padded smem tile (row stride 36 floats: conflict-free for both
+// the row-wise float4 writes and the 4-rows-x-128B reads) and then works in the transposed mapping:
+// lane = (row & 3 within a group of 4, 4-column group), so one warp instruction covers 4 rows x 128 B.
+// ------------------------------------------------------------------------------------------
+constexpr int kEpiStageFloats = 32 * 36;  // per warp
+
+struct RowMap {  // tile-local row -> global row (pixel) index
+  int conv, M, H, W, h0, w0, b, tile_ok;
+  long long m0;
+  __device__ __forceinline__ bool map(int r, long long& grow) const {
+    if (conv) {
+      const int h = h0 + r / kConvTW, w = w0 + r % kConvTW;
+      grow = (static_cast<long long>(b) * H + h) * W + w;
+      return tile_ok && (h < H) && (w < W);
+    }
+    grow = m0 + r;
+    return tile_ok && (grow < M);
+  }
+};
+
+__device__ __forceinline__ RowMap make_rowmap(const GemmParams& p, int m_tile) {
+  RowMap rm;
+  rm.conv = p.conv;
+  rm.M = p.M;
+  rm.H = p.H;
+  rm.W = p.W;
+  rm.tile_ok = m_tile < p.num_m_tiles;
+  rm.m0 = static_cast<long long>(m_tile) * kGemmBM;
+  rm.h0 = rm.w0 = rm.b = 0;
+  if (p.conv) {
+    const int per_img = p.tiles_h * p.tiles_w;
+    rm.b = m_tile / per_img;
+    const int t = m_tile % per_img;
+    rm.h0 = (t / p.tiles_w) * kConvTH;
+    rm.w0 = (t % p.tiles_w) * kConvTW;
+  }
+  return rm;
+}
+
+__device__ __forceinline__ float4 f4_fma(float4 a, float4 s, float4 b) {
+  return make_float4(fmaf(a.x, s.x, b.x), fmaf(a.y, s.y, b.y), fmaf(a.z, s.z, b.z), fmaf(a.w, s.w, b.w));
+}
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) {
+  return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+__device__ __forceinline__ uint2 f4_to_h4(float4 a) {
+  __half2 lo = __floats2half2_rn(a.x, a.y), hi = __floats2half2_rn(a.z, a.w);
+  uint2 o;
+  o.x = *reinterpret_cast<uint32_t*>(&lo);
+  o.y = *reinterpret_cast<uint32_t*>(&hi);
+  return o;
+}
+
+// v: this thread's 32 accumulators (row = quarter*32 + lane, columns [n0, n0+32)). N % 4 == 0.
+__device__ __forceinline__ void gemm_epilogue_chunk_coalesced(const GemmEpi& e, int N, const uint32_t (&v)[32],
+                                                              float* stage, int quarter, int lane, int n0,
+                                                              const RowMap& rm) {
+  float4* srow = reinterpret_cast<float4*>(stage + lane * 36);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    srow[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                          __uint_as_float(v[4 * j + 3]));
+  __syncwarp();
+  const int c4 = lane & 7, rsub = lane >> 3;
+  const int col = n0 + 4 * c4;
+  if (col < N) {
+    const float4 one = make_float4(1.f, 1.f, 1.f, 1.f), zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 sc = e.scale ? __ldg(reinterpret_cast<const float4*>(e.scale + col)) : one;
+    float4 bs = (e.bias && e.bias_group_rows == 0) ? __ldg(reinterpret_cast<const float4*>(e.bias + col)) : zero;
+    // depth-to-space column decode (constant per lane)
+    int d_di = 0, d_dj = 0, d_co = 0;
+    if (e.store == STORE_D2S) {
+      const int ij = col / e.d2s_cout;
+      d_co = col - ij * e.d2s_cout;
+      d_di = ij / e.d2s_s;
+      d_dj = ij - d_di * e.d2s_s;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rl = 4 * i + rsub;
+      long long grow;
+      if (!rm.map(quarter * 32 + rl, grow)) continue;
+      float4 a = *reinterpret_cast<const float4*>(stage + rl * 36 + 4 * c4);
+      if (e.bias_group_rows > 0)
+        bs = __ldg(reinterpret_cast<const float4*>(e.bias + (grow / e.bias_group_rows) * static_cast<long long>(N) + col));
+      a = f4_fma(a, sc, bs);
+      if (e.act == ACT_GELU) {
+        a = make_float4(gelu_erf(a.x), gelu_erf(a.y), gelu_erf(a.z), gelu_erf(a.w));
+      } else if (e.act == ACT_QUICKGELU) {
+        a = make_float4(quick_gelu(a.x), quick_gelu(a.y), quick_gelu(a.z), quick_gelu(a.w));
+      } else if (e.act == ACT_RELU) {
+        a = make_float4(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f), fmaxf(a.z, 0.f), fmaxf(a.w, 0.f));
+      }
+      if (e.store == STORE_ROWMAJOR) {
+        const long long off = grow * e.ldc + col;
+        if (e.res_f32) a = f4_add(a, *reinterpret_cast<const float4*>(e.res_f32 + off));
+        if (e.res2_f32) a = f4_add(a, *reinterpret_cast<const float4*>(e.res2_f32 + off));
+        if (e.out_f32) *reinterpret_cast<float4*>(e.out_f32 + off) = a;
+        if (e.out_f16) {
+          uint2 h = f4_to_h4(a);
+          if (e.res_f16) {  // fp16 residual stream: round the branch output first, then add in fp16
+            const uint2 q = *reinterpret_cast<const uint2*>(e.res_f16 + off);
+            __half2 lo = __hadd2(*reinterpret_cast<const __half2*>(&q.x), *reinterpret_cast<__half2*>(&h.x));
+            __half2 hi = __hadd2(*reinterpret_cast<const __half2*>(&q.y), *reinterpret_cast<__half2*>(&h.y));
+            h.x = *reinterpret_cast<uint32_t*>(&lo);
+            h.y = *reinterpret_cast<uint32_t*>(&hi);
+          }
+          *reinterpret_cast<uint2*>(e.out_f16 + off) = h;
+        }
+        if (e.out_f16_relu)
+          *reinterpret_cast<uint2*>(e.out_f16_relu + off) =
+              f4_to_h4(make_float4(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f), fmaxf(a.z, 0.f), fmaxf(a.w, 0.f)));
+      } else {  // STORE_D2S: row grow = (b*h + y)*w + x -> NHWC [B, h*s, w*s, cout] pixel (y*s+di, x*s+dj)
+        const int hw = e.d2s_h * e.d2s_w;
+        const int b = static_cast<int>(grow / hw);
+        const int yx = static_cast<int>(grow - static_cast<long long>(b) * hw);
+        const int y = yx / e.d2s_w, x = yx - y * e.d2s_w;
+        const long long orow =
+            (static_cast<long long>(b) * (e.d2s_h * e.d2s_s) + (y * e.d2s_s + d_di)) * (e.d2s_w * e.d2s_s) +
+            (x * e.d2s_s + d_dj);
+        *reinterpret_cast<uint2*>(e.out_f16 + orow * e.d2s_cout + d_co) = f4_to_h4(a);
+      }
+    }
+  }
+  __syncwarp();
+}
+
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BN>;
@@ -305,6 +439,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     constexpr int kColsPerWarp = BN / (kGemmEpiWarps / 4);
     const int r = quarter * 32 + lane;            // row inside the 128-row tile
     const GemmEpi& e = p.e;
+    float* stage = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 256) + ew * kEpiStageFloats;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -327,6 +462,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       mbar_wait(&tmem_full[acc], acc_phase, 4);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * kColsPerWarp;
+      const RowMap rm = make_rowmap(p, m_tile);
+      const bool coalesced = (e.store != STORE_NCHW_T) && ((p.N & 3) == 0);
       const long long bias_off =
           (e.bias_group_rows > 0) ? (grow / e.bias_group_rows) * static_cast<long long>(p.N) : 0;
 #pragma unroll 1
@@ -337,8 +474,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         __syncwarp();
         tmem_ld32(t_row + c * 32, v);
         tmem_ld_wait();
-        if (!valid) continue;
-        gemm_epilogue_chunk(e, p.N, v, grow, n0, bias_off);
+        if (coalesced)
+          gemm_epilogue_chunk_coalesced(e, p.N, v, stage, quarter, lane, n0, rm);
+        else if (valid)
+          gemm_epilogue_chunk(e, p.N, v, grow, n0, bias_off);
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
@@ -370,9 +509,9 @@ struct Gemm2Cfg {
   static constexpr int kABytes = kGemmBM * kGemmBK * 2;
   static constexpr int kBBytes = (BN / 2) * kGemmBK * 2;  // this CTA's half of the weight tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 6 : 8;
+  static constexpr int kStages = (BN == 256) ? 5 : 7;
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + kGemmEpiWarps * 32 * 36 * 4;
 };
 
 template <int BN>
@@ -490,6 +629,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
     constexpr int kColsPerWarp = BN / (kGemmEpiWarps / 4);
     const int r = quarter * 32 + lane;
     const GemmEpi& e = p.e;
+    float* stage = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 256) + ew * kEpiStageFloats;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
@@ -512,6 +652,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
       mbar_wait(&tmem_full[acc], acc_phase, 24);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * kColsPerWarp;
+      const RowMap rm = make_rowmap(p, m_tile);
+      const bool coalesced = (e.store != STORE_NCHW_T) && ((p.N & 3) == 0);
       const long long bias_off =
           (e.bias_group_rows > 0 && valid) ? (grow / e.bias_group_rows) * static_cast<long long>(p.N) : 0;
 #pragma unroll 1
@@ -522,7 +664,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
         __syncwarp();
         tmem_ld32(t_row + c * 32, v);
         tmem_ld_wait();
-        if (valid) gemm_epilogue_chunk(e, p.N, v, grow, n0, bias_off);
+        if (coalesced)
+          gemm_epilogue_chunk_coalesced(e, p.N, v, stage, quarter, lane, n0, rm);
+        else if (valid)
+          gemm_epilogue_chunk(e, p.N, v, grow, n0, bias_off);
       }
       tc_fence_before();
       __syncwarp();
