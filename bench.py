@@ -260,7 +260,7 @@ def main():
         if args.dump_profile:
             with open(args.dump_profile, "w") as f:
                 json.dump([{"ms": m, "kind": k, "gflop": fl / 1e9} for m, k, fl in prof], f)
-        by = {0: [0.0, 0.0, 0], 1: [0.0, 0.0, 0], 2: [0.0, 0.0, 0], 3: [0.0, 0.0, 0]}
+        by = {k: [0.0, 0.0, 0] for k in range(5)}  # 0 elementwise, 1 GEMM, 2 MHSA, 3 LayerNorm, 4 memset
         for ms, kind, fl in prof:
             by[kind][0] += ms
             by[kind][1] += fl

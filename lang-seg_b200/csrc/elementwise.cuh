@@ -1,40 +1,47 @@
 // lseg_b200 — HBM-bound helper kernels (vectorised / warp-shuffle) for the LSeg forward path.
-// Each kernel cites the reference line it restates; all are plain grid-stride or warp-per-row
-// kernels sized in multiples of the SM count by their launchers.
+// Each kernel cites the reference line it restates. Index math is kept OFF the per-element path: rows /
+// planes / pixels come from blockIdx (2-D/3-D grids), so a thread's work is "load 16 B, convert, store
+// 16 B" without the 64-bit div/mod chains of a flat grid-stride loop (those made the first version of
+// the x2 logits upsample instruction-bound at 1.6 TB/s instead of HBM-bound).
 #pragma once
 #include "common.cuh"
 
 namespace lseg {
 
+#define LSEG_LAUNCH_CHECK()                   \
+  do {                                        \
+    LSEG_CHECK_CUDA(cudaGetLastError());      \
+    return 0;                                 \
+  } while (0)
+
 // ------------------------------------------------------------------------------------------
 // patchify: x fp32 NCHW [B,3,H,W] -> A fp16 [B*gh*gw, 768], column = c*256 + py*16 + px, which is
 // the flattening of the patch-embed Conv2d(3,1024,k16,s16) weight (modules/models/lseg_vit.py:179),
 // so the conv becomes one GEMM with the weight used as stored.
+// grid (ceil(gw*192/256), B*gh): one thread = 4 pixels of one patch row.
 // ------------------------------------------------------------------------------------------
-__global__ void patchify_kernel(const float* __restrict__ x, __half* __restrict__ a, int B, int H, int W) {
+__global__ void patchify_kernel(const float* __restrict__ x, __half* __restrict__ a, int H, int W) {
   const int gh = H / 16, gw = W / 16;
-  const long long total = static_cast<long long>(B) * gh * gw * 3 * 16 * 4;  // one thread = 4 pixels of a patch row
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int px4 = static_cast<int>(i & 3);
-    long long t = i >> 2;
-    const int py = static_cast<int>(t & 15);
-    t >>= 4;
-    const int c = static_cast<int>(t % 3);
-    t /= 3;
-    const int gx = static_cast<int>(t % gw);
-    t /= gw;
-    const int gy = static_cast<int>(t % gh);
-    const int b = static_cast<int>(t / gh);
-    const float4 v = *reinterpret_cast<const float4*>(
-        x + ((static_cast<long long>(b) * 3 + c) * H + gy * 16 + py) * W + gx * 16 + px4 * 4);
-    __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
-    __half* dst = a + (static_cast<long long>(b) * gh * gw + gy * gw + gx) * 768 + c * 256 + py * 16 + px4 * 4;
-    uint2 o;
-    o.x = *reinterpret_cast<uint32_t*>(&h0);
-    o.y = *reinterpret_cast<uint32_t*>(&h1);
-    *reinterpret_cast<uint2*>(dst) = o;
-  }
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= gw * 192) return;
+  const int b = blockIdx.y / gh, gy = blockIdx.y - b * gh;
+  const int px4 = i & 3, py = (i >> 2) & 15;
+  const int rest = i >> 6;  // gx*3 + c
+  const int gx = rest / 3, c = rest - gx * 3;
+  const float4 v = *reinterpret_cast<const float4*>(
+      x + ((static_cast<long long>(b) * 3 + c) * H + gy * 16 + py) * W + gx * 16 + px4 * 4);
+  __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+  uint2 o;
+  o.x = *reinterpret_cast<uint32_t*>(&h0);
+  o.y = *reinterpret_cast<uint32_t*>(&h1);
+  __half* dst = a + (static_cast<long long>(blockIdx.y) * gw + gx) * 768 + c * 256 + py * 16 + px4 * 4;
+  *reinterpret_cast<uint2*>(dst) = o;
+}
+static inline int launch_patchify(const float* x, __half* a, int B, int H, int W, cudaStream_t s) {
+  const int gw = W / 16, gh = H / 16;
+  dim3 grid((gw * 192 + 255) / 256, B * gh);
+  patchify_kernel<<<grid, 256, 0, s>>>(x, a, H, W);
+  LSEG_LAUNCH_CHECK();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -66,26 +73,26 @@ __global__ void pos_resize_kernel(const float* __restrict__ pos, float* __restri
 // ------------------------------------------------------------------------------------------
 // token assembly (modules/models/lseg_vit.py:188-193): x[b,0] = cls + pos[0];
 // x[b,1+t] = patch[b*T+t] (bias already added by the GEMM) + pos[1+t].   fp32 [B, 1+T, D]
+// one block per token row.
 // ------------------------------------------------------------------------------------------
 __global__ void assemble_tokens_kernel(const float* __restrict__ patch, const float* __restrict__ cls,
-                                       const float* __restrict__ pos, float* __restrict__ x, int B, int T, int D) {
-  const int d4 = D / 4;
-  const long long total = static_cast<long long>(B) * (T + 1) * d4;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % d4);
-    const long long row = i / d4;
-    const int t = static_cast<int>(row % (T + 1));
-    const int b = static_cast<int>(row / (T + 1));
-    const float4 pe = reinterpret_cast<const float4*>(pos + static_cast<long long>(t) * D)[c];
-    float4 v;
-    if (t == 0)
-      v = reinterpret_cast<const float4*>(cls)[c];
-    else
-      v = reinterpret_cast<const float4*>(patch + (static_cast<long long>(b) * T + (t - 1)) * D)[c];
-    v.x += pe.x; v.y += pe.y; v.z += pe.z; v.w += pe.w;
-    reinterpret_cast<float4*>(x + row * D)[c] = v;
+                                       const float* __restrict__ pos, float* __restrict__ x, int T, int D) {
+  const int row = blockIdx.x;
+  const int b = row / (T + 1), t = row - b * (T + 1);
+  const float* src = (t == 0) ? cls : patch + (static_cast<long long>(b) * T + (t - 1)) * D;
+  const float* pe = pos + static_cast<long long>(t) * D;
+  float* dst = x + static_cast<long long>(row) * D;
+  for (int c = threadIdx.x; c < D / 4; c += blockDim.x) {
+    float4 v = reinterpret_cast<const float4*>(src)[c];
+    const float4 q = reinterpret_cast<const float4*>(pe)[c];
+    v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+    reinterpret_cast<float4*>(dst)[c] = v;
   }
+}
+static inline int launch_assemble_tokens(const float* patch, const float* cls, const float* pos, float* x, int B, int T,
+                                         int D, cudaStream_t s) {
+  assemble_tokens_kernel<<<B * (T + 1), 256, 0, s>>>(patch, cls, pos, x, T, D);
+  LSEG_LAUNCH_CHECK();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -151,82 +158,82 @@ __global__ void layernorm_kernel(const TIn* __restrict__ x, const float* __restr
 
 // ------------------------------------------------------------------------------------------
 // readout split (modules/models/lseg_vit.py:79-90): tap fp32 [B, 1+T, D] ->
-//   tok fp16 [B*T, D] (patch tokens) and cls fp16 [B, D].
+//   tok fp16 [B*T, D] (patch tokens) and cls fp16 [B, D].   one block per token row.
 // ------------------------------------------------------------------------------------------
 __global__ void readout_split_kernel(const float* __restrict__ tap, __half* __restrict__ tok,
-                                     __half* __restrict__ cls, int B, int T, int D) {
-  const int d4 = D / 4;
-  const long long total = static_cast<long long>(B) * (T + 1) * d4;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % d4);
-    const long long row = i / d4;
-    const int t = static_cast<int>(row % (T + 1));
-    const int b = static_cast<int>(row / (T + 1));
-    const float4 v = reinterpret_cast<const float4*>(tap + row * D)[c];
+                                     __half* __restrict__ cls, int T, int D) {
+  const int row = blockIdx.x;
+  const int b = row / (T + 1), t = row - b * (T + 1);
+  const float* src = tap + static_cast<long long>(row) * D;
+  __half* dst = (t == 0) ? cls + static_cast<long long>(b) * D : tok + (static_cast<long long>(b) * T + (t - 1)) * D;
+  for (int c = threadIdx.x; c < D / 4; c += blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(src)[c];
     __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
     uint2 o;
     o.x = *reinterpret_cast<uint32_t*>(&h0);
     o.y = *reinterpret_cast<uint32_t*>(&h1);
-    __half* dst = (t == 0) ? cls + static_cast<long long>(b) * D : tok + (static_cast<long long>(b) * T + (t - 1)) * D;
     reinterpret_cast<uint2*>(dst)[c] = o;
   }
+}
+static inline int launch_readout_split(const float* tap, __half* tok, __half* cls, int B, int T, int D,
+                                       cudaStream_t s) {
+  readout_split_kernel<<<B * (T + 1), 256, 0, s>>>(tap, tok, cls, T, D);
+  LSEG_LAUNCH_CHECK();
 }
 
 // ------------------------------------------------------------------------------------------
 // im2col for the one strided conv (act_postprocess4[4]: 3x3 s2 p1, modules/models/lseg_vit.py:516-522):
-// NHWC fp16 [B,H,W,C] -> [B*Ho*Wo, 9*C], tap-major columns, zero halo.
+// NHWC fp16 [B,H,W,C] -> [B*Ho*Wo, 9*C], tap-major columns, zero halo. grid (Wo, Ho, B).
 // ------------------------------------------------------------------------------------------
-__global__ void im2col_3x3_s2_kernel(const __half* __restrict__ x, __half* __restrict__ a, int B, int H, int W,
-                                     int C) {
-  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+__global__ void im2col_3x3_s2_kernel(const __half* __restrict__ x, __half* __restrict__ a, int H, int W, int C) {
+  const int ox = blockIdx.x, oy = blockIdx.y, b = blockIdx.z;
+  const int Wo = gridDim.x, Ho = gridDim.y;
   const int c8 = C / 8;
-  const long long total = static_cast<long long>(B) * Ho * Wo * 9 * c8;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % c8);
-    long long t = i / c8;
-    const int tap = static_cast<int>(t % 9);
-    t /= 9;
-    const int ox = static_cast<int>(t % Wo);
-    t /= Wo;
-    const int oy = static_cast<int>(t % Ho);
-    const int b = static_cast<int>(t / Ho);
+  __half* dst = a + ((static_cast<long long>(b) * Ho + oy) * Wo + ox) * 9 * C;
+  for (int tap = 0; tap < 9; ++tap) {
     const int iy = oy * 2 - 1 + tap / 3, ix = ox * 2 - 1 + tap % 3;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (iy >= 0 && iy < H && ix >= 0 && ix < W)
-      v = reinterpret_cast<const uint4*>(x + ((static_cast<long long>(b) * H + iy) * W + ix) * C)[c];
-    reinterpret_cast<uint4*>(a + ((static_cast<long long>(b) * Ho + oy) * Wo + ox) * 9 * C + static_cast<long long>(tap) * C)[c] = v;
+    const bool in = iy >= 0 && iy < H && ix >= 0 && ix < W;
+    const __half* src = x + ((static_cast<long long>(b) * H + iy) * W + ix) * C;
+    for (int c = threadIdx.x; c < c8; c += blockDim.x) {
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (in) v = reinterpret_cast<const uint4*>(src)[c];
+      reinterpret_cast<uint4*>(dst + static_cast<long long>(tap) * C)[c] = v;
+    }
   }
+}
+static inline int launch_im2col_3x3_s2(const __half* x, __half* a, int B, int H, int W, int C, cudaStream_t s) {
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  im2col_3x3_s2_kernel<<<dim3(Wo, Ho, B), 128, 0, s>>>(x, a, H, W, C);
+  LSEG_LAUNCH_CHECK();
 }
 
 // ------------------------------------------------------------------------------------------
 // bilinear x2, align_corners=True, NHWC fp16 -> NHWC fp16 (fusion blocks, lseg_blocks.py:352-354).
 // src = dst * (in-1)/(out-1), computed like ATen (float scale, float product).
+// grid (ceil(Wo/8), Ho, B), 256 threads: 8 output pixels x 32 channel groups of 8.
 // ------------------------------------------------------------------------------------------
-__global__ void upsample2x_nhwc_kernel(const __half* __restrict__ x, __half* __restrict__ y, int B, int H, int W,
-                                       int C) {
+__global__ void upsample2x_nhwc_kernel(const __half* __restrict__ x, __half* __restrict__ y, int H, int W, int C) {
   const int Ho = 2 * H, Wo = 2 * W, c8 = C / 8;
+  const int oy = blockIdx.y, b = blockIdx.z;
+  const int ox = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (ox >= Wo) return;
   const float sh = (Ho > 1) ? static_cast<float>(H - 1) / (Ho - 1) : 0.f;
   const float sw = (Wo > 1) ? static_cast<float>(W - 1) / (Wo - 1) : 0.f;
-  const long long total = static_cast<long long>(B) * Ho * Wo * c8;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % c8);
-    long long t = i / c8;
-    const int ox = static_cast<int>(t % Wo);
-    t /= Wo;
-    const int oy = static_cast<int>(t % Ho);
-    const int b = static_cast<int>(t / Ho);
-    const float fy = sh * oy, fx = sw * ox;
-    const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
-    const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
-    const float ly = fy - y0, lx = fx - x0, hy = 1.f - ly, hx = 1.f - lx;
-    const __half* base = x + static_cast<long long>(b) * H * W * C;
-    const uint4 q00 = reinterpret_cast<const uint4*>(base + (static_cast<long long>(y0) * W + x0) * C)[c];
-    const uint4 q01 = reinterpret_cast<const uint4*>(base + (static_cast<long long>(y0) * W + x1) * C)[c];
-    const uint4 q10 = reinterpret_cast<const uint4*>(base + (static_cast<long long>(y1) * W + x0) * C)[c];
-    const uint4 q11 = reinterpret_cast<const uint4*>(base + (static_cast<long long>(y1) * W + x1) * C)[c];
+  const float fy = sh * oy, fx = sw * ox;
+  const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+  const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+  const float ly = fy - y0, lx = fx - x0, hy = 1.f - ly, hx = 1.f - lx;
+  const __half* base = x + static_cast<long long>(b) * H * W * C;
+  const __half* p00 = base + (static_cast<long long>(y0) * W + x0) * C;
+  const __half* p01 = base + (static_cast<long long>(y0) * W + x1) * C;
+  const __half* p10 = base + (static_cast<long long>(y1) * W + x0) * C;
+  const __half* p11 = base + (static_cast<long long>(y1) * W + x1) * C;
+  __half* dst = y + ((static_cast<long long>(b) * Ho + oy) * Wo + ox) * C;
+  for (int c = threadIdx.x & 31; c < c8; c += 32) {
+    const uint4 q00 = reinterpret_cast<const uint4*>(p00)[c];
+    const uint4 q01 = reinterpret_cast<const uint4*>(p01)[c];
+    const uint4 q10 = reinterpret_cast<const uint4*>(p10)[c];
+    const uint4 q11 = reinterpret_cast<const uint4*>(p11)[c];
     const __half2* a00 = reinterpret_cast<const __half2*>(&q00);
     const __half2* a01 = reinterpret_cast<const __half2*>(&q01);
     const __half2* a10 = reinterpret_cast<const __half2*>(&q10);
@@ -240,8 +247,12 @@ __global__ void upsample2x_nhwc_kernel(const __half* __restrict__ x, __half* __r
       oh[k] = __floats2half2_rn(hy * (hx * f00.x + lx * f01.x) + ly * (hx * f10.x + lx * f11.x),
                                 hy * (hx * f00.y + lx * f01.y) + ly * (hx * f10.y + lx * f11.y));
     }
-    reinterpret_cast<uint4*>(y + ((static_cast<long long>(b) * Ho + oy) * Wo + ox) * C)[c] = o;
+    reinterpret_cast<uint4*>(dst)[c] = o;
   }
+}
+static inline int launch_upsample2x_nhwc(const __half* x, __half* y, int B, int H, int W, int C, cudaStream_t s) {
+  upsample2x_nhwc_kernel<<<dim3((2 * W + 7) / 8, 2 * H, B), 256, 0, s>>>(x, y, H, W, C);
+  LSEG_LAUNCH_CHECK();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -297,58 +308,69 @@ __global__ void l2norm_f16_kernel(const __half* __restrict__ x, __half* __restri
 }
 
 // ------------------------------------------------------------------------------------------
-// output head (modules/models/lseg_net.py:196,203): fp16 logits [B,K,h,w] (values of the fp16
-// matmul) -> .float() -> bilinear x2 align_corners=True -> fp32 NCHW [B,K,2h,2w].
-// HBM-write-bound: each thread produces 4 consecutive outputs (one float4 store).
+// output head (modules/models/lseg_net.py:196,203): fp16 logits [planes,H,W] (values of the fp16
+// matmul) -> .float() -> bilinear x2 align_corners=True -> fp32 [planes,2H,2W].
+// HBM-write-bound (K*H*W*4 B per image). grid (ceil(Ho/8), planes); a block of 128 threads produces 8
+// output rows of one plane, each thread 4 consecutive outputs (one streaming float4 store) per row; the
+// horizontal taps/weights are computed once per thread and reused for the 8 rows.
 // ------------------------------------------------------------------------------------------
-__global__ void upsample2x_nchw_kernel(const __half* __restrict__ x, float* __restrict__ y, long long planes, int H,
-                                       int W) {
+__global__ void upsample2x_nchw_kernel(const __half* __restrict__ x, float* __restrict__ y, int H, int W) {
   const int Ho = 2 * H, Wo = 2 * W, w4 = Wo / 4;
+  const long long pl = blockIdx.y;
   const float sh = (Ho > 1) ? static_cast<float>(H - 1) / (Ho - 1) : 0.f;
   const float sw = (Wo > 1) ? static_cast<float>(W - 1) / (Wo - 1) : 0.f;
-  const long long total = planes * Ho * w4;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int xq = static_cast<int>(i % w4);
-    long long t = i / w4;
-    const int oy = static_cast<int>(t % Ho);
-    const long long pl = t / Ho;
-    const float fy = sh * oy;
-    const int y0 = static_cast<int>(fy);
-    const int y1 = min(y0 + 1, H - 1);
-    const float ly = fy - y0, hy = 1.f - ly;
-    const __half* r0 = x + (pl * H + y0) * W;
-    const __half* r1 = x + (pl * H + y1) * W;
-    float o[4];
+  const __half* plane = x + pl * H * W;
+  float* oplane = y + pl * Ho * Wo;
+  for (int xq = threadIdx.x; xq < w4; xq += blockDim.x) {
+    int x0[4], x1[4];
+    float lx[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int ox = xq * 4 + k;
-      const float fx = sw * ox;
-      const int x0 = static_cast<int>(fx);
-      const int x1 = min(x0 + 1, W - 1);
-      const float lx = fx - x0, hx = 1.f - lx;
-      o[k] = hy * (hx * __half2float(r0[x0]) + lx * __half2float(r0[x1])) +
-             ly * (hx * __half2float(r1[x0]) + lx * __half2float(r1[x1]));
+      const float fx = sw * (xq * 4 + k);
+      x0[k] = static_cast<int>(fx);
+      x1[k] = min(x0[k] + 1, W - 1);
+      lx[k] = fx - x0[k];
     }
-    __stcs(reinterpret_cast<float4*>(y + (pl * Ho + oy) * Wo + xq * 4), make_float4(o[0], o[1], o[2], o[3]));
+#pragma unroll 2
+    for (int r = 0; r < 8; ++r) {
+      const int oy = blockIdx.x * 8 + r;
+      if (oy >= Ho) break;
+      const float fy = sh * oy;
+      const int y0 = static_cast<int>(fy);
+      const int y1 = min(y0 + 1, H - 1);
+      const float ly = fy - y0, hy = 1.f - ly;
+      const __half* r0 = plane + y0 * W;
+      const __half* r1 = plane + y1 * W;
+      float o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float hx = 1.f - lx[k];
+        o[k] = hy * (hx * __half2float(r0[x0[k]]) + lx[k] * __half2float(r0[x1[k]])) +
+               ly * (hx * __half2float(r1[x0[k]]) + lx[k] * __half2float(r1[x1[k]]));
+      }
+      __stcs(reinterpret_cast<float4*>(oplane + static_cast<long long>(oy) * Wo + xq * 4),
+             make_float4(o[0], o[1], o[2], o[3]));
+    }
   }
+}
+static inline int launch_upsample2x_nchw(const __half* x, float* y, long long planes, int H, int W, cudaStream_t s) {
+  upsample2x_nchw_kernel<<<dim3((2 * H + 7) / 8, static_cast<unsigned>(planes)), 128, 0, s>>>(x, y, H, W);
+  LSEG_LAUNCH_CHECK();
 }
 
 // ------------------------------------------------------------------------------------------
 // CLIP text tower glue
 // ------------------------------------------------------------------------------------------
-// x = token_embedding(text).half() + positional_embedding.half()   (fp16 add)
+// x = token_embedding(text).half() + positional_embedding.half()   (fp16 add). one block per token.
 __global__ void text_embed_kernel(const long long* __restrict__ tokens, const float* __restrict__ tok_emb,
-                                  const float* __restrict__ pos_emb, __half* __restrict__ x, int K, int L, int Wd) {
-  const long long total = static_cast<long long>(K) * L * Wd;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int d = static_cast<int>(i % Wd);
-    const long long row = i / Wd;
-    const int t = static_cast<int>(row % L);
-    const long long id = tokens[row];
-    x[i] = __hadd(__float2half_rn(tok_emb[id * Wd + d]), __float2half_rn(pos_emb[static_cast<long long>(t) * Wd + d]));
-  }
+                                  const float* __restrict__ pos_emb, __half* __restrict__ x, int L, int Wd) {
+  const int row = blockIdx.x;
+  const int t = row % L;
+  const long long id = tokens[row];
+  const float* e = tok_emb + id * Wd;
+  const float* pe = pos_emb + static_cast<long long>(t) * Wd;
+  for (int d = threadIdx.x; d < Wd; d += blockDim.x)
+    x[static_cast<long long>(row) * Wd + d] = __hadd(__float2half_rn(e[d]), __float2half_rn(pe[d]));
 }
 // rows at the EOT position: text.argmax(-1) (first maximal id), gathered after ln_final.
 __global__ void text_eot_gather_kernel(const long long* __restrict__ tokens, const __half* __restrict__ x,

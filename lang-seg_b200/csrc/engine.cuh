@@ -23,7 +23,7 @@ struct CallCtx {
   float* out;
 };
 using StepFn = std::function<int(const CallCtx&, cudaStream_t)>;
-enum StepKind { KIND_EW = 0, KIND_GEMM = 1, KIND_MHSA = 2, KIND_LN = 3 };
+enum StepKind { KIND_EW = 0, KIND_GEMM = 1, KIND_MHSA = 2, KIND_LN = 3, KIND_MEMSET = 4 };
 // One launch of the forward: the closure plus what bench.py's roofline needs (kernel class and
 // the ALGORITHMIC flops of this launch, 2*M*N*K for GEMMs, 4*N^2*dh per head for attention).
 struct Step {
@@ -62,6 +62,7 @@ struct ImagePlan {
   std::map<std::string, const void*> debug;
   // head buffers needed by the per-call tail
   __half* featn = nullptr;
+  float* feat_sumsq = nullptr;
   __half* logits_lr = nullptr;
   size_t logits_cap_k = 0;
   ~ImagePlan() { arena.release(); }
@@ -227,10 +228,7 @@ static int build_image_plan(lseg_engine* eng, int B, int H, int W, cudaStream_t 
   }
 
   steps.push_back([=](const CallCtx& c, cudaStream_t s) {
-    const long long total = BT * 3 * 16 * 4;
-    patchify_kernel<<<ew_grid(total, 256), 256, 0, s>>>(c.x, patch_a, B, H, W);
-    LSEG_CHECK_CUDA(cudaGetLastError());
-    return 0;
+    return launch_patchify(c.x, patch_a, B, H, W, s);
   });
   {
     GemmEpi e = epi_none();
@@ -242,10 +240,7 @@ static int build_image_plan(lseg_engine* eng, int B, int H, int W, cudaStream_t 
   {
     const float* cls = w.cls_token;
     steps.push_back([=](const CallCtx&, cudaStream_t s) {
-      const long long total = M * (D / 4);
-      assemble_tokens_kernel<<<ew_grid(total, 256), 256, 0, s>>>(patch_out, cls, pos, xbuf, B, T, D);
-      LSEG_CHECK_CUDA(cudaGetLastError());
-      return 0;
+      return launch_assemble_tokens(patch_out, cls, pos, xbuf, B, T, D, s);
     });
   }
   float* xin = xbuf;
@@ -321,10 +316,7 @@ static int build_image_plan(lseg_engine* eng, int B, int H, int W, cudaStream_t 
   for (int k = 0; k < 4; ++k) {
     const float* tap = taps[k];
     steps.push_back([=](const CallCtx&, cudaStream_t s) {
-      const long long total = M * (D / 4);
-      readout_split_kernel<<<ew_grid(total, 256), 256, 0, s>>>(tap, tok, cls16, B, T, D);
-      LSEG_CHECK_CUDA(cudaGetLastError());
-      return 0;
+      return launch_readout_split(tap, tok, cls16, B, T, D, s);
     });
     {  // per-image half of the readout projection: cls * W[:,1024:]^T + b
       GemmEpi e = epi_none();
@@ -371,10 +363,7 @@ static int build_image_plan(lseg_engine* eng, int B, int H, int W, cudaStream_t 
       LSEG_ALLOC(a4, __half, rows4 * 9 * 1024);
       LSEG_ALLOC(l4, __half, rows4 * 1024);
       steps.push_back([=](const CallCtx&, cudaStream_t s) {
-        const long long total = rows4 * 9 * (1024 / 8);
-        im2col_3x3_s2_kernel<<<ew_grid(total, 256), 256, 0, s>>>(pk, a4, B, gh, gw, 1024);
-        LSEG_CHECK_CUDA(cudaGetLastError());
-        return 0;
+        return launch_im2col_3x3_s2(pk, a4, B, gh, gw, 1024, s);
       });
       GemmEpi e = epi_none();
       e.bias = w.post4_conv.b;
@@ -422,10 +411,7 @@ static int build_image_plan(lseg_engine* eng, int B, int H, int W, cudaStream_t 
     if (add_rcu(steps, w.rcu2[k], rcu2_in_relu, rcu2_in_f32, nullptr, tmp, B, h, ww, nullptr, r2, nullptr)) return -1;
     LSEG_ALLOC(up, __half, px * 4 * 256);
     steps.push_back([=](const CallCtx&, cudaStream_t s) {
-      const long long total = px * 4 * (256 / 8);
-      upsample2x_nhwc_kernel<<<ew_grid(total, 256), 256, 0, s>>>(r2, up, B, h, ww, 256);
-      LSEG_CHECK_CUDA(cudaGetLastError());
-      return 0;
+      return launch_upsample2x_nhwc(r2, up, B, h, ww, 256, s);
     });
     GemmEpi e = epi_none();
     e.bias = w.out_conv[k].b;
@@ -445,24 +431,28 @@ static int build_image_plan(lseg_engine* eng, int B, int H, int W, cudaStream_t 
 
   // ---- head1 + pixel normalisation (lseg_net.py:185-191) ----
   const long long BP = static_cast<long long>(B) * (H / 2) * (W / 2);
-  LSEG_ALLOC(feat, float, BP * 512);
+  // The pixel embedding is written once, un-normalised, in fp16, together with its fp32 squared row
+  // norm (accumulated from the fp32 accumulators); the pixel x text GEMM applies logit_scale / ||row|| in
+  // its epilogue. Same quantity as the reference's normalise -> half -> scale -> matmul up to where the
+  // fp16 roundings fall, without the 118 MB/img fp32 feature round trip and the separate norm pass.
   LSEG_ALLOC(featn, __half, BP * 512);
+  LSEG_ALLOC(feat_sumsq, float, BP);
+  steps.emplace_back(
+      [=](const CallCtx&, cudaStream_t s) {
+        LSEG_CHECK_CUDA(cudaMemsetAsync(feat_sumsq, 0, sizeof(float) * BP, s));
+        return 0;
+      },
+      KIND_MEMSET, 0.0);
   {
     GemmEpi e = epi_none();
     e.bias = w.head1.b;
-    e.out_f32 = feat;
+    e.out_f16 = featn;
+    e.out_row_sumsq = feat_sumsq;
     e.ldc = 512;
     if (add_gemm(steps, path1_f16, 256, (int)BP, (int)BP, w.head1, e)) return -1;
   }
-  {
-    const float ls = w.logit_scale;
-    steps.push_back([=](const CallCtx&, cudaStream_t s) {
-      l2norm_scale_kernel<<<static_cast<int>((BP + 7) / 8), 256, 0, s>>>(feat, featn, BP, 512, ls);
-      LSEG_CHECK_CUDA(cudaGetLastError());
-      return 0;
-    });
-  }
   plan->featn = featn;
+  plan->feat_sumsq = feat_sumsq;
   eng->img = std::move(plan);
   return 0;
 }
@@ -516,7 +506,7 @@ static int run_forward(lseg_engine* eng, const CallCtx& ctx, int B, int H, int W
   if (prof && prof->mark(stream)) return -1;
   for (auto& st : plan.steps) {
     if (st(ctx, stream)) return -1;
-    ++launches;
+    if (st.kind != KIND_MEMSET) ++launches;  // count our kernels only
     if (prof) {
       if (prof->mark(stream)) return -1;
       prof->kind.push_back(st.kind);
@@ -543,6 +533,8 @@ static int run_forward(lseg_engine* eng, const CallCtx& ctx, int B, int H, int W
     d.e.store = STORE_NCHW_T;
     d.e.nchw_p = (int)P;
     d.e.nchw_k = ctx.K;
+    d.e.row_sumsq = plan.feat_sumsq + static_cast<long long>(g) * P;
+    d.e.row_scale = eng->w.logit_scale;
     GemmPlan gp;
     if (gemm_plan(d, &gp)) return -1;
     if (gemm_run(gp, stream)) return -1;
@@ -556,9 +548,7 @@ static int run_forward(lseg_engine* eng, const CallCtx& ctx, int B, int H, int W
   // ---- scratch.output_conv: bilinear x2, align_corners=True (lseg_net.py:203) ----
   {
     const long long planes = static_cast<long long>(B) * ctx.K;
-    const long long total = planes * H * (W / 4);
-    upsample2x_nchw_kernel<<<ew_grid(total, 256), 256, 0, stream>>>(plan.logits_lr, ctx.out, planes, h2, w2);
-    LSEG_CHECK_CUDA(cudaGetLastError());
+    if (launch_upsample2x_nchw(plan.logits_lr, ctx.out, planes, h2, w2, stream)) return -1;
     ++launches;
     if (prof) {
       if (prof->mark(stream)) return -1;
@@ -606,8 +596,7 @@ static int build_text_plan(lseg_engine* eng, int K) {
   const float* tok_emb = w.tok_emb;
   const float* text_pos = w.text_pos;
   steps.push_back([=](const long long* tokens, __half*, cudaStream_t s) {
-    const long long total = M * Wd;
-    text_embed_kernel<<<ew_grid(total, 256), 256, 0, s>>>(tokens, tok_emb, text_pos, tx, K, L, Wd);
+    text_embed_kernel<<<static_cast<unsigned>(M), 128, 0, s>>>(tokens, tok_emb, text_pos, tx, L, Wd);
     LSEG_CHECK_CUDA(cudaGetLastError());
     return 0;
   });

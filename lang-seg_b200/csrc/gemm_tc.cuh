@@ -2,18 +2,30 @@
 //
 //   C[M,N] = epilogue( A[M,K] * W[N,K]^T )       fp16 operands, fp32 accumulate in TMEM
 //
-// One kernel covers every dense contraction of the LSeg forward path (SURVEY.md §2b k1,k4,k6-k8,
+// One kernel family covers every dense contraction of the LSeg forward path (SURVEY.md §2b k1,k4,k6-k8,
 // k10-k17,k19): linear layers, 1x1 convs, kernel==stride transposed convs (depth-to-space store),
 // and 3x3 stride-1 convs as implicit GEMM (the A tile of tap (dy,dx) is a shifted 4-D TMA box of
 // the NHWC activation; TMA zero-fills the padding halo).
 //
 // Roles (one CTA per SM, persistent over a static round-robin tile list):
 //   warp 0   TMA producer       : fills the A/B smem ring (128B-swizzled, K-major)
-//   warp 1   MMA issuer         : one thread issues tcgen05.mma 128 x BN x 16, commits to mbarriers
+//   warp 1   MMA issuer         : one thread issues tcgen05.mma, commits to mbarriers
 //   warp 2   TMEM allocator
-//   warps 4+ epilogue           : tcgen05.ld accumulator -> regs -> bias/scale/act/residual -> global
+//   warps 4+ epilogue           : tcgen05.ld accumulator -> regs -> scale/bias/act/residual -> global
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
 // the main loop of tile i+1.
+//
+// Two variants:
+//   gemm_tc2_kernel  CTA pair (tcgen05 cta_group::2, UMMA 256 x BN x 16): default. Shared memory
+//                    bandwidth is the binding resource of an SS-mode UMMA main loop (every byte TMA
+//                    writes is read back by the tensor core: 128x256x64 per CTA moves 2 x 48 KB per 512
+//                    MMA cycles = 192 B/clk against ~128 B/clk/SM); the pair splits the weight tile, so
+//                    each SM stages 32 KB per step instead of 48 KB. Measured: 3x3 conv 1186 TFLOP/s
+//                    (pair) vs 1070 (single), fc2 951 vs 810.
+//   gemm_tc_kernel   single CTA (LSEG_GEMM_1CTA=1), kept for A/B measurements.
+// The epilogue stores straight from registers (thread <-> accumulator row). Staging it through shared
+// memory for coalescing was measured and rejected: it competes with the main loop for the same smem
+// bandwidth and made every GEMM 1.3-2.3x slower.
 #pragma once
 #include "common.cuh"
 
@@ -44,6 +56,9 @@ struct GemmEpi {
   int store;               // GemmStore
   int d2s_s, d2s_cout, d2s_h, d2s_w;  // depth-to-space: input grid h x w, upscale s, cout channels
   int nchw_p, nchw_k;      // STORE_NCHW_T: pixels per image, channel count (n < nchw_k stored)
+  const float* row_sumsq;  // STORE_NCHW_T only, nullable: result *= row_scale * rsqrt(row_sumsq[row])
+  float row_scale;
+  float* out_row_sumsq;    // nullable: atomically accumulates sum_n result[row,n]^2 (fp32, pre-rounding)
 };
 
 struct GemmParams {
@@ -59,38 +74,44 @@ struct GemmParams {
   GemmEpi e;
 };
 
-template <int BN>
-struct GemmCfg {
-  static constexpr int kABytes = kGemmBM * kGemmBK * 2;
-  static constexpr int kBBytes = BN * kGemmBK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 3 : 5;
-  static constexpr int kTmemCols = 2 * BN;
-  // stages | 256 B of mbarriers | per-warp epilogue transpose tiles
-  static constexpr int kSmemBytes =
-      kStages * kStageBytes + 1024 /*align slack*/ + 256 + kGemmEpiWarps * 32 * 36 * 4;
-};
-
 // ------------------------------------------------------------------------------------------
-// Epilogue of one 32-column chunk of one output row (shared by the 1-CTA and 2-CTA kernels):
-// v = 32 fp32 accumulators of row `grow`, columns [n0, n0+32).
+// Epilogue of one 32-column chunk of one output row: v = the row's fp32 accumulators for columns
+// [n0, n0+32); res = that row's fp32 residual for the same columns when has_res (prefetched by the caller).
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void gemm_epilogue_chunk(const GemmEpi& e, int N, const uint32_t (&v)[32], long long grow,
-                                                    int n0, long long bias_off) {
-  const bool valid = true;
+__device__ __forceinline__ void gemm_epilogue_chunk(const GemmEpi& e, int N, const uint32_t (&v)[32],
+                                                    const float4 (&res)[8], bool has_res, long long grow, int n0,
+                                                    long long bias_off) {
   const int nvalid = min(32, N - n0);
-  
   float f[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-  if (e.scale) {
+  if (nvalid == 32) {  // uniform-address 16 B loads: one broadcast transaction each
+    if (e.scale) {
+      const float4* sp = reinterpret_cast<const float4*>(e.scale + n0);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) f[i] *= (i < nvalid) ? __ldg(e.scale + n0 + i) : 0.f;
-  }
-  if (e.bias) {
-    const float* bp = e.bias + ((e.bias_group_rows > 0 && valid) ? bias_off : 0) + n0;
+      for (int j = 0; j < 8; ++j) {
+        const float4 s = __ldg(sp + j);
+        f[4 * j] *= s.x; f[4 * j + 1] *= s.y; f[4 * j + 2] *= s.z; f[4 * j + 3] *= s.w;
+      }
+    }
+    if (e.bias) {
+      const float4* bp = reinterpret_cast<const float4*>(e.bias + bias_off + n0);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) f[i] += (i < nvalid) ? __ldg(bp + i) : 0.f;
+      for (int j = 0; j < 8; ++j) {
+        const float4 b = __ldg(bp + j);
+        f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+      }
+    }
+  } else {
+    if (e.scale) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] *= (i < nvalid) ? __ldg(e.scale + n0 + i) : 0.f;
+    }
+    if (e.bias) {
+      const float* bp = e.bias + bias_off + n0;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] += (i < nvalid) ? __ldg(bp + i) : 0.f;
+    }
   }
   if (e.act == ACT_GELU) {
 #pragma unroll
@@ -102,15 +123,28 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmEpi& e, int N, con
 #pragma unroll
     for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
   }
+  if (e.out_row_sumsq) {
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) ss = fmaf((i < nvalid) ? f[i] : 0.f, f[i], ss);
+    atomicAdd(e.out_row_sumsq + grow, ss);
+  }
   if (e.store == STORE_ROWMAJOR) {
     const long long off = grow * e.ldc + n0;
     if (nvalid == 32) {
       if (e.res_f32) {
-        const float4* rp = reinterpret_cast<const float4*>(e.res_f32 + off);
+        if (has_res) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 q = rp[i];
-          f[4 * i + 0] += q.x; f[4 * i + 1] += q.y; f[4 * i + 2] += q.z; f[4 * i + 3] += q.w;
+          for (int i = 0; i < 8; ++i) {
+            f[4 * i + 0] += res[i].x; f[4 * i + 1] += res[i].y; f[4 * i + 2] += res[i].z; f[4 * i + 3] += res[i].w;
+          }
+        } else {
+          const float4* rp = reinterpret_cast<const float4*>(e.res_f32 + off);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 q = rp[i];
+            f[4 * i + 0] += q.x; f[4 * i + 1] += q.y; f[4 * i + 2] += q.z; f[4 * i + 3] += q.w;
+          }
         }
       }
       if (e.res2_f32) {
@@ -187,9 +221,14 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmEpi& e, int N, con
     uint4* op = reinterpret_cast<uint4*>(e.out_f16 + orow * e.d2s_cout + co0);
 #pragma unroll
     for (int i = 0; i < 4; ++i) op[i] = *reinterpret_cast<uint4*>(&h[4 * i]);
-  } else {  // STORE_NCHW_T : out[(b*K + n)*P + p], fp16
+  } else {  // STORE_NCHW_T : out[(b*K + n)*P + p], fp16 (lanes = consecutive pixels -> coalesced)
     const int b = static_cast<int>(grow / e.nchw_p);
     const int pix = static_cast<int>(grow - static_cast<long long>(b) * e.nchw_p);
+    if (e.row_sumsq) {  // deferred pixel normalisation: logit_scale / ||feature row||
+      const float rs = e.row_scale * rsqrtf(__ldg(e.row_sumsq + grow));
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] *= rs;
+    }
     __half* op = e.out_f16 + (static_cast<long long>(b) * e.nchw_k + n0) * e.nchw_p + pix;
 #pragma unroll
     for (int i = 0; i < 32; ++i)
@@ -197,137 +236,76 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmEpi& e, int N, con
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// Coalesced epilogue (row-major and depth-to-space stores).
-// tcgen05.ld hands every thread one ROW of the accumulator, so storing straight from registers makes
-// each warp-level access touch 32 different 128 B lines (ncu: the L1TEX wavefront queue, not HBM, bounded
-// the fp32 residual epilogues: proj GEMM at 369 TFLOP/s). Each epilogue warp therefore transposes its
-// 32 x 32 fp32 chunk through a private padded smem tile (row stride 36 floats: conflict-free for both
-// the row-wise float4 writes and the 4-rows-x-128B reads) and then works in the transposed mapping:
-// lane = (row & 3 within a group of 4, 4-column group), so one warp instruction covers 4 rows x 128 B.
-// ------------------------------------------------------------------------------------------
-constexpr int kEpiStageFloats = 32 * 36;  // per warp
-
-struct RowMap {  // tile-local row -> global row (pixel) index
-  int conv, M, H, W, h0, w0, b, tile_ok;
-  long long m0;
-  __device__ __forceinline__ bool map(int r, long long& grow) const {
-    if (conv) {
-      const int h = h0 + r / kConvTW, w = w0 + r % kConvTW;
-      grow = (static_cast<long long>(b) * H + h) * W + w;
-      return tile_ok && (h < H) && (w < W);
-    }
-    grow = m0 + r;
-    return tile_ok && (grow < M);
-  }
-};
-
-__device__ __forceinline__ RowMap make_rowmap(const GemmParams& p, int m_tile) {
-  RowMap rm;
-  rm.conv = p.conv;
-  rm.M = p.M;
-  rm.H = p.H;
-  rm.W = p.W;
-  rm.tile_ok = m_tile < p.num_m_tiles;
-  rm.m0 = static_cast<long long>(m_tile) * kGemmBM;
-  rm.h0 = rm.w0 = rm.b = 0;
+// tile-local row -> global row (pixel) index + validity
+__device__ __forceinline__ bool gemm_row_map(const GemmParams& p, int m_tile, int r, long long& grow) {
   if (p.conv) {
     const int per_img = p.tiles_h * p.tiles_w;
-    rm.b = m_tile / per_img;
+    const int b = m_tile / per_img;
     const int t = m_tile % per_img;
-    rm.h0 = (t / p.tiles_w) * kConvTH;
-    rm.w0 = (t % p.tiles_w) * kConvTW;
+    const int h = (t / p.tiles_w) * kConvTH + r / kConvTW;
+    const int w = (t % p.tiles_w) * kConvTW + r % kConvTW;
+    grow = (static_cast<long long>(b) * p.H + h) * p.W + w;
+    return (m_tile < p.num_m_tiles) && (h < p.H) && (w < p.W);
   }
-  return rm;
+  grow = static_cast<long long>(m_tile) * kGemmBM + r;
+  return (m_tile < p.num_m_tiles) && (grow < p.M);
 }
 
-__device__ __forceinline__ float4 f4_fma(float4 a, float4 s, float4 b) {
-  return make_float4(fmaf(a.x, s.x, b.x), fmaf(a.y, s.y, b.y), fmaf(a.z, s.z, b.z), fmaf(a.w, s.w, b.w));
-}
-__device__ __forceinline__ float4 f4_add(float4 a, float4 b) {
-  return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
-}
-__device__ __forceinline__ uint2 f4_to_h4(float4 a) {
-  __half2 lo = __floats2half2_rn(a.x, a.y), hi = __floats2half2_rn(a.z, a.w);
-  uint2 o;
-  o.x = *reinterpret_cast<uint32_t*>(&lo);
-  o.y = *reinterpret_cast<uint32_t*>(&hi);
-  return o;
+// Epilogue of one 128 x (ncols) accumulator slab for one warp. The fp32 residual of chunk c+1 is
+// requested before chunk c is processed, and that of chunk 0 before the accumulator is even ready, so the
+// residual read latency overlaps the main loop / the previous chunk instead of serialising with it.
+template <typename WaitFn>
+__device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t t_row, int n_base, int ncols,
+                                                   int m_tile, int r, WaitFn wait_accumulator) {
+  const GemmEpi& e = p.e;
+  long long grow;
+  const bool valid = gemm_row_map(p, m_tile, r, grow);
+  const bool pre = valid && e.res_f32 && (e.store == STORE_ROWMAJOR);
+  const long long bias_off =
+      (e.bias_group_rows > 0 && valid) ? (grow / e.bias_group_rows) * static_cast<long long>(p.N) : 0;
+  float4 rnext[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) rnext[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (pre && n_base + 32 <= p.N) {
+    const float4* rp = reinterpret_cast<const float4*>(e.res_f32 + grow * e.ldc + n_base);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) rnext[j] = rp[j];
+  }
+  wait_accumulator();
+  tc_fence_after();
+#pragma unroll 1
+  for (int c = 0; c < ncols / 32; ++c) {
+    const int n0 = n_base + c * 32;
+    if (n0 >= p.N) break;  // warp-uniform
+    float4 rcur[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) rcur[j] = rnext[j];
+    const bool has_res = pre && (n0 + 32 <= p.N);
+    if (pre && (c + 1) * 32 < ncols && n0 + 64 <= p.N) {
+      const float4* rp = reinterpret_cast<const float4*>(e.res_f32 + grow * e.ldc + n0 + 32);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) rnext[j] = rp[j];
+    }
+    uint32_t v[32];
+    __syncwarp();
+    tmem_ld32(t_row + c * 32, v);
+    tmem_ld_wait();
+    if (valid) gemm_epilogue_chunk(e, p.N, v, rcur, has_res, grow, n0, bias_off);
+  }
 }
 
-// v: this thread's 32 accumulators (row = quarter*32 + lane, columns [n0, n0+32)). N % 4 == 0.
-__device__ __forceinline__ void gemm_epilogue_chunk_coalesced(const GemmEpi& e, int N, const uint32_t (&v)[32],
-                                                              float* stage, int quarter, int lane, int n0,
-                                                              const RowMap& rm) {
-  float4* srow = reinterpret_cast<float4*>(stage + lane * 36);
-#pragma unroll
-  for (int j = 0; j < 8; ++j)
-    srow[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                          __uint_as_float(v[4 * j + 3]));
-  __syncwarp();
-  const int c4 = lane & 7, rsub = lane >> 3;
-  const int col = n0 + 4 * c4;
-  if (col < N) {
-    const float4 one = make_float4(1.f, 1.f, 1.f, 1.f), zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 sc = e.scale ? __ldg(reinterpret_cast<const float4*>(e.scale + col)) : one;
-    float4 bs = (e.bias && e.bias_group_rows == 0) ? __ldg(reinterpret_cast<const float4*>(e.bias + col)) : zero;
-    // depth-to-space column decode (constant per lane)
-    int d_di = 0, d_dj = 0, d_co = 0;
-    if (e.store == STORE_D2S) {
-      const int ij = col / e.d2s_cout;
-      d_co = col - ij * e.d2s_cout;
-      d_di = ij / e.d2s_s;
-      d_dj = ij - d_di * e.d2s_s;
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int rl = 4 * i + rsub;
-      long long grow;
-      if (!rm.map(quarter * 32 + rl, grow)) continue;
-      float4 a = *reinterpret_cast<const float4*>(stage + rl * 36 + 4 * c4);
-      if (e.bias_group_rows > 0)
-        bs = __ldg(reinterpret_cast<const float4*>(e.bias + (grow / e.bias_group_rows) * static_cast<long long>(N) + col));
-      a = f4_fma(a, sc, bs);
-      if (e.act == ACT_GELU) {
-        a = make_float4(gelu_erf(a.x), gelu_erf(a.y), gelu_erf(a.z), gelu_erf(a.w));
-      } else if (e.act == ACT_QUICKGELU) {
-        a = make_float4(quick_gelu(a.x), quick_gelu(a.y), quick_gelu(a.z), quick_gelu(a.w));
-      } else if (e.act == ACT_RELU) {
-        a = make_float4(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f), fmaxf(a.z, 0.f), fmaxf(a.w, 0.f));
-      }
-      if (e.store == STORE_ROWMAJOR) {
-        const long long off = grow * e.ldc + col;
-        if (e.res_f32) a = f4_add(a, *reinterpret_cast<const float4*>(e.res_f32 + off));
-        if (e.res2_f32) a = f4_add(a, *reinterpret_cast<const float4*>(e.res2_f32 + off));
-        if (e.out_f32) *reinterpret_cast<float4*>(e.out_f32 + off) = a;
-        if (e.out_f16) {
-          uint2 h = f4_to_h4(a);
-          if (e.res_f16) {  // fp16 residual stream: round the branch output first, then add in fp16
-            const uint2 q = *reinterpret_cast<const uint2*>(e.res_f16 + off);
-            __half2 lo = __hadd2(*reinterpret_cast<const __half2*>(&q.x), *reinterpret_cast<__half2*>(&h.x));
-            __half2 hi = __hadd2(*reinterpret_cast<const __half2*>(&q.y), *reinterpret_cast<__half2*>(&h.y));
-            h.x = *reinterpret_cast<uint32_t*>(&lo);
-            h.y = *reinterpret_cast<uint32_t*>(&hi);
-          }
-          *reinterpret_cast<uint2*>(e.out_f16 + off) = h;
-        }
-        if (e.out_f16_relu)
-          *reinterpret_cast<uint2*>(e.out_f16_relu + off) =
-              f4_to_h4(make_float4(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f), fmaxf(a.z, 0.f), fmaxf(a.w, 0.f)));
-      } else {  // STORE_D2S: row grow = (b*h + y)*w + x -> NHWC [B, h*s, w*s, cout] pixel (y*s+di, x*s+dj)
-        const int hw = e.d2s_h * e.d2s_w;
-        const int b = static_cast<int>(grow / hw);
-        const int yx = static_cast<int>(grow - static_cast<long long>(b) * hw);
-        const int y = yx / e.d2s_w, x = yx - y * e.d2s_w;
-        const long long orow =
-            (static_cast<long long>(b) * (e.d2s_h * e.d2s_s) + (y * e.d2s_s + d_di)) * (e.d2s_w * e.d2s_s) +
-            (x * e.d2s_s + d_dj);
-        *reinterpret_cast<uint2*>(e.out_f16 + orow * e.d2s_cout + d_co) = f4_to_h4(a);
-      }
-    }
-  }
-  __syncwarp();
-}
+// ==========================================================================================
+// single-CTA kernel
+// ==========================================================================================
+template <int BN>
+struct GemmCfg {
+  static constexpr int kABytes = kGemmBM * kGemmBK * 2;
+  static constexpr int kBBytes = BN * kGemmBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
 
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
@@ -438,47 +416,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     const int half = ew >> 2;                     // column half handled by this warp
     constexpr int kColsPerWarp = BN / (kGemmEpiWarps / 4);
     const int r = quarter * 32 + lane;            // row inside the 128-row tile
-    const GemmEpi& e = p.e;
-    float* stage = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 256) + ew * kEpiStageFloats;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_tile = tile % p.num_m_tiles;
       const int n_tile = tile / p.num_m_tiles;
-      long long grow;
-      bool valid;
-      if (p.conv) {
-        const int per_img = p.tiles_h * p.tiles_w;
-        const int b = m_tile / per_img;
-        const int t = m_tile % per_img;
-        const int h = (t / p.tiles_w) * kConvTH + r / kConvTW;
-        const int w = (t % p.tiles_w) * kConvTW + r % kConvTW;
-        valid = (h < p.H) && (w < p.W);
-        grow = (static_cast<long long>(b) * p.H + h) * p.W + w;
-      } else {
-        grow = static_cast<long long>(m_tile) * kGemmBM + r;
-        valid = grow < p.M;
-      }
-      mbar_wait(&tmem_full[acc], acc_phase, 4);
-      tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * kColsPerWarp;
-      const RowMap rm = make_rowmap(p, m_tile);
-      const bool coalesced = (e.store != STORE_NCHW_T) && ((p.N & 3) == 0);
-      const long long bias_off =
-          (e.bias_group_rows > 0) ? (grow / e.bias_group_rows) * static_cast<long long>(p.N) : 0;
-#pragma unroll 1
-      for (int c = 0; c < kColsPerWarp / 32; ++c) {
-        const int n0 = n_tile * BN + half * kColsPerWarp + c * 32;
-        if (n0 >= p.N) break;  // warp-uniform
-        uint32_t v[32];
-        __syncwarp();
-        tmem_ld32(t_row + c * 32, v);
-        tmem_ld_wait();
-        if (coalesced)
-          gemm_epilogue_chunk_coalesced(e, p.N, v, stage, quarter, lane, n0, rm);
-        else if (valid)
-          gemm_epilogue_chunk(e, p.N, v, grow, n0, bias_off);
-      }
+      gemm_epilogue_tile(p, t_row, n_tile * BN + half * kColsPerWarp, kColsPerWarp, m_tile, r,
+                         [&]() { mbar_wait(&tmem_full[acc], acc_phase, 4); });
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
       acc ^= 1;
@@ -496,10 +441,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
 
 // ==========================================================================================
 // CTA-pair variant (tcgen05 cta_group::2): a cluster of two CTAs (one TPC) computes a 256 x BN tile.
-// Each CTA stages its own 128 A rows and HALF of the weight tile, so the bytes pulled from L2 per MMA
-// drop by a third (A 16 KB + B 16 KB instead of 16 + 32 per 128x256x64 step) — the 1-CTA kernel is
-// L2->SM bandwidth bound at ~85 flop/B. The even CTA issues tcgen05.mma.cta_group::2 (M = 256) for
-// the pair; both CTAs run a TMA producer and 8 epilogue warps over their own 128 TMEM lanes.
+// Each CTA stages its own 128 A rows and HALF of the weight tile; the even CTA issues
+// tcgen05.mma.cta_group::2 (M = 256) for the pair; both CTAs run a TMA producer and 8 epilogue warps
+// over their own 128 TMEM lanes.
 //   full barrier   : in the leader, armed with the pair's byte count; both CTAs' TMA credit it
 //   empty barrier  : per CTA, released by a multicast tcgen05.commit
 //   tmem full      : per CTA (multicast commit);  tmem empty: in the leader, 2 x 8 warp arrivals
@@ -509,9 +453,9 @@ struct Gemm2Cfg {
   static constexpr int kABytes = kGemmBM * kGemmBK * 2;
   static constexpr int kBBytes = (BN / 2) * kGemmBK * 2;  // this CTA's half of the weight tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 5 : 7;
+  static constexpr int kStages = (BN == 256) ? 6 : 8;
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + kGemmEpiWarps * 32 * 36 * 4;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
 };
 
 template <int BN>
@@ -628,47 +572,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
     const int half = ew >> 2;
     constexpr int kColsPerWarp = BN / (kGemmEpiWarps / 4);
     const int r = quarter * 32 + lane;
-    const GemmEpi& e = p.e;
-    float* stage = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 256) + ew * kEpiStageFloats;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int m_tile = (tile % m_pairs) * 2 + static_cast<int>(rank);
       const int n_tile = tile / m_pairs;
-      long long grow;
-      bool valid = m_tile < p.num_m_tiles;
-      if (p.conv) {
-        const int per_img = p.tiles_h * p.tiles_w;
-        const int b = m_tile / per_img;
-        const int t = m_tile % per_img;
-        const int h = (t / p.tiles_w) * kConvTH + r / kConvTW;
-        const int w = (t % p.tiles_w) * kConvTW + r % kConvTW;
-        valid = valid && (h < p.H) && (w < p.W);
-        grow = (static_cast<long long>(b) * p.H + h) * p.W + w;
-      } else {
-        grow = static_cast<long long>(m_tile) * kGemmBM + r;
-        valid = valid && (grow < p.M);
-      }
-      mbar_wait(&tmem_full[acc], acc_phase, 24);
-      tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * kColsPerWarp;
-      const RowMap rm = make_rowmap(p, m_tile);
-      const bool coalesced = (e.store != STORE_NCHW_T) && ((p.N & 3) == 0);
-      const long long bias_off =
-          (e.bias_group_rows > 0 && valid) ? (grow / e.bias_group_rows) * static_cast<long long>(p.N) : 0;
-#pragma unroll 1
-      for (int c = 0; c < kColsPerWarp / 32; ++c) {
-        const int n0 = n_tile * BN + half * kColsPerWarp + c * 32;
-        if (n0 >= p.N) break;  // warp-uniform
-        uint32_t v[32];
-        __syncwarp();
-        tmem_ld32(t_row + c * 32, v);
-        tmem_ld_wait();
-        if (coalesced)
-          gemm_epilogue_chunk_coalesced(e, p.N, v, stage, quarter, lane, n0, rm);
-        else if (valid)
-          gemm_epilogue_chunk(e, p.N, v, grow, n0, bias_off);
-      }
+      gemm_epilogue_tile(p, t_row, n_tile * BN + half * kColsPerWarp, kColsPerWarp, m_tile, r,
+                         [&]() { mbar_wait(&tmem_full[acc], acc_phase, 24); });
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);  // leader's barrier: 2 CTAs x 8 warps
@@ -686,7 +597,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 }
 
 // ------------------------------------------------------------------------------------------
-// Host launchers
+// Host-side description of one GEMM
 // ------------------------------------------------------------------------------------------
 struct GemmDesc {
   // A operand

@@ -250,14 +250,6 @@ static int mhsa_run(const MhsaPlan& plan, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------------
 // elementwise launch helpers
 // ------------------------------------------------------------------------------------------
-static inline int ew_grid(long long total, int threads) {
-  long long blocks = (total + threads - 1) / threads;
-  const long long cap = static_cast<long long>(g_num_sms > 0 ? g_num_sms : 148) * 16;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  return static_cast<int>(blocks);
-}
-
 static int run_layernorm(const void* x, int in_f16, const float* g, const float* b, __half* y, long long M, int C,
                          float eps, cudaStream_t s) {
   if (C % 128 != 0 || C > 1024) {
@@ -313,6 +305,9 @@ static void fill_epi(const lseg_gemm_args* a, GemmEpi* e) {
   e->d2s_w = a->d2s_w;
   e->nchw_p = a->nchw_p;
   e->nchw_k = a->nchw_k;
+  e->row_sumsq = a->row_sumsq;
+  e->row_scale = a->row_scale;
+  e->out_row_sumsq = a->out_row_sumsq;
 }
 
 int lseg_gemm(const lseg_gemm_args* a, void* stream) {
@@ -367,11 +362,7 @@ int lseg_patchify(const float* x, void* a, int B, int H, int W, void* stream) {
     set_error("patchify: H, W must be multiples of 16");
     return -1;
   }
-  const long long total = static_cast<long long>(B) * (H / 16) * (W / 16) * 3 * 16 * 4;
-  patchify_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<__half*>(a), B, H,
-                                                                                      W);
-  LSEG_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  return launch_patchify(x, static_cast<__half*>(a), B, H, W, static_cast<cudaStream_t>(stream));
 }
 
 int lseg_pos_resize(const float* pos, float* out, int g0, int gh, int gw, int D, void* stream) {
@@ -384,39 +375,25 @@ int lseg_pos_resize(const float* pos, float* out, int g0, int gh, int gw, int D,
 int lseg_assemble_tokens(const float* patch, const float* cls, const float* pos, float* x, int B, int T, int D,
                          void* stream) {
   if (ensure_init()) return -1;
-  const long long total = static_cast<long long>(B) * (T + 1) * (D / 4);
-  assemble_tokens_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(patch, cls, pos, x, B, T,
-                                                                                             D);
-  LSEG_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  return launch_assemble_tokens(patch, cls, pos, x, B, T, D, static_cast<cudaStream_t>(stream));
 }
 
 int lseg_readout_split(const float* tap, void* tok, void* cls, int B, int T, int D, void* stream) {
   if (ensure_init()) return -1;
-  const long long total = static_cast<long long>(B) * (T + 1) * (D / 4);
-  readout_split_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      tap, static_cast<__half*>(tok), static_cast<__half*>(cls), B, T, D);
-  LSEG_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  return launch_readout_split(tap, static_cast<__half*>(tok), static_cast<__half*>(cls), B, T, D,
+                              static_cast<cudaStream_t>(stream));
 }
 
 int lseg_im2col_3x3_s2(const void* x, void* a, int B, int H, int W, int C, void* stream) {
   if (ensure_init()) return -1;
-  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-  const long long total = static_cast<long long>(B) * Ho * Wo * 9 * (C / 8);
-  im2col_3x3_s2_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(x), static_cast<__half*>(a), B, H, W, C);
-  LSEG_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  return launch_im2col_3x3_s2(static_cast<const __half*>(x), static_cast<__half*>(a), B, H, W, C,
+                              static_cast<cudaStream_t>(stream));
 }
 
 int lseg_upsample2x_nhwc(const void* x, void* y, int B, int H, int W, int C, void* stream) {
   if (ensure_init()) return -1;
-  const long long total = static_cast<long long>(B) * 4 * H * W * (C / 8);
-  upsample2x_nhwc_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(x), static_cast<__half*>(y), B, H, W, C);
-  LSEG_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  return launch_upsample2x_nhwc(static_cast<const __half*>(x), static_cast<__half*>(y), B, H, W, C,
+                                static_cast<cudaStream_t>(stream));
 }
 
 int lseg_l2norm_scale(const float* x, void* y, long long M, int C, float logit_scale, void* stream) {
@@ -446,19 +423,14 @@ int lseg_upsample2x_nchw(const void* x, float* y, long long planes, int H, int W
     set_error("upsample2x_nchw: output width must be a multiple of 4");
     return -1;
   }
-  const long long total = planes * 2 * H * (2 * W / 4);
-  upsample2x_nchw_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(x), y, planes, H, W);
-  LSEG_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  return launch_upsample2x_nchw(static_cast<const __half*>(x), y, planes, H, W, static_cast<cudaStream_t>(stream));
 }
 
 int lseg_text_embed(const int64_t* tokens, const float* tok_emb, const float* pos_emb, void* x, int K, int L, int Wd,
                     void* stream) {
   if (ensure_init()) return -1;
-  const long long total = static_cast<long long>(K) * L * Wd;
-  text_embed_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const long long*>(tokens), tok_emb, pos_emb, static_cast<__half*>(x), K, L, Wd);
+  text_embed_kernel<<<K * L, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(tokens), tok_emb, pos_emb, static_cast<__half*>(x), L, Wd);
   LSEG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

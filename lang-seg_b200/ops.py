@@ -48,7 +48,7 @@ def read_watchdog():
 
 def gemm(a, w, N=None, *, bias=None, bias_group_rows=0, scale=None, act=ACT_NONE, res_f32=None, res2_f32=None,
          res_f16=None, out_f32=None, out_f16=None, out_f16_relu=None, ldc=None, M=None,
-         conv=None, store=STORE_ROWMAJOR, d2s=None, nchw=None):
+         conv=None, store=STORE_ROWMAJOR, d2s=None, nchw=None, row_sumsq=None, row_scale=1.0, out_row_sumsq=None):
     """C = epi(A W^T).  a: fp16 [M,K] (or NHWC [B,H,W,C] when conv=(ksize,pad)); w: fp16 [rows>=N, Ktot]."""
     args = GemmArgs()
     args.a = _ptr(a, torch.float16)
@@ -80,6 +80,9 @@ def gemm(a, w, N=None, *, bias=None, bias_group_rows=0, scale=None, act=ACT_NONE
         args.d2s_s, args.d2s_cout, args.d2s_h, args.d2s_w = d2s
     if nchw is not None:
         args.nchw_p, args.nchw_k = nchw
+    args.row_sumsq = _ptr(row_sumsq, torch.float32)
+    args.row_scale = float(row_scale)
+    args.out_row_sumsq = _ptr(out_row_sumsq, torch.float32)
     check(load().lseg_gemm(C.byref(args), _stream()))
 
 

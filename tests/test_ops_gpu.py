@@ -134,6 +134,29 @@ def test_gemm_nchw_store(ops, K):
     _close(out, ref, 1e-3, "nchw store")
 
 
+def test_deferred_row_normalisation(ops):
+    """head1 -> pixel x text with the L2 normalisation deferred into the second GEMM's epilogue
+    (lseg_net.py:185-196): logits = logit_scale * (x / ||x||) . t"""
+    B, P, K = 2, 1280, 150
+    path = _rand((B * P, 256), 40)
+    w1 = _rand((512, 256), 41, 0.06)
+    b1 = _rand((512,), 42, 0.05, torch.float32)
+    t = _rand((K, 512), 43, 0.05)
+    t = (t.float() / t.float().norm(dim=-1, keepdim=True)).half()
+    feat16 = torch.zeros((B * P, 512), dtype=torch.float16, device="cuda")
+    sumsq = torch.zeros((B * P,), dtype=torch.float32, device="cuda")
+    ops.gemm(path, ops.pad_rows(w1), 512, bias=b1, out_f16=feat16, out_row_sumsq=sumsq)
+    x = path.float() @ w1.float().t() + b1
+    _close(sumsq, (x * x).sum(-1), 1e-4, "row sumsq")
+    out = torch.zeros((B, K, P), dtype=torch.float16, device="cuda")
+    ls = math.exp(math.log(1 / 0.07))
+    ops.gemm(feat16, ops.pad_rows(t), K, out_f16=out, store=ops.STORE_NCHW_T, nchw=(P, K), row_sumsq=sumsq,
+             row_scale=ls)
+    img = (x / x.norm(dim=-1, keepdim=True)).half()
+    ref = ((torch.tensor(ls) * img) @ t.t()).float().view(B, P, K).permute(0, 2, 1)  # the reference's fp16 recipe
+    _close(out, ref, 2e-3, "deferred normalisation vs reference recipe")
+
+
 @pytest.mark.parametrize("B,N,heads,causal", [(2, 901, 16, False), (3, 77, 8, True), (1, 37, 16, False),
                                               (1, 300, 2, True)])
 def test_mhsa(ops, B, N, heads, causal):
