@@ -68,10 +68,12 @@ typedef struct lseg_gemm_args {
   int store;
   int d2s_s, d2s_cout, d2s_h, d2s_w;
   int nchw_p, nchw_k;
-  /* deferred row normalisation (head1 -> pixel x text, lseg_net.py:185-194): a GEMM can accumulate
-   * sum_n result[row,n]^2 into out_row_sumsq[row] (fp32 atomics, buffer zeroed by the caller), and an
-   * LSEG_STORE_NCHW_T GEMM can scale each row by row_scale * rsqrt(row_sumsq[row]) before rounding. */
+  /* deferred row normalisation (head1 -> pixel x text, lseg_net.py:185-194): a GEMM can write the partial
+   * squared norms of its result rows, out_row_sumsq[row, n/32] = sum over that 32-column chunk (fp32, no
+   * atomics: deterministic), and an LSEG_STORE_NCHW_T GEMM can scale each row by
+   * row_scale * rsqrt(sum_i row_sumsq[row, i], i < row_sumsq_parts) before rounding to fp16. */
   const float* row_sumsq;
+  int row_sumsq_parts;
   float row_scale;
   float* out_row_sumsq;
 } lseg_gemm_args;

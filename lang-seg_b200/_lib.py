@@ -29,7 +29,8 @@ class GemmArgs(C.Structure):
         ("ldc", C.c_longlong), ("store", C.c_int),
         ("d2s_s", C.c_int), ("d2s_cout", C.c_int), ("d2s_h", C.c_int), ("d2s_w", C.c_int),
         ("nchw_p", C.c_int), ("nchw_k", C.c_int),
-        ("row_sumsq", C.c_void_p), ("row_scale", C.c_float), ("out_row_sumsq", C.c_void_p),
+        ("row_sumsq", C.c_void_p), ("row_sumsq_parts", C.c_int), ("row_scale", C.c_float),
+        ("out_row_sumsq", C.c_void_p),
     ]
 
 

@@ -436,13 +436,7 @@ static int build_image_plan(lseg_engine* eng, int B, int H, int W, cudaStream_t 
   // its epilogue. Same quantity as the reference's normalise -> half -> scale -> matmul up to where the
   // fp16 roundings fall, without the 118 MB/img fp32 feature round trip and the separate norm pass.
   LSEG_ALLOC(featn, __half, BP * 512);
-  LSEG_ALLOC(feat_sumsq, float, BP);
-  steps.emplace_back(
-      [=](const CallCtx&, cudaStream_t s) {
-        LSEG_CHECK_CUDA(cudaMemsetAsync(feat_sumsq, 0, sizeof(float) * BP, s));
-        return 0;
-      },
-      KIND_MEMSET, 0.0);
+  LSEG_ALLOC(feat_sumsq, float, BP * 16);  // [row, 512/32] partial squared norms
   {
     GemmEpi e = epi_none();
     e.bias = w.head1.b;
@@ -533,7 +527,8 @@ static int run_forward(lseg_engine* eng, const CallCtx& ctx, int B, int H, int W
     d.e.store = STORE_NCHW_T;
     d.e.nchw_p = (int)P;
     d.e.nchw_k = ctx.K;
-    d.e.row_sumsq = plan.feat_sumsq + static_cast<long long>(g) * P;
+    d.e.row_sumsq = plan.feat_sumsq + static_cast<long long>(g) * P * 16;
+    d.e.row_sumsq_parts = 16;
     d.e.row_scale = eng->w.logit_scale;
     GemmPlan gp;
     if (gemm_plan(d, &gp)) return -1;

@@ -56,9 +56,10 @@ struct GemmEpi {
   int store;               // GemmStore
   int d2s_s, d2s_cout, d2s_h, d2s_w;  // depth-to-space: input grid h x w, upscale s, cout channels
   int nchw_p, nchw_k;      // STORE_NCHW_T: pixels per image, channel count (n < nchw_k stored)
-  const float* row_sumsq;  // STORE_NCHW_T only, nullable: result *= row_scale * rsqrt(row_sumsq[row])
+  const float* row_sumsq;  // STORE_NCHW_T only, nullable: [rows, row_sumsq_parts] partial squared norms;
+  int row_sumsq_parts;     //   result *= row_scale * rsqrt(sum of the row's parts)
   float row_scale;
-  float* out_row_sumsq;    // nullable: atomically accumulates sum_n result[row,n]^2 (fp32, pre-rounding)
+  float* out_row_sumsq;    // nullable: [rows, ceil(N/32)] partial sums of result^2 (fp32, pre-rounding)
 };
 
 struct GemmParams {
@@ -71,6 +72,8 @@ struct GemmParams {
   int H, W, kw, pad;
   int tiles_h, tiles_w;
   int num_m_tiles, num_n_tiles;
+  int probe;  // measurement only (tools/gemm_probe.py; results are garbage when non-zero):
+              //   1 = skip epilogue work, 2 = skip TMA loads, 4 = skip MMA issue   (CTA-pair kernel)
   GemmEpi e;
 };
 
@@ -123,11 +126,11 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmEpi& e, int N, con
 #pragma unroll
     for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
   }
-  if (e.out_row_sumsq) {
-    float ss = 0.f;
+  if (e.out_row_sumsq) {  // per-(row, 32-column chunk) partial, summed in fixed order by the consumer:
+    float ss = 0.f;       // deterministic (no atomics), so batch-8 == batch-1 bit for bit
 #pragma unroll
     for (int i = 0; i < 32; ++i) ss = fmaf((i < nvalid) ? f[i] : 0.f, f[i], ss);
-    atomicAdd(e.out_row_sumsq + grow, ss);
+    e.out_row_sumsq[grow * ((N + 31) >> 5) + (n0 >> 5)] = ss;
   }
   if (e.store == STORE_ROWMAJOR) {
     const long long off = grow * e.ldc + n0;
@@ -225,7 +228,10 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmEpi& e, int N, con
     const int b = static_cast<int>(grow / e.nchw_p);
     const int pix = static_cast<int>(grow - static_cast<long long>(b) * e.nchw_p);
     if (e.row_sumsq) {  // deferred pixel normalisation: logit_scale / ||feature row||
-      const float rs = e.row_scale * rsqrtf(__ldg(e.row_sumsq + grow));
+      float ss = 0.f;
+      const float* sp = e.row_sumsq + grow * e.row_sumsq_parts;
+      for (int i = 0; i < e.row_sumsq_parts; ++i) ss += __ldg(sp + i);
+      const float rs = e.row_scale * rsqrtf(ss);
 #pragma unroll
       for (int i = 0; i < 32; ++i) f[i] *= rs;
     }
@@ -273,6 +279,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
   }
   wait_accumulator();
   tc_fence_after();
+  if (p.probe & 1) return;
 #pragma unroll 1
   for (int c = 0; c < ncols / 32; ++c) {
     const int n0 = n_base + c * 32;
@@ -520,6 +527,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
           mbar_wait(&empty_bar[stage], phase ^ 1, 21);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
+          if (p.probe & 2) {
+            if (rank == 0) mbar_arrive(&full_bar[stage]);
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
           if (p.conv) {
             const int tap = kit / p.k_chunks;
@@ -551,11 +563,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
           tc_fence_after();
           const uint32_t a_base = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t b_base = a_base + Cfg::kABytes;
+          if (!(p.probe & 4)) {
 #pragma unroll
-          for (int k = 0; k < kGemmBK / 16; ++k) {
-            const uint64_t da = umma_desc_sw128(a_base + k * 32, 1024, 0);
-            const uint64_t db = umma_desc_sw128(b_base + k * 32, 1024, 0);
-            umma_f16_ss_2cta(d_tmem, da, db, idesc, (kit | k) != 0);
+            for (int k = 0; k < kGemmBK / 16; ++k) {
+              const uint64_t da = umma_desc_sw128(a_base + k * 32, 1024, 0);
+              const uint64_t db = umma_desc_sw128(b_base + k * 32, 1024, 0);
+              umma_f16_ss_2cta(d_tmem, da, db, idesc, (kit | k) != 0);
+            }
           }
           umma_commit_2cta(&empty_bar[stage], 0x3);  // both CTAs' smem slots
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }

@@ -38,6 +38,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 static PFN_encodeTiled g_encode = nullptr;
 static int g_num_sms = 0;
 static int g_gemm_two_cta = 1;
+static int g_gemm_probe = 0;
 static std::once_flag g_init_flag;
 static int g_init_status = -1;
 
@@ -72,6 +73,8 @@ static void init_once() {
   {  // LSEG_GEMM_1CTA=1 selects the single-CTA GEMM (A/B comparisons, debugging)
     const char* env = getenv("LSEG_GEMM_1CTA");
     g_gemm_two_cta = (env && env[0] == '1') ? 0 : 1;
+    const char* pr = getenv("LSEG_GEMM_PROBE");  // measurement only, see GemmParams::probe
+    g_gemm_probe = pr ? atoi(pr) : 0;
   }
   cudaFuncSetAttribute(mhsa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMhsaSmemBytes);
   cudaFuncSetAttribute(mhsa_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
@@ -151,6 +154,7 @@ static int gemm_plan(const GemmDesc& d, GemmPlan* plan) {
   p.k_chunks = d.K / kGemmBK;
   p.k_iters = p.k_chunks * taps;
   p.conv = d.conv;
+  p.probe = g_gemm_probe;
   p.e = d.e;
   if (d.conv) {
     p.H = d.H;
@@ -306,6 +310,7 @@ static void fill_epi(const lseg_gemm_args* a, GemmEpi* e) {
   e->nchw_p = a->nchw_p;
   e->nchw_k = a->nchw_k;
   e->row_sumsq = a->row_sumsq;
+  e->row_sumsq_parts = a->row_sumsq_parts;
   e->row_scale = a->row_scale;
   e->out_row_sumsq = a->out_row_sumsq;
 }

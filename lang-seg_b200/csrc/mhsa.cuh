@@ -55,10 +55,8 @@ __device__ __forceinline__ float mhsa_exp_chunk(const uint32_t (&s)[32], float c
       if (!(kv < n_tokens && kv <= kv_limit)) p0 = 0.f;
       if (!(kv + 1 < n_tokens && kv + 1 <= kv_limit)) p1 = 0.f;
     }
-    const __half2 hh = __floats2half2_rn(p0, p1);
-    ph[i >> 1] = hh;
-    const float2 back = __half22float2(hh);  // sum exactly what the MMA multiplies
-    sum += back.x + back.y;
+    ph[i >> 1] = __floats2half2_rn(p0, p1);
+    sum += p0 + p1;  // fp32 row sum (the fp16 rounding of P is zero-mean noise at 2^-12)
   }
   return sum;
 }
@@ -222,14 +220,35 @@ __global__ void __launch_bounds__(kMhsaThreads, 2) mhsa_kernel(const __grid_cons
       }
       mx *= c;
       const bool move = mx > m_ref + kMhsaTau;  // also true on the first tile (m_ref = -inf)
-      // P buffer free and O quiescent once PV_{j-1} has retired
-      if (j > 0) mbar_wait(o_done, (j - 1) & 1, 20);
-      if (__any_sync(0xffffffffu, move)) {
+      const bool any_move = __any_sync(0xffffffffu, move);
+      float factor = 1.f;
+      if (any_move) {
         const float m_new = move ? mx : m_ref;
-        const float factor = (m_ref == -INFINITY) ? 0.f : ex2_approx(m_ref - m_new);
+        factor = (m_ref == -INFINITY) ? 0.f : ex2_approx(m_ref - m_new);
         l_run *= factor;
         m_ref = m_new;
-        if (j > 0) {  // rescale the TMEM-resident output row (warp-collective, factor = 1 for unmoved rows)
+      }
+      const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
+      // p = exp2(s*c - m_ref) into registers first: PV_{j-1} (which still owns the P buffer and O) runs
+      // on the tensor pipe underneath the exponentials
+      float l_tile = 0.f;
+      __half2 ph0[16], ph1[16], ph2[16], ph3[16];
+      if (need_mask) {
+        l_tile += mhsa_exp_chunk<true>(s0, c, m_use, kv0 + 0, p.n_tokens, kv_limit, ph0);
+        l_tile += mhsa_exp_chunk<true>(s1, c, m_use, kv0 + 32, p.n_tokens, kv_limit, ph1);
+        l_tile += mhsa_exp_chunk<true>(s2, c, m_use, kv0 + 64, p.n_tokens, kv_limit, ph2);
+        l_tile += mhsa_exp_chunk<true>(s3, c, m_use, kv0 + 96, p.n_tokens, kv_limit, ph3);
+      } else {
+        l_tile += mhsa_exp_chunk<false>(s0, c, m_use, kv0 + 0, p.n_tokens, kv_limit, ph0);
+        l_tile += mhsa_exp_chunk<false>(s1, c, m_use, kv0 + 32, p.n_tokens, kv_limit, ph1);
+        l_tile += mhsa_exp_chunk<false>(s2, c, m_use, kv0 + 64, p.n_tokens, kv_limit, ph2);
+        l_tile += mhsa_exp_chunk<false>(s3, c, m_use, kv0 + 96, p.n_tokens, kv_limit, ph3);
+      }
+      l_run += l_tile;
+      // P buffer free and O quiescent once PV_{j-1} has retired
+      if (j > 0) {
+        mbar_wait(o_done, (j - 1) & 1, 20);
+        if (any_move) {  // rescale the TMEM-resident output row (warp-collective, factor = 1 for unmoved rows)
           tc_fence_after();
 #pragma unroll 1
           for (int cc = 0; cc < 4; ++cc) {
@@ -244,27 +263,21 @@ __global__ void __launch_bounds__(kMhsaThreads, 2) mhsa_kernel(const __grid_cons
           tmem_st_wait();
         }
       }
-      const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
-      // p = exp2(s*c - m_ref), fp16 P -> swizzled smem: columns [cc*32, cc*32+32) land in sub-tile (cc>>1),
-      // 16-byte chunks ((cc&1)*4 + t) ^ (r&7)
-      float l_tile = 0.f;
-#define LSEG_MHSA_CHUNK(S, CC)                                                                              \
-  {                                                                                                         \
-    __half2 ph[16];                                                                                         \
-    l_tile += need_mask ? mhsa_exp_chunk<true>(S, c, m_use, kv0 + (CC) * 32, p.n_tokens, kv_limit, ph)       \
-                        : mhsa_exp_chunk<false>(S, c, m_use, kv0 + (CC) * 32, p.n_tokens, kv_limit, ph);     \
-    uint8_t* sub = p_row + ((CC) >> 1) * kMhsaTileBytes;                                                    \
-    _Pragma("unroll") for (int t = 0; t < 4; ++t) {                                                         \
-      const int chunk = ((((CC) & 1) * 4 + t) ^ sw);                                                        \
-      *reinterpret_cast<uint4*>(sub + chunk * 16) = *reinterpret_cast<uint4*>(&ph[4 * t]);                  \
-    }                                                                                                       \
+      // fp16 P -> swizzled smem: columns [cc*32, cc*32+32) land in sub-tile (cc>>1), 16-byte chunks
+      // ((cc&1)*4 + t) ^ (r&7)
+#define LSEG_MHSA_STORE(PH, CC)                                                               \
+  {                                                                                           \
+    uint8_t* sub = p_row + ((CC) >> 1) * kMhsaTileBytes;                                      \
+    _Pragma("unroll") for (int t = 0; t < 4; ++t) {                                           \
+      const int chunk = ((((CC) & 1) * 4 + t) ^ sw);                                          \
+      *reinterpret_cast<uint4*>(sub + chunk * 16) = *reinterpret_cast<uint4*>(&PH[4 * t]);    \
+    }                                                                                         \
   }
-      LSEG_MHSA_CHUNK(s0, 0)
-      LSEG_MHSA_CHUNK(s1, 1)
-      LSEG_MHSA_CHUNK(s2, 2)
-      LSEG_MHSA_CHUNK(s3, 3)
-#undef LSEG_MHSA_CHUNK
-      l_run += l_tile;
+      LSEG_MHSA_STORE(ph0, 0)
+      LSEG_MHSA_STORE(ph1, 1)
+      LSEG_MHSA_STORE(ph2, 2)
+      LSEG_MHSA_STORE(ph3, 3)
+#undef LSEG_MHSA_STORE
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full);

@@ -147,12 +147,57 @@ class _LSegBase(nn.Module):
             raise NotImplementedError("arch_option 1/2 head blocks are not part of the B200 hot path yet")
         self.channels_last = False
         self.out_c = 512
-        self.clip_pretrained = _ClipTextHolder()
-        self.pretrained = _pretrained_holder()
-        self.scratch = _scratch_holder(self.out_c)
+        # holders are built on the meta device (no per-module default init: 400 M parameters would take
+        # ~11 s of single-threaded CPU RNG) and then materialised with one cheap pass, see _fast_init
+        with torch.device("meta"):
+            self.clip_pretrained = _ClipTextHolder()
+            self.pretrained = _pretrained_holder()
+            self.scratch = _scratch_holder(self.out_c)
         self.logit_scale = torch.tensor(reference_logit_scale())
         self.clip_pretrained._owner = weakref.ref(self)
         self._shared = {"engines": {}, "text_cache": {}, "lock": threading.Lock(), "master": weakref.ref(self)}
+        self._fast_init()
+
+    def _fast_init(self):
+        """Materialise parameters on CPU: weights ~ U(+-1/sqrt(fan_in)) (torch's Linear/Conv default),
+        LayerNorm/BatchNorm at identity, biases zero, embeddings/tokens small. Real use loads a checkpoint
+        over this (load_state_dict / BaseModel.load); benchmarks run on it as 'random init'."""
+        self.to_empty(device="cpu")
+        # CPU RNG is ~25 M values/s; draw one block of U(-1,1) with a prime length and tile it (memcpy
+        # speed) with a moving offset — rows of a weight never line up with the period
+        period = 4194301
+        base = torch.rand(period, generator=torch.Generator().manual_seed(0)) * 2.0 - 1.0
+        cursor = 0
+        norm_like = set()
+        for name, mod in self.named_modules():
+            if isinstance(mod, nn.BatchNorm2d):
+                mod.reset_running_stats()
+            if isinstance(mod, (nn.BatchNorm2d, nn.LayerNorm)):
+                norm_like.add(name)
+        with torch.no_grad():
+            for name, p in self.named_parameters():
+                owner = name.rsplit(".", 1)[0]
+                if owner in norm_like:
+                    p.fill_(1.0 if name.endswith("weight") else 0.0)
+                elif name.endswith("logit_scale"):
+                    p.fill_(2.6592600)
+                elif p.dim() >= 2:
+                    fan_in = p[0].numel() if p.dim() > 1 else p.numel()
+                    if name.endswith(("cls_token", "pos_embed", "positional_embedding", "token_embedding.weight")):
+                        bound = 0.03
+                    else:
+                        bound = fan_in ** -0.5
+                    n = p.numel()
+                    flat = p.view(-1)
+                    done = 0
+                    while done < n:
+                        take = min(n - done, period - cursor)
+                        flat[done:done + take] = base[cursor:cursor + take]
+                        done += take
+                        cursor = (cursor + take) % period
+                    p.mul_(bound)
+                else:
+                    p.zero_()
 
     # -- weight management -------------------------------------------------------------------
     def _invalidate(self):

@@ -81,6 +81,7 @@ def gemm(a, w, N=None, *, bias=None, bias_group_rows=0, scale=None, act=ACT_NONE
     if nchw is not None:
         args.nchw_p, args.nchw_k = nchw
     args.row_sumsq = _ptr(row_sumsq, torch.float32)
+    args.row_sumsq_parts = int(row_sumsq.shape[1]) if row_sumsq is not None else 0
     args.row_scale = float(row_scale)
     args.out_row_sumsq = _ptr(out_row_sumsq, torch.float32)
     check(load().lseg_gemm(C.byref(args), _stream()))

@@ -61,5 +61,11 @@ def argmax_report(got, ref, margin_eps):
 
 
 def oracle_forward(x, tokens, seed=0, stages=True):
-    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    oracle_threads()
     return O.lseg_forward(x, tokens, state_dict(seed), return_stages=stages)
+
+
+def oracle_threads():
+    """torch's CPU kernels on these small matrices get SLOWER beyond ~16 threads (measured 64 s per 480x480
+    forward with 128 threads vs 1.5 s with 16 on the GPU box's host), and GPU-box time is budgeted."""
+    torch.set_num_threads(max(1, min(16, os.cpu_count() or 1)))

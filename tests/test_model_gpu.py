@@ -15,9 +15,11 @@ import os
 import pytest
 import torch
 
-from parity_util import NET_KW, argmax_report, oracle_forward, rel_err, rms_rel_err, state_dict, synth
+from parity_util import (NET_KW, argmax_report, oracle_forward, oracle_threads, rel_err, rms_rel_err, state_dict,
+                         synth)
 
 pytestmark = pytest.mark.gpu
+oracle_threads()
 
 LOGIT_TOL = 4e-3      # max-abs error relative to max |logit|
 STAGE_TOL = 4e-3      # same metric on intermediate activations

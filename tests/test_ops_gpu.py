@@ -144,10 +144,10 @@ def test_deferred_row_normalisation(ops):
     t = _rand((K, 512), 43, 0.05)
     t = (t.float() / t.float().norm(dim=-1, keepdim=True)).half()
     feat16 = torch.zeros((B * P, 512), dtype=torch.float16, device="cuda")
-    sumsq = torch.zeros((B * P,), dtype=torch.float32, device="cuda")
+    sumsq = torch.zeros((B * P, 16), dtype=torch.float32, device="cuda")  # [row, 512/32] partial sums
     ops.gemm(path, ops.pad_rows(w1), 512, bias=b1, out_f16=feat16, out_row_sumsq=sumsq)
     x = path.float() @ w1.float().t() + b1
-    _close(sumsq, (x * x).sum(-1), 1e-4, "row sumsq")
+    _close(sumsq, (x * x).view(B * P, 16, 32).sum(-1), 1e-4, "row sumsq parts")
     out = torch.zeros((B, K, P), dtype=torch.float16, device="cuda")
     ls = math.exp(math.log(1 / 0.07))
     ops.gemm(feat16, ops.pad_rows(t), K, out_f16=out, store=ops.STORE_NCHW_T, nchw=(P, K), row_sumsq=sumsq,

@@ -14,7 +14,7 @@ import torch
 from parity_util import O, rel_err, state_dict, synth
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
-torch.set_num_threads(max(1, os.cpu_count() or 1))
+torch.set_num_threads(max(1, min(16, os.cpu_count() or 1)))
 
 # The reference's text tower (nn.MultiheadAttention, fp16) and the restated one differ by fp16 rounding
 # order only; measured 2.0e-3 of max|logit| when the fixtures were generated (make_golden.py log).
