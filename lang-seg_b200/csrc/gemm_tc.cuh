@@ -74,6 +74,12 @@ struct GemmParams {
   int num_m_tiles, num_n_tiles;
   int probe;  // measurement only (tools/gemm_probe.py; results are garbage when non-zero):
               //   1 = skip epilogue work, 2 = skip TMA loads, 4 = skip MMA issue   (CTA-pair kernel)
+  // TMA-store epilogue (CTA-pair kernel, row-major fp16 output only): each epilogue warp packs its 32 rows x
+  // 64 columns into a private 128B-swizzled smem tile and one lane issues a bulk tensor store, instead of 32
+  // lanes writing 32 different rows (one L1TEX wavefront per 16 B). plain: 2-D {N, M} box {64, 32};
+  // conv: 4-D {N, W, H, B} box {64, 16, 2, 1}. The tensor map clips the M / H / W / N tails.
+  int tma_store;
+  CUtensorMap tma_c;
   GemmEpi e;
 };
 
@@ -81,11 +87,10 @@ struct GemmParams {
 // Epilogue of one 32-column chunk of one output row: v = the row's fp32 accumulators for columns
 // [n0, n0+32); res = that row's fp32 residual for the same columns when has_res (prefetched by the caller).
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void gemm_epilogue_chunk(const GemmEpi& e, int N, const uint32_t (&v)[32],
-                                                    const float4 (&res)[8], bool has_res, long long grow, int n0,
-                                                    long long bias_off) {
+// math part: f = act(v * scale + bias); optional partial squared row norm
+__device__ __forceinline__ void gemm_epilogue_math(const GemmEpi& e, int N, const uint32_t (&v)[32], long long grow,
+                                                   int n0, long long bias_off, bool row_valid, float (&f)[32]) {
   const int nvalid = min(32, N - n0);
-  float f[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
   if (nvalid == 32) {  // uniform-address 16 B loads: one broadcast transaction each
@@ -126,12 +131,18 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmEpi& e, int N, con
 #pragma unroll
     for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
   }
-  if (e.out_row_sumsq) {  // per-(row, 32-column chunk) partial, summed in fixed order by the consumer:
+  if (e.out_row_sumsq && row_valid) {  // per-(row, 32-column chunk) partial, summed in fixed order by the consumer:
     float ss = 0.f;       // deterministic (no atomics), so batch-8 == batch-1 bit for bit
 #pragma unroll
     for (int i = 0; i < 32; ++i) ss = fmaf((i < nvalid) ? f[i] : 0.f, f[i], ss);
     e.out_row_sumsq[grow * ((N + 31) >> 5) + (n0 >> 5)] = ss;
   }
+}
+
+// store part, straight from registers (thread <-> row)
+__device__ __forceinline__ void gemm_epilogue_store(const GemmEpi& e, int N, float (&f)[32], const float4 (&res)[8],
+                                                    bool has_res, long long grow, int n0) {
+  const int nvalid = min(32, N - n0);
   if (e.store == STORE_ROWMAJOR) {
     const long long off = grow * e.ldc + n0;
     if (nvalid == 32) {
@@ -260,12 +271,73 @@ __device__ __forceinline__ bool gemm_row_map(const GemmParams& p, int m_tile, in
 // Epilogue of one 128 x (ncols) accumulator slab for one warp. The fp32 residual of chunk c+1 is
 // requested before chunk c is processed, and that of chunk 0 before the accumulator is even ready, so the
 // residual read latency overlaps the main loop / the previous chunk instead of serialising with it.
+constexpr int kEpiStageBytes = 2 * 4096;  // per epilogue warp: two 32-row x 128 B swizzled tiles (TMA-store path)
+
 template <typename WaitFn>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t t_row, int n_base, int ncols,
-                                                   int m_tile, int r, WaitFn wait_accumulator) {
+                                                   int m_tile, int r, WaitFn wait_accumulator,
+                                                   uint8_t* stage_buf = nullptr, int* store_groups = nullptr) {
   const GemmEpi& e = p.e;
   long long grow;
   const bool valid = gemm_row_map(p, m_tile, r, grow);
+  if (p.tma_store && stage_buf) {
+    // ---------------- TMA-store path: fp16 row-major output ----------------
+    const int lane = r & 31, quarter = r >> 5;
+    const long long grow_c = valid ? grow : 0;  // keep per-row lookups in range; the store clips invalid rows
+    const long long bias_off = (e.bias_group_rows > 0) ? (grow_c / e.bias_group_rows) * static_cast<long long>(p.N) : 0;
+    int crd_w = 0, crd_h = 0, crd_b = 0;
+    if (p.conv) {
+      const int per_img = p.tiles_h * p.tiles_w;
+      crd_b = m_tile / per_img;
+      const int t = m_tile % per_img;
+      crd_h = (t / p.tiles_w) * kConvTH + quarter * 2;
+      crd_w = (t % p.tiles_w) * kConvTW;
+    }
+    wait_accumulator();
+    tc_fence_after();
+    if (p.probe & 1) return;
+    int groups = *store_groups;
+#pragma unroll 1
+    for (int c = 0; c < ncols / 32; ++c) {
+      const int n0 = n_base + c * 32;
+      if (n0 >= p.N) break;  // warp-uniform
+      uint32_t v[32];
+      __syncwarp();
+      tmem_ld32(t_row + c * 32, v);
+      tmem_ld_wait();
+      float f[32];
+      gemm_epilogue_math(e, p.N, v, grow_c, n0, bias_off, valid, f);
+      uint8_t* buf = stage_buf + (groups & 1) * 4096;
+      if ((c & 1) == 0 && groups >= 2) {  // the store issued two groups ago must have finished READING this buffer
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        __half2 h[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[8 * t + 2 * i], f[8 * t + 2 * i + 1]);
+        const int chunk = ((c & 1) * 4 + t) ^ (lane & 7);
+        *reinterpret_cast<uint4*>(buf + lane * 128 + chunk * 16) = *reinterpret_cast<uint4*>(h);
+      }
+      const bool last = ((c & 1) == 1) || (c + 1 == ncols / 32) || (n0 + 32 >= p.N);
+      if (last) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          const int col0 = n_base + (c & ~1) * 32;
+          if (p.conv)
+            tma_store_4d(&p.tma_c, buf, col0, crd_w, crd_h, crd_b);
+          else
+            tma_store_2d(&p.tma_c, buf, col0, m_tile * kGemmBM + quarter * 32);
+          tma_store_commit();
+        }
+        ++groups;
+      }
+    }
+    *store_groups = groups;
+    return;
+  }
   const bool pre = valid && e.res_f32 && (e.store == STORE_ROWMAJOR);
   const long long bias_off =
       (e.bias_group_rows > 0 && valid) ? (grow / e.bias_group_rows) * static_cast<long long>(p.N) : 0;
@@ -297,7 +369,11 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
     __syncwarp();
     tmem_ld32(t_row + c * 32, v);
     tmem_ld_wait();
-    if (valid) gemm_epilogue_chunk(e, p.N, v, rcur, has_res, grow, n0, bias_off);
+    if (valid) {
+      float f[32];
+      gemm_epilogue_math(e, p.N, v, grow, n0, bias_off, true, f);
+      gemm_epilogue_store(e, p.N, f, rcur, has_res, grow, n0);
+    }
   }
 }
 
@@ -460,9 +536,11 @@ struct Gemm2Cfg {
   static constexpr int kABytes = kGemmBM * kGemmBK * 2;
   static constexpr int kBBytes = (BN / 2) * kGemmBK * 2;  // this CTA's half of the weight tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 6 : 8;
+  static constexpr int kStages = (BN == 256) ? 5 : 6;
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  // stages | per-warp TMA-store staging (1024 B aligned) | mbarriers
+  static constexpr int kStageOutBytes = kGemmEpiWarps * kEpiStageBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStageOutBytes + 1024 + 256;
 };
 
 template <int BN>
@@ -471,7 +549,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
   using Cfg = Gemm2Cfg<BN>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* stage_out = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + Cfg::kStageOutBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + Cfg::kStages;
   uint64_t* tmem_full = bars + 2 * Cfg::kStages;
@@ -586,6 +665,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
     const int half = ew >> 2;
     constexpr int kColsPerWarp = BN / (kGemmEpiWarps / 4);
     const int r = quarter * 32 + lane;
+    uint8_t* stage_buf = stage_out + ew * kEpiStageBytes;
+    int store_groups = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
@@ -593,13 +674,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
       const int n_tile = tile / m_pairs;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * kColsPerWarp;
       gemm_epilogue_tile(p, t_row, n_tile * BN + half * kColsPerWarp, kColsPerWarp, m_tile, r,
-                         [&]() { mbar_wait(&tmem_full[acc], acc_phase, 24); });
+                         [&]() { mbar_wait(&tmem_full[acc], acc_phase, 24); }, stage_buf, &store_groups);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);  // leader's barrier: 2 CTAs x 8 warps
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (lane == 0) tma_store_wait_all();  // outstanding bulk stores read this CTA's smem
   }
 
   tc_fence_before();

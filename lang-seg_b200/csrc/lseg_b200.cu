@@ -183,6 +183,28 @@ static int gemm_plan(const GemmDesc& d, GemmPlan* plan) {
     const uint32_t box[2] = {kGemmBK, (uint32_t)(plan->two_cta ? bn / 2 : bn)};
     if (make_tmap_f16(&p.tma_b, d.w, 2, dims, str, box)) return -1;
   }
+  // TMA-store epilogue: plain fp16 row-major outputs of the CTA-pair kernel (QKV, fc1, readout, 1x1 / 3x3
+  // convs feeding the next conv, head1, text in_proj / c_fc)
+  p.tma_store = 0;
+  {
+    const GemmEpi& e = p.e;
+    static const bool disabled = getenv("LSEG_GEMM_NO_TMA_STORE") != nullptr;
+    if (plan->two_cta && !disabled && e.store == STORE_ROWMAJOR && e.out_f16 && !e.out_f32 && !e.out_f16_relu &&
+        !e.res_f16 && !e.res_f32 && !e.res2_f32 && (e.ldc % 8 == 0) && (d.N % 8 == 0) && d.N >= 64) {
+      if (d.conv) {
+        const uint64_t dims[4] = {(uint64_t)d.N, (uint64_t)d.W, (uint64_t)d.H, (uint64_t)d.B};
+        const uint64_t str[3] = {(uint64_t)e.ldc * 2, (uint64_t)e.ldc * d.W * 2, (uint64_t)e.ldc * d.W * d.H * 2};
+        const uint32_t box[4] = {64, kConvTW, 2, 1};
+        if (make_tmap_f16(&p.tma_c, e.out_f16, 4, dims, str, box)) return -1;
+      } else {
+        const uint64_t dims[2] = {(uint64_t)d.N, (uint64_t)d.M};
+        const uint64_t str[1] = {(uint64_t)e.ldc * 2};
+        const uint32_t box[2] = {64, 32};
+        if (make_tmap_f16(&p.tma_c, e.out_f16, 2, dims, str, box)) return -1;
+      }
+      p.tma_store = 1;
+    }
+  }
   if (plan->two_cta) {
     const int pair_tiles = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
     const int max_pairs = g_num_sms / 2;
