@@ -310,51 +310,86 @@ __global__ void l2norm_f16_kernel(const __half* __restrict__ x, __half* __restri
 // ------------------------------------------------------------------------------------------
 // output head (modules/models/lseg_net.py:196,203): fp16 logits [planes,H,W] (values of the fp16
 // matmul) -> .float() -> bilinear x2 align_corners=True -> fp32 [planes,2H,2W].
-// HBM-write-bound (K*H*W*4 B per image). grid (ceil(Ho/8), planes); a block of 128 threads produces 8
-// output rows of one plane, each thread 4 consecutive outputs (one streaming float4 store) per row; the
-// horizontal taps/weights are computed once per thread and reused for the 8 rows.
+// HBM-write-bound (K*H*W*4 B per image). Separable: a WARP owns kUpRows consecutive output rows of one
+// plane; per row it (1) blends the two source rows vertically into a private smem line (16 B loads,
+// coalesced), (2) blends horizontally from that line — 2 LDS + 2 FMA per output — and streams float4
+// stores (512 B contiguous per warp instruction). The horizontal taps/weights live in registers and are
+// reused for all of the warp's rows. grid (ceil(Ho / (8 warps * kUpRows)), planes), W % 8 == 0, W <= 512.
 // ------------------------------------------------------------------------------------------
+constexpr int kUpRows = 4;      // output rows per warp
+constexpr int kUpMaxW = 512;    // widest source row (smem line)
 __global__ void upsample2x_nchw_kernel(const __half* __restrict__ x, float* __restrict__ y, int H, int W) {
+  __shared__ __align__(16) float line[8][kUpMaxW];
   const int Ho = 2 * H, Wo = 2 * W, w4 = Wo / 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long pl = blockIdx.y;
   const float sh = (Ho > 1) ? static_cast<float>(H - 1) / (Ho - 1) : 0.f;
   const float sw = (Wo > 1) ? static_cast<float>(W - 1) / (Wo - 1) : 0.f;
   const __half* plane = x + pl * H * W;
   float* oplane = y + pl * Ho * Wo;
-  for (int xq = threadIdx.x; xq < w4; xq += blockDim.x) {
-    int x0[4], x1[4];
-    float lx[4];
+  float* v = line[warp];
+  // horizontal taps of this lane's float4 groups xq = lane + 32*i (Wo <= 1024 -> at most 8 groups)
+  int x0[8][4];
+  float lx[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const float fx = sw * (xq * 4 + k);
-      x0[k] = static_cast<int>(fx);
-      x1[k] = min(x0[k] + 1, W - 1);
-      lx[k] = fx - x0[k];
+      const float fx = sw * ((lane + 32 * i) * 4 + k);
+      x0[i][k] = min(static_cast<int>(fx), W - 1);
+      lx[i][k] = fx - static_cast<int>(fx);
     }
-#pragma unroll 2
-    for (int r = 0; r < 8; ++r) {
-      const int oy = blockIdx.x * 8 + r;
-      if (oy >= Ho) break;
-      const float fy = sh * oy;
-      const int y0 = static_cast<int>(fy);
-      const int y1 = min(y0 + 1, H - 1);
-      const float ly = fy - y0, hy = 1.f - ly;
-      const __half* r0 = plane + y0 * W;
-      const __half* r1 = plane + y1 * W;
-      float o[4];
+  }
+  const int oy0 = (blockIdx.x * 8 + warp) * kUpRows;
+  for (int rr = 0; rr < kUpRows; ++rr) {
+    const int oy = oy0 + rr;
+    if (oy >= Ho) break;  // warp-uniform
+    const float fy = sh * oy;
+    const int y0 = static_cast<int>(fy);
+    const int y1 = min(y0 + 1, H - 1);
+    const float ly = fy - y0, hy = 1.f - ly;
+    const uint4* r0 = reinterpret_cast<const uint4*>(plane + y0 * W);
+    const uint4* r1 = reinterpret_cast<const uint4*>(plane + y1 * W);
+    __syncwarp();
+    for (int c = lane; c < W / 8; c += 32) {
+      const uint4 a = r0[c], b = r1[c];
+      const __half2* ah = reinterpret_cast<const __half2*>(&a);
+      const __half2* bh = reinterpret_cast<const __half2*>(&b);
+      float o[8];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float hx = 1.f - lx[k];
-        o[k] = hy * (hx * __half2float(r0[x0[k]]) + lx[k] * __half2float(r0[x1[k]])) +
-               ly * (hx * __half2float(r1[x0[k]]) + lx[k] * __half2float(r1[x1[k]]));
+        const float2 fa = __half22float2(ah[k]), fb = __half22float2(bh[k]);
+        o[2 * k] = hy * fa.x + ly * fb.x;
+        o[2 * k + 1] = hy * fa.y + ly * fb.y;
       }
-      __stcs(reinterpret_cast<float4*>(oplane + static_cast<long long>(oy) * Wo + xq * 4),
-             make_float4(o[0], o[1], o[2], o[3]));
+      reinterpret_cast<float4*>(v)[2 * c] = make_float4(o[0], o[1], o[2], o[3]);
+      reinterpret_cast<float4*>(v)[2 * c + 1] = make_float4(o[4], o[5], o[6], o[7]);
+    }
+    __syncwarp();
+    float* orow = oplane + static_cast<long long>(oy) * Wo;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int xq = lane + 32 * i;
+      if (xq < w4) {
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int xa = x0[i][k], xb = min(xa + 1, W - 1);
+          o[k] = (1.f - lx[i][k]) * v[xa] + lx[i][k] * v[xb];
+        }
+        __stcs(reinterpret_cast<float4*>(orow + xq * 4), make_float4(o[0], o[1], o[2], o[3]));
+      }
     }
   }
 }
 static inline int launch_upsample2x_nchw(const __half* x, float* y, long long planes, int H, int W, cudaStream_t s) {
-  upsample2x_nchw_kernel<<<dim3((2 * H + 7) / 8, static_cast<unsigned>(planes)), 128, 0, s>>>(x, y, H, W);
+  if (W % 8 != 0 || W > kUpMaxW || planes > 65535) {
+    set_error("upsample2x_nchw: needs W %% 8 == 0, W <= %d, planes <= 65535 (W=%d planes=%lld)", kUpMaxW, W, planes);
+    return -1;
+  }
+  const int rows_per_block = 8 * kUpRows;
+  upsample2x_nchw_kernel<<<dim3((2 * H + rows_per_block - 1) / rows_per_block, static_cast<unsigned>(planes)), 256, 0,
+                           s>>>(x, y, H, W);
   LSEG_LAUNCH_CHECK();
 }
 

@@ -79,6 +79,7 @@ struct GemmParams {
   // lanes writing 32 different rows (one L1TEX wavefront per 16 B). plain: 2-D {N, M} box {64, 32};
   // conv: 4-D {N, W, H, B} box {64, 16, 2, 1}. The tensor map clips the M / H / W / N tails.
   int tma_store;
+  int transposed;  // CTA-pair kernel, BN = 256: compute D^T (see gemm_epilogue_tile_t)
   CUtensorMap tma_c;
   GemmEpi e;
 };
@@ -377,6 +378,90 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// TRANSPOSED epilogue (CTA-pair kernel, BN = 256, row-major stores with fp32/fp16 residuals or fp32 output).
+// The pair computes D^T = W_tile * A_tile^T (the two K-major operands simply swap roles in the UMMA), so a
+// TMEM lane is an output COLUMN n and the 256 TMEM columns are the pair's 256 output rows. A warp-level
+// access for one output row then touches 32 consecutive n = one 128 B line (fp32): residual reads and
+// result writes are perfectly coalesced with no shared-memory staging, and bias/scale are per-thread
+// scalars. (In the normal orientation each 16 B access of a warp hits 32 different lines — one L1TEX
+// wavefront each — which bounded the proj / fc2 / RCU-conv2 epilogues at 2-3x their main-loop time.)
+// ------------------------------------------------------------------------------------------
+template <typename WaitFn>
+__device__ __forceinline__ void gemm_epilogue_tile_t(const GemmParams& p, uint32_t t_row, int n, int m_tile,
+                                                     WaitFn wait_accumulator) {
+  const GemmEpi& e = p.e;
+  const bool n_ok = n < p.N;
+  const float sc = (e.scale && n_ok) ? __ldg(e.scale + n) : 1.f;
+  const float bs = (e.bias && n_ok) ? __ldg(e.bias + n) : 0.f;
+  // row r of the 128-row tile -> element offset of (row, n) and validity (warp-uniform)
+  const bool tile_ok = m_tile < p.num_m_tiles;
+  int cb = 0, ch0 = 0, cw0 = 0;
+  if (p.conv) {
+    const int per_img = p.tiles_h * p.tiles_w;
+    cb = m_tile / per_img;
+    const int t = m_tile % per_img;
+    ch0 = (t / p.tiles_w) * kConvTH;
+    cw0 = (t % p.tiles_w) * kConvTW;
+  }
+  auto row_off = [&](int r, bool& ok) -> long long {
+    long long grow;
+    if (p.conv) {
+      const int h = ch0 + r / kConvTW, w = cw0 + r % kConvTW;
+      ok = tile_ok && (h < p.H) && (w < p.W);
+      grow = (static_cast<long long>(cb) * p.H + h) * p.W + w;
+    } else {
+      grow = static_cast<long long>(m_tile) * kGemmBM + r;
+      ok = tile_ok && (grow < p.M);
+    }
+    return grow * e.ldc + n;
+  };
+  wait_accumulator();
+  tc_fence_after();
+  if (p.probe & 1) return;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t v[32];
+    __syncwarp();
+    tmem_ld32(t_row + c * 32, v);
+    float r1[32];
+    if (e.res_f32) {  // issued while the TMEM load is in flight
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        bool ok;
+        const long long off = row_off(c * 32 + i, ok);
+        r1[i] = (ok && n_ok) ? e.res_f32[off] : 0.f;
+      }
+    }
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      float x = fmaf(__uint_as_float(v[i]), sc, bs);
+      if (e.act == ACT_GELU) x = gelu_erf(x);
+      else if (e.act == ACT_QUICKGELU) x = quick_gelu(x);
+      else if (e.act == ACT_RELU) x = fmaxf(x, 0.f);
+      if (e.res_f32) x += r1[i];
+      v[i] = __float_as_uint(x);
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      bool ok;
+      const long long off = row_off(c * 32 + i, ok);
+      if (ok && n_ok) {
+        float x = __uint_as_float(v[i]);
+        if (e.res2_f32) x += e.res2_f32[off];
+        if (e.out_f32) e.out_f32[off] = x;
+        if (e.out_f16) {
+          __half hx = __float2half_rn(x);
+          if (e.res_f16) hx = __hadd(e.res_f16[off], hx);  // fp16 residual stream (CLIP text tower)
+          e.out_f16[off] = hx;
+        }
+        if (e.out_f16_relu) e.out_f16_relu[off] = __float2half_rn(fmaxf(x, 0.f));
+      }
+    }
+  }
+}
+
 // ==========================================================================================
 // single-CTA kernel
 // ==========================================================================================
@@ -647,7 +732,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
             for (int k = 0; k < kGemmBK / 16; ++k) {
               const uint64_t da = umma_desc_sw128(a_base + k * 32, 1024, 0);
               const uint64_t db = umma_desc_sw128(b_base + k * 32, 1024, 0);
-              umma_f16_ss_2cta(d_tmem, da, db, idesc, (kit | k) != 0);
+              if (p.transposed)  // D^T = W * A^T: weight rows become TMEM lanes
+                umma_f16_ss_2cta(d_tmem, db, da, idesc, (kit | k) != 0);
+              else
+                umma_f16_ss_2cta(d_tmem, da, db, idesc, (kit | k) != 0);
             }
           }
           umma_commit_2cta(&empty_bar[stage], 0x3);  // both CTAs' smem slots
@@ -673,8 +761,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
       const int m_tile = (tile % m_pairs) * 2 + static_cast<int>(rank);
       const int n_tile = tile / m_pairs;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * kColsPerWarp;
-      gemm_epilogue_tile(p, t_row, n_tile * BN + half * kColsPerWarp, kColsPerWarp, m_tile, r,
-                         [&]() { mbar_wait(&tmem_full[acc], acc_phase, 24); }, stage_buf, &store_groups);
+      if (BN == 256 && p.transposed) {
+        // lanes = this CTA's 128 weight rows (output columns); TMEM column half h = the 128 output rows
+        // staged by CTA h of the pair
+        gemm_epilogue_tile_t(p, t_row, n_tile * BN + static_cast<int>(rank) * 128 + quarter * 32 + lane,
+                             (tile % m_pairs) * 2 + half, [&]() { mbar_wait(&tmem_full[acc], acc_phase, 24); });
+      } else {
+        gemm_epilogue_tile(p, t_row, n_tile * BN + half * kColsPerWarp, kColsPerWarp, m_tile, r,
+                           [&]() { mbar_wait(&tmem_full[acc], acc_phase, 24); }, stage_buf, &store_groups);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);  // leader's barrier: 2 CTAs x 8 warps

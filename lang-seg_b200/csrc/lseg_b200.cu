@@ -204,6 +204,13 @@ static int gemm_plan(const GemmDesc& d, GemmPlan* plan) {
       }
       p.tma_store = 1;
     }
+    // every other row-major epilogue (fp32 residual stream, fp32 / multiple outputs, fp16 residual) runs
+    // transposed so that its global accesses coalesce
+    static const bool no_transpose = getenv("LSEG_GEMM_NO_TRANSPOSE") != nullptr;
+    p.transposed = (plan->two_cta && bn == 256 && !no_transpose && !p.tma_store && e.store == STORE_ROWMAJOR &&
+                    e.bias_group_rows == 0 && !e.out_row_sumsq)
+                       ? 1
+                       : 0;
   }
   if (plan->two_cta) {
     const int pair_tiles = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
