@@ -15,17 +15,24 @@
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
 // the main loop of tile i+1.
 //
-// Two variants:
-//   gemm_tc2_kernel  CTA pair (tcgen05 cta_group::2, UMMA 256 x BN x 16): default. Shared memory
-//                    bandwidth is the binding resource of an SS-mode UMMA main loop (every byte TMA
-//                    writes is read back by the tensor core: 128x256x64 per CTA moves 2 x 48 KB per 512
-//                    MMA cycles = 192 B/clk against ~128 B/clk/SM); the pair splits the weight tile, so
-//                    each SM stages 32 KB per step instead of 48 KB. Measured: 3x3 conv 1186 TFLOP/s
-//                    (pair) vs 1070 (single), fc2 951 vs 810.
-//   gemm_tc_kernel   single CTA (LSEG_GEMM_1CTA=1), kept for A/B measurements.
-// The epilogue stores straight from registers (thread <-> accumulator row). Staging it through shared
-// memory for coalescing was measured and rejected: it competes with the main loop for the same smem
-// bandwidth and made every GEMM 1.3-2.3x slower.
+// Kernels
+//   gemm_tc2_kernel<BN, EPI>  CTA pair (tcgen05 cta_group::2, UMMA 256 x BN x 16): default. Shared-memory
+//        bandwidth is the binding resource of an SS-mode UMMA main loop (every byte TMA writes is read back by
+//        the tensor core); the pair splits the weight tile, so each SM stages 32 KB per k-step instead of 48.
+//   gemm_tc_kernel<BN>        single CTA (LSEG_GEMM_1CTA=1), direct epilogue only; kept for A/B measurements.
+//
+// Epilogue modes (measured with tools/gemm_probe.py: the main loop alone runs at 1300-1400 TFLOP/s, so for
+// K <= 1024 the epilogue decides the speed):
+//   EPI_DIRECT   stores straight from registers, thread <-> accumulator row. Every 16 B access of a warp
+//                touches 32 different 128 B lines = 32 L1TEX wavefronts; fine for long-K tiles, 2-3x the
+//                main-loop time for K = 1024.
+//   EPI_TMA_F16  fp16 row-major outputs: each epilogue warp packs 32 rows x 64 columns into a private
+//                128B-swizzled smem tile and one lane issues a bulk tensor store (QKV 58 -> 42 us).
+//   EPI_TMA_ADD  in-place fp32 residual stream (x += A W^T + b): the warp stages 32 x 32 fp32 results and
+//                issues a bulk tensor REDUCE-ADD, so the residual is never read by the SM at all.
+// Rejected after measurement: a full smem transpose of the accumulator (competes with the main loop for smem
+// bandwidth: every GEMM 1.3-2.3x slower) and computing D^T so that lanes map to columns (4 B accesses: 4x
+// the LSU instructions, proj 39 -> 84 us).
 #pragma once
 #include "common.cuh"
 
@@ -40,6 +47,7 @@ constexpr int kGemmThreads = 128 + 32 * kGemmEpiWarps;
 
 enum GemmAct { ACT_NONE = 0, ACT_GELU = 1, ACT_QUICKGELU = 2, ACT_RELU = 3 };
 enum GemmStore { STORE_ROWMAJOR = 0, STORE_D2S = 1, STORE_NCHW_T = 2 };
+enum GemmEpiMode { EPI_DIRECT = 0, EPI_TMA_F16 = 1, EPI_TMA_ADD = 2 };
 
 struct GemmEpi {
   const float* bias;       // [N] (or [groups, N] when bias_group_rows > 0); nullable
@@ -65,6 +73,9 @@ struct GemmEpi {
 struct GemmParams {
   CUtensorMap tma_a;  // plain: 2-D {K, M}; conv: 4-D {C, W, H, B}
   CUtensorMap tma_b;  // 2-D {Ktot, N}, Ktot = taps * C, tap-major
+  CUtensorMap tma_c;  // output map of the TMA epilogues. EPI_TMA_F16: fp16, plain 2-D {N, M} box {64, 32} /
+                      // conv 4-D {N, W, H, B} box {64, 16, 2, 1}. EPI_TMA_ADD: fp32 2-D {N, M} box {32, 32}.
+                      // The map clips the M / H / W / N tails, so partial tiles need no masking.
   int M, N;
   int k_iters;   // total K chunks of 64 (taps * C/64)
   int k_chunks;  // chunks per tap (C/64); == k_iters for plain
@@ -74,21 +85,13 @@ struct GemmParams {
   int num_m_tiles, num_n_tiles;
   int probe;  // measurement only (tools/gemm_probe.py; results are garbage when non-zero):
               //   1 = skip epilogue work, 2 = skip TMA loads, 4 = skip MMA issue   (CTA-pair kernel)
-  // TMA-store epilogue (CTA-pair kernel, row-major fp16 output only): each epilogue warp packs its 32 rows x
-  // 64 columns into a private 128B-swizzled smem tile and one lane issues a bulk tensor store, instead of 32
-  // lanes writing 32 different rows (one L1TEX wavefront per 16 B). plain: 2-D {N, M} box {64, 32};
-  // conv: 4-D {N, W, H, B} box {64, 16, 2, 1}. The tensor map clips the M / H / W / N tails.
-  int tma_store;
-  int transposed;  // CTA-pair kernel, BN = 256: compute D^T (see gemm_epilogue_tile_t)
-  CUtensorMap tma_c;
   GemmEpi e;
 };
 
 // ------------------------------------------------------------------------------------------
-// Epilogue of one 32-column chunk of one output row: v = the row's fp32 accumulators for columns
-// [n0, n0+32); res = that row's fp32 residual for the same columns when has_res (prefetched by the caller).
+// Epilogue math of one 32-column chunk of one output row: f = act(v * scale + bias), plus the optional
+// partial squared row norm. v = the row's fp32 accumulators for columns [n0, n0+32).
 // ------------------------------------------------------------------------------------------
-// math part: f = act(v * scale + bias); optional partial squared row norm
 __device__ __forceinline__ void gemm_epilogue_math(const GemmEpi& e, int N, const uint32_t (&v)[32], long long grow,
                                                    int n0, long long bias_off, bool row_valid, float (&f)[32]) {
   const int nvalid = min(32, N - n0);
@@ -132,15 +135,15 @@ __device__ __forceinline__ void gemm_epilogue_math(const GemmEpi& e, int N, cons
 #pragma unroll
     for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
   }
-  if (e.out_row_sumsq && row_valid) {  // per-(row, 32-column chunk) partial, summed in fixed order by the consumer:
-    float ss = 0.f;       // deterministic (no atomics), so batch-8 == batch-1 bit for bit
+  if (e.out_row_sumsq && row_valid) {  // per-(row, 32-column chunk) partial, summed in fixed order by the
+    float ss = 0.f;                    // consumer: deterministic (no atomics), batch-8 == batch-1 bit for bit
 #pragma unroll
     for (int i = 0; i < 32; ++i) ss = fmaf((i < nvalid) ? f[i] : 0.f, f[i], ss);
     e.out_row_sumsq[grow * ((N + 31) >> 5) + (n0 >> 5)] = ss;
   }
 }
 
-// store part, straight from registers (thread <-> row)
+// EPI_DIRECT store part, straight from registers (thread <-> row)
 __device__ __forceinline__ void gemm_epilogue_store(const GemmEpi& e, int N, float (&f)[32], const float4 (&res)[8],
                                                     bool has_res, long long grow, int n0) {
   const int nvalid = min(32, N - n0);
@@ -239,14 +242,6 @@ __device__ __forceinline__ void gemm_epilogue_store(const GemmEpi& e, int N, flo
   } else {  // STORE_NCHW_T : out[(b*K + n)*P + p], fp16 (lanes = consecutive pixels -> coalesced)
     const int b = static_cast<int>(grow / e.nchw_p);
     const int pix = static_cast<int>(grow - static_cast<long long>(b) * e.nchw_p);
-    if (e.row_sumsq) {  // deferred pixel normalisation: logit_scale / ||feature row||
-      float ss = 0.f;
-      const float* sp = e.row_sumsq + grow * e.row_sumsq_parts;
-      for (int i = 0; i < e.row_sumsq_parts; ++i) ss += __ldg(sp + i);
-      const float rs = e.row_scale * rsqrtf(ss);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) f[i] *= rs;
-    }
     __half* op = e.out_f16 + (static_cast<long long>(b) * e.nchw_k + n0) * e.nchw_p + pix;
 #pragma unroll
     for (int i = 0; i < 32; ++i)
@@ -269,22 +264,71 @@ __device__ __forceinline__ bool gemm_row_map(const GemmParams& p, int m_tile, in
   return (m_tile < p.num_m_tiles) && (grow < p.M);
 }
 
-// Epilogue of one 128 x (ncols) accumulator slab for one warp. The fp32 residual of chunk c+1 is
-// requested before chunk c is processed, and that of chunk 0 before the accumulator is even ready, so the
-// residual read latency overlaps the main loop / the previous chunk instead of serialising with it.
-constexpr int kEpiStageBytes = 2 * 4096;  // per epilogue warp: two 32-row x 128 B swizzled tiles (TMA-store path)
+constexpr int kEpiStageBytes = 2 * 4096;  // per epilogue warp: two 32-row x 128 B swizzled tiles (TMA epilogues)
 
-template <typename WaitFn>
+// Epilogue of one 128 x (ncols) accumulator slab for one warp (r = quarter*32 + lane = this thread's row).
+template <int EPI, typename WaitFn>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t t_row, int n_base, int ncols,
-                                                   int m_tile, int r, WaitFn wait_accumulator,
-                                                   uint8_t* stage_buf = nullptr, int* store_groups = nullptr) {
+                                                   int m_tile, int r, WaitFn wait_accumulator, uint8_t* stage_buf,
+                                                   int& store_groups) {
   const GemmEpi& e = p.e;
   long long grow;
   const bool valid = gemm_row_map(p, m_tile, r, grow);
-  if (p.tma_store && stage_buf) {
-    // ---------------- TMA-store path: fp16 row-major output ----------------
+  if constexpr (EPI == EPI_DIRECT) {
+    // The fp32 residual of chunk c+1 is requested before chunk c is processed, and that of chunk 0 before the
+    // accumulator is even ready, so the residual read latency overlaps the main loop / the previous chunk.
+    const bool pre = valid && e.res_f32 && (e.store == STORE_ROWMAJOR);
+    const long long bias_off =
+        (e.bias_group_rows > 0 && valid) ? (grow / e.bias_group_rows) * static_cast<long long>(p.N) : 0;
+    float4 rnext[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) rnext[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pre && n_base + 32 <= p.N) {
+      const float4* rp = reinterpret_cast<const float4*>(e.res_f32 + grow * e.ldc + n_base);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) rnext[j] = rp[j];
+    }
+    float row_mul = 1.f;
+    if (e.row_sumsq && valid) {  // deferred pixel normalisation: logit_scale / ||feature row||, once per tile
+      float ss = 0.f;
+      const float* sp = e.row_sumsq + grow * e.row_sumsq_parts;
+      for (int i = 0; i < e.row_sumsq_parts; ++i) ss += __ldg(sp + i);
+      row_mul = e.row_scale * rsqrtf(ss);
+    }
+    wait_accumulator();
+    tc_fence_after();
+    if (p.probe & 1) return;
+#pragma unroll 1
+    for (int c = 0; c < ncols / 32; ++c) {
+      const int n0 = n_base + c * 32;
+      if (n0 >= p.N) break;  // warp-uniform
+      float4 rcur[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) rcur[j] = rnext[j];
+      const bool has_res = pre && (n0 + 32 <= p.N);
+      if (pre && (c + 1) * 32 < ncols && n0 + 64 <= p.N) {
+        const float4* rp = reinterpret_cast<const float4*>(e.res_f32 + grow * e.ldc + n0 + 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rnext[j] = rp[j];
+      }
+      uint32_t v[32];
+      __syncwarp();
+      tmem_ld32(t_row + c * 32, v);
+      tmem_ld_wait();
+      if (valid) {
+        float f[32];
+        gemm_epilogue_math(e, p.N, v, grow, n0, bias_off, true, f);
+        if (e.row_sumsq) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] *= row_mul;
+        }
+        gemm_epilogue_store(e, p.N, f, rcur, has_res, grow, n0);
+      }
+    }
+  } else {
+    // ---------------- TMA epilogues: results leave through a per-warp swizzled smem tile ----------------
     const int lane = r & 31, quarter = r >> 5;
-    const long long grow_c = valid ? grow : 0;  // keep per-row lookups in range; the store clips invalid rows
+    const long long grow_c = valid ? grow : 0;  // keep per-row lookups in range; the tensor map clips the rest
     const long long bias_off = (e.bias_group_rows > 0) ? (grow_c / e.bias_group_rows) * static_cast<long long>(p.N) : 0;
     int crd_w = 0, crd_h = 0, crd_b = 0;
     if (p.conv) {
@@ -297,7 +341,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
     wait_accumulator();
     tc_fence_after();
     if (p.probe & 1) return;
-    int groups = *store_groups;
+    int groups = store_groups;
 #pragma unroll 1
     for (int c = 0; c < ncols / 32; ++c) {
       const int n0 = n_base + c * 32;
@@ -309,161 +353,56 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
       float f[32];
       gemm_epilogue_math(e, p.N, v, grow_c, n0, bias_off, valid, f);
       uint8_t* buf = stage_buf + (groups & 1) * 4096;
-      if ((c & 1) == 0 && groups >= 2) {  // the store issued two groups ago must have finished READING this buffer
+      const bool first_of_group = (EPI == EPI_TMA_ADD) || ((c & 1) == 0);
+      if (first_of_group && groups >= 2) {  // the bulk op issued two groups ago must be done READING this buffer
         if (lane == 0) tma_store_wait_read<1>();
         __syncwarp();
       }
+      if constexpr (EPI == EPI_TMA_F16) {
+        // 32 rows x 64 fp16 columns per group: this chunk fills 16-byte slots (c&1)*4 .. +3 of the row
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        __half2 h[4];
+        for (int t = 0; t < 4; ++t) {
+          __half2 h[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[8 * t + 2 * i], f[8 * t + 2 * i + 1]);
-        const int chunk = ((c & 1) * 4 + t) ^ (lane & 7);
-        *reinterpret_cast<uint4*>(buf + lane * 128 + chunk * 16) = *reinterpret_cast<uint4*>(h);
+          for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[8 * t + 2 * i], f[8 * t + 2 * i + 1]);
+          const int slot = ((c & 1) * 4 + t) ^ (lane & 7);
+          *reinterpret_cast<uint4*>(buf + lane * 128 + slot * 16) = *reinterpret_cast<uint4*>(h);
+        }
+      } else {
+        // 32 rows x 32 fp32 columns per group
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const int slot = t ^ (lane & 7);
+          *reinterpret_cast<float4*>(buf + lane * 128 + slot * 16) =
+              make_float4(f[4 * t], f[4 * t + 1], f[4 * t + 2], f[4 * t + 3]);
+        }
       }
-      const bool last = ((c & 1) == 1) || (c + 1 == ncols / 32) || (n0 + 32 >= p.N);
-      if (last) {
+      const bool last_of_group =
+          (EPI == EPI_TMA_ADD) || ((c & 1) == 1) || (c + 1 == ncols / 32) || (n0 + 32 >= p.N);
+      if (last_of_group) {
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          const int col0 = n_base + (c & ~1) * 32;
-          if (p.conv)
-            tma_store_4d(&p.tma_c, buf, col0, crd_w, crd_h, crd_b);
-          else
-            tma_store_2d(&p.tma_c, buf, col0, m_tile * kGemmBM + quarter * 32);
+          if constexpr (EPI == EPI_TMA_F16) {
+            const int col0 = n_base + (c & ~1) * 32;
+            if (p.conv)
+              tma_store_4d(&p.tma_c, buf, col0, crd_w, crd_h, crd_b);
+            else
+              tma_store_2d(&p.tma_c, buf, col0, m_tile * kGemmBM + quarter * 32);
+          } else {
+            tma_reduce_add_2d(&p.tma_c, buf, n0, m_tile * kGemmBM + quarter * 32);
+          }
           tma_store_commit();
         }
         ++groups;
       }
     }
-    *store_groups = groups;
-    return;
-  }
-  const bool pre = valid && e.res_f32 && (e.store == STORE_ROWMAJOR);
-  const long long bias_off =
-      (e.bias_group_rows > 0 && valid) ? (grow / e.bias_group_rows) * static_cast<long long>(p.N) : 0;
-  float4 rnext[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) rnext[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (pre && n_base + 32 <= p.N) {
-    const float4* rp = reinterpret_cast<const float4*>(e.res_f32 + grow * e.ldc + n_base);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) rnext[j] = rp[j];
-  }
-  wait_accumulator();
-  tc_fence_after();
-  if (p.probe & 1) return;
-#pragma unroll 1
-  for (int c = 0; c < ncols / 32; ++c) {
-    const int n0 = n_base + c * 32;
-    if (n0 >= p.N) break;  // warp-uniform
-    float4 rcur[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) rcur[j] = rnext[j];
-    const bool has_res = pre && (n0 + 32 <= p.N);
-    if (pre && (c + 1) * 32 < ncols && n0 + 64 <= p.N) {
-      const float4* rp = reinterpret_cast<const float4*>(e.res_f32 + grow * e.ldc + n0 + 32);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) rnext[j] = rp[j];
-    }
-    uint32_t v[32];
-    __syncwarp();
-    tmem_ld32(t_row + c * 32, v);
-    tmem_ld_wait();
-    if (valid) {
-      float f[32];
-      gemm_epilogue_math(e, p.N, v, grow, n0, bias_off, true, f);
-      gemm_epilogue_store(e, p.N, f, rcur, has_res, grow, n0);
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// TRANSPOSED epilogue (CTA-pair kernel, BN = 256, row-major stores with fp32/fp16 residuals or fp32 output).
-// The pair computes D^T = W_tile * A_tile^T (the two K-major operands simply swap roles in the UMMA), so a
-// TMEM lane is an output COLUMN n and the 256 TMEM columns are the pair's 256 output rows. A warp-level
-// access for one output row then touches 32 consecutive n = one 128 B line (fp32): residual reads and
-// result writes are perfectly coalesced with no shared-memory staging, and bias/scale are per-thread
-// scalars. (In the normal orientation each 16 B access of a warp hits 32 different lines — one L1TEX
-// wavefront each — which bounded the proj / fc2 / RCU-conv2 epilogues at 2-3x their main-loop time.)
-// ------------------------------------------------------------------------------------------
-template <typename WaitFn>
-__device__ __forceinline__ void gemm_epilogue_tile_t(const GemmParams& p, uint32_t t_row, int n, int m_tile,
-                                                     WaitFn wait_accumulator) {
-  const GemmEpi& e = p.e;
-  const bool n_ok = n < p.N;
-  const float sc = (e.scale && n_ok) ? __ldg(e.scale + n) : 1.f;
-  const float bs = (e.bias && n_ok) ? __ldg(e.bias + n) : 0.f;
-  // row r of the 128-row tile -> element offset of (row, n) and validity (warp-uniform)
-  const bool tile_ok = m_tile < p.num_m_tiles;
-  int cb = 0, ch0 = 0, cw0 = 0;
-  if (p.conv) {
-    const int per_img = p.tiles_h * p.tiles_w;
-    cb = m_tile / per_img;
-    const int t = m_tile % per_img;
-    ch0 = (t / p.tiles_w) * kConvTH;
-    cw0 = (t % p.tiles_w) * kConvTW;
-  }
-  auto row_off = [&](int r, bool& ok) -> long long {
-    long long grow;
-    if (p.conv) {
-      const int h = ch0 + r / kConvTW, w = cw0 + r % kConvTW;
-      ok = tile_ok && (h < p.H) && (w < p.W);
-      grow = (static_cast<long long>(cb) * p.H + h) * p.W + w;
-    } else {
-      grow = static_cast<long long>(m_tile) * kGemmBM + r;
-      ok = tile_ok && (grow < p.M);
-    }
-    return grow * e.ldc + n;
-  };
-  wait_accumulator();
-  tc_fence_after();
-  if (p.probe & 1) return;
-#pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
-    uint32_t v[32];
-    __syncwarp();
-    tmem_ld32(t_row + c * 32, v);
-    float r1[32];
-    if (e.res_f32) {  // issued while the TMEM load is in flight
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        bool ok;
-        const long long off = row_off(c * 32 + i, ok);
-        r1[i] = (ok && n_ok) ? e.res_f32[off] : 0.f;
-      }
-    }
-    tmem_ld_wait();
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      float x = fmaf(__uint_as_float(v[i]), sc, bs);
-      if (e.act == ACT_GELU) x = gelu_erf(x);
-      else if (e.act == ACT_QUICKGELU) x = quick_gelu(x);
-      else if (e.act == ACT_RELU) x = fmaxf(x, 0.f);
-      if (e.res_f32) x += r1[i];
-      v[i] = __float_as_uint(x);
-    }
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      bool ok;
-      const long long off = row_off(c * 32 + i, ok);
-      if (ok && n_ok) {
-        float x = __uint_as_float(v[i]);
-        if (e.res2_f32) x += e.res2_f32[off];
-        if (e.out_f32) e.out_f32[off] = x;
-        if (e.out_f16) {
-          __half hx = __float2half_rn(x);
-          if (e.res_f16) hx = __hadd(e.res_f16[off], hx);  // fp16 residual stream (CLIP text tower)
-          e.out_f16[off] = hx;
-        }
-        if (e.out_f16_relu) e.out_f16_relu[off] = __float2half_rn(fmaxf(x, 0.f));
-      }
-    }
+    store_groups = groups;
   }
 }
 
 // ==========================================================================================
-// single-CTA kernel
+// single-CTA kernel (EPI_DIRECT only)
 // ==========================================================================================
 template <int BN>
 struct GemmCfg {
@@ -586,12 +525,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     const int r = quarter * 32 + lane;            // row inside the 128-row tile
     int acc = 0;
     uint32_t acc_phase = 0;
+    int unused_groups = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_tile = tile % p.num_m_tiles;
       const int n_tile = tile / p.num_m_tiles;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * kColsPerWarp;
-      gemm_epilogue_tile(p, t_row, n_tile * BN + half * kColsPerWarp, kColsPerWarp, m_tile, r,
-                         [&]() { mbar_wait(&tmem_full[acc], acc_phase, 4); });
+      gemm_epilogue_tile<EPI_DIRECT>(p, t_row, n_tile * BN + half * kColsPerWarp, kColsPerWarp, m_tile, r,
+                                     [&]() { mbar_wait(&tmem_full[acc], acc_phase, 4); }, nullptr, unused_groups);
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
       acc ^= 1;
@@ -616,22 +556,22 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
 //   empty barrier  : per CTA, released by a multicast tcgen05.commit
 //   tmem full      : per CTA (multicast commit);  tmem empty: in the leader, 2 x 8 warp arrivals
 // ==========================================================================================
-template <int BN>
+template <int BN, int EPI>
 struct Gemm2Cfg {
   static constexpr int kABytes = kGemmBM * kGemmBK * 2;
   static constexpr int kBBytes = (BN / 2) * kGemmBK * 2;  // this CTA's half of the weight tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 5 : 6;
+  // stages | per-warp TMA-epilogue staging (1024 B aligned) | mbarriers
+  static constexpr int kStageOutBytes = (EPI == EPI_DIRECT) ? 0 : kGemmEpiWarps * kEpiStageBytes;
+  static constexpr int kStages = (BN == 256) ? ((EPI == EPI_DIRECT) ? 6 : 5) : ((EPI == EPI_DIRECT) ? 8 : 6);
   static constexpr int kTmemCols = 2 * BN;
-  // stages | per-warp TMA-store staging (1024 B aligned) | mbarriers
-  static constexpr int kStageOutBytes = kGemmEpiWarps * kEpiStageBytes;
   static constexpr int kSmemBytes = kStages * kStageBytes + kStageOutBytes + 1024 + 256;
 };
 
-template <int BN>
+template <int BN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
     gemm_tc2_kernel(const __grid_constant__ GemmParams p) {
-  using Cfg = Gemm2Cfg<BN>;
+  using Cfg = Gemm2Cfg<BN, EPI>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_out = smem + Cfg::kStages * Cfg::kStageBytes;
@@ -651,6 +591,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tma_a);
     tma_prefetch_desc(&p.tma_b);
+    if (EPI != EPI_DIRECT) tma_prefetch_desc(&p.tma_c);
     for (int i = 0; i < Cfg::kStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -732,10 +673,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
             for (int k = 0; k < kGemmBK / 16; ++k) {
               const uint64_t da = umma_desc_sw128(a_base + k * 32, 1024, 0);
               const uint64_t db = umma_desc_sw128(b_base + k * 32, 1024, 0);
-              if (p.transposed)  // D^T = W * A^T: weight rows become TMEM lanes
-                umma_f16_ss_2cta(d_tmem, db, da, idesc, (kit | k) != 0);
-              else
-                umma_f16_ss_2cta(d_tmem, da, db, idesc, (kit | k) != 0);
+              umma_f16_ss_2cta(d_tmem, da, db, idesc, (kit | k) != 0);
             }
           }
           umma_commit_2cta(&empty_bar[stage], 0x3);  // both CTAs' smem slots
@@ -761,22 +699,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
       const int m_tile = (tile % m_pairs) * 2 + static_cast<int>(rank);
       const int n_tile = tile / m_pairs;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * kColsPerWarp;
-      if (BN == 256 && p.transposed) {
-        // lanes = this CTA's 128 weight rows (output columns); TMEM column half h = the 128 output rows
-        // staged by CTA h of the pair
-        gemm_epilogue_tile_t(p, t_row, n_tile * BN + static_cast<int>(rank) * 128 + quarter * 32 + lane,
-                             (tile % m_pairs) * 2 + half, [&]() { mbar_wait(&tmem_full[acc], acc_phase, 24); });
-      } else {
-        gemm_epilogue_tile(p, t_row, n_tile * BN + half * kColsPerWarp, kColsPerWarp, m_tile, r,
-                           [&]() { mbar_wait(&tmem_full[acc], acc_phase, 24); }, stage_buf, &store_groups);
-      }
+      gemm_epilogue_tile<EPI>(p, t_row, n_tile * BN + half * kColsPerWarp, kColsPerWarp, m_tile, r,
+                              [&]() { mbar_wait(&tmem_full[acc], acc_phase, 24); }, stage_buf, store_groups);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);  // leader's barrier: 2 CTAs x 8 warps
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    if (lane == 0) tma_store_wait_all();  // outstanding bulk stores read this CTA's smem
+    if (EPI != EPI_DIRECT && lane == 0) tma_store_wait_all();  // outstanding bulk ops read this CTA's smem
   }
 
   tc_fence_before();

@@ -68,8 +68,16 @@ static void init_once() {
   g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
   cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256>::kSmemBytes);
   cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::kSmemBytes);
-  cudaFuncSetAttribute(gemm_tc2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg<256>::kSmemBytes);
-  cudaFuncSetAttribute(gemm_tc2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg<128>::kSmemBytes);
+#define LSEG_SET_SMEM_TC2(BN_, EPI_)                                                             \
+  cudaFuncSetAttribute(gemm_tc2_kernel<BN_, EPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                       Gemm2Cfg<BN_, EPI_>::kSmemBytes)
+  LSEG_SET_SMEM_TC2(256, EPI_DIRECT);
+  LSEG_SET_SMEM_TC2(256, EPI_TMA_F16);
+  LSEG_SET_SMEM_TC2(256, EPI_TMA_ADD);
+  LSEG_SET_SMEM_TC2(128, EPI_DIRECT);
+  LSEG_SET_SMEM_TC2(128, EPI_TMA_F16);
+  LSEG_SET_SMEM_TC2(128, EPI_TMA_ADD);
+#undef LSEG_SET_SMEM_TC2
   {  // LSEG_GEMM_1CTA=1 selects the single-CTA GEMM (A/B comparisons, debugging)
     const char* env = getenv("LSEG_GEMM_1CTA");
     g_gemm_two_cta = (env && env[0] == '1') ? 0 : 1;
@@ -85,8 +93,14 @@ static int ensure_init() {
   return g_init_status;
 }
 
+static int make_tmap(CUtensorMap* out, CUtensorMapDataType dtype, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box);
 int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box) {
+  return make_tmap(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, base, rank, dims, strides_bytes, box);
+}
+static int make_tmap(CUtensorMap* out, CUtensorMapDataType dtype, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box) {
   cuuint64_t gdim[5];
   cuuint64_t gstr[5];
   cuuint32_t bdim[5];
@@ -101,7 +115,7 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
     set_error("tensor map base %p is not 16-byte aligned", base);
     return -1;
   }
-  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
+  CUresult r = g_encode(out, dtype, rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -130,6 +144,7 @@ struct GemmPlan {
   int bn;
   int grid;
   int two_cta;  // 1: CTA-pair kernel (tcgen05 cta_group::2), 0: single-CTA kernel
+  int epi;      // GemmEpiMode (CTA-pair kernel)
 };
 
 static int gemm_plan(const GemmDesc& d, GemmPlan* plan) {
@@ -185,12 +200,13 @@ static int gemm_plan(const GemmDesc& d, GemmPlan* plan) {
   }
   // TMA-store epilogue: plain fp16 row-major outputs of the CTA-pair kernel (QKV, fc1, readout, 1x1 / 3x3
   // convs feeding the next conv, head1, text in_proj / c_fc)
-  p.tma_store = 0;
+  plan->epi = EPI_DIRECT;
   {
     const GemmEpi& e = p.e;
     static const bool disabled = getenv("LSEG_GEMM_NO_TMA_STORE") != nullptr;
-    if (plan->two_cta && !disabled && e.store == STORE_ROWMAJOR && e.out_f16 && !e.out_f32 && !e.out_f16_relu &&
-        !e.res_f16 && !e.res_f32 && !e.res2_f32 && (e.ldc % 8 == 0) && (d.N % 8 == 0) && d.N >= 64) {
+    const bool rowmajor = plan->two_cta && !disabled && e.store == STORE_ROWMAJOR && (d.N % 8 == 0) && d.N >= 64;
+    if (rowmajor && e.out_f16 && !e.out_f32 && !e.out_f16_relu && !e.res_f16 && !e.res_f32 && !e.res2_f32 &&
+        (e.ldc % 8 == 0)) {
       if (d.conv) {
         const uint64_t dims[4] = {(uint64_t)d.N, (uint64_t)d.W, (uint64_t)d.H, (uint64_t)d.B};
         const uint64_t str[3] = {(uint64_t)e.ldc * 2, (uint64_t)e.ldc * d.W * 2, (uint64_t)e.ldc * d.W * d.H * 2};
@@ -202,15 +218,16 @@ static int gemm_plan(const GemmDesc& d, GemmPlan* plan) {
         const uint32_t box[2] = {64, 32};
         if (make_tmap_f16(&p.tma_c, e.out_f16, 2, dims, str, box)) return -1;
       }
-      p.tma_store = 1;
+      plan->epi = EPI_TMA_F16;
+    } else if (rowmajor && !d.conv && e.out_f32 && e.res_f32 == e.out_f32 && !e.res2_f32 && !e.res_f16 &&
+               !e.out_f16 && !e.out_f16_relu && !e.out_row_sumsq && (e.ldc % 4 == 0)) {
+      // in-place fp32 residual stream: x += A W^T + b through a bulk tensor reduce-add (x is never read)
+      const uint64_t dims[2] = {(uint64_t)d.N, (uint64_t)d.M};
+      const uint64_t str[1] = {(uint64_t)e.ldc * 4};
+      const uint32_t box[2] = {32, 32};
+      if (make_tmap(&p.tma_c, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, e.out_f32, 2, dims, str, box)) return -1;
+      plan->epi = EPI_TMA_ADD;
     }
-    // every other row-major epilogue (fp32 residual stream, fp32 / multiple outputs, fp16 residual) runs
-    // transposed so that its global accesses coalesce
-    static const bool no_transpose = getenv("LSEG_GEMM_NO_TRANSPOSE") != nullptr;
-    p.transposed = (plan->two_cta && bn == 256 && !no_transpose && !p.tma_store && e.store == STORE_ROWMAJOR &&
-                    e.bias_group_rows == 0 && !e.out_row_sumsq)
-                       ? 1
-                       : 0;
   }
   if (plan->two_cta) {
     const int pair_tiles = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
@@ -234,10 +251,18 @@ static int gemm_plan(const GemmDesc& d, GemmPlan* plan) {
 static int gemm_run(const GemmPlan& plan, cudaStream_t stream) {
   if (plan.grid <= 0) return 0;
   if (plan.two_cta) {
-    if (plan.bn == 256)
-      gemm_tc2_kernel<256><<<plan.grid, kGemmThreads, Gemm2Cfg<256>::kSmemBytes, stream>>>(plan.p);
-    else
-      gemm_tc2_kernel<128><<<plan.grid, kGemmThreads, Gemm2Cfg<128>::kSmemBytes, stream>>>(plan.p);
+#define LSEG_LAUNCH_TC2(BN_, EPI_) \
+  gemm_tc2_kernel<BN_, EPI_><<<plan.grid, kGemmThreads, Gemm2Cfg<BN_, EPI_>::kSmemBytes, stream>>>(plan.p)
+    if (plan.bn == 256) {
+      if (plan.epi == EPI_TMA_F16) LSEG_LAUNCH_TC2(256, EPI_TMA_F16);
+      else if (plan.epi == EPI_TMA_ADD) LSEG_LAUNCH_TC2(256, EPI_TMA_ADD);
+      else LSEG_LAUNCH_TC2(256, EPI_DIRECT);
+    } else {
+      if (plan.epi == EPI_TMA_F16) LSEG_LAUNCH_TC2(128, EPI_TMA_F16);
+      else if (plan.epi == EPI_TMA_ADD) LSEG_LAUNCH_TC2(128, EPI_TMA_ADD);
+      else LSEG_LAUNCH_TC2(128, EPI_DIRECT);
+    }
+#undef LSEG_LAUNCH_TC2
     LSEG_CHECK_CUDA(cudaGetLastError());
     return 0;
   }

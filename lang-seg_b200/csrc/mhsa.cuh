@@ -45,7 +45,7 @@ struct MhsaParams {
 template <bool MASK>
 __device__ __forceinline__ float mhsa_exp_chunk(const uint32_t (&s)[32], float c, float m, int kv_base, int n_tokens,
                                                 int kv_limit, __half2 (&ph)[16]) {
-  float sum = 0.f;
+  float sum0 = 0.f, sum1 = 0.f;  // two chains: the row sum must not serialise behind the MUFU results
 #pragma unroll
   for (int i = 0; i < 32; i += 2) {
     float p0 = ex2_approx(fmaf(__uint_as_float(s[i]), c, -m));
@@ -56,9 +56,10 @@ __device__ __forceinline__ float mhsa_exp_chunk(const uint32_t (&s)[32], float c
       if (!(kv + 1 < n_tokens && kv + 1 <= kv_limit)) p1 = 0.f;
     }
     ph[i >> 1] = __floats2half2_rn(p0, p1);
-    sum += p0 + p1;  // fp32 row sum (the fp16 rounding of P is zero-mean noise at 2^-12)
+    sum0 += p0;  // fp32 row sum (the fp16 rounding of P is zero-mean noise at 2^-12)
+    sum1 += p1;
   }
-  return sum;
+  return sum0 + sum1;
 }
 
 __global__ void __launch_bounds__(kMhsaThreads, 2) mhsa_kernel(const __grid_constant__ MhsaParams p) {
@@ -105,8 +106,8 @@ __global__ void __launch_bounds__(kMhsaThreads, 2) mhsa_kernel(const __grid_cons
       mbar_init(&v_empty[i], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(s_free, 128);
-    mbar_init(p_full, 128);
+    mbar_init(s_free, 4);  // one elected arrival per softmax warp (after __syncwarp)
+    mbar_init(p_full, 4);
     mbar_init(o_done, 1);
     mbar_fence_init();
   }
@@ -199,7 +200,8 @@ __global__ void __launch_bounds__(kMhsaThreads, 2) mhsa_kernel(const __grid_cons
       tmem_ld32(tS + lane_off + 96, s3);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(s_free);  // the MMA warp may overwrite S with the next tile's scores
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free);  // the MMA warp may overwrite S with the next tile's scores
       // row max (raw scores; masked keys excluded)
       float mx = -INFINITY;
       if (need_mask) {
@@ -212,11 +214,15 @@ __global__ void __launch_bounds__(kMhsaThreads, 2) mhsa_kernel(const __grid_cons
           mx = fmaxf(mx, (kv + 96 < p.n_tokens && kv + 96 <= kv_limit) ? __uint_as_float(s3[i]) : -INFINITY);
         }
       } else {
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;  // 4 independent chains
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          mx = fmaxf(mx, fmaxf(__uint_as_float(s0[i]), __uint_as_float(s1[i])));
-          mx = fmaxf(mx, fmaxf(__uint_as_float(s2[i]), __uint_as_float(s3[i])));
+          m0 = fmaxf(m0, __uint_as_float(s0[i]));
+          m1 = fmaxf(m1, __uint_as_float(s1[i]));
+          m2 = fmaxf(m2, __uint_as_float(s2[i]));
+          m3 = fmaxf(m3, __uint_as_float(s3[i]));
         }
+        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
       }
       mx *= c;
       const bool move = mx > m_ref + kMhsaTau;  // also true on the first tile (m_ref = -inf)
@@ -278,9 +284,10 @@ __global__ void __launch_bounds__(kMhsaThreads, 2) mhsa_kernel(const __grid_cons
       LSEG_MHSA_STORE(ph2, 2)
       LSEG_MHSA_STORE(ph3, 3)
 #undef LSEG_MHSA_STORE
-      fence_proxy_async_smem();
+      fence_proxy_async_smem();  // every writer makes its P stores visible to the async (UMMA) proxy ...
       tc_fence_before();
-      mbar_arrive(p_full);
+      __syncwarp();              // ... before the warp's single elected arrival
+      if (lane == 0) mbar_arrive(p_full);
     }
     // epilogue: O / l
     mbar_wait(o_done, (nkv - 1) & 1, 25);

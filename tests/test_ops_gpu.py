@@ -77,6 +77,10 @@ def test_gemm_gelu_residual_relu(ops):
     ops.gemm(a, wp, N, bias=bias, scale=scale, res_f32=x, res2_f32=res2, out_f32=x, out_f16_relu=relu16)
     _close(x, acc, 2e-4, "scale/bias/res in-place")
     _close(relu16, acc.clamp_min(0), 1e-3, "relu copy")
+    # in-place fp32 residual stream x += A W^T + b (bulk tensor reduce-add epilogue), M not a tile multiple
+    x2 = res.clone()
+    ops.gemm(a, wp, N, bias=bias, res_f32=x2, out_f32=x2)
+    _close(x2, a.float() @ w.float().t() + bias + res, 2e-4, "in-place residual (reduce-add)")
     # grouped (per-image) bias rows
     gb = _rand((2, N), 10, 1.0, torch.float32)
     out32 = torch.zeros((M, N), dtype=torch.float32, device="cuda")
