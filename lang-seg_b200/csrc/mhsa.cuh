@@ -6,29 +6,32 @@
 // modules/models/lseg_vit.py:26-39) and CLIP's causal nn.MultiheadAttention (Appendix A.2) without
 // ever materialising the [B, heads, N, N] score tensor.
 //
-// One CTA = one 128-row query tile of one (image, head); 2 CTAs co-reside per SM.
+// One CTA = one 128-row query tile of one (image, head); 2 CTAs co-reside per SM. 10 warps:
 //   warp 0      : TMA producer (Q once; K and V tiles of 128 keys through separate 2-deep rings — a K
 //                 slot is released as soon as its S MMA retires, a V slot after its PV MMA) + TMEM alloc
 //   warp 1      : MMA issuer:  S_j = Q K_j^T (128x128x64, both K-major)      -> TMEM cols [0,128)
 //                              O  += P_j V_j (128x64x128, A = P K-major smem, B = V MN-major smem)
 //                                                                          -> TMEM cols [128,192)
-//                 S_{j+1} is issued as soon as the softmax warps have pulled S_j into registers, so the
-//                 tensor pipe runs ahead of the exponentials.
-//   warps 2..5  : softmax, thread <-> query row (tcgen05.ld 32x32b): the whole 128-wide S row is held in
-//                 registers (single pass), P is written to smem as fp16 in the 128B-swizzled K-major
-//                 layout, and O stays in TMEM across key tiles. The running max is LAZY: the exponent
-//                 offset m_ref only moves when a tile's row max exceeds it by more than 2^kTau, in which
-//                 case l and the TMEM-resident O row are rescaled (rare after the first tiles).
+//                 S_{j+1} is issued as soon as the softmax warps have read S_j for the last time.
+//   warps 2..9  : softmax, thread <-> query row (tcgen05.ld 32x32b); the two warps that share a TMEM lane
+//                 quarter split the 128 keys of a tile in halves (64 score registers each) and exchange
+//                 their partial row maxima through smem + a 64-thread named barrier. The profile of the
+//                 4-warp version was latency-bound (IPC 0.4, MUFU 36 % busy): 16 softmax warps per SM instead
+//                 of 8 hide the dependent-issue and TMEM/barrier latencies. P is written to smem as fp16 in the
+//                 128B-swizzled K-major layout, O stays in TMEM across key tiles. The running max is LAZY:
+//                 the exponent offset m_ref only moves when a tile's row max exceeds it by more than
+//                 2^kMhsaTau, in which case l and the TMEM-resident O row are rescaled (rare after tile 0).
 #pragma once
 #include "common.cuh"
 
 namespace lseg {
 
-constexpr int kMhsaThreads = 192;
+constexpr int kMhsaThreads = 320;
 constexpr int kMhsaTile = 128;
 constexpr int kMhsaDh = 64;
 constexpr int kMhsaTileBytes = kMhsaTile * kMhsaDh * 2;  // 16 KB
-constexpr int kMhsaSmemBytes = kMhsaTileBytes * (1 + 2 + 2 + 2) + 256;
+// Q | K x2 | V x2 | P (2 sub-tiles) | 128 B mbarriers | 512 B partial-max exchange | pad
+constexpr int kMhsaSmemBytes = kMhsaTileBytes * (1 + 2 + 2 + 2) + 768;
 constexpr float kMhsaTau = 8.0f;  // log2 headroom before the exponent offset is moved
 
 struct MhsaParams {
@@ -40,6 +43,10 @@ struct MhsaParams {
   int causal;
   float scale_log2e;    // dh^-0.5 * log2(e)
 };
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 
 // exp2(s*c - m) for one 32-column chunk -> fp16 pairs + fp32 partial row sum. MASK: apply key bounds.
 template <bool MASK>
@@ -62,6 +69,23 @@ __device__ __forceinline__ float mhsa_exp_chunk(const uint32_t (&s)[32], float c
   return sum0 + sum1;
 }
 
+template <bool MASK>
+__device__ __forceinline__ float mhsa_max_chunk(const uint32_t (&s)[32], int kv_base, int n_tokens, int kv_limit) {
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    float a = __uint_as_float(s[i]), b = __uint_as_float(s[i + 1]);
+    if (MASK) {
+      const int kv = kv_base + i;
+      if (!(kv < n_tokens && kv <= kv_limit)) a = -INFINITY;
+      if (!(kv + 1 < n_tokens && kv + 1 <= kv_limit)) b = -INFINITY;
+    }
+    m0 = fmaxf(m0, a);
+    m1 = fmaxf(m1, b);
+  }
+  return fmaxf(m0, m1);
+}
+
 __global__ void __launch_bounds__(kMhsaThreads, 2) mhsa_kernel(const __grid_constant__ MhsaParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
@@ -79,6 +103,7 @@ __global__ void __launch_bounds__(kMhsaThreads, 2) mhsa_kernel(const __grid_cons
   uint64_t* p_full = bars + 11;
   uint64_t* o_done = bars + 12;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  __half* xch = reinterpret_cast<__half*>(smem + 7 * kMhsaTileBytes + 128);  // [2 halves][128 rows]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -106,8 +131,8 @@ __global__ void __launch_bounds__(kMhsaThreads, 2) mhsa_kernel(const __grid_cons
       mbar_init(&v_empty[i], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(s_free, 4);  // one elected arrival per softmax warp (after __syncwarp)
-    mbar_init(p_full, 4);
+    mbar_init(s_free, 8);  // one elected arrival per softmax warp (after __syncwarp)
+    mbar_init(p_full, 8);
     mbar_init(o_done, 1);
     mbar_fence_init();
   }
@@ -119,112 +144,104 @@ __global__ void __launch_bounds__(kMhsaThreads, 2) mhsa_kernel(const __grid_cons
   const uint32_t tS = tmem_base;
   const uint32_t tO = tmem_base + 128;
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      mbar_expect_tx(q_full, kMhsaTileBytes);
-      tma_load_3d(sQ, &p.tma_qkv, q_full, h * kMhsaDh, q0, b);
-      for (int j = 0; j < nkv; ++j) {
-        const int s = j & 1;
-        const uint32_t par = ((j >> 1) & 1) ^ 1;
-        mbar_wait(&k_empty[s], par, 11);
-        mbar_expect_tx(&k_full[s], kMhsaTileBytes);
-        tma_load_3d(sK + s * kMhsaTileBytes, &p.tma_qkv, &k_full[s], p.D + h * kMhsaDh, j * kMhsaTile, b);
-        mbar_wait(&v_empty[s], par, 12);
-        mbar_expect_tx(&v_full[s], kMhsaTileBytes);
-        tma_load_3d(sV + s * kMhsaTileBytes, &p.tma_qkv, &v_full[s], 2 * p.D + h * kMhsaDh, j * kMhsaTile, b);
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_f16(128, 128, 0, 0);  // Q K^T : A, B K-major
-      constexpr uint32_t idesc_o = umma_idesc_f16(128, 64, 0, 1);   // P V   : A K-major, B MN-major
-      const uint32_t q_base = smem_u32(sQ);
-      const uint32_t p_base = smem_u32(sP);
-      auto issue_s = [&](int j) {
-        const uint32_t k_base = smem_u32(sK + (j & 1) * kMhsaTileBytes);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16_ss(tS, umma_desc_sw128(q_base + k * 32, 1024, 0), umma_desc_sw128(k_base + k * 32, 1024, 0),
-                      idesc_s, k != 0);
-        umma_commit(s_full);
-        umma_commit(&k_empty[j & 1]);
-      };
-      mbar_wait(q_full, 0, 13);
-      mbar_wait(&k_full[0], 0, 14);
-      tc_fence_after();
-      issue_s(0);
-      for (int j = 0; j < nkv; ++j) {
-        if (j + 1 < nkv) {
-          mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1, 15);
-          mbar_wait(s_free, j & 1, 16);  // S_j now lives in the softmax warps' registers
-          tc_fence_after();
-          issue_s(j + 1);
+  if (warp < 2) {
+    if (warp == 0) {
+      // ===================== TMA producer =====================
+      if (lane == 0) {
+        mbar_expect_tx(q_full, kMhsaTileBytes);
+        tma_load_3d(sQ, &p.tma_qkv, q_full, h * kMhsaDh, q0, b);
+        for (int j = 0; j < nkv; ++j) {
+          const int s = j & 1;
+          const uint32_t par = ((j >> 1) & 1) ^ 1;
+          mbar_wait(&k_empty[s], par, 11);
+          mbar_expect_tx(&k_full[s], kMhsaTileBytes);
+          tma_load_3d(sK + s * kMhsaTileBytes, &p.tma_qkv, &k_full[s], p.D + h * kMhsaDh, j * kMhsaTile, b);
+          mbar_wait(&v_empty[s], par, 12);
+          mbar_expect_tx(&v_full[s], kMhsaTileBytes);
+          tma_load_3d(sV + s * kMhsaTileBytes, &p.tma_qkv, &v_full[s], 2 * p.D + h * kMhsaDh, j * kMhsaTile, b);
         }
-        mbar_wait(&v_full[j & 1], (j >> 1) & 1, 17);
-        mbar_wait(p_full, j & 1, 18);
-        tc_fence_after();
-        const uint32_t v_base = smem_u32(sV + (j & 1) * kMhsaTileBytes);
+      }
+    } else if (warp == 1) {
+      // ===================== MMA issuer =====================
+      if (lane == 0) {
+        constexpr uint32_t idesc_s = umma_idesc_f16(128, 128, 0, 0);  // Q K^T : A, B K-major
+        constexpr uint32_t idesc_o = umma_idesc_f16(128, 64, 0, 1);   // P V   : A K-major, B MN-major
+        const uint32_t q_base = smem_u32(sQ);
+        const uint32_t p_base = smem_u32(sP);
+        auto issue_s = [&](int j) {
+          const uint32_t k_base = smem_u32(sK + (j & 1) * kMhsaTileBytes);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_f16_ss(tO, umma_desc_sw128(p_base + (k >> 2) * kMhsaTileBytes + (k & 3) * 32, 1024, 0),
-                      umma_desc_sw128(v_base + k * 2048, 1024, 8192), idesc_o, (j | k) != 0);
-        umma_commit(o_done);
-        umma_commit(&v_empty[j & 1]);
+          for (int k = 0; k < 4; ++k)
+            umma_f16_ss(tS, umma_desc_sw128(q_base + k * 32, 1024, 0), umma_desc_sw128(k_base + k * 32, 1024, 0),
+                        idesc_s, k != 0);
+          umma_commit(s_full);
+          umma_commit(&k_empty[j & 1]);
+        };
+        mbar_wait(q_full, 0, 13);
+        mbar_wait(&k_full[0], 0, 14);
+        tc_fence_after();
+        issue_s(0);
+        for (int j = 0; j < nkv; ++j) {
+          if (j + 1 < nkv) {
+            mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1, 15);
+            mbar_wait(s_free, j & 1, 16);  // S_j now lives in the softmax warps' registers
+            tc_fence_after();
+            issue_s(j + 1);
+          }
+          mbar_wait(&v_full[j & 1], (j >> 1) & 1, 17);
+          mbar_wait(p_full, j & 1, 18);
+          tc_fence_after();
+          const uint32_t v_base = smem_u32(sV + (j & 1) * kMhsaTileBytes);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_f16_ss(tO, umma_desc_sw128(p_base + (k >> 2) * kMhsaTileBytes + (k & 3) * 32, 1024, 0),
+                        umma_desc_sw128(v_base + k * 2048, 1024, 8192), idesc_o, (j | k) != 0);
+          umma_commit(o_done);
+          umma_commit(&v_empty[j & 1]);
+        }
       }
     }
   } else {
-    // ===================== softmax warps =====================
-    const int quarter = warp & 3;
+    // ===================== softmax warps 2..9 =====================
+    const int quarter = warp & 3;        // TMEM lane quarter (warps w and w+4 share it)
+    const int hf = (warp - 2) >> 2;      // which 64 keys of the tile / which 32 output columns at the end
     const int r = quarter * 32 + lane;
     const int q = q0 + r;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     const float c = p.scale_log2e;
     const int kv_limit = p.causal ? q : 0x7fffffff;
-    float m_ref = -INFINITY;  // exponent offset currently baked into l and O
-    float l_run = 0.f;
-    uint8_t* p_row = sP + r * 128;
+    float m_ref = -INFINITY;  // exponent offset currently baked into l and O (identical in both warps of a row)
+    float l_run = 0.f;        // this warp's share of the row sum
+    uint8_t* p_row = sP + hf * kMhsaTileBytes + r * 128;
     const int sw = r & 7;
 
     for (int j = 0; j < nkv; ++j) {
-      const int kv0 = j * kMhsaTile;
-      const bool need_mask = (kv0 + kMhsaTile > p.n_tokens) || (p.causal && (kv0 + kMhsaTile - 1 > q0));
+      const int kv0 = j * kMhsaTile + hf * 64;
+      const bool need_mask = (j * kMhsaTile + kMhsaTile > p.n_tokens) || (p.causal && (j * kMhsaTile + kMhsaTile - 1 > q0));
       mbar_wait(s_full, j & 1, 19);
       tc_fence_after();
-      uint32_t s0[32], s1[32], s2[32], s3[32];
-      __syncwarp();
-      tmem_ld32(tS + lane_off + 0, s0);
-      tmem_ld32(tS + lane_off + 32, s1);
-      tmem_ld32(tS + lane_off + 64, s2);
-      tmem_ld32(tS + lane_off + 96, s3);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(s_free);  // the MMA warp may overwrite S with the next tile's scores
-      // row max (raw scores; masked keys excluded)
-      float mx = -INFINITY;
-      if (need_mask) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int kv = kv0 + i;
-          mx = fmaxf(mx, (kv < p.n_tokens && kv <= kv_limit) ? __uint_as_float(s0[i]) : -INFINITY);
-          mx = fmaxf(mx, (kv + 32 < p.n_tokens && kv + 32 <= kv_limit) ? __uint_as_float(s1[i]) : -INFINITY);
-          mx = fmaxf(mx, (kv + 64 < p.n_tokens && kv + 64 <= kv_limit) ? __uint_as_float(s2[i]) : -INFINITY);
-          mx = fmaxf(mx, (kv + 96 < p.n_tokens && kv + 96 <= kv_limit) ? __uint_as_float(s3[i]) : -INFINITY);
-        }
-      } else {
-        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;  // 4 independent chains
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          m0 = fmaxf(m0, __uint_as_float(s0[i]));
-          m1 = fmaxf(m1, __uint_as_float(s1[i]));
-          m2 = fmaxf(m2, __uint_as_float(s2[i]));
-          m3 = fmaxf(m3, __uint_as_float(s3[i]));
-        }
-        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      // pass 1: row max over this warp's 64 keys (the scores are re-read from TMEM in pass 2: holding 64 of
+      // them across the exchange does not fit the 2-CTA/SM register budget), then exchange with the sibling
+      // warp (same rows, other 64 keys)
+      float pm;
+      {
+        uint32_t s0[32], s1[32];
+        __syncwarp();
+        tmem_ld32(tS + lane_off + hf * 64, s0);
+        tmem_ld32(tS + lane_off + hf * 64 + 32, s1);
+        tmem_ld_wait();
+        pm = need_mask ? fmaxf(mhsa_max_chunk<true>(s0, kv0, p.n_tokens, kv_limit),
+                               mhsa_max_chunk<true>(s1, kv0 + 32, p.n_tokens, kv_limit))
+                       : fmaxf(mhsa_max_chunk<false>(s0, kv0, p.n_tokens, kv_limit),
+                               mhsa_max_chunk<false>(s1, kv0 + 32, p.n_tokens, kv_limit));
       }
-      mx *= c;
+      // both warps must use the SAME offset: exchange fp16-rounded values and round the own one too (the
+      // offset only has to be shared and within 2^tau of the true max, not exact)
+      const __half pm_h = __float2half_rn(pm * c);
+      xch[hf * 128 + r] = pm_h;
+      named_bar_sync(1 + quarter, 64);
+      const float mx = fmaxf(__half2float(pm_h), __half2float(xch[(hf ^ 1) * 128 + r]));
+      named_bar_sync(1 + quarter, 64);  // the slot may be rewritten only after the sibling has read it
       const bool move = mx > m_ref + kMhsaTau;  // also true on the first tile (m_ref = -inf)
       const bool any_move = __any_sync(0xffffffffu, move);
       float factor = 1.f;
@@ -235,26 +252,10 @@ __global__ void __launch_bounds__(kMhsaThreads, 2) mhsa_kernel(const __grid_cons
         m_ref = m_new;
       }
       const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
-      // p = exp2(s*c - m_ref) into registers first: PV_{j-1} (which still owns the P buffer and O) runs
-      // on the tensor pipe underneath the exponentials
-      float l_tile = 0.f;
-      __half2 ph0[16], ph1[16], ph2[16], ph3[16];
-      if (need_mask) {
-        l_tile += mhsa_exp_chunk<true>(s0, c, m_use, kv0 + 0, p.n_tokens, kv_limit, ph0);
-        l_tile += mhsa_exp_chunk<true>(s1, c, m_use, kv0 + 32, p.n_tokens, kv_limit, ph1);
-        l_tile += mhsa_exp_chunk<true>(s2, c, m_use, kv0 + 64, p.n_tokens, kv_limit, ph2);
-        l_tile += mhsa_exp_chunk<true>(s3, c, m_use, kv0 + 96, p.n_tokens, kv_limit, ph3);
-      } else {
-        l_tile += mhsa_exp_chunk<false>(s0, c, m_use, kv0 + 0, p.n_tokens, kv_limit, ph0);
-        l_tile += mhsa_exp_chunk<false>(s1, c, m_use, kv0 + 32, p.n_tokens, kv_limit, ph1);
-        l_tile += mhsa_exp_chunk<false>(s2, c, m_use, kv0 + 64, p.n_tokens, kv_limit, ph2);
-        l_tile += mhsa_exp_chunk<false>(s3, c, m_use, kv0 + 96, p.n_tokens, kv_limit, ph3);
-      }
-      l_run += l_tile;
       // P buffer free and O quiescent once PV_{j-1} has retired
       if (j > 0) {
         mbar_wait(o_done, (j - 1) & 1, 20);
-        if (any_move) {  // rescale the TMEM-resident output row (warp-collective, factor = 1 for unmoved rows)
+        if (any_move && hf == 0) {  // rescale the TMEM-resident output row (warp-collective; factor = 1 if unmoved)
           tc_fence_after();
 #pragma unroll 1
           for (int cc = 0; cc < 4; ++cc) {
@@ -269,46 +270,61 @@ __global__ void __launch_bounds__(kMhsaThreads, 2) mhsa_kernel(const __grid_cons
           tmem_st_wait();
         }
       }
-      // fp16 P -> swizzled smem: columns [cc*32, cc*32+32) land in sub-tile (cc>>1), 16-byte chunks
-      // ((cc&1)*4 + t) ^ (r&7)
-#define LSEG_MHSA_STORE(PH, CC)                                                               \
-  {                                                                                           \
-    uint8_t* sub = p_row + ((CC) >> 1) * kMhsaTileBytes;                                      \
-    _Pragma("unroll") for (int t = 0; t < 4; ++t) {                                           \
-      const int chunk = ((((CC) & 1) * 4 + t) ^ sw);                                          \
-      *reinterpret_cast<uint4*>(sub + chunk * 16) = *reinterpret_cast<uint4*>(&PH[4 * t]);    \
-    }                                                                                         \
-  }
-      LSEG_MHSA_STORE(ph0, 0)
-      LSEG_MHSA_STORE(ph1, 1)
-      LSEG_MHSA_STORE(ph2, 2)
-      LSEG_MHSA_STORE(ph3, 3)
-#undef LSEG_MHSA_STORE
+      // p = exp2(s*c - m_ref) -> fp16 -> swizzled smem: this warp owns sub-tile hf (64 keys = 8 16-byte slots per row)
+      float l_tile = 0.f;
+      {
+        uint32_t s0[32];
+        __syncwarp();
+        tmem_ld32(tS + lane_off + hf * 64, s0);
+        tmem_ld_wait();
+        __half2 ph[16];
+        l_tile += need_mask ? mhsa_exp_chunk<true>(s0, c, m_use, kv0, p.n_tokens, kv_limit, ph)
+                            : mhsa_exp_chunk<false>(s0, c, m_use, kv0, p.n_tokens, kv_limit, ph);
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          *reinterpret_cast<uint4*>(p_row + ((t ^ sw) * 16)) = *reinterpret_cast<uint4*>(&ph[4 * t]);
+      }
+      {
+        uint32_t s1[32];
+        __syncwarp();
+        tmem_ld32(tS + lane_off + hf * 64 + 32, s1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_free);  // S_j fully consumed: the MMA warp may issue the next tile's scores
+        __half2 ph[16];
+        l_tile += need_mask ? mhsa_exp_chunk<true>(s1, c, m_use, kv0 + 32, p.n_tokens, kv_limit, ph)
+                            : mhsa_exp_chunk<false>(s1, c, m_use, kv0 + 32, p.n_tokens, kv_limit, ph);
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          *reinterpret_cast<uint4*>(p_row + (((4 + t) ^ sw) * 16)) = *reinterpret_cast<uint4*>(&ph[4 * t]);
+      }
+      l_run += l_tile;
       fence_proxy_async_smem();  // every writer makes its P stores visible to the async (UMMA) proxy ...
       tc_fence_before();
       __syncwarp();              // ... before the warp's single elected arrival
       if (lane == 0) mbar_arrive(p_full);
     }
-    // epilogue: O / l
+    // epilogue: O / l. The P buffer is dead once the last PV has retired: reuse it to add up the two l shares.
     mbar_wait(o_done, (nkv - 1) & 1, 25);
     tc_fence_after();
-    const float inv = 1.0f / l_run;
-    __half* op = p.out + (static_cast<long long>(b) * p.n_tokens + q) * p.D + h * kMhsaDh;
+    float* lx = reinterpret_cast<float*>(sP);
+    lx[hf * 128 + r] = l_run;
+    named_bar_sync(1 + quarter, 64);
+    const float inv = 1.0f / (l_run + lx[(hf ^ 1) * 128 + r]);
+    __half* op = p.out + (static_cast<long long>(b) * p.n_tokens + q) * p.D + h * kMhsaDh + hf * 32;
+    uint32_t o[32];
+    __syncwarp();
+    tmem_ld32(tO + lane_off + hf * 32, o);
+    tmem_ld_wait();
+    if (q < p.n_tokens) {
 #pragma unroll
-    for (int cc = 0; cc < 2; ++cc) {
-      uint32_t o[32];
-      __syncwarp();
-      tmem_ld32(tO + lane_off + cc * 32, o);
-      tmem_ld_wait();
-      if (q < p.n_tokens) {
+      for (int t = 0; t < 4; ++t) {
+        __half2 hh[4];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          __half2 hh[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            hh[i] = __floats2half2_rn(__uint_as_float(o[t * 8 + 2 * i]) * inv, __uint_as_float(o[t * 8 + 2 * i + 1]) * inv);
-          reinterpret_cast<uint4*>(op)[cc * 4 + t] = *reinterpret_cast<uint4*>(hh);
-        }
+        for (int i = 0; i < 4; ++i)
+          hh[i] = __floats2half2_rn(__uint_as_float(o[t * 8 + 2 * i]) * inv, __uint_as_float(o[t * 8 + 2 * i + 1]) * inv);
+        reinterpret_cast<uint4*>(op)[t] = *reinterpret_cast<uint4*>(hh);
       }
     }
   }
