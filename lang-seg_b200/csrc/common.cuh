@@ -76,6 +76,35 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
   if (mbar_try_wait(bar, parity)) return;
   mbar_wait_slow(bar, parity, tag);
 }
+// Latency-critical variant: try_wait WITHOUT a suspend-time hint (the hardware re-checks after its short
+// default window instead of parking the thread), for waits that sit on a kernel's critical path.
+__device__ __forceinline__ bool mbar_try_wait_spin(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity, int tag) {
+  const long long t0 = clock64();
+  uint32_t polls = 0;
+  while (!mbar_try_wait_spin(bar, parity)) {
+    if ((++polls & 0xFFFu) != 0) continue;
+    if (*reinterpret_cast<volatile int*>(&g_watchdog[0]) != 0) return;
+    if (clock64() - t0 > kWatchdogCycles) {
+      if (atomicCAS(&g_watchdog[0], 0, tag) == 0) {
+        g_watchdog[1] = blockIdx.x;
+        g_watchdog[2] = threadIdx.x;
+        g_watchdog[3] = static_cast<int>(parity);
+      }
+      return;
+    }
+  }
+}
 
 // ---- proxies / fences --------------------------------------------------------------------
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05.mma operand reads)

@@ -318,6 +318,7 @@ __global__ void l2norm_f16_kernel(const __half* __restrict__ x, __half* __restri
 // ------------------------------------------------------------------------------------------
 constexpr int kUpRows = 4;      // output rows per warp
 constexpr int kUpMaxW = 512;    // widest source row (smem line)
+template <bool STREAM>  // STREAM: st.global.cs stores (A/B switch LSEG_UPSAMPLE_CS=1; default plain stores)
 __global__ void upsample2x_nchw_kernel(const __half* __restrict__ x, float* __restrict__ y, int H, int W) {
   __shared__ __align__(16) float line[8][kUpMaxW];
   const int Ho = 2 * H, Wo = 2 * W, w4 = Wo / 4;
@@ -328,18 +329,6 @@ __global__ void upsample2x_nchw_kernel(const __half* __restrict__ x, float* __re
   const __half* plane = x + pl * H * W;
   float* oplane = y + pl * Ho * Wo;
   float* v = line[warp];
-  // horizontal taps of this lane's float4 groups xq = lane + 32*i (Wo <= 1024 -> at most 8 groups)
-  int x0[8][4];
-  float lx[8][4];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float fx = sw * ((lane + 32 * i) * 4 + k);
-      x0[i][k] = min(static_cast<int>(fx), W - 1);
-      lx[i][k] = fx - static_cast<int>(fx);
-    }
-  }
   const int oy0 = (blockIdx.x * 8 + warp) * kUpRows;
   for (int rr = 0; rr < kUpRows; ++rr) {
     const int oy = oy0 + rr;
@@ -367,17 +356,24 @@ __global__ void upsample2x_nchw_kernel(const __half* __restrict__ x, float* __re
     }
     __syncwarp();
     float* orow = oplane + static_cast<long long>(oy) * Wo;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int xq = lane + 32 * i;
-      if (xq < w4) {
+    // horizontal taps are recomputed per output (4 flops) instead of cached: caching them cost 64
+    // registers per thread and capped the SM at one resident block
+#pragma unroll 2
+    for (int xq = lane; xq < w4; xq += 32) {
+      {
         float o[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const int xa = x0[i][k], xb = min(xa + 1, W - 1);
-          o[k] = (1.f - lx[i][k]) * v[xa] + lx[i][k] * v[xb];
+          const float fx = sw * (xq * 4 + k);
+          const int xi = static_cast<int>(fx);
+          const float lxk = fx - xi;
+          const int xa = min(xi, W - 1), xb = min(xa + 1, W - 1);
+          o[k] = (1.f - lxk) * v[xa] + lxk * v[xb];
         }
-        __stcs(reinterpret_cast<float4*>(orow + xq * 4), make_float4(o[0], o[1], o[2], o[3]));
+        if (STREAM)
+          __stcs(reinterpret_cast<float4*>(orow + xq * 4), make_float4(o[0], o[1], o[2], o[3]));
+        else
+          *reinterpret_cast<float4*>(orow + xq * 4) = make_float4(o[0], o[1], o[2], o[3]);
       }
     }
   }
@@ -388,8 +384,12 @@ static inline int launch_upsample2x_nchw(const __half* x, float* y, long long pl
     return -1;
   }
   const int rows_per_block = 8 * kUpRows;
-  upsample2x_nchw_kernel<<<dim3((2 * H + rows_per_block - 1) / rows_per_block, static_cast<unsigned>(planes)), 256, 0,
-                           s>>>(x, y, H, W);
+  static const bool stream_stores = getenv("LSEG_UPSAMPLE_CS") != nullptr;
+  const dim3 grid((2 * H + rows_per_block - 1) / rows_per_block, static_cast<unsigned>(planes));
+  if (stream_stores)
+    upsample2x_nchw_kernel<true><<<grid, 256, 0, s>>>(x, y, H, W);
+  else
+    upsample2x_nchw_kernel<false><<<grid, 256, 0, s>>>(x, y, H, W);
   LSEG_LAUNCH_CHECK();
 }
 

@@ -84,8 +84,10 @@ static void init_once() {
     const char* pr = getenv("LSEG_GEMM_PROBE");  // measurement only, see GemmParams::probe
     g_gemm_probe = pr ? atoi(pr) : 0;
   }
-  cudaFuncSetAttribute(mhsa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMhsaSmemBytes);
-  cudaFuncSetAttribute(mhsa_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(mhsa_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMhsaSmemBytes);
+  cudaFuncSetAttribute(mhsa_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(mhsa_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMhsaSmemBytes);
+  cudaFuncSetAttribute(mhsa_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   g_init_status = 0;
 }
 static int ensure_init() {
@@ -300,7 +302,11 @@ static int mhsa_plan(const MhsaDesc& d, MhsaPlan* plan) {
   return 0;
 }
 static int mhsa_run(const MhsaPlan& plan, cudaStream_t stream) {
-  mhsa_kernel<<<plan.grid, kMhsaThreads, kMhsaSmemBytes, stream>>>(plan.p);
+  static const bool spin = getenv("LSEG_MHSA_SPIN") != nullptr;
+  if (spin)
+    mhsa_kernel<true><<<plan.grid, kMhsaThreads, kMhsaSmemBytes, stream>>>(plan.p);
+  else
+    mhsa_kernel<false><<<plan.grid, kMhsaThreads, kMhsaSmemBytes, stream>>>(plan.p);
   LSEG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -86,7 +86,16 @@ __device__ __forceinline__ float mhsa_max_chunk(const uint32_t (&s)[32], int kv_
   return fmaxf(m0, m1);
 }
 
+// SPIN: barrier waits re-poll without a suspend hint (lower wake-up latency, more issue slots burnt);
+// A/B switch LSEG_MHSA_SPIN=1.
+template <bool SPIN>
 __global__ void __launch_bounds__(kMhsaThreads, 2) mhsa_kernel(const __grid_constant__ MhsaParams p) {
+  auto wait_bar = [](uint64_t* bar, uint32_t parity, int tag) {
+    if (SPIN)
+      mbar_wait_spin(bar, parity, tag);
+    else
+      mbar_wait(bar, parity, tag);
+  };
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sK = smem + kMhsaTileBytes;      // 2 stages
@@ -153,10 +162,10 @@ __global__ void __launch_bounds__(kMhsaThreads, 2) mhsa_kernel(const __grid_cons
         for (int j = 0; j < nkv; ++j) {
           const int s = j & 1;
           const uint32_t par = ((j >> 1) & 1) ^ 1;
-          mbar_wait(&k_empty[s], par, 11);
+          wait_bar(&k_empty[s], par, 11);
           mbar_expect_tx(&k_full[s], kMhsaTileBytes);
           tma_load_3d(sK + s * kMhsaTileBytes, &p.tma_qkv, &k_full[s], p.D + h * kMhsaDh, j * kMhsaTile, b);
-          mbar_wait(&v_empty[s], par, 12);
+          wait_bar(&v_empty[s], par, 12);
           mbar_expect_tx(&v_full[s], kMhsaTileBytes);
           tma_load_3d(sV + s * kMhsaTileBytes, &p.tma_qkv, &v_full[s], 2 * p.D + h * kMhsaDh, j * kMhsaTile, b);
         }
@@ -177,19 +186,19 @@ __global__ void __launch_bounds__(kMhsaThreads, 2) mhsa_kernel(const __grid_cons
           umma_commit(s_full);
           umma_commit(&k_empty[j & 1]);
         };
-        mbar_wait(q_full, 0, 13);
-        mbar_wait(&k_full[0], 0, 14);
+        wait_bar(q_full, 0, 13);
+        wait_bar(&k_full[0], 0, 14);
         tc_fence_after();
         issue_s(0);
         for (int j = 0; j < nkv; ++j) {
           if (j + 1 < nkv) {
-            mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1, 15);
-            mbar_wait(s_free, j & 1, 16);  // S_j now lives in the softmax warps' registers
+            wait_bar(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1, 15);
+            wait_bar(s_free, j & 1, 16);  // S_j now lives in the softmax warps' registers
             tc_fence_after();
             issue_s(j + 1);
           }
-          mbar_wait(&v_full[j & 1], (j >> 1) & 1, 17);
-          mbar_wait(p_full, j & 1, 18);
+          wait_bar(&v_full[j & 1], (j >> 1) & 1, 17);
+          wait_bar(p_full, j & 1, 18);
           tc_fence_after();
           const uint32_t v_base = smem_u32(sV + (j & 1) * kMhsaTileBytes);
 #pragma unroll
@@ -218,7 +227,7 @@ __global__ void __launch_bounds__(kMhsaThreads, 2) mhsa_kernel(const __grid_cons
     for (int j = 0; j < nkv; ++j) {
       const int kv0 = j * kMhsaTile + hf * 64;
       const bool need_mask = (j * kMhsaTile + kMhsaTile > p.n_tokens) || (p.causal && (j * kMhsaTile + kMhsaTile - 1 > q0));
-      mbar_wait(s_full, j & 1, 19);
+      wait_bar(s_full, j & 1, 19);
       tc_fence_after();
       // pass 1: row max over this warp's 64 keys (the scores are re-read from TMEM in pass 2: holding 64 of
       // them across the exchange does not fit the 2-CTA/SM register budget), then exchange with the sibling
@@ -254,7 +263,7 @@ __global__ void __launch_bounds__(kMhsaThreads, 2) mhsa_kernel(const __grid_cons
       const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
       // P buffer free and O quiescent once PV_{j-1} has retired
       if (j > 0) {
-        mbar_wait(o_done, (j - 1) & 1, 20);
+        wait_bar(o_done, (j - 1) & 1, 20);
         if (any_move && hf == 0) {  // rescale the TMEM-resident output row (warp-collective; factor = 1 if unmoved)
           tc_fence_after();
 #pragma unroll 1
@@ -306,7 +315,7 @@ __global__ void __launch_bounds__(kMhsaThreads, 2) mhsa_kernel(const __grid_cons
       if (lane == 0) mbar_arrive(p_full);
     }
     // epilogue: O / l. The P buffer is dead once the last PV has retired: reuse it to add up the two l shares.
-    mbar_wait(o_done, (nkv - 1) & 1, 25);
+    wait_bar(o_done, (nkv - 1) & 1, 25);
     tc_fence_after();
     float* lx = reinterpret_cast<float*>(sP);
     lx[hf * 128 + r] = l_run;

@@ -36,4 +36,8 @@ x = torch.randn(7208, 1024, device="cuda")
 g = torch.ones(1024, device="cuda")
 out["layernorm_us"] = bench(lambda: ops.layernorm(x, g, g, 1e-6), 50)
 out["layernorm_rw_GBs"] = 7208 * 1024 * 6 / out["layernorm_us"] / 1e3
+qkv = torch.randn(8, 901, 3072, device="cuda").half()
+out["mhsa_us"] = bench(lambda: ops.mhsa(qkv, 8, 901, 16, False), 20)
+out["mhsa_tflops"] = 4.0 * 8 * 16 * 901 * 901 * 64 / out["mhsa_us"] / 1e6
+out["env"] = {k: v for k, v in os.environ.items() if k.startswith("LSEG_")}
 print(json.dumps(out))
