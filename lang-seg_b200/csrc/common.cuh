@@ -330,19 +330,22 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
 // ---- misc math ---------------------------------------------------------------------------
 __device__ __forceinline__ float ex2_approx(float x);
 // Exact-erf GELU, 0.5 x (1 + erf(x / sqrt 2)) (timm Mlp / ProjectReadout use nn.GELU()), with erf from
-// Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below the fp16 rounding of the result): two MUFU
-// (rcp, ex2) + ~12 FMA-pipe ops instead of erff()'s branchy ~30. Written without the 1 + erf
-// cancellation: gelu(x) = x * (x >= 0 ? 1 - h : h),  h = 0.5 * poly(t) * exp(-x^2 / 2).
+// Exact-erf GELU x * Phi(x) with Phi(x) = 1 / (1 + 2^(x * P(x^2))): P is a degree-4 minimax fit (tools/fit_gelu.py:
+// reweighted least squares against scipy erfc on [-7, 7], coefficients carry the -log2(e)); |gelu error| <= 3.7e-6 over
+// all x in fp32 arithmetic, i.e. below the fp16 rounding of the stored activation wherever that activation is
+// not already in fp16's subnormal range. 10 issue slots (2 MUFU) instead of the 20 of the Abramowitz-Stegun
+// 7.1.26 form used before (the fc1 epilogue is issue-bound). P(u) < 0 for all u >= 0, so the sigmoid saturates
+// monotonically outside the fitted range.
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float ax = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
-  float poly = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
-  poly = fmaf(t, poly, 0.5f * 1.421413741f);
-  poly = fmaf(t, poly, 0.5f * -0.284496736f);
-  poly = fmaf(t, poly, 0.5f * 0.254829592f);
-  poly *= t;
-  const float h = poly * ex2_approx(-1.4426950408889634f * ax * ax);
-  return x * (x >= 0.f ? 1.0f - h : h);
+  const float u = x * x;
+  float p = fmaf(u, -3.228989445e-06f, 8.823814435e-05f);
+  p = fmaf(p, u, 3.602744768e-04f);
+  p = fmaf(p, u, -1.052266877e-01f);
+  p = fmaf(p, u, -2.302045391e+00f);
+  const float e = ex2_approx(x * p);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return x * r;
 }
 // CLIP QuickGELU evaluated the way the fp16 reference does it: h = half(x); half(1.702*h);
 // half(sigmoid(.)); half(h * .)  (x * torch.sigmoid(1.702 * x) on a HalfTensor).

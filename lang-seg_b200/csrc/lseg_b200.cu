@@ -14,6 +14,7 @@
 #include "elementwise.cuh"
 #include "gemm_tc.cuh"
 #include "mhsa.cuh"
+#include "mhsa2.cuh"
 
 namespace lseg {
 
@@ -88,6 +89,10 @@ static void init_once() {
   cudaFuncSetAttribute(mhsa_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   cudaFuncSetAttribute(mhsa_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMhsaSmemBytes);
   cudaFuncSetAttribute(mhsa_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(mhsa2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kM2SmemBytes);
+  cudaFuncSetAttribute(mhsa2_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(mhsa2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kM2SmemBytes);
+  cudaFuncSetAttribute(mhsa2_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   g_init_status = 0;
 }
 static int ensure_init() {
@@ -292,6 +297,8 @@ static int mhsa_plan(const MhsaDesc& d, MhsaPlan* plan) {
   const uint64_t str[2] = {(uint64_t)3 * D * 2, (uint64_t)3 * D * d.N * 2};
   const uint32_t box[3] = {kMhsaDh, kMhsaTile, 1};
   if (make_tmap_f16(&p.tma_qkv, d.qkv, 3, dims, str, box)) return -1;
+  const uint32_t box64[3] = {kMhsaDh, kM2KT, 1};
+  if (make_tmap_f16(&p.tma_t64, d.qkv, 3, dims, str, box64)) return -1;
   p.out = d.out;
   p.n_tokens = d.N;
   p.heads = d.heads;
@@ -303,6 +310,15 @@ static int mhsa_plan(const MhsaDesc& d, MhsaPlan* plan) {
 }
 static int mhsa_run(const MhsaPlan& plan, cudaStream_t stream) {
   static const bool spin = getenv("LSEG_MHSA_SPIN") != nullptr;
+  static const bool v3 = getenv("LSEG_MHSA_V3") != nullptr;  // A/B: the single-stream kernel of mhsa.cuh
+  if (!v3) {
+    if (spin)
+      mhsa2_kernel<true><<<plan.grid, kM2Threads, kM2SmemBytes, stream>>>(plan.p);
+    else
+      mhsa2_kernel<false><<<plan.grid, kM2Threads, kM2SmemBytes, stream>>>(plan.p);
+    LSEG_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   if (spin)
     mhsa_kernel<true><<<plan.grid, kMhsaThreads, kMhsaSmemBytes, stream>>>(plan.p);
   else

@@ -36,6 +36,7 @@ constexpr float kMhsaTau = 8.0f;  // log2 headroom before the exponent offset is
 
 struct MhsaParams {
   CUtensorMap tma_qkv;  // 3-D {3*D, N, B} fp16, box {64, 128, 1}
+  CUtensorMap tma_t64;  // same tensor, box {64, 64, 1} (mhsa2.cuh: 64-key tiles, Q as two boxes)
   __half* out;          // [B*N, D]
   int n_tokens;
   int heads;

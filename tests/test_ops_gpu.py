@@ -161,11 +161,15 @@ def test_deferred_row_normalisation(ops):
     _close(out, ref, 2e-3, "deferred normalisation vs reference recipe")
 
 
-@pytest.mark.parametrize("B,N,heads,causal", [(2, 901, 16, False), (3, 77, 8, True), (1, 37, 16, False),
-                                              (1, 300, 2, True)])
-def test_mhsa(ops, B, N, heads, causal):
+@pytest.mark.parametrize("B,N,heads,causal,amp", [
+    (2, 901, 16, False, 1.0), (3, 77, 8, True, 1.0), (1, 37, 16, False, 1.0), (1, 300, 2, True, 1.0),
+    # tile-boundary cases of the 64-key two-stream kernel: one tile only (second stream empty), exact multiples,
+    # 1..2 keys in the tail tile, odd/even tile counts; amp 3 makes the running-max offset move (O rescale path)
+    (1, 64, 1, False, 1.0), (1, 65, 1, True, 1.0), (1, 128, 2, False, 1.0), (1, 130, 2, False, 3.0),
+    (1, 1025, 2, False, 1.0), (2, 300, 2, False, 3.0), (1, 193, 1, True, 3.0)])
+def test_mhsa(ops, B, N, heads, causal, amp):
     D = heads * 64
-    qkv = _rand((B, N, 3 * D), 19, 1.0)
+    qkv = _rand((B, N, 3 * D), 19, amp)
     out = ops.mhsa(qkv, B, N, heads, causal)
     q, k, v = qkv.float().view(B, N, 3, heads, 64).permute(2, 0, 3, 1, 4)
     s = (q @ k.transpose(-1, -2)) * 0.125

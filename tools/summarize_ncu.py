@@ -67,5 +67,37 @@ def full(path):
         print()
 
 
+def traffic(path):
+    """Per-kernel DRAM bytes (read + write) per launch from a --metrics dram__bytes_* capture."""
+    with open(path) as f:
+        lines = [l for l in f if not l.startswith("==")]
+    per = collections.OrderedDict()
+    for r in csv.DictReader(lines):
+        d = per.setdefault(r["ID"], {"name": r["Kernel Name"].split("(")[0][:40], "grid": r["Grid Size"]})
+        d[r["Metric Name"]] = float(r["Metric Value"].replace(",", ""))
+    agg = collections.OrderedDict()
+    for d in per.values():
+        a = agg.setdefault((d["name"], d["grid"]), [0, 0.0, 0.0, 0.0])
+        a[0] += 1
+        a[1] += d.get("gpu__time_duration.sum", 0.0)
+        a[2] += d.get("dram__bytes_read.sum", 0.0)
+        a[3] += d.get("dram__bytes_write.sum", 0.0)
+    print(f"DRAM traffic per launch ({len(per)} launches; dram__bytes_read.sum + dram__bytes_write.sum)\n")
+    print("| kernel | grid | launches | avg us | avg read MB | avg write MB | avg traffic MB |")
+    print("|---|---|---:|---:|---:|---:|---:|")
+    fam = collections.OrderedDict()
+    for (name, grid), a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        n = a[0]
+        print(f"| `{name}` | {grid} | {n} | {a[1] / n / 1e3:.1f} | {a[2] / n / 1e6:.2f} | {a[3] / n / 1e6:.2f} | "
+              f"{(a[2] + a[3]) / n / 1e6:.2f} |")
+        key = "gemm" if "gemm" in name else ("mhsa" if "mhsa" in name else name)
+        f = fam.setdefault(key, [0, 0.0])
+        f[0] += n
+        f[1] += a[2] + a[3]
+    print()
+    for k, f in fam.items():
+        print(f"family `{k}`: {f[0]} launches, mean traffic {f[1] / f[0] / 1e6:.2f} MB per launch")
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2])
