@@ -82,6 +82,10 @@ int lseg_gemm(const lseg_gemm_args* args, void* stream);
 /* Fused MHSA, head_dim 64 (k5; timm Attention restated at lseg_vit.py:26-39; CLIP text MHA).
  * qkv fp16 [B, N, 3*heads*64] (q|k|v thirds) -> out fp16 [B*N, heads*64]. */
 int lseg_mhsa(const void* qkv, void* out, int B, int N, int heads, int causal, void* stream);
+/* Debug: same computation, additionally stamps clock64() at the pipeline hand-off points of 16 sampled CTAs into
+ * trace ([16][10 warps][256] uint64 device memory, zero-initialised by the caller); tools/mhsa_trace.py. */
+int lseg_mhsa_trace(const void* qkv, void* out, int B, int N, int heads, int causal, unsigned long long* trace,
+                    void* stream);
 
 /* LayerNorm over the last dim (k3): x fp32 (in_f16=0) or fp16 (in_f16=1) [M,C] -> y fp16. */
 int lseg_layernorm(const void* x, int in_f16, const float* gamma, const float* beta, void* y, long long M, int C,

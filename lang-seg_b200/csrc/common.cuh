@@ -53,6 +53,30 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking phase test (for a thread that multiplexes several barriers), and a try_wait whose hardware
+// suspend is bounded by `ns` instead of kTryWaitHintNs.
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_try_wait_ns(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
 __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, int tag) {
   // try_wait suspends the thread in hardware for a bounded time, so this loop is not a hot spin.
   // The watchdog bookkeeping (a global-memory flag read, ~1 us) runs only every 256 failed polls so
@@ -75,6 +99,25 @@ __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, int 
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
   if (mbar_try_wait(bar, parity)) return;
   mbar_wait_slow(bar, parity, tag);
+}
+// Fully inlined wait (hinted try_wait): for waits that sit between long-lived register state — the out-of-line
+// mbar_wait_slow is a real call, and live registers around it are spilled per the ABI.
+__device__ __forceinline__ void mbar_wait_inl(uint64_t* bar, uint32_t parity, int tag) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t polls = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++polls & 0xFFu) != 0) continue;
+    if (*reinterpret_cast<volatile int*>(&g_watchdog[0]) != 0) return;
+    if (clock64() - t0 > kWatchdogCycles) {
+      if (atomicCAS(&g_watchdog[0], 0, tag) == 0) {
+        g_watchdog[1] = blockIdx.x;
+        g_watchdog[2] = threadIdx.x;
+        g_watchdog[3] = static_cast<int>(parity);
+      }
+      return;
+    }
+  }
 }
 // Latency-critical variant: try_wait WITHOUT a suspend-time hint (the hardware re-checks after its short
 // default window instead of parking the thread), for waits that sit on a kernel's critical path.
@@ -105,6 +148,21 @@ __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity, i
     }
   }
 }
+
+// One lane of a converged warp (elect.sync): the MMA / TMA warps run converged with warp-uniform values (which the
+// compiler then keeps in uniform registers) and only predicate the tcgen05 / bulk-copy instruction itself on this
+// — a `if (lane == 0) { ... }` region makes every descriptor operand go through an ELECT + R2UR waterfall
+// (~20 dependent instructions, ~130 clk per tcgen05.mma measured).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ int warp_idx_sync() { return __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0); }
 
 // ---- proxies / fences --------------------------------------------------------------------
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05.mma operand reads)
@@ -203,7 +261,18 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
       "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
-// 16-column variants (keep register pressure low on rarely taken paths)
+// 8- and 16-column variants (keep register pressure low on rarely taken paths)
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "

@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
   uint64_t* tmem_empty = bars + 2 * Cfg::kStages + 2; // [2]
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 4);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_idx_sync();  // provably warp-uniform: role branches and their operands stay on the uniform datapath
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -452,7 +452,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // The warp stays converged and only the bulk-copy / tcgen05 instructions are predicated on one elected lane:
+    // inside an `if (lane == 0)` region every descriptor operand went through an ELECT + R2UR waterfall
+    // (~20 dependent instructions, ~130 clk per tcgen05.mma), which made the single-thread issue rate, not the
+    // tensor pipe, the limit of the mainloop.
+    {
+      const bool leader = elect_one_sync();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -471,23 +476,32 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           mbar_wait(&empty_bar[stage], phase ^ 1, 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
-          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          int c0 = kit * kGemmBK, c1 = m_tile * kGemmBM, c2 = 0;
           if (p.conv) {
             const int tap = kit / p.k_chunks;
             const int c = kit - tap * p.k_chunks;
             const int dy = tap / p.kw, dx = tap - dy * p.kw;
-            tma_load_4d(sa, &p.tma_a, &full_bar[stage], c * kGemmBK, cw0 + dx - p.pad, ch0 + dy - p.pad, cb);
-          } else {
-            tma_load_2d(sa, &p.tma_a, &full_bar[stage], kit * kGemmBK, m_tile * kGemmBM);
+            c0 = c * kGemmBK;
+            c1 = cw0 + dx - p.pad;
+            c2 = ch0 + dy - p.pad;
           }
-          tma_load_2d(sb, &p.tma_b, &full_bar[stage], kit * kGemmBK, n0);
+          if (leader) {
+            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            if (p.conv)
+              tma_load_4d(sa, &p.tma_a, &full_bar[stage], c0, c1, c2, cb);
+            else
+              tma_load_2d(sa, &p.tma_a, &full_bar[stage], c0, c1);
+            tma_load_2d(sb, &p.tma_b, &full_bar[stage], kit * kGemmBK, n0);
+          }
+          __syncwarp();
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (converged warp, one elected issuing lane) =====================
+    {
+      const bool leader = elect_one_sync();
       constexpr uint32_t idesc = umma_idesc_f16(kGemmBM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -502,16 +516,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           tc_fence_after();
           const uint32_t a_base = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t b_base = a_base + Cfg::kABytes;
+          if (leader) {
 #pragma unroll
-          for (int k = 0; k < kGemmBK / 16; ++k) {
-            const uint64_t da = umma_desc_sw128(a_base + k * 32, 1024, 0);
-            const uint64_t db = umma_desc_sw128(b_base + k * 32, 1024, 0);
-            umma_f16_ss(d_tmem, da, db, idesc, (kit | k) != 0);
+            for (int k = 0; k < kGemmBK / 16; ++k) {
+              const uint64_t da = umma_desc_sw128(a_base + k * 32, 1024, 0);
+              const uint64_t db = umma_desc_sw128(b_base + k * 32, 1024, 0);
+              umma_f16_ss(d_tmem, da, db, idesc, (kit | k) != 0);
+            }
+            umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          __syncwarp();
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        if (leader) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -582,7 +600,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
   uint64_t* tmem_empty = bars + 2 * Cfg::kStages + 2;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 4);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_idx_sync();  // provably warp-uniform: role branches and their operands stay on the uniform datapath
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();  // 0 = leader
   const int pair = blockIdx.x >> 1;
@@ -612,8 +630,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
   const int num_tiles = m_pairs * p.num_n_tiles;  // pair tiles (256 x BN)
 
   if (warp == 0) {
-    // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
+    // ===================== TMA producer (both CTAs; converged warp, elected issuing lane) =====================
+    {
+      const bool leader = elect_one_sync();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
@@ -633,27 +652,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
           if (p.probe & 2) {
-            if (rank == 0) mbar_arrive(&full_bar[stage]);
+            if (rank == 0 && leader) mbar_arrive(&full_bar[stage]);
+            __syncwarp();
             if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
             continue;
           }
-          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+          int c0 = kit * kGemmBK, c1 = m_tile * kGemmBM, c2 = 0;
           if (p.conv) {
             const int tap = kit / p.k_chunks;
             const int c = kit - tap * p.k_chunks;
             const int dy = tap / p.kw, dx = tap - dy * p.kw;
-            tma_load_4d_2sm(sa, &p.tma_a, &full_bar[stage], c * kGemmBK, cw0 + dx - p.pad, ch0 + dy - p.pad, cb);
-          } else {
-            tma_load_2d_2sm(sa, &p.tma_a, &full_bar[stage], kit * kGemmBK, m_tile * kGemmBM);
+            c0 = c * kGemmBK;
+            c1 = cw0 + dx - p.pad;
+            c2 = ch0 + dy - p.pad;
           }
-          tma_load_2d_2sm(sb, &p.tma_b, &full_bar[stage], kit * kGemmBK, n0);
+          if (leader) {
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+            if (p.conv)
+              tma_load_4d_2sm(sa, &p.tma_a, &full_bar[stage], c0, c1, c2, cb);
+            else
+              tma_load_2d_2sm(sa, &p.tma_a, &full_bar[stage], c0, c1);
+            tma_load_2d_2sm(sb, &p.tma_b, &full_bar[stage], kit * kGemmBK, n0);
+          }
+          __syncwarp();
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA only) =====================
-    if (lane == 0 && rank == 0) {
+    // ===================== MMA issuer (leader CTA only; converged warp, elected issuing lane) =====================
+    if (rank == 0) {
+      const bool leader = elect_one_sync();
       constexpr uint32_t idesc = umma_idesc_f16(2 * kGemmBM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -668,18 +697,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
           tc_fence_after();
           const uint32_t a_base = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t b_base = a_base + Cfg::kABytes;
-          if (!(p.probe & 4)) {
+          if (leader) {
+            if (!(p.probe & 4)) {
 #pragma unroll
-            for (int k = 0; k < kGemmBK / 16; ++k) {
-              const uint64_t da = umma_desc_sw128(a_base + k * 32, 1024, 0);
-              const uint64_t db = umma_desc_sw128(b_base + k * 32, 1024, 0);
-              umma_f16_ss_2cta(d_tmem, da, db, idesc, (kit | k) != 0);
+              for (int k = 0; k < kGemmBK / 16; ++k) {
+                const uint64_t da = umma_desc_sw128(a_base + k * 32, 1024, 0);
+                const uint64_t db = umma_desc_sw128(b_base + k * 32, 1024, 0);
+                umma_f16_ss_2cta(d_tmem, da, db, idesc, (kit | k) != 0);
+              }
             }
+            umma_commit_2cta(&empty_bar[stage], 0x3);  // both CTAs' smem slots
           }
-          umma_commit_2cta(&empty_bar[stage], 0x3);  // both CTAs' smem slots
+          __syncwarp();
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit_2cta(&tmem_full[acc], 0x3);
+        if (leader) umma_commit_2cta(&tmem_full[acc], 0x3);
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }

@@ -93,6 +93,8 @@ static void init_once() {
   cudaFuncSetAttribute(mhsa2_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   cudaFuncSetAttribute(mhsa2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kM2SmemBytes);
   cudaFuncSetAttribute(mhsa2_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(mhsa2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kM2SmemBytes);
+  cudaFuncSetAttribute(mhsa2_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   g_init_status = 0;
 }
 static int ensure_init() {
@@ -429,6 +431,23 @@ int lseg_mhsa(const void* qkv, void* out, int B, int N, int heads, int causal, v
   MhsaPlan plan;
   if (mhsa_plan(d, &plan)) return -1;
   return mhsa_run(plan, static_cast<cudaStream_t>(stream));
+}
+
+int lseg_mhsa_trace(const void* qkv, void* out, int B, int N, int heads, int causal, unsigned long long* trace,
+                    void* stream) {
+  MhsaDesc d;
+  d.qkv = static_cast<const __half*>(qkv);
+  d.out = static_cast<__half*>(out);
+  d.B = B;
+  d.N = N;
+  d.heads = heads;
+  d.causal = causal;
+  MhsaPlan plan;
+  if (mhsa_plan(d, &plan)) return -1;
+  plan.p.trace = trace;
+  mhsa2_kernel<false, true><<<plan.grid, kM2Threads, kM2SmemBytes, static_cast<cudaStream_t>(stream)>>>(plan.p);
+  LSEG_CHECK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 int lseg_layernorm(const void* x, int in_f16, const float* gamma, const float* beta, void* y, long long M, int C,

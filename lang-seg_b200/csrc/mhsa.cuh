@@ -43,6 +43,7 @@ struct MhsaParams {
   int D;
   int causal;
   float scale_log2e;    // dh^-0.5 * log2(e)
+  unsigned long long* trace;  // debug timeline buffer (mhsa2 TRACE instantiation only), else nullptr
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
@@ -72,19 +73,21 @@ __device__ __forceinline__ float mhsa_exp_chunk(const uint32_t (&s)[32], float c
 
 template <bool MASK>
 __device__ __forceinline__ float mhsa_max_chunk(const uint32_t (&s)[32], int kv_base, int n_tokens, int kv_limit) {
-  float m0 = -INFINITY, m1 = -INFINITY;
+  float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four chains: the reduction is latency-bound
 #pragma unroll
-  for (int i = 0; i < 32; i += 2) {
-    float a = __uint_as_float(s[i]), b = __uint_as_float(s[i + 1]);
-    if (MASK) {
-      const int kv = kv_base + i;
-      if (!(kv < n_tokens && kv <= kv_limit)) a = -INFINITY;
-      if (!(kv + 1 < n_tokens && kv + 1 <= kv_limit)) b = -INFINITY;
+  for (int i = 0; i < 32; i += 8) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float a = __uint_as_float(s[i + 2 * u]), b = __uint_as_float(s[i + 2 * u + 1]);
+      if (MASK) {
+        const int kv = kv_base + i + 2 * u;
+        if (!(kv < n_tokens && kv <= kv_limit)) a = -INFINITY;
+        if (!(kv + 1 < n_tokens && kv + 1 <= kv_limit)) b = -INFINITY;
+      }
+      m[u] = fmaxf(m[u], fmaxf(a, b));
     }
-    m0 = fmaxf(m0, a);
-    m1 = fmaxf(m1, b);
   }
-  return fmaxf(m0, m1);
+  return fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
 }
 
 // SPIN: barrier waits re-poll without a suspend hint (lower wake-up latency, more issue slots burnt);

@@ -17,8 +17,10 @@
 //   * row groups of 32 that lie entirely beyond the sequence (the last query tile has 5 valid rows of 128)
 //     skip the softmax arithmetic: their P rows are garbage, which only reaches their own (unstored) O rows.
 //
-// Warps: 0 TMA producer (Q; K and V 64-key tiles through 4-deep rings) + TMEM alloc; 1 MMA issuer;
-//        2..5 softmax stream A; 6..9 softmax stream B (warp & 3 = TMEM lane quarter).
+// Warps: 0 TMA producer (Q; K and V 64-key tiles through 4-deep rings; issuing a 64-row box costs the thread
+//        300-500 clk, which is why it is not folded into the MMA thread) + TMEM alloc; 1 MMA issuer: one thread
+//        multiplexes both streams by polling the hand-off barriers, PV first; 2..5 softmax stream A;
+//        6..9 softmax stream B (warp & 3 = TMEM lane quarter).
 // TMEM (256 columns, 2 CTAs/SM): S_A [0,64) S_B [64,128) O_A [128,192) O_B [192,256).
 #pragma once
 #include "common.cuh"
@@ -35,13 +37,15 @@ constexpr int kM2PBytes = 128 * kM2KT * 2;     // 16 KB per stream
 // Q | K ring | V ring | P_A P_B | mbarriers + tmem slot
 constexpr int kM2SmemBytes = kM2QBytes + 2 * kM2Stages * kM2KvBytes + 2 * kM2PBytes + 1024;
 
-template <bool SPIN>
+// TRACE: debug instantiation that stamps clock64() at the hand-off points of 16 sampled CTAs into p.trace
+// ([16 CTAs][10 warps][256] of (clock << 8 | tag)); tools/mhsa_trace.py prints the timeline.
+template <bool SPIN, bool TRACE = false>
 __global__ void __launch_bounds__(kM2Threads, 2) mhsa2_kernel(const __grid_constant__ MhsaParams p) {
   auto wait_bar = [](uint64_t* bar, uint32_t parity, int tag) {
     if (SPIN)
       mbar_wait_spin(bar, parity, tag);
     else
-      mbar_wait(bar, parity, tag);
+      mbar_wait_inl(bar, parity, tag);
   };
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
@@ -60,12 +64,22 @@ __global__ void __launch_bounds__(kM2Threads, 2) mhsa2_kernel(const __grid_const
   uint64_t* o_done = bars + 23;   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_idx_sync();
   const int lane = threadIdx.x & 31;
   const int q_tile = blockIdx.x;
   const int b = blockIdx.y / p.heads;
   const int h = blockIdx.y % p.heads;
   const int q0 = q_tile * 128;
+  int trace_n = 0;
+  unsigned long long* trace_w = nullptr;
+  if (TRACE) {
+    const int cta_lin = blockIdx.y * gridDim.x + blockIdx.x;
+    const int slot = (cta_lin % 128 == 0) ? cta_lin / 128 : ((cta_lin % 128 == 7) ? 8 + cta_lin / 128 : -1);
+    if (slot >= 0 && slot < 16 && lane == 0) trace_w = p.trace + (slot * 10 + warp) * 256;
+  }
+  auto TR = [&](int tag) {
+    if (TRACE && trace_w && trace_n < 254) trace_w[trace_n++] = (static_cast<unsigned long long>(clock64()) << 8) | tag;
+  };
 
   if ((smem_u32(smem) & 1023u) != 0) {  // layout contract of the swizzled tiles
     if (threadIdx.x == 0) atomicCAS(&g_watchdog[0], 0, 99);
@@ -99,6 +113,7 @@ __global__ void __launch_bounds__(kM2Threads, 2) mhsa2_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  TR(0);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -112,52 +127,120 @@ __global__ void __launch_bounds__(kM2Threads, 2) mhsa2_kernel(const __grid_const
         wait_bar(&k_empty[slot], par, 11);
         mbar_expect_tx(&k_full[slot], kM2KvBytes);
         tma_load_3d(sK + slot * kM2KvBytes, &p.tma_t64, &k_full[slot], p.D + h * kMhsaDh, j * kM2KT, b);
+        TR(20);
         wait_bar(&v_empty[slot], par, 12);
         mbar_expect_tx(&v_full[slot], kM2KvBytes);
         tma_load_3d(sV + slot * kM2KvBytes, &p.tma_t64, &v_full[slot], 2 * p.D + h * kMhsaDh, j * kM2KT, b);
+        TR(21);
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    {
+      const bool leader = elect_one_sync();  // the one lane that issues (and commits) every MMA of this CTA
       constexpr uint32_t idesc_o = umma_idesc_f16(128, 64, 0, 1);  // P V : A K-major, B (V) MN-major
       const uint32_t q_base = smem_u32(sQ);
-      auto issue_s = [&](int j) {  // S_j = Q K_j^T, 128 x cols x 64
-        const int s = j & 1, t = j >> 1, slot = j & (kM2Stages - 1);
-        wait_bar(&k_full[slot], (j / kM2Stages) & 1, 14);
-        if (t > 0) wait_bar(&s_free[s], (t - 1) & 1, 16);  // S_{j-2} now lives in the softmax warps' registers
-        tc_fence_after();
+      auto issue_s = [&](int j) {  // S_j = Q K_j^T, 128 x cols x 64 (operands known to be ready)
+        const int s = j & 1, slot = j & (kM2Stages - 1);
         const uint32_t idesc_s = umma_idesc_f16(128, tile_cols(j), 0, 0);
         const uint32_t k_base = smem_u32(sK + slot * kM2KvBytes);
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16_ss(tmem_base + s * 64, umma_desc_sw128(q_base + k * 32, 1024, 0),
-                      umma_desc_sw128(k_base + k * 32, 1024, 0), idesc_s, k != 0);
-        umma_commit(&s_full[s]);
-        umma_commit(&k_empty[slot]);
+          for (int k = 0; k < 4; ++k)
+            umma_f16_ss(tmem_base + s * 64, umma_desc_sw128(q_base + k * 32, 1024, 0),
+                        umma_desc_sw128(k_base + k * 32, 1024, 0), idesc_s, k != 0);
+          umma_commit(&s_full[s]);
+          umma_commit(&k_empty[slot]);
+        }
+        __syncwarp();
+        TR(11);
       };
       auto issue_pv = [&](int j) {  // O_s += P_j V_j, 128 x 64 x cols
         const int s = j & 1, t = j >> 1, slot = j & (kM2Stages - 1);
-        wait_bar(&v_full[slot], (j / kM2Stages) & 1, 17);
-        wait_bar(&p_full[s], t & 1, 18);
-        tc_fence_after();
         const uint32_t p_base = smem_u32(sP + s * kM2PBytes);
         const uint32_t v_base = smem_u32(sV + slot * kM2KvBytes);
         const int ksteps = tile_cols(j) >> 4;
-        for (int k = 0; k < ksteps; ++k)
-          umma_f16_ss(tmem_base + 128 + s * 64, umma_desc_sw128(p_base + k * 32, 1024, 0),
-                      umma_desc_sw128(v_base + k * 2048, 1024, 8192), idesc_o, (t | k) != 0);
-        umma_commit(&o_done[s]);
-        umma_commit(&v_empty[slot]);
+        if (leader) {
+          if (ksteps == 4) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16_ss(tmem_base + 128 + s * 64, umma_desc_sw128(p_base + k * 32, 1024, 0),
+                          umma_desc_sw128(v_base + k * 2048, 1024, 8192), idesc_o, (t | k) != 0);
+          } else {
+            for (int k = 0; k < ksteps; ++k)
+              umma_f16_ss(tmem_base + 128 + s * 64, umma_desc_sw128(p_base + k * 32, 1024, 0),
+                          umma_desc_sw128(v_base + k * 2048, 1024, 8192), idesc_o, (t | k) != 0);
+          }
+          umma_commit(&o_done[s]);
+          umma_commit(&v_empty[slot]);
+        }
+        __syncwarp();
+        TR(13);
       };
       wait_bar(q_full, 0, 13);
-      issue_s(0);
-      if (nkt > 1) issue_s(1);
-      for (int j = 0; j < nkt; j += 2) {
-        if (j + 2 < nkt) issue_s(j + 2);
-        if (j + 3 < nkt) issue_s(j + 3);
-        issue_pv(j);
-        if (j + 1 < nkt) issue_pv(j + 1);
+      // One thread multiplexes both streams: whatever is ready is issued, PV first (it is on the streams'
+      // critical path: the next P store waits for it; the next S is only needed a tile later).
+      int s_next[2] = {0, 1}, pv_next[2] = {0, 1};
+      int remaining = 2 * nkt;
+      const long long t_start = clock64();
+      uint32_t idle = 0;
+      while (remaining > 0) {
+        bool did = false;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const int j = pv_next[s];
+          if (j < nkt && j < s_next[s] && mbar_test(&p_full[s], (j >> 1) & 1) &&
+              mbar_test(&v_full[j & (kM2Stages - 1)], (j / kM2Stages) & 1)) {
+            TR(31);
+            tc_fence_after();
+            TR(12);
+            issue_pv(j);
+            pv_next[s] = j + 2;
+            --remaining;
+            did = true;
+          }
+        }
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const int j = s_next[s];
+          if (j < nkt && (j < 2 || mbar_test(&s_free[s], ((j >> 1) - 1) & 1)) &&
+              mbar_test(&k_full[j & (kM2Stages - 1)], (j / kM2Stages) & 1)) {
+            tc_fence_after();
+            TR(10);
+            issue_s(j);
+            s_next[s] = j + 2;
+            --remaining;
+            did = true;
+          }
+        }
+        if (TRACE && !did) {
+          int mask = 0;
+          for (int s = 0; s < 2; ++s) {
+            const int j = pv_next[s];
+            if (j < nkt) {
+              mask |= (mbar_test(&p_full[s], (j >> 1) & 1) ? 1 : 0) << (2 * s);
+              mask |= (mbar_test(&v_full[j & (kM2Stages - 1)], (j / kM2Stages) & 1) ? 2 : 0) << (2 * s);
+            }
+          }
+          TR(32 + mask);
+        }
+        if (!did) {
+          // park briefly on the older pending P hand-off instead of burning the SMSP's issue slots
+          const int sp = (pv_next[0] <= pv_next[1]) ? 0 : 1;
+          const int jp = pv_next[sp];
+          if (jp < nkt) mbar_try_wait_ns(&p_full[sp], (jp >> 1) & 1, 100);
+          if ((++idle & 0x3FFu) == 0) {
+            if (*reinterpret_cast<volatile int*>(&g_watchdog[0]) != 0) break;
+            if (clock64() - t_start > kWatchdogCycles) {
+              if (atomicCAS(&g_watchdog[0], 0, 18) == 0) {
+                g_watchdog[1] = blockIdx.x;
+                g_watchdog[2] = threadIdx.x;
+                g_watchdog[3] = remaining;
+              }
+              break;
+            }
+          }
+        }
       }
     }
   } else {
@@ -185,24 +268,30 @@ __global__ void __launch_bounds__(kM2Threads, 2) mhsa2_kernel(const __grid_const
       const bool need_mask = (kv0 + kM2KT > kv_end) || (p.causal && (kv0 + kM2KT - 1 > q0));
       wait_bar(&s_full[s], t & 1, 19);
       tc_fence_after();
-      uint32_t s0[32], s1[32];
-      if (row_active) {
-        __syncwarp();
-        tmem_ld32(tS, s0);
-        if (nc > 32) tmem_ld32(tS + 32, s1);
-        tmem_ld_wait();
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_free[s]);  // scores are in registers: the stream's next S MMA may start
+      TR(1);
+      // Pass 1: row max over the tile (both 32-column chunks in flight together; nothing else is live).
+      // Pass 2 re-reads the chunks one at a time: holding all 64 scores AND the fp16 results would spill at the
+      // 96 registers that 2 CTAs/SM allow, and spills are ruinous here (the smem carve-out leaves almost no L1).
       bool any_move = false;
       float factor = 1.f, m_use = 0.f;
       if (row_active) {
-        float pm = need_mask ? mhsa_max_chunk<true>(s0, kv0, p.n_tokens, kv_limit)
-                             : mhsa_max_chunk<false>(s0, kv0, p.n_tokens, kv_limit);
-        if (nc > 32)
+        float pm;
+        {
+          uint32_t s0[32];
+          __syncwarp();
+          tmem_ld32(tS, s0);
+          tmem_ld_wait();
+          pm = need_mask ? mhsa_max_chunk<true>(s0, kv0, p.n_tokens, kv_limit)
+                         : mhsa_max_chunk<false>(s0, kv0, p.n_tokens, kv_limit);
+        }
+        if (nc > 32) {
+          uint32_t s1[32];
+          __syncwarp();
+          tmem_ld32(tS + 32, s1);
+          tmem_ld_wait();
           pm = fmaxf(pm, need_mask ? mhsa_max_chunk<true>(s1, kv0 + 32, p.n_tokens, kv_limit)
                                    : mhsa_max_chunk<false>(s1, kv0 + 32, p.n_tokens, kv_limit));
+        }
         const float mx = pm * c;
         const bool move = mx > m_ref + kMhsaTau;  // lazy offset: also true on the stream's first unmasked tile
         any_move = __any_sync(0xffffffffu, move);
@@ -214,52 +303,71 @@ __global__ void __launch_bounds__(kM2Threads, 2) mhsa2_kernel(const __grid_const
         }
         m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
       }
-      // P_s buffer free and O_s quiescent once the stream's previous PV has retired
+      TR(2);
+      // Pass 2: p = exp2(s*c - m_ref) as packed fp16. The first chunk is computed and the second chunk is fetched
+      // (which releases S for the stream's next S MMA) BEFORE waiting for the stream's previous PV: only the P
+      // store and the (rare) O rescale need the P buffer free / O quiescent, so the MMA latency hides here.
+      __half2 ph[16];
+      uint32_t sc1[32];
+      float l_tile = 0.f;
+      const bool second = row_active && nc > 32;  // warp-uniform
+      if (row_active) {
+        uint32_t sc0[32];
+        __syncwarp();
+        tmem_ld32(tS, sc0);
+        tmem_ld_wait();
+        l_tile = need_mask ? mhsa_exp_chunk<true>(sc0, c, m_use, kv0, p.n_tokens, kv_limit, ph)
+                           : mhsa_exp_chunk<false>(sc0, c, m_use, kv0, p.n_tokens, kv_limit, ph);
+        __syncwarp();
+        tmem_ld32(tS + 32, sc1);  // unconditional (columns beyond a short tail tile are stale but allocated)
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[s]);  // last read of S_j: the stream's next S MMA may start
+      TR(3);
       if (t > 0) {
         wait_bar(&o_done[s], (t - 1) & 1, 20);
         if (any_move) {  // rescale the TMEM-resident output row (warp-collective; factor = 1 for unmoved rows)
           tc_fence_after();
 #pragma unroll 1
-          for (int cc = 0; cc < 4; ++cc) {
-            uint32_t o[16];
+          for (int cc = 0; cc < 8; ++cc) {
+            uint32_t o[8];
             __syncwarp();
-            tmem_ld16(tO + cc * 16, o);
+            tmem_ld8(tO + cc * 8, o);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
-            tmem_st16(tO + cc * 16, o);
+            for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+            tmem_st8(tO + cc * 8, o);
           }
           tmem_st_wait();
         }
       }
+      TR(4);
       if (row_active) {
-        // p = exp2(s*c - m_ref) -> fp16 -> 128B-swizzled K-major smem row (8 16-byte slots = 64 keys)
-        float l_tile;
-        {
-          __half2 ph[16];
-          l_tile = need_mask ? mhsa_exp_chunk<true>(s0, c, m_use, kv0, p.n_tokens, kv_limit, ph)
-                             : mhsa_exp_chunk<false>(s0, c, m_use, kv0, p.n_tokens, kv_limit, ph);
+        // fp16 P row -> 128B-swizzled K-major smem (8 16-byte slots = 64 keys)
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            *reinterpret_cast<uint4*>(p_row + ((i ^ sw) * 16)) = *reinterpret_cast<uint4*>(&ph[4 * i]);
-        }
-        if (nc > 32) {
-          __half2 ph[16];
-          l_tile += need_mask ? mhsa_exp_chunk<true>(s1, c, m_use, kv0 + 32, p.n_tokens, kv_limit, ph)
-                              : mhsa_exp_chunk<false>(s1, c, m_use, kv0 + 32, p.n_tokens, kv_limit, ph);
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<uint4*>(p_row + ((i ^ sw) * 16)) = *reinterpret_cast<uint4*>(&ph[4 * i]);
+        if (second) {
+          l_tile += need_mask ? mhsa_exp_chunk<true>(sc1, c, m_use, kv0 + 32, p.n_tokens, kv_limit, ph)
+                              : mhsa_exp_chunk<false>(sc1, c, m_use, kv0 + 32, p.n_tokens, kv_limit, ph);
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             *reinterpret_cast<uint4*>(p_row + (((4 + i) ^ sw) * 16)) = *reinterpret_cast<uint4*>(&ph[4 * i]);
         }
         l_run += l_tile;
       }
+      TR(5);
       fence_proxy_async_smem();  // P stores visible to the async (UMMA) proxy ...
       tc_fence_before();
       __syncwarp();              // ... before the warp's single elected arrival
       if (lane == 0) mbar_arrive(&p_full[s]);
+      TR(6);
     }
     // ---- merge the two streams and write O / l; each warp emits 32 of the 64 output columns ----
     if (n_s > 0) wait_bar(&o_done[s], (n_s - 1) & 1, 25);
+    TR(7);
     if (row_active) {
       // the stream's P buffer is dead once its last PV has retired: use it to publish (m, l)
       reinterpret_cast<float2*>(sP + s * kM2PBytes)[r] = make_float2(m_ref, l_run);
@@ -299,8 +407,10 @@ __global__ void __launch_bounds__(kM2Threads, 2) mhsa2_kernel(const __grid_const
     }
   }
 
+  TR(8);
   tc_fence_before();
   __syncthreads();
+  TR(99);
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
