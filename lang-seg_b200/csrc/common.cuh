@@ -4,6 +4,7 @@
 // host-side tensor-map factory. Everything here is written for sm_100a only; there is no
 // fallback path.
 #pragma once
+#include <cstdlib>
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -148,6 +149,14 @@ __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity, i
     }
   }
 }
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------
+// Every per-step kernel is launched with programmaticStreamSerializationAllowed: its CTAs may become resident and
+// run their prologue (barrier init, TMEM alloc, tensor-map prefetch) while the previous kernel of the stream is
+// still draining. griddep_wait() blocks until that previous grid has completed and its writes are visible; it
+// must precede the first access to any global memory another kernel of the step reads or writes.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // One lane of a converged warp (elect.sync): the MMA / TMA warps run converged with warp-uniform values (which the
 // compiler then keeps in uniform registers) and only predicate the tcgen05 / bulk-copy instruction itself on this
@@ -457,6 +466,24 @@ const char* get_error();
       return -1;                                                                               \
     }                                                                                          \
   } while (0)
+
+// Kernel launch with the PDL attribute (see griddep_wait above); LSEG_NO_PDL=1 falls back to plain launches.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     Args&&... args) {
+  static const bool no_pdl = getenv("LSEG_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = no_pdl ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // Encode a tiled fp16 tensor map (rank 2..4), 128-byte swizzle, zero OOB fill.
 // dims/box are innermost-first, strides_bytes[i] is the byte stride of dim i+1.

@@ -21,6 +21,8 @@ namespace lseg {
 // grid (ceil(gw*192/256), B*gh): one thread = 4 pixels of one patch row.
 // ------------------------------------------------------------------------------------------
 __global__ void patchify_kernel(const float* __restrict__ x, __half* __restrict__ a, int H, int W) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int gh = H / 16, gw = W / 16;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= gw * 192) return;
@@ -40,7 +42,7 @@ __global__ void patchify_kernel(const float* __restrict__ x, __half* __restrict_
 static inline int launch_patchify(const float* x, __half* a, int B, int H, int W, cudaStream_t s) {
   const int gw = W / 16, gh = H / 16;
   dim3 grid((gw * 192 + 255) / 256, B * gh);
-  patchify_kernel<<<grid, 256, 0, s>>>(x, a, H, W);
+  launch_pdl(patchify_kernel, grid, dim3(256), 0, s, x, a, H, W);
   LSEG_LAUNCH_CHECK();
 }
 
@@ -77,6 +79,8 @@ __global__ void pos_resize_kernel(const float* __restrict__ pos, float* __restri
 // ------------------------------------------------------------------------------------------
 __global__ void assemble_tokens_kernel(const float* __restrict__ patch, const float* __restrict__ cls,
                                        const float* __restrict__ pos, float* __restrict__ x, int T, int D) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int row = blockIdx.x;
   const int b = row / (T + 1), t = row - b * (T + 1);
   const float* src = (t == 0) ? cls : patch + (static_cast<long long>(b) * T + (t - 1)) * D;
@@ -91,7 +95,7 @@ __global__ void assemble_tokens_kernel(const float* __restrict__ patch, const fl
 }
 static inline int launch_assemble_tokens(const float* patch, const float* cls, const float* pos, float* x, int B, int T,
                                          int D, cudaStream_t s) {
-  assemble_tokens_kernel<<<B * (T + 1), 256, 0, s>>>(patch, cls, pos, x, T, D);
+  launch_pdl(assemble_tokens_kernel, dim3(B * (T + 1)), dim3(256), 0, s, patch, cls, pos, x, T, D);
   LSEG_LAUNCH_CHECK();
 }
 
@@ -104,6 +108,8 @@ template <typename TIn>
 __global__ void layernorm_kernel(const TIn* __restrict__ x, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, __half* __restrict__ y, long long M, int C,
                                  float eps) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int lane = threadIdx.x & 31;
   const long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -162,6 +168,8 @@ __global__ void layernorm_kernel(const TIn* __restrict__ x, const float* __restr
 // ------------------------------------------------------------------------------------------
 __global__ void readout_split_kernel(const float* __restrict__ tap, __half* __restrict__ tok,
                                      __half* __restrict__ cls, int T, int D) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int row = blockIdx.x;
   const int b = row / (T + 1), t = row - b * (T + 1);
   const float* src = tap + static_cast<long long>(row) * D;
@@ -177,7 +185,7 @@ __global__ void readout_split_kernel(const float* __restrict__ tap, __half* __re
 }
 static inline int launch_readout_split(const float* tap, __half* tok, __half* cls, int B, int T, int D,
                                        cudaStream_t s) {
-  readout_split_kernel<<<B * (T + 1), 256, 0, s>>>(tap, tok, cls, T, D);
+  launch_pdl(readout_split_kernel, dim3(B * (T + 1)), dim3(256), 0, s, tap, tok, cls, T, D);
   LSEG_LAUNCH_CHECK();
 }
 
@@ -186,6 +194,8 @@ static inline int launch_readout_split(const float* tap, __half* tok, __half* cl
 // NHWC fp16 [B,H,W,C] -> [B*Ho*Wo, 9*C], tap-major columns, zero halo. grid (Wo, Ho, B).
 // ------------------------------------------------------------------------------------------
 __global__ void im2col_3x3_s2_kernel(const __half* __restrict__ x, __half* __restrict__ a, int H, int W, int C) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int ox = blockIdx.x, oy = blockIdx.y, b = blockIdx.z;
   const int Wo = gridDim.x, Ho = gridDim.y;
   const int c8 = C / 8;
@@ -203,7 +213,7 @@ __global__ void im2col_3x3_s2_kernel(const __half* __restrict__ x, __half* __res
 }
 static inline int launch_im2col_3x3_s2(const __half* x, __half* a, int B, int H, int W, int C, cudaStream_t s) {
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-  im2col_3x3_s2_kernel<<<dim3(Wo, Ho, B), 128, 0, s>>>(x, a, H, W, C);
+  launch_pdl(im2col_3x3_s2_kernel, dim3(Wo, Ho, B), dim3(128), 0, s, x, a, H, W, C);
   LSEG_LAUNCH_CHECK();
 }
 
@@ -213,6 +223,8 @@ static inline int launch_im2col_3x3_s2(const __half* x, __half* a, int B, int H,
 // grid (ceil(Wo/8), Ho, B), 256 threads: 8 output pixels x 32 channel groups of 8.
 // ------------------------------------------------------------------------------------------
 __global__ void upsample2x_nhwc_kernel(const __half* __restrict__ x, __half* __restrict__ y, int H, int W, int C) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int Ho = 2 * H, Wo = 2 * W, c8 = C / 8;
   const int oy = blockIdx.y, b = blockIdx.z;
   const int ox = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -251,7 +263,7 @@ __global__ void upsample2x_nhwc_kernel(const __half* __restrict__ x, __half* __r
   }
 }
 static inline int launch_upsample2x_nhwc(const __half* x, __half* y, int B, int H, int W, int C, cudaStream_t s) {
-  upsample2x_nhwc_kernel<<<dim3((2 * W + 7) / 8, 2 * H, B), 256, 0, s>>>(x, y, H, W, C);
+  launch_pdl(upsample2x_nhwc_kernel, dim3((2 * W + 7) / 8, 2 * H, B), dim3(256), 0, s, x, y, H, W, C);
   LSEG_LAUNCH_CHECK();
 }
 
@@ -320,6 +332,8 @@ constexpr int kUpRows = 4;      // output rows per warp
 constexpr int kUpMaxW = 512;    // widest source row (smem line)
 template <bool STREAM>  // STREAM: st.global.cs stores (A/B switch LSEG_UPSAMPLE_CS=1; default plain stores)
 __global__ void upsample2x_nchw_kernel(const __half* __restrict__ x, float* __restrict__ y, int H, int W) {
+  griddep_launch_dependents();
+  griddep_wait();
   __shared__ __align__(16) float line[8][kUpMaxW];
   const int Ho = 2 * H, Wo = 2 * W, w4 = Wo / 4;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -387,9 +401,9 @@ static inline int launch_upsample2x_nchw(const __half* x, float* y, long long pl
   static const bool stream_stores = getenv("LSEG_UPSAMPLE_CS") != nullptr;
   const dim3 grid((2 * H + rows_per_block - 1) / rows_per_block, static_cast<unsigned>(planes));
   if (stream_stores)
-    upsample2x_nchw_kernel<true><<<grid, 256, 0, s>>>(x, y, H, W);
+    launch_pdl(upsample2x_nchw_kernel<true>, grid, dim3(256), 0, s, x, y, H, W);
   else
-    upsample2x_nchw_kernel<false><<<grid, 256, 0, s>>>(x, y, H, W);
+    launch_pdl(upsample2x_nchw_kernel<false>, grid, dim3(256), 0, s, x, y, H, W);
   LSEG_LAUNCH_CHECK();
 }
 

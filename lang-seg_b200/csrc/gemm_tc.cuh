@@ -442,11 +442,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     }
     mbar_fence_init();
   }
+  griddep_launch_dependents();
   if (warp == 2) tmem_alloc(tmem_base_slot, Cfg::kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  griddep_wait();  // everything above overlapped the previous kernel's tail; operands / outputs are touched below
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
 
@@ -620,11 +622,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
     }
     mbar_fence_init();
   }
+  griddep_launch_dependents();
   if (warp == 2) tmem_alloc_2cta(tmem_base_slot, Cfg::kTmemCols);
   tc_fence_before();
   cluster_sync_all();  // barriers + TMEM of BOTH CTAs exist before any cross-CTA traffic
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  griddep_wait();  // everything above overlapped the previous kernel's tail; operands / outputs are touched below
 
   const int m_pairs = (p.num_m_tiles + 1) >> 1;
   const int num_tiles = m_pairs * p.num_n_tiles;  // pair tiles (256 x BN)

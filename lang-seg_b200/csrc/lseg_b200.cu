@@ -261,7 +261,7 @@ static int gemm_run(const GemmPlan& plan, cudaStream_t stream) {
   if (plan.grid <= 0) return 0;
   if (plan.two_cta) {
 #define LSEG_LAUNCH_TC2(BN_, EPI_) \
-  gemm_tc2_kernel<BN_, EPI_><<<plan.grid, kGemmThreads, Gemm2Cfg<BN_, EPI_>::kSmemBytes, stream>>>(plan.p)
+  launch_pdl(gemm_tc2_kernel<BN_, EPI_>, dim3(plan.grid), dim3(kGemmThreads), Gemm2Cfg<BN_, EPI_>::kSmemBytes, stream, plan.p)
     if (plan.bn == 256) {
       if (plan.epi == EPI_TMA_F16) LSEG_LAUNCH_TC2(256, EPI_TMA_F16);
       else if (plan.epi == EPI_TMA_ADD) LSEG_LAUNCH_TC2(256, EPI_TMA_ADD);
@@ -276,9 +276,9 @@ static int gemm_run(const GemmPlan& plan, cudaStream_t stream) {
     return 0;
   }
   if (plan.bn == 256)
-    gemm_tc_kernel<256><<<plan.grid, kGemmThreads, GemmCfg<256>::kSmemBytes, stream>>>(plan.p);
+    launch_pdl(gemm_tc_kernel<256>, dim3(plan.grid), dim3(kGemmThreads), GemmCfg<256>::kSmemBytes, stream, plan.p);
   else
-    gemm_tc_kernel<128><<<plan.grid, kGemmThreads, GemmCfg<128>::kSmemBytes, stream>>>(plan.p);
+    launch_pdl(gemm_tc_kernel<128>, dim3(plan.grid), dim3(kGemmThreads), GemmCfg<128>::kSmemBytes, stream, plan.p);
   LSEG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -315,9 +315,9 @@ static int mhsa_run(const MhsaPlan& plan, cudaStream_t stream) {
   static const bool v3 = getenv("LSEG_MHSA_V3") != nullptr;  // A/B: the single-stream kernel of mhsa.cuh
   if (!v3) {
     if (spin)
-      mhsa2_kernel<true><<<plan.grid, kM2Threads, kM2SmemBytes, stream>>>(plan.p);
+      launch_pdl(mhsa2_kernel<true, false>, plan.grid, dim3(kM2Threads), kM2SmemBytes, stream, plan.p);
     else
-      mhsa2_kernel<false><<<plan.grid, kM2Threads, kM2SmemBytes, stream>>>(plan.p);
+      launch_pdl(mhsa2_kernel<false, false>, plan.grid, dim3(kM2Threads), kM2SmemBytes, stream, plan.p);
     LSEG_CHECK_CUDA(cudaGetLastError());
     return 0;
   }
@@ -341,9 +341,9 @@ static int run_layernorm(const void* x, int in_f16, const float* g, const float*
   const int rows_per_block = 8;
   const int grid = static_cast<int>((M + rows_per_block - 1) / rows_per_block);
   if (in_f16)
-    layernorm_kernel<__half><<<grid, rows_per_block * 32, 0, s>>>(static_cast<const __half*>(x), g, b, y, M, C, eps);
+    launch_pdl(layernorm_kernel<__half>, dim3(grid), dim3(rows_per_block * 32), 0, s, static_cast<const __half*>(x), g, b, y, M, C, eps);
   else
-    layernorm_kernel<float><<<grid, rows_per_block * 32, 0, s>>>(static_cast<const float*>(x), g, b, y, M, C, eps);
+    launch_pdl(layernorm_kernel<float>, dim3(grid), dim3(rows_per_block * 32), 0, s, static_cast<const float*>(x), g, b, y, M, C, eps);
   LSEG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

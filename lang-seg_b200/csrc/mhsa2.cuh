@@ -108,11 +108,13 @@ __global__ void __launch_bounds__(kM2Threads, 2) mhsa2_kernel(const __grid_const
     }
     mbar_fence_init();
   }
+  griddep_launch_dependents();
   if (warp == 0) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();  // the QKV GEMM must have completed before the first TMA load / output store
   TR(0);
 
   if (warp == 0) {
