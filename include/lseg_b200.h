@@ -82,6 +82,9 @@ int lseg_gemm(const lseg_gemm_args* args, void* stream);
 /* Fused MHSA, head_dim 64 (k5; timm Attention restated at lseg_vit.py:26-39; CLIP text MHA).
  * qkv fp16 [B, N, 3*heads*64] (q|k|v thirds) -> out fp16 [B*N, heads*64]. */
 int lseg_mhsa(const void* qkv, void* out, int B, int N, int heads, int causal, void* stream);
+/* Debug: GEMMs planned after this call stamp clock64() at the epilogue / MMA hand-off points of two CTA pairs
+ * into trace ([2][12 warps][512] uint64 device memory, zeroed by the caller; NULL switches it off). */
+int lseg_debug_gemm_trace(unsigned long long* trace);
 /* Debug: same computation, additionally stamps clock64() at the pipeline hand-off points of 16 sampled CTAs into
  * trace ([16][10 warps][256] uint64 device memory, zero-initialised by the caller); tools/mhsa_trace.py. */
 int lseg_mhsa_trace(const void* qkv, void* out, int B, int N, int heads, int causal, unsigned long long* trace,

@@ -395,6 +395,16 @@ __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar, uint16_t cta_mas
       "h"(cta_mask)
       : "memory");
 }
+// Same, without release semantics: for hand-offs whose payload is TMEM (ordered by tcgen05.fence) — the default
+// .release.cluster arrive drains the warp's earlier global/shared writes first (~1.6k clk after TMA-store epilogues).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
 // Arrive on the mbarrier at the same smem offset in CTA `cta` of the cluster.
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
   asm volatile(

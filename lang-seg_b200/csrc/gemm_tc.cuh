@@ -83,21 +83,74 @@ struct GemmParams {
   int H, W, kw, pad;
   int tiles_h, tiles_w;
   int num_m_tiles, num_n_tiles;
+  unsigned long long* trace;  // debug timeline ([2 pairs][12 warps][512] of clock64 << 8 | tag), normally nullptr
   int probe;  // measurement only (tools/gemm_probe.py; results are garbage when non-zero):
               //   1 = skip epilogue work, 2 = skip TMA loads, 4 = skip MMA issue   (CTA-pair kernel)
   GemmEpi e;
+};
+
+// Debug timeline of one warp (tools/gemm_trace.py): stamps are dropped when w == nullptr (always, outside the tool).
+struct GemmTrace {
+  unsigned long long* w = nullptr;
+  int n = 0;
+  __device__ __forceinline__ void operator()(int tag) {
+    if (w && n < 510) w[n++] = (static_cast<unsigned long long>(clock64()) << 8) | static_cast<unsigned>(tag);
+  }
 };
 
 // ------------------------------------------------------------------------------------------
 // Epilogue math of one 32-column chunk of one output row: f = act(v * scale + bias), plus the optional
 // partial squared row norm. v = the row's fp32 accumulators for columns [n0, n0+32).
 // ------------------------------------------------------------------------------------------
+// Per-column constants of the (up to) 128 columns a warp handles in one tile, held in registers: lane l keeps
+// columns 4l..4l+3 (zeros beyond N), fetched with ONE coalesced 16-byte load per lane before the accumulator is
+// even awaited; chunk c then takes them by shuffle. The per-chunk global loads this replaces cost ~700 clk of
+// exposed latency per 32-column chunk (profiles: tools/gemm_trace.py), the largest single item of the epilogue.
+struct GemmColConst {
+  float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 scale = make_float4(0.f, 0.f, 0.f, 0.f);
+  bool on = false;  // warp-uniform: false -> per-chunk global loads (row-dependent bias)
+};
+__device__ __forceinline__ GemmColConst gemm_col_const(const GemmEpi& e, int N, int n_base, int ncols, int lane) {
+  GemmColConst cc;
+  cc.on = (e.bias_group_rows == 0) && ((N & 3) == 0);
+  if (cc.on) {
+    const int col = n_base + 4 * lane;
+    const bool in = (4 * lane < ncols) && (col < N);
+    if (e.bias && in) cc.bias = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+    if (e.scale && in) cc.scale = __ldg(reinterpret_cast<const float4*>(e.scale + col));
+  }
+  return cc;
+}
+
 __device__ __forceinline__ void gemm_epilogue_math(const GemmEpi& e, int N, const uint32_t (&v)[32], long long grow,
-                                                   int n0, long long bias_off, bool row_valid, float (&f)[32]) {
+                                                   int n0, long long bias_off, bool row_valid, float (&f)[32],
+                                                   const GemmColConst& cc, int chunk) {
   const int nvalid = min(32, N - n0);
 #pragma unroll
   for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-  if (nvalid == 32) {  // uniform-address 16 B loads: one broadcast transaction each
+  if (cc.on) {
+    if (e.scale) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int src = chunk * 8 + j;
+        f[4 * j] *= __shfl_sync(0xffffffffu, cc.scale.x, src);
+        f[4 * j + 1] *= __shfl_sync(0xffffffffu, cc.scale.y, src);
+        f[4 * j + 2] *= __shfl_sync(0xffffffffu, cc.scale.z, src);
+        f[4 * j + 3] *= __shfl_sync(0xffffffffu, cc.scale.w, src);
+      }
+    }
+    if (e.bias) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int src = chunk * 8 + j;
+        f[4 * j] += __shfl_sync(0xffffffffu, cc.bias.x, src);
+        f[4 * j + 1] += __shfl_sync(0xffffffffu, cc.bias.y, src);
+        f[4 * j + 2] += __shfl_sync(0xffffffffu, cc.bias.z, src);
+        f[4 * j + 3] += __shfl_sync(0xffffffffu, cc.bias.w, src);
+      }
+    }
+  } else if (nvalid == 32) {  // uniform-address 16 B loads: one broadcast transaction each
     if (e.scale) {
       const float4* sp = reinterpret_cast<const float4*>(e.scale + n0);
 #pragma unroll
@@ -270,7 +323,7 @@ constexpr int kEpiStageBytes = 2 * 4096;  // per epilogue warp: two 32-row x 128
 template <int EPI, typename WaitFn>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t t_row, int n_base, int ncols,
                                                    int m_tile, int r, WaitFn wait_accumulator, uint8_t* stage_buf,
-                                                   int& store_groups) {
+                                                   int& store_groups, GemmTrace& tr) {
   const GemmEpi& e = p.e;
   long long grow;
   const bool valid = gemm_row_map(p, m_tile, r, grow);
@@ -288,6 +341,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
 #pragma unroll
       for (int j = 0; j < 8; ++j) rnext[j] = rp[j];
     }
+    const GemmColConst cc = gemm_col_const(e, p.N, n_base, ncols, r & 31);
     float row_mul = 1.f;
     if (e.row_sumsq && valid) {  // deferred pixel normalisation: logit_scale / ||feature row||, once per tile
       float ss = 0.f;
@@ -315,9 +369,9 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
       __syncwarp();
       tmem_ld32(t_row + c * 32, v);
       tmem_ld_wait();
+      float f[32];
+      gemm_epilogue_math(e, p.N, v, grow, n0, bias_off, valid, f, cc, c);  // all lanes: it shuffles
       if (valid) {
-        float f[32];
-        gemm_epilogue_math(e, p.N, v, grow, n0, bias_off, true, f);
         if (e.row_sumsq) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] *= row_mul;
@@ -338,8 +392,11 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
       crd_h = (t / p.tiles_w) * kConvTH + quarter * 2;
       crd_w = (t % p.tiles_w) * kConvTW;
     }
+    const GemmColConst cc = gemm_col_const(e, p.N, n_base, ncols, lane);
+    const bool leader = elect_one_sync();  // issues (and owns the bulk groups of) this warp's TMA stores
     wait_accumulator();
     tc_fence_after();
+    tr(1);
     if (p.probe & 1) return;
     int groups = store_groups;
 #pragma unroll 1
@@ -350,14 +407,17 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
       __syncwarp();
       tmem_ld32(t_row + c * 32, v);
       tmem_ld_wait();
+      tr(2);
       float f[32];
-      gemm_epilogue_math(e, p.N, v, grow_c, n0, bias_off, valid, f);
+      gemm_epilogue_math(e, p.N, v, grow_c, n0, bias_off, valid, f, cc, c);
+      tr(3);
       uint8_t* buf = stage_buf + (groups & 1) * 4096;
       const bool first_of_group = (EPI == EPI_TMA_ADD) || ((c & 1) == 0);
       if (first_of_group && groups >= 2) {  // the bulk op issued two groups ago must be done READING this buffer
-        if (lane == 0) tma_store_wait_read<1>();
+        if (leader) tma_store_wait_read<1>();
         __syncwarp();
       }
+      tr(4);
       if constexpr (EPI == EPI_TMA_F16) {
         // 32 rows x 64 fp16 columns per group: this chunk fills 16-byte slots (c&1)*4 .. +3 of the row
 #pragma unroll
@@ -377,24 +437,27 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
               make_float4(f[4 * t], f[4 * t + 1], f[4 * t + 2], f[4 * t + 3]);
         }
       }
+      tr(5);
       const bool last_of_group =
           (EPI == EPI_TMA_ADD) || ((c & 1) == 1) || (c + 1 == ncols / 32) || (n0 + 32 >= p.N);
       if (last_of_group) {
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
+        const int col0 = n_base + (c & ~1) * 32;
+        const int row0 = m_tile * kGemmBM + quarter * 32;
+        if (leader) {
           if constexpr (EPI == EPI_TMA_F16) {
-            const int col0 = n_base + (c & ~1) * 32;
             if (p.conv)
               tma_store_4d(&p.tma_c, buf, col0, crd_w, crd_h, crd_b);
             else
-              tma_store_2d(&p.tma_c, buf, col0, m_tile * kGemmBM + quarter * 32);
+              tma_store_2d(&p.tma_c, buf, col0, row0);
           } else {
-            tma_reduce_add_2d(&p.tma_c, buf, n0, m_tile * kGemmBM + quarter * 32);
+            tma_reduce_add_2d(&p.tma_c, buf, n0, row0);
           }
           tma_store_commit();
         }
         ++groups;
+        tr(6);
       }
     }
     store_groups = groups;
@@ -546,12 +609,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     int acc = 0;
     uint32_t acc_phase = 0;
     int unused_groups = 0;
+    GemmTrace tr;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_tile = tile % p.num_m_tiles;
       const int n_tile = tile / p.num_m_tiles;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * kColsPerWarp;
       gemm_epilogue_tile<EPI_DIRECT>(p, t_row, n_tile * BN + half * kColsPerWarp, kColsPerWarp, m_tile, r,
-                                     [&]() { mbar_wait(&tmem_full[acc], acc_phase, 4); }, nullptr, unused_groups);
+                                     [&]() { mbar_wait(&tmem_full[acc], acc_phase, 4); }, nullptr, unused_groups, tr);
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
       acc ^= 1;
@@ -688,6 +752,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
     if (rank == 0) {
       const bool leader = elect_one_sync();
       constexpr uint32_t idesc = umma_idesc_f16(2 * kGemmBM, BN, 0, 0);
+      GemmTrace tr;
+      if (p.trace && lane == 0 && (pair == 0 || pair == num_pairs / 2)) tr.w = p.trace + ((pair == 0 ? 0 : 1) * 12 + warp) * 512;
+      tr(0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -695,6 +762,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 22);
         tc_fence_after();
+        tr(10);
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kit = 0; kit < p.k_iters; ++kit) {
           mbar_wait(&full_bar[stage], phase, 23);
@@ -717,6 +785,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
         }
         if (leader) umma_commit_2cta(&tmem_full[acc], 0x3);
         __syncwarp();
+        tr(12);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -732,19 +801,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
     int store_groups = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    GemmTrace tr;
+    if (p.trace && lane == 0 && rank == 0 && (pair == 0 || pair == num_pairs / 2))
+      tr.w = p.trace + ((pair == 0 ? 0 : 1) * 12 + warp) * 512;
+    tr(0);
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int m_tile = (tile % m_pairs) * 2 + static_cast<int>(rank);
       const int n_tile = tile / m_pairs;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * kColsPerWarp;
       gemm_epilogue_tile<EPI>(p, t_row, n_tile * BN + half * kColsPerWarp, kColsPerWarp, m_tile, r,
-                              [&]() { mbar_wait(&tmem_full[acc], acc_phase, 24); }, stage_buf, store_groups);
+                              [&]() { mbar_wait(&tmem_full[acc], acc_phase, 24); }, stage_buf, store_groups, tr);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);  // leader's barrier: 2 CTAs x 8 warps
+      if (lane == 0) mbar_arrive_cluster_relaxed(&tmem_empty[acc], 0);  // leader CTA's barrier: 2 CTAs x 8 warps
+      tr(7);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    if (EPI != EPI_DIRECT && lane == 0) tma_store_wait_all();  // outstanding bulk ops read this CTA's smem
+    if (EPI != EPI_DIRECT && elect_one_sync()) tma_store_wait_all();  // outstanding bulk ops read this CTA's smem
   }
 
   tc_fence_before();

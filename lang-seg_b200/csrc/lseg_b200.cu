@@ -39,6 +39,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 static PFN_encodeTiled g_encode = nullptr;
 static int g_num_sms = 0;
 static int g_gemm_two_cta = 1;
+static unsigned long long* g_gemm_trace = nullptr;  // debug (lseg_debug_gemm_trace)
 static int g_gemm_probe = 0;
 static std::once_flag g_init_flag;
 static int g_init_status = -1;
@@ -164,7 +165,13 @@ static int gemm_plan(const GemmDesc& d, GemmPlan* plan) {
     set_error("gemm: K=%d must be a multiple of %d", d.K, kGemmBK);
     return -1;
   }
-  const int bn = (d.N > 128) ? 256 : 128;
+  int bn = (d.N > 128) ? 256 : 128;
+  {
+    // experiment knob: tile width of the in-place residual GEMMs (proj / fc2), optionally only up to a K
+    static const int add_bn = getenv("LSEG_GEMM_ADD_BN") ? atoi(getenv("LSEG_GEMM_ADD_BN")) : 0;
+    static const int add_maxk = getenv("LSEG_GEMM_ADD_MAXK") ? atoi(getenv("LSEG_GEMM_ADD_MAXK")) : (1 << 30);
+    if (add_bn == 128 && !d.conv && d.e.out_f32 && d.e.res_f32 == d.e.out_f32 && d.K <= add_maxk) bn = 128;
+  }
   plan->bn = bn;
   plan->two_cta = g_gemm_two_cta;
   const int taps = d.conv ? d.kh * d.kw : 1;
@@ -179,6 +186,7 @@ static int gemm_plan(const GemmDesc& d, GemmPlan* plan) {
   p.k_iters = p.k_chunks * taps;
   p.conv = d.conv;
   p.probe = g_gemm_probe;
+  p.trace = g_gemm_trace;
   p.e = d.e;
   if (d.conv) {
     p.H = d.H;
@@ -431,6 +439,11 @@ int lseg_mhsa(const void* qkv, void* out, int B, int N, int heads, int causal, v
   MhsaPlan plan;
   if (mhsa_plan(d, &plan)) return -1;
   return mhsa_run(plan, static_cast<cudaStream_t>(stream));
+}
+
+int lseg_debug_gemm_trace(unsigned long long* trace) {
+  g_gemm_trace = trace;
+  return 0;
 }
 
 int lseg_mhsa_trace(const void* qkv, void* out, int B, int N, int heads, int causal, unsigned long long* trace,
