@@ -418,6 +418,36 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
 // ---- misc math ---------------------------------------------------------------------------
 __device__ __forceinline__ float ex2_approx(float x);
 // Exact-erf GELU, 0.5 x (1 + erf(x / sqrt 2)) (timm Mlp / ProjectReadout use nn.GELU()), with erf from
+// 2^x on the FMA/ALU pipes (no MUFU): Cody-Waite split x = n + f, f in [-0.5, 0.5] via the 1.5*2^23 rounding trick,
+// minimax polynomial for 2^f (tools/fit_exp2.py: relative error 7.5e-5 / 2.7e-6 / 2.3e-7 for degree 3 / 4 / 5),
+// exponent added by integer arithmetic on the bit pattern: ~9 issue slots instead of one MUFU instruction (8 clk
+// of the MUFU pipe per warp, tools/probes/mufu_probe.cu). Kept as a measured experiment: neither the attention
+// softmax (LSEG_MHSA_POLY=2|3|4: 64 -> 72-77 us) nor the GELU epilogue got faster — both are bound by issue
+// slots / latency of their few warps, not by MUFU throughput. Requires -126 <= x <= 126 (the callers clamp).
+template <int DEG>
+__device__ __forceinline__ float exp2_poly(float x) {
+  const float r = x + 12582912.f;  // 1.5 * 2^23: the low mantissa bits of r now hold round(x)
+  const float f = x - (r - 12582912.f);
+  float p;
+  if (DEG == 3) {
+    p = fmaf(f, 5.517166885e-02f, 2.426111221e-01f);
+    p = fmaf(p, f, 6.932609855e-01f);
+    p = fmaf(p, f, 9.999280736e-01f);
+  } else if (DEG == 4) {
+    p = fmaf(f, 9.570101897e-03f, 5.591786033e-02f);
+    p = fmaf(p, f, 2.402474483e-01f);
+    p = fmaf(p, f, 6.931218147e-01f);
+    p = fmaf(p, f, 9.999992614e-01f);
+  } else {
+    p = fmaf(f, 1.327647190e-03f, 9.675541334e-03f);
+    p = fmaf(p, f, 5.550713274e-02f);
+    p = fmaf(p, f, 2.402211972e-01f);
+    p = fmaf(p, f, 6.931469671e-01f);
+    p = fmaf(p, f, 1.000000072e+00f);
+  }
+  return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
+}
+
 // Exact-erf GELU x * Phi(x) with Phi(x) = 1 / (1 + 2^(x * P(x^2))): P is a degree-4 minimax fit (tools/fit_gelu.py:
 // reweighted least squares against scipy erfc on [-7, 7], coefficients carry the -log2(e)); |gelu error| <= 3.7e-6 over
 // all x in fp32 arithmetic, i.e. below the fp16 rounding of the stored activation wherever that activation is
@@ -430,6 +460,8 @@ __device__ __forceinline__ float gelu_erf(float x) {
   p = fmaf(p, u, 3.602744768e-04f);
   p = fmaf(p, u, -1.052266877e-01f);
   p = fmaf(p, u, -2.302045391e+00f);
+  // (exp2_poly<4> here instead of the MUFU ex2 was measured SLOWER: fc1 51.8 -> 58.9 us; the epilogue is bound by
+  // issue slots of its 8 warps, not by the MUFU pipe)
   const float e = ex2_approx(x * p);
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));

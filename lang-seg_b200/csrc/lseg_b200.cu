@@ -90,12 +90,15 @@ static void init_once() {
   cudaFuncSetAttribute(mhsa_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   cudaFuncSetAttribute(mhsa_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMhsaSmemBytes);
   cudaFuncSetAttribute(mhsa_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-  cudaFuncSetAttribute(mhsa2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kM2SmemBytes);
-  cudaFuncSetAttribute(mhsa2_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-  cudaFuncSetAttribute(mhsa2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kM2SmemBytes);
-  cudaFuncSetAttribute(mhsa2_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-  cudaFuncSetAttribute(mhsa2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kM2SmemBytes);
-  cudaFuncSetAttribute(mhsa2_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+#define LSEG_M2_ATTR(K)                                                                       \
+  cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, kM2SmemBytes);          \
+  cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, 100)
+  LSEG_M2_ATTR((mhsa2_kernel<0, false>));
+  LSEG_M2_ATTR((mhsa2_kernel<2, false>));
+  LSEG_M2_ATTR((mhsa2_kernel<3, false>));
+  LSEG_M2_ATTR((mhsa2_kernel<4, false>));
+  LSEG_M2_ATTR((mhsa2_kernel<kMhsaPolyDefault, true>));
+#undef LSEG_M2_ATTR
   g_init_status = 0;
 }
 static int ensure_init() {
@@ -322,10 +325,13 @@ static int mhsa_run(const MhsaPlan& plan, cudaStream_t stream) {
   static const bool spin = getenv("LSEG_MHSA_SPIN") != nullptr;
   static const bool v3 = getenv("LSEG_MHSA_V3") != nullptr;  // A/B: the single-stream kernel of mhsa.cuh
   if (!v3) {
-    if (spin)
-      launch_pdl(mhsa2_kernel<true, false>, plan.grid, dim3(kM2Threads), kM2SmemBytes, stream, plan.p);
-    else
-      launch_pdl(mhsa2_kernel<false, false>, plan.grid, dim3(kM2Threads), kM2SmemBytes, stream, plan.p);
+    static const int poly = getenv("LSEG_MHSA_POLY") ? atoi(getenv("LSEG_MHSA_POLY")) : kMhsaPolyDefault;
+    switch (poly) {
+      case 2: launch_pdl(mhsa2_kernel<2, false>, plan.grid, dim3(kM2Threads), kM2SmemBytes, stream, plan.p); break;
+      case 4: launch_pdl(mhsa2_kernel<4, false>, plan.grid, dim3(kM2Threads), kM2SmemBytes, stream, plan.p); break;
+      case 3: launch_pdl(mhsa2_kernel<3, false>, plan.grid, dim3(kM2Threads), kM2SmemBytes, stream, plan.p); break;
+      default: launch_pdl(mhsa2_kernel<0, false>, plan.grid, dim3(kM2Threads), kM2SmemBytes, stream, plan.p); break;
+    }
     LSEG_CHECK_CUDA(cudaGetLastError());
     return 0;
   }
@@ -458,7 +464,7 @@ int lseg_mhsa_trace(const void* qkv, void* out, int B, int N, int heads, int cau
   MhsaPlan plan;
   if (mhsa_plan(d, &plan)) return -1;
   plan.p.trace = trace;
-  mhsa2_kernel<false, true><<<plan.grid, kM2Threads, kM2SmemBytes, static_cast<cudaStream_t>(stream)>>>(plan.p);
+  mhsa2_kernel<kMhsaPolyDefault, true><<<plan.grid, kM2Threads, kM2SmemBytes, static_cast<cudaStream_t>(stream)>>>(plan.p);
   LSEG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

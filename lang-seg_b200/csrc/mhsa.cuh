@@ -51,14 +51,17 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
 }
 
 // exp2(s*c - m) for one 32-column chunk -> fp16 pairs + fp32 partial row sum. MASK: apply key bounds.
-template <bool MASK>
+// POLY of every 8 exponentials are evaluated on the FMA pipe (exp2_poly<3>, relative error 7.5e-5 — below the
+// fp16 rounding of P) instead of the MUFU pipe, which is the bound of this kernel.
+template <bool MASK, int POLY = 0>
 __device__ __forceinline__ float mhsa_exp_chunk(const uint32_t (&s)[32], float c, float m, int kv_base, int n_tokens,
                                                 int kv_limit, __half2 (&ph)[16]) {
   float sum0 = 0.f, sum1 = 0.f;  // two chains: the row sum must not serialise behind the MUFU results
 #pragma unroll
   for (int i = 0; i < 32; i += 2) {
-    float p0 = ex2_approx(fmaf(__uint_as_float(s[i]), c, -m));
-    float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), c, -m));
+    const float x0 = fmaf(__uint_as_float(s[i]), c, -m), x1 = fmaf(__uint_as_float(s[i + 1]), c, -m);
+    float p0 = ((i & 7) < POLY) ? exp2_poly<3>(fmaxf(x0, -126.f)) : ex2_approx(x0);
+    float p1 = (((i + 1) & 7) < POLY) ? exp2_poly<3>(fmaxf(x1, -126.f)) : ex2_approx(x1);
     if (MASK) {
       const int kv = kv_base + i;
       if (!(kv < n_tokens && kv <= kv_limit)) p0 = 0.f;

@@ -29,6 +29,7 @@
 namespace lseg {
 
 constexpr int kM2Threads = 320;
+constexpr int kMhsaPolyDefault = 0;  // of every 8 exponentials on the FMA pipe (LSEG_MHSA_POLY=2|3|4: measured slower)
 constexpr int kM2KT = 64;                      // keys per tile
 constexpr int kM2KvBytes = kM2KT * kMhsaDh * 2;  // 8 KB
 constexpr int kM2Stages = 4;
@@ -37,15 +38,13 @@ constexpr int kM2PBytes = 128 * kM2KT * 2;     // 16 KB per stream
 // Q | K ring | V ring | P_A P_B | mbarriers + tmem slot
 constexpr int kM2SmemBytes = kM2QBytes + 2 * kM2Stages * kM2KvBytes + 2 * kM2PBytes + 1024;
 
+// POLY: how many of every 8 exponentials run on the FMA pipe (mhsa_exp_chunk).
 // TRACE: debug instantiation that stamps clock64() at the hand-off points of 16 sampled CTAs into p.trace
 // ([16 CTAs][10 warps][256] of (clock << 8 | tag)); tools/mhsa_trace.py prints the timeline.
-template <bool SPIN, bool TRACE = false>
+template <int POLY, bool TRACE = false>
 __global__ void __launch_bounds__(kM2Threads, 2) mhsa2_kernel(const __grid_constant__ MhsaParams p) {
   auto wait_bar = [](uint64_t* bar, uint32_t parity, int tag) {
-    if (SPIN)
-      mbar_wait_spin(bar, parity, tag);
-    else
-      mbar_wait_inl(bar, parity, tag);
+    mbar_wait_inl(bar, parity, tag);
   };
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
@@ -318,8 +317,8 @@ __global__ void __launch_bounds__(kM2Threads, 2) mhsa2_kernel(const __grid_const
         __syncwarp();
         tmem_ld32(tS, sc0);
         tmem_ld_wait();
-        l_tile = need_mask ? mhsa_exp_chunk<true>(sc0, c, m_use, kv0, p.n_tokens, kv_limit, ph)
-                           : mhsa_exp_chunk<false>(sc0, c, m_use, kv0, p.n_tokens, kv_limit, ph);
+        l_tile = need_mask ? mhsa_exp_chunk<true, POLY>(sc0, c, m_use, kv0, p.n_tokens, kv_limit, ph)
+                           : mhsa_exp_chunk<false, POLY>(sc0, c, m_use, kv0, p.n_tokens, kv_limit, ph);
         __syncwarp();
         tmem_ld32(tS + 32, sc1);  // unconditional (columns beyond a short tail tile are stale but allocated)
         tmem_ld_wait();
@@ -352,8 +351,8 @@ __global__ void __launch_bounds__(kM2Threads, 2) mhsa2_kernel(const __grid_const
         for (int i = 0; i < 4; ++i)
           *reinterpret_cast<uint4*>(p_row + ((i ^ sw) * 16)) = *reinterpret_cast<uint4*>(&ph[4 * i]);
         if (second) {
-          l_tile += need_mask ? mhsa_exp_chunk<true>(sc1, c, m_use, kv0 + 32, p.n_tokens, kv_limit, ph)
-                              : mhsa_exp_chunk<false>(sc1, c, m_use, kv0 + 32, p.n_tokens, kv_limit, ph);
+          l_tile += need_mask ? mhsa_exp_chunk<true, POLY>(sc1, c, m_use, kv0 + 32, p.n_tokens, kv_limit, ph)
+                              : mhsa_exp_chunk<false, POLY>(sc1, c, m_use, kv0 + 32, p.n_tokens, kv_limit, ph);
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             *reinterpret_cast<uint4*>(p_row + (((4 + i) ^ sw) * 16)) = *reinterpret_cast<uint4*>(&ph[4 * i]);
