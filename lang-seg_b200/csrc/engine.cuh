@@ -57,6 +57,7 @@ struct Arena {
 
 struct ImagePlan {
   int B = 0, H = 0, W = 0;
+  int epoch = 0;  // g_plan_epoch at build time (options baked into the GEMM plans)
   Arena arena;
   std::vector<Step> steps;
   std::map<std::string, const void*> debug;
@@ -200,6 +201,7 @@ static int build_image_plan(lseg_engine* eng, int B, int H, int W, cudaStream_t 
   plan->B = B;
   plan->H = H;
   plan->W = W;
+  plan->epoch = g_plan_epoch;
   Arena& arena = plan->arena;
   std::vector<Step>& steps = plan->steps;
   const int gh = H / 16, gw = W / 16, T = gh * gw, N = T + 1;
@@ -485,7 +487,7 @@ static int run_forward(lseg_engine* eng, const CallCtx& ctx, int B, int H, int W
     return -1;
   }
   LSEG_CHECK_CUDA(cudaSetDevice(eng->device));
-  if (!eng->img || eng->img->B != B || eng->img->H != H || eng->img->W != W) {
+  if (!eng->img || eng->img->B != B || eng->img->H != H || eng->img->W != W || eng->img->epoch != g_plan_epoch) {
     eng->img.reset();
     if (build_image_plan(eng, B, H, W, stream)) return -1;
   }

@@ -83,6 +83,7 @@ struct GemmParams {
   int H, W, kw, pad;
   int tiles_h, tiles_w;
   int num_m_tiles, num_n_tiles;
+  int split_k;   // EPI_TMA_ADD only: balance (tile, k-chunk) units over the CTA pairs instead of whole tiles
   unsigned long long* trace;  // debug timeline ([2 pairs][12 warps][512] of clock64 << 8 | tag), normally nullptr
   int probe;  // measurement only (tools/gemm_probe.py; results are garbage when non-zero):
               //   1 = skip epilogue work, 2 = skip TMA loads, 4 = skip MMA issue   (CTA-pair kernel)
@@ -90,11 +91,17 @@ struct GemmParams {
 };
 
 // Debug timeline of one warp (tools/gemm_trace.py): stamps are dropped when w == nullptr (always, outside the tool).
+// The stamp itself is an out-of-line call so that the untraced kernel pays one predicated branch per site, not a
+// predicated copy of the stamp code.
+__device__ __noinline__ int gemm_trace_stamp(unsigned long long* w, int n, int tag) {
+  if (n < 510) w[n++] = (static_cast<unsigned long long>(clock64()) << 8) | static_cast<unsigned>(tag);
+  return n;
+}
 struct GemmTrace {
   unsigned long long* w = nullptr;
   int n = 0;
   __device__ __forceinline__ void operator()(int tag) {
-    if (w && n < 510) w[n++] = (static_cast<unsigned long long>(clock64()) << 8) | static_cast<unsigned>(tag);
+    if (w) n = gemm_trace_stamp(w, n, tag);
   }
 };
 
@@ -125,7 +132,7 @@ __device__ __forceinline__ GemmColConst gemm_col_const(const GemmEpi& e, int N, 
 
 __device__ __forceinline__ void gemm_epilogue_math(const GemmEpi& e, int N, const uint32_t (&v)[32], long long grow,
                                                    int n0, long long bias_off, bool row_valid, float (&f)[32],
-                                                   const GemmColConst& cc, int chunk) {
+                                                   const GemmColConst& cc, int chunk, bool use_bias = true) {
   const int nvalid = min(32, N - n0);
 #pragma unroll
   for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
@@ -140,7 +147,7 @@ __device__ __forceinline__ void gemm_epilogue_math(const GemmEpi& e, int N, cons
         f[4 * j + 3] *= __shfl_sync(0xffffffffu, cc.scale.w, src);
       }
     }
-    if (e.bias) {
+    if (e.bias && use_bias) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int src = chunk * 8 + j;
@@ -323,7 +330,7 @@ constexpr int kEpiStageBytes = 2 * 4096;  // per epilogue warp: two 32-row x 128
 template <int EPI, typename WaitFn>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t t_row, int n_base, int ncols,
                                                    int m_tile, int r, WaitFn wait_accumulator, uint8_t* stage_buf,
-                                                   int& store_groups, GemmTrace& tr) {
+                                                   int& store_groups, GemmTrace& tr, bool first_k = true) {
   const GemmEpi& e = p.e;
   long long grow;
   const bool valid = gemm_row_map(p, m_tile, r, grow);
@@ -409,7 +416,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
       tmem_ld_wait();
       tr(2);
       float f[32];
-      gemm_epilogue_math(e, p.N, v, grow_c, n0, bias_off, valid, f, cc, c);
+      gemm_epilogue_math(e, p.N, v, grow_c, n0, bias_off, valid, f, cc, c, first_k);
       tr(3);
       uint8_t* buf = stage_buf + (groups & 1) * 4096;
       const bool first_of_group = (EPI == EPI_TMA_ADD) || ((c & 1) == 0);
@@ -697,13 +704,56 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
   const int m_pairs = (p.num_m_tiles + 1) >> 1;
   const int num_tiles = m_pairs * p.num_n_tiles;  // pair tiles (256 x BN)
 
+  // Work schedule of this CTA pair. Default: whole 256 x BN tiles, pair, pair + P, ... . split_k (in-place residual
+  // GEMMs only, whose epilogue is a reduce-add and therefore composes over partial sums): the (tile, k-chunk) units
+  // are dealt out evenly, so a pair handles a contiguous range that may start / end inside a tile — 116 tiles on 74
+  // pairs are 2 waves of whole tiles but only 1.57 tiles of work per pair. The bias is added by the k = 0 segment.
+  struct Sched {
+    int tile_next, tile_step, num_tiles, k_iters;
+    long long unit, unit_end;
+    bool split;
+    __device__ bool next(int& tile, int& k0, int& k1) {
+      if (!split) {
+        if (tile_next >= num_tiles) return false;
+        tile = tile_next;
+        tile_next += tile_step;
+        k0 = 0;
+        k1 = k_iters;
+        return true;
+      }
+      if (unit >= unit_end) return false;
+      tile = static_cast<int>(unit / k_iters);
+      k0 = static_cast<int>(unit - static_cast<long long>(tile) * k_iters);
+      const long long left = unit_end - unit;
+      k1 = (k_iters - k0 < left) ? k_iters : k0 + static_cast<int>(left);
+      unit += k1 - k0;
+      return true;
+    }
+  };
+  auto make_sched = [&]() {
+    Sched sc;
+    sc.tile_next = pair;
+    sc.tile_step = num_pairs;
+    sc.num_tiles = num_tiles;
+    sc.k_iters = p.k_iters;
+    sc.split = (EPI == EPI_TMA_ADD) && p.split_k;
+    const long long units = static_cast<long long>(num_tiles) * p.k_iters;
+    // boundaries on multiples of 4 k-chunks: no sliver segments whose epilogue would cost more than their MMAs
+    sc.unit = ((units * pair / num_pairs) + 3) & ~3ll;
+    sc.unit_end = (pair + 1 == num_pairs) ? units : (((units * (pair + 1) / num_pairs) + 3) & ~3ll);
+    if (sc.unit_end > units) sc.unit_end = units;
+    return sc;
+  };
+
   if (warp == 0) {
     // ===================== TMA producer (both CTAs; converged warp, elected issuing lane) =====================
     {
       const bool leader = elect_one_sync();
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      Sched sc = make_sched();
+      int tile, k_begin, k_end;
+      while (sc.next(tile, k_begin, k_end)) {
         const int m_tile = (tile % m_pairs) * 2 + static_cast<int>(rank);
         const int n_tile = tile / m_pairs;
         const int n0 = n_tile * BN + static_cast<int>(rank) * (BN / 2);
@@ -715,7 +765,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
           ch0 = (t / p.tiles_w) * kConvTH;
           cw0 = (t % p.tiles_w) * kConvTW;
         }
-        for (int kit = 0; kit < p.k_iters; ++kit) {
+        for (int kit = k_begin; kit < k_end; ++kit) {
           mbar_wait(&empty_bar[stage], phase ^ 1, 21);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
@@ -759,12 +809,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      Sched sc = make_sched();
+      int tile, k_begin, k_end;
+      while (sc.next(tile, k_begin, k_end)) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 22);
         tc_fence_after();
         tr(10);
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kit = 0; kit < p.k_iters; ++kit) {
+        for (int kit = k_begin; kit < k_end; ++kit) {
           mbar_wait(&full_bar[stage], phase, 23);
           tc_fence_after();
           const uint32_t a_base = smem_u32(smem + stage * Cfg::kStageBytes);
@@ -775,7 +827,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
               for (int k = 0; k < kGemmBK / 16; ++k) {
                 const uint64_t da = umma_desc_sw128(a_base + k * 32, 1024, 0);
                 const uint64_t db = umma_desc_sw128(b_base + k * 32, 1024, 0);
-                umma_f16_ss_2cta(d_tmem, da, db, idesc, (kit | k) != 0);
+                umma_f16_ss_2cta(d_tmem, da, db, idesc, (kit != k_begin) || (k != 0));
               }
             }
             umma_commit_2cta(&empty_bar[stage], 0x3);  // both CTAs' smem slots
@@ -805,12 +857,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
     if (p.trace && lane == 0 && rank == 0 && (pair == 0 || pair == num_pairs / 2))
       tr.w = p.trace + ((pair == 0 ? 0 : 1) * 12 + warp) * 512;
     tr(0);
-    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+    Sched sc = make_sched();
+    int tile, k_begin, k_end;
+    while (sc.next(tile, k_begin, k_end)) {
       const int m_tile = (tile % m_pairs) * 2 + static_cast<int>(rank);
       const int n_tile = tile / m_pairs;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * kColsPerWarp;
       gemm_epilogue_tile<EPI>(p, t_row, n_tile * BN + half * kColsPerWarp, kColsPerWarp, m_tile, r,
-                              [&]() { mbar_wait(&tmem_full[acc], acc_phase, 24); }, stage_buf, store_groups, tr);
+                              [&]() { mbar_wait(&tmem_full[acc], acc_phase, 24); }, stage_buf, store_groups, tr,
+                              k_begin == 0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster_relaxed(&tmem_empty[acc], 0);  // leader CTA's barrier: 2 CTAs x 8 warps

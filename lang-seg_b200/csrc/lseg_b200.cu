@@ -39,6 +39,8 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 static PFN_encodeTiled g_encode = nullptr;
 static int g_num_sms = 0;
 static int g_gemm_two_cta = 1;
+static int g_deterministic = 0;  // 1: no split-K (bit-reproducible sums); LSEG_DETERMINISTIC / lseg_set_deterministic
+static int g_plan_epoch = 0;     // bumped when an option that is baked into cached plans changes
 static unsigned long long* g_gemm_trace = nullptr;  // debug (lseg_debug_gemm_trace)
 static int g_gemm_probe = 0;
 static std::once_flag g_init_flag;
@@ -83,6 +85,7 @@ static void init_once() {
   {  // LSEG_GEMM_1CTA=1 selects the single-CTA GEMM (A/B comparisons, debugging)
     const char* env = getenv("LSEG_GEMM_1CTA");
     g_gemm_two_cta = (env && env[0] == '1') ? 0 : 1;
+    if (getenv("LSEG_DETERMINISTIC")) g_deterministic = 1;
     const char* pr = getenv("LSEG_GEMM_PROBE");  // measurement only, see GemmParams::probe
     g_gemm_probe = pr ? atoi(pr) : 0;
   }
@@ -247,6 +250,12 @@ static int gemm_plan(const GemmDesc& d, GemmPlan* plan) {
       const uint32_t box[2] = {32, 32};
       if (make_tmap(&p.tma_c, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, e.out_f32, 2, dims, str, box)) return -1;
       plan->epi = EPI_TMA_ADD;
+      // stream-K style balancing when whole tiles would leave a ragged last wave
+      const int pair_tiles = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
+      const int max_pairs = g_num_sms / 2;
+      static const int min_kit = getenv("LSEG_SPLITK_MIN_KITERS") ? atoi(getenv("LSEG_SPLITK_MIN_KITERS")) : 32;
+      p.split_k =
+          (!g_deterministic && pair_tiles > max_pairs && pair_tiles % max_pairs != 0 && p.k_iters >= min_kit) ? 1 : 0;
     }
   }
   if (plan->two_cta) {
@@ -445,6 +454,13 @@ int lseg_mhsa(const void* qkv, void* out, int B, int N, int heads, int causal, v
   MhsaPlan plan;
   if (mhsa_plan(d, &plan)) return -1;
   return mhsa_run(plan, static_cast<cudaStream_t>(stream));
+}
+
+int lseg_set_deterministic(int on) {
+  if (ensure_init()) return -1;
+  if ((on != 0) != (g_deterministic != 0)) ++g_plan_epoch;
+  g_deterministic = on ? 1 : 0;
+  return 0;
 }
 
 int lseg_debug_gemm_trace(unsigned long long* trace) {

@@ -93,6 +93,12 @@ def mhsa(qkv, B, N, heads, causal=False):
     return out
 
 
+def set_deterministic(on):
+    """True: fixed summation order everywhere (bit-reproducible); False (default): the in-place residual GEMMs may
+    split K across CTA pairs (include/lseg_b200.h lseg_set_deterministic)."""
+    check(load().lseg_set_deterministic(int(bool(on))))
+
+
 def mhsa_trace(qkv, B, N, heads, causal=False):
     """Debug: (out, trace[16 CTAs, 10 warps, 256]) with clock64 << 8 | tag stamps (tools/mhsa_trace.py)."""
     out = torch.empty((B * N, heads * 64), dtype=torch.float16, device=qkv.device)
