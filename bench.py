@@ -269,14 +269,22 @@ def main():
         g_ms_, g_fl, g_n = by[1]
         m_ms, m_fl, m_n = by[2]
         ach = g_fl / (g_ms_ / 1e3) / 1e12 if g_ms_ > 0 else 0.0
-        roofline = {"kernel": "gemm_tc_kernel (tcgen05 GEMM / implicit conv, all launches of one step)",
+        traffic, traffic_m = None, None  # DRAM bytes per launch from the committed ncu capture (profiles/), if any
+        try:
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")) as f:
+                tj = json.load(f)
+            traffic, traffic_m = tj["gemm"]["dram_bytes_per_launch"], tj["mhsa"]["dram_bytes_per_launch"]
+        except (OSError, KeyError, ValueError):
+            pass
+        roofline = {"kernel": "gemm_tc2_kernel (tcgen05 GEMM / implicit conv, all launches of one step)",
                     "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                     "peak_source": f"{peak_src} bf16 sustained (kernel timed inside a long step)",
                     "launches": g_n, "avg_launch_ms": g_ms_ / max(g_n, 1), "share_of_step": g_ms_ / tot,
-                    "traffic": None}
+                    "traffic": traffic,
+                    "traffic_note": "dram__bytes_read+write per launch, ncu capture profiles/r01_traffic.md"}
         ach_m = m_fl / (m_ms / 1e3) / 1e12 if m_ms > 0 else 0.0
-        mhsa_roof = {"kernel": "mhsa_kernel", "bound": "tensor", "achieved": ach_m, "peak": peak_tf,
-                     "unit": "TFLOP/s", "frac": ach_m / peak_tf, "launches": m_n,
+        mhsa_roof = {"kernel": "mhsa2_kernel", "bound": "tensor", "achieved": ach_m, "peak": peak_tf,
+                     "unit": "TFLOP/s", "frac": ach_m / peak_tf, "launches": m_n, "traffic": traffic_m,
                      "avg_launch_ms": m_ms / max(m_n, 1), "share_of_step": m_ms / tot}
         breakdown = {"gemm_ms": g_ms_, "mhsa_ms": m_ms, "layernorm_ms": by[3][0], "elementwise_ms": by[0][0],
                      "sum_ms": tot}

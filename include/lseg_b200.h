@@ -82,9 +82,10 @@ int lseg_gemm(const lseg_gemm_args* args, void* stream);
 /* Fused MHSA, head_dim 64 (k5; timm Attention restated at lseg_vit.py:26-39; CLIP text MHA).
  * qkv fp16 [B, N, 3*heads*64] (q|k|v thirds) -> out fp16 [B*N, heads*64]. */
 int lseg_mhsa(const void* qkv, void* out, int B, int N, int heads, int causal, void* stream);
-/* 1: every floating-point sum is formed in a fixed order (bit-reproducible across runs and batch sizes); 0 (default):
- * the in-place residual GEMMs (attention proj, MLP fc2) may split a tile's K range over two CTA pairs whose partial
- * sums are reduce-added in arrival order (differences at the fp32 rounding level). Also LSEG_DETERMINISTIC=1. */
+/* 1 (default): every floating-point sum is formed in a fixed order (bit-reproducible across runs and batch sizes).
+ * 0 (or LSEG_SPLITK=1): the in-place residual GEMM of the MLP (fc2) may split a tile's K range over two CTA pairs whose
+ * partial sums are reduce-added in arrival order (differences at the fp32 rounding level; fc2 55 -> 51 us in
+ * isolation, not visible in the end-to-end step time, hence off). */
 int lseg_set_deterministic(int on);
 /* Debug: GEMMs planned after this call stamp clock64() at the epilogue / MMA hand-off points of two CTA pairs
  * into trace ([2][12 warps][512] uint64 device memory, zeroed by the caller; NULL switches it off). */

@@ -39,7 +39,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 static PFN_encodeTiled g_encode = nullptr;
 static int g_num_sms = 0;
 static int g_gemm_two_cta = 1;
-static int g_deterministic = 0;  // 1: no split-K (bit-reproducible sums); LSEG_DETERMINISTIC / lseg_set_deterministic
+static int g_deterministic = 1;  // 1 (default): fixed summation order; 0: split-K allowed (LSEG_SPLITK=1 / lseg_set_deterministic(0))
 static int g_plan_epoch = 0;     // bumped when an option that is baked into cached plans changes
 static unsigned long long* g_gemm_trace = nullptr;  // debug (lseg_debug_gemm_trace)
 static int g_gemm_probe = 0;
@@ -85,7 +85,7 @@ static void init_once() {
   {  // LSEG_GEMM_1CTA=1 selects the single-CTA GEMM (A/B comparisons, debugging)
     const char* env = getenv("LSEG_GEMM_1CTA");
     g_gemm_two_cta = (env && env[0] == '1') ? 0 : 1;
-    if (getenv("LSEG_DETERMINISTIC")) g_deterministic = 1;
+    if (getenv("LSEG_SPLITK")) g_deterministic = 0;
     const char* pr = getenv("LSEG_GEMM_PROBE");  // measurement only, see GemmParams::probe
     g_gemm_probe = pr ? atoi(pr) : 0;
   }

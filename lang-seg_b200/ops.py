@@ -94,7 +94,7 @@ def mhsa(qkv, B, N, heads, causal=False):
 
 
 def set_deterministic(on):
-    """True: fixed summation order everywhere (bit-reproducible); False (default): the in-place residual GEMMs may
+    """True (default): fixed summation order everywhere (bit-reproducible); False: the in-place residual GEMMs may
     split K across CTA pairs (include/lseg_b200.h lseg_set_deterministic)."""
     check(load().lseg_set_deterministic(int(bool(on))))
 
