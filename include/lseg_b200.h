@@ -88,7 +88,7 @@ int lseg_mhsa(const void* qkv, void* out, int B, int N, int heads, int causal, v
  * isolation, not visible in the end-to-end step time, hence off). */
 int lseg_set_deterministic(int on);
 /* Debug: GEMMs planned after this call stamp clock64() at the epilogue / MMA hand-off points of two CTA pairs
- * into trace ([2][12 warps][512] uint64 device memory, zeroed by the caller; NULL switches it off). */
+ * into trace ([2][20 warps][512] uint64 device memory, zeroed by the caller; NULL switches it off). */
 int lseg_debug_gemm_trace(unsigned long long* trace);
 /* Debug: same computation, additionally stamps clock64() at the pipeline hand-off points of 16 sampled CTAs into
  * trace ([16][10 warps][256] uint64 device memory, zero-initialised by the caller); tools/mhsa_trace.py. */

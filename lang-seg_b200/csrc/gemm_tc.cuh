@@ -327,7 +327,9 @@ __device__ __forceinline__ bool gemm_row_map(const GemmParams& p, int m_tile, in
 constexpr int kEpiStageBytes = 2 * 4096;  // per epilogue warp: two 32-row x 128 B swizzled tiles (TMA epilogues)
 
 // Epilogue of one 128 x (ncols) accumulator slab for one warp (r = quarter*32 + lane = this thread's row).
-template <int EPI, typename WaitFn>
+// SINGLE_BUF: one 4 KB staging tile per warp instead of two (16-epilogue-warp configuration, where a warp emits one
+// store group per tile and the previous tile's bulk store has long finished reading the buffer).
+template <int EPI, bool SINGLE_BUF = false, typename WaitFn>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t t_row, int n_base, int ncols,
                                                    int m_tile, int r, WaitFn wait_accumulator, uint8_t* stage_buf,
                                                    int& store_groups, GemmTrace& tr, bool first_k = true) {
@@ -418,10 +420,15 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
       float f[32];
       gemm_epilogue_math(e, p.N, v, grow_c, n0, bias_off, valid, f, cc, c, first_k);
       tr(3);
-      uint8_t* buf = stage_buf + (groups & 1) * 4096;
+      uint8_t* buf = SINGLE_BUF ? stage_buf : stage_buf + (groups & 1) * 4096;
       const bool first_of_group = (EPI == EPI_TMA_ADD) || ((c & 1) == 0);
-      if (first_of_group && groups >= 2) {  // the bulk op issued two groups ago must be done READING this buffer
-        if (leader) tma_store_wait_read<1>();
+      if (first_of_group && groups >= (SINGLE_BUF ? 1 : 2)) {  // the bulk op that last used this buffer must be done READING it
+        if (leader) {
+          if (SINGLE_BUF)
+            tma_store_wait_read<0>();
+          else
+            tma_store_wait_read<1>();
+        }
         __syncwarp();
       }
       tr(4);
@@ -621,7 +628,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       const int m_tile = tile % p.num_m_tiles;
       const int n_tile = tile / p.num_m_tiles;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * kColsPerWarp;
-      gemm_epilogue_tile<EPI_DIRECT>(p, t_row, n_tile * BN + half * kColsPerWarp, kColsPerWarp, m_tile, r,
+      gemm_epilogue_tile<EPI_DIRECT, false>(p, t_row, n_tile * BN + half * kColsPerWarp, kColsPerWarp, m_tile, r,
                                      [&]() { mbar_wait(&tmem_full[acc], acc_phase, 4); }, nullptr, unused_groups, tr);
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
@@ -647,22 +654,30 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
 //   empty barrier  : per CTA, released by a multicast tcgen05.commit
 //   tmem full      : per CTA (multicast commit);  tmem empty: in the leader, 2 x 8 warp arrivals
 // ==========================================================================================
-template <int BN, int EPI>
+template <int BN, int EPI, int EW = 8>
 struct Gemm2Cfg {
   static constexpr int kABytes = kGemmBM * kGemmBK * 2;
   static constexpr int kBBytes = (BN / 2) * kGemmBK * 2;  // this CTA's half of the weight tile
   static constexpr int kStageBytes = kABytes + kBBytes;
+  // Epilogue warps EW: 8, or 16 (fp16 TMA-store epilogue of 256-wide tiles only: 4 warps per TMEM lane quarter, 64
+  // columns each). The planner picks 16 where the epilogue, not the main loop, bounds the tile — K <= 512 (head1
+  // 251 -> 185 us, 1x1 out_conv 110 -> 87 us) and the GELU epilogue of fc1 (61 -> 58 us); with long K the extra
+  // warps only take issue slots from the producer / MMA warps (QKV +2 us, 3x3 convs +6 us).
+  static_assert(EW == 8 || (EW == 16 && EPI == EPI_TMA_F16 && BN == 256), "16 epilogue warps: TMA fp16 store, BN 256");
+  static constexpr int kEpiWarps = EW;
+  static constexpr int kThreads = 128 + 32 * kEpiWarps;
+  static constexpr int kEpiBufBytes = (kEpiWarps == 16) ? 4096 : kEpiStageBytes;
   // stages | per-warp TMA-epilogue staging (1024 B aligned) | mbarriers
-  static constexpr int kStageOutBytes = (EPI == EPI_DIRECT) ? 0 : kGemmEpiWarps * kEpiStageBytes;
+  static constexpr int kStageOutBytes = (EPI == EPI_DIRECT) ? 0 : kEpiWarps * kEpiBufBytes;
   static constexpr int kStages = (BN == 256) ? ((EPI == EPI_DIRECT) ? 6 : 5) : ((EPI == EPI_DIRECT) ? 8 : 6);
   static constexpr int kTmemCols = 2 * BN;
   static constexpr int kSmemBytes = kStages * kStageBytes + kStageOutBytes + 1024 + 256;
 };
 
-template <int BN, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+template <int BN, int EPI, int EW = 8>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((Gemm2Cfg<BN, EPI, EW>::kThreads), 1)
     gemm_tc2_kernel(const __grid_constant__ GemmParams p) {
-  using Cfg = Gemm2Cfg<BN, EPI>;
+  using Cfg = Gemm2Cfg<BN, EPI, EW>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_out = smem + Cfg::kStages * Cfg::kStageBytes;
@@ -689,7 +704,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 2 * kGemmEpiWarps);
+      mbar_init(&tmem_empty[i], 2 * Cfg::kEpiWarps);
     }
     mbar_fence_init();
   }
@@ -803,7 +818,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
       const bool leader = elect_one_sync();
       constexpr uint32_t idesc = umma_idesc_f16(2 * kGemmBM, BN, 0, 0);
       GemmTrace tr;
-      if (p.trace && lane == 0 && (pair == 0 || pair == num_pairs / 2)) tr.w = p.trace + ((pair == 0 ? 0 : 1) * 12 + warp) * 512;
+      if (p.trace && lane == 0 && (pair == 0 || pair == num_pairs / 2)) tr.w = p.trace + ((pair == 0 ? 0 : 1) * 20 + warp) * 512;
       tr(0);
       int stage = 0;
       uint32_t phase = 0;
@@ -847,15 +862,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
     const int ew = warp - 4;
     const int quarter = warp & 3;
     const int half = ew >> 2;
-    constexpr int kColsPerWarp = BN / (kGemmEpiWarps / 4);
+    constexpr int kColsPerWarp = BN / (Cfg::kEpiWarps / 4);
     const int r = quarter * 32 + lane;
-    uint8_t* stage_buf = stage_out + ew * kEpiStageBytes;
+    uint8_t* stage_buf = stage_out + ew * Cfg::kEpiBufBytes;
     int store_groups = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     GemmTrace tr;
     if (p.trace && lane == 0 && rank == 0 && (pair == 0 || pair == num_pairs / 2))
-      tr.w = p.trace + ((pair == 0 ? 0 : 1) * 12 + warp) * 512;
+      tr.w = p.trace + ((pair == 0 ? 0 : 1) * 20 + warp) * 512;
     tr(0);
     Sched sc = make_sched();
     int tile, k_begin, k_end;
@@ -863,7 +878,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
       const int m_tile = (tile % m_pairs) * 2 + static_cast<int>(rank);
       const int n_tile = tile / m_pairs;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * kColsPerWarp;
-      gemm_epilogue_tile<EPI>(p, t_row, n_tile * BN + half * kColsPerWarp, kColsPerWarp, m_tile, r,
+      gemm_epilogue_tile<EPI, Cfg::kEpiWarps == 16>(p, t_row, n_tile * BN + half * kColsPerWarp, kColsPerWarp, m_tile, r,
                               [&]() { mbar_wait(&tmem_full[acc], acc_phase, 24); }, stage_buf, store_groups, tr,
                               k_begin == 0);
       tc_fence_before();

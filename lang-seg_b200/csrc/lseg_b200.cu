@@ -82,6 +82,8 @@ static void init_once() {
   LSEG_SET_SMEM_TC2(128, EPI_TMA_F16);
   LSEG_SET_SMEM_TC2(128, EPI_TMA_ADD);
 #undef LSEG_SET_SMEM_TC2
+  cudaFuncSetAttribute(gemm_tc2_kernel<256, EPI_TMA_F16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       Gemm2Cfg<256, EPI_TMA_F16, 16>::kSmemBytes);
   {  // LSEG_GEMM_1CTA=1 selects the single-CTA GEMM (A/B comparisons, debugging)
     const char* env = getenv("LSEG_GEMM_1CTA");
     g_gemm_two_cta = (env && env[0] == '1') ? 0 : 1;
@@ -159,6 +161,7 @@ struct GemmPlan {
   GemmParams p;
   int bn;
   int grid;
+  int ew16;     // 1: 16 epilogue warps (short-K / GELU fp16 TMA-store GEMMs)
   int two_cta;  // 1: CTA-pair kernel (tcgen05 cta_group::2), 0: single-CTA kernel
   int epi;      // GemmEpiMode (CTA-pair kernel)
 };
@@ -224,6 +227,7 @@ static int gemm_plan(const GemmDesc& d, GemmPlan* plan) {
   // TMA-store epilogue: plain fp16 row-major outputs of the CTA-pair kernel (QKV, fc1, readout, 1x1 / 3x3
   // convs feeding the next conv, head1, text in_proj / c_fc)
   plan->epi = EPI_DIRECT;
+  plan->ew16 = 0;
   {
     const GemmEpi& e = p.e;
     static const bool disabled = getenv("LSEG_GEMM_NO_TMA_STORE") != nullptr;
@@ -242,6 +246,7 @@ static int gemm_plan(const GemmDesc& d, GemmPlan* plan) {
         if (make_tmap_f16(&p.tma_c, e.out_f16, 2, dims, str, box)) return -1;
       }
       plan->epi = EPI_TMA_F16;
+      plan->ew16 = (bn == 256 && (p.k_iters <= 8 || e.act == ACT_GELU)) ? 1 : 0;
     } else if (rowmajor && !d.conv && e.out_f32 && e.res_f32 == e.out_f32 && !e.res2_f32 && !e.res_f16 &&
                !e.out_f16 && !e.out_f16_relu && !e.out_row_sumsq && (e.ldc % 4 == 0)) {
       // in-place fp32 residual stream: x += A W^T + b through a bulk tensor reduce-add (x is never read)
@@ -281,9 +286,12 @@ static int gemm_run(const GemmPlan& plan, cudaStream_t stream) {
   if (plan.grid <= 0) return 0;
   if (plan.two_cta) {
 #define LSEG_LAUNCH_TC2(BN_, EPI_) \
-  launch_pdl(gemm_tc2_kernel<BN_, EPI_>, dim3(plan.grid), dim3(kGemmThreads), Gemm2Cfg<BN_, EPI_>::kSmemBytes, stream, plan.p)
+  launch_pdl(gemm_tc2_kernel<BN_, EPI_>, dim3(plan.grid), dim3(Gemm2Cfg<BN_, EPI_>::kThreads), Gemm2Cfg<BN_, EPI_>::kSmemBytes, stream, plan.p)
     if (plan.bn == 256) {
-      if (plan.epi == EPI_TMA_F16) LSEG_LAUNCH_TC2(256, EPI_TMA_F16);
+      if (plan.epi == EPI_TMA_F16 && plan.ew16)
+        launch_pdl(gemm_tc2_kernel<256, EPI_TMA_F16, 16>, dim3(plan.grid), dim3(Gemm2Cfg<256, EPI_TMA_F16, 16>::kThreads),
+                   Gemm2Cfg<256, EPI_TMA_F16, 16>::kSmemBytes, stream, plan.p);
+      else if (plan.epi == EPI_TMA_F16) LSEG_LAUNCH_TC2(256, EPI_TMA_F16);
       else if (plan.epi == EPI_TMA_ADD) LSEG_LAUNCH_TC2(256, EPI_TMA_ADD);
       else LSEG_LAUNCH_TC2(256, EPI_DIRECT);
     } else {

@@ -28,14 +28,14 @@ else:
 for _ in range(3):
     fn()
 torch.cuda.synchronize()
-tr = torch.zeros((2, 12, 512), dtype=torch.int64, device="cuda")
+tr = torch.zeros((2, 20, 512), dtype=torch.int64, device="cuda")
 load().lseg_debug_gemm_trace(C.c_void_p(tr.data_ptr()))
 fn()
 torch.cuda.synchronize()
 load().lseg_debug_gemm_trace(None)
 tr = tr.cpu().numpy()
 for slot in range(2):
-    ts = [int(x) >> 8 for wv in range(12) for x in tr[slot, wv] if x]
+    ts = [int(x) >> 8 for wv in range(20) for x in tr[slot, wv] if x]
     if not ts:
         continue
     t0 = min(ts)
