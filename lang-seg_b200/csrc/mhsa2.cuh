@@ -270,53 +270,53 @@ __global__ void __launch_bounds__(kM2Threads, 2) mhsa2_kernel(const __grid_const
       wait_bar(&s_full[s], t & 1, 19);
       tc_fence_after();
       TR(1);
-      // Pass 1: row max over the tile (both 32-column chunks in flight together; nothing else is live).
-      // Pass 2 re-reads the chunks one at a time: holding all 64 scores AND the fp16 results would spill at the
-      // 96 registers that 2 CTAs/SM allow, and spills are ruinous here (the smem carve-out leaves almost no L1).
-      bool any_move = false;
-      float factor = 1.f, m_use = 0.f;
-      if (row_active) {
-        float pm;
-        {
-          uint32_t s0[32];
+      // Single pass over S, one 32-column chunk at a time (holding all 64 scores plus the fp16 results would spill at
+      // the 96 registers that 2 CTAs/SM allow, and spills are ruinous here: the smem carve-out leaves almost no
+      // L1). The running offset m_ref is LAZY and is checked per chunk on the registers that feed the exponentials
+      // anyway: it only moves when a chunk's row max exceeds it by more than 2^kMhsaTau (first chunk of the stream,
+      // then rarely), in which case l, the TMEM-resident O row and — for the second chunk — the already
+      // stored first half of P are rescaled. No separate max pass, no second trip to TMEM.
+      auto rescale_o = [&](float factor) {  // warp-collective; factor = 1 for rows whose offset did not move
+        tc_fence_after();
+#pragma unroll 1
+        for (int cc = 0; cc < 8; ++cc) {
+          uint32_t o[8];
           __syncwarp();
-          tmem_ld32(tS, s0);
+          tmem_ld8(tO + cc * 8, o);
           tmem_ld_wait();
-          pm = need_mask ? mhsa_max_chunk<true>(s0, kv0, p.n_tokens, kv_limit)
-                         : mhsa_max_chunk<false>(s0, kv0, p.n_tokens, kv_limit);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+          tmem_st8(tO + cc * 8, o);
         }
-        if (nc > 32) {
-          uint32_t s1[32];
-          __syncwarp();
-          tmem_ld32(tS + 32, s1);
-          tmem_ld_wait();
-          pm = fmaxf(pm, need_mask ? mhsa_max_chunk<true>(s1, kv0 + 32, p.n_tokens, kv_limit)
-                                   : mhsa_max_chunk<false>(s1, kv0 + 32, p.n_tokens, kv_limit));
-        }
+        tmem_st_wait();
+      };
+      auto move_offset = [&](float pm, float& factor) -> bool {  // returns the warp-uniform "some row moved"
         const float mx = pm * c;
-        const bool move = mx > m_ref + kMhsaTau;  // lazy offset: also true on the stream's first unmasked tile
-        any_move = __any_sync(0xffffffffu, move);
-        if (any_move) {
+        const bool move = mx > m_ref + kMhsaTau;  // also true on the stream's first unmasked chunk (m_ref = -inf)
+        const bool any = __any_sync(0xffffffffu, move);
+        factor = 1.f;
+        if (any) {
           const float m_new = move ? mx : m_ref;
           factor = (m_ref == -INFINITY) ? 0.f : ex2_approx(m_ref - m_new);
-          l_run *= factor;
           m_ref = m_new;
         }
-        m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
-      }
-      TR(2);
-      // Pass 2: p = exp2(s*c - m_ref) as packed fp16. The first chunk is computed and the second chunk is fetched
-      // (which releases S for the stream's next S MMA) BEFORE waiting for the stream's previous PV: only the P
-      // store and the (rare) O rescale need the P buffer free / O quiescent, so the MMA latency hides here.
+        return any;
+      };
       __half2 ph[16];
       uint32_t sc1[32];
-      float l_tile = 0.f;
+      float l_tile = 0.f, factor0 = 1.f;
+      bool any0 = false;
       const bool second = row_active && nc > 32;  // warp-uniform
       if (row_active) {
         uint32_t sc0[32];
         __syncwarp();
         tmem_ld32(tS, sc0);
         tmem_ld_wait();
+        const float pm = need_mask ? mhsa_max_chunk<true>(sc0, kv0, p.n_tokens, kv_limit)
+                                   : mhsa_max_chunk<false>(sc0, kv0, p.n_tokens, kv_limit);
+        any0 = move_offset(pm, factor0);
+        if (any0) l_run *= factor0;
+        const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
         l_tile = need_mask ? mhsa_exp_chunk<true, POLY>(sc0, c, m_use, kv0, p.n_tokens, kv_limit, ph)
                            : mhsa_exp_chunk<false, POLY>(sc0, c, m_use, kv0, p.n_tokens, kv_limit, ph);
         __syncwarp();
@@ -327,22 +327,10 @@ __global__ void __launch_bounds__(kM2Threads, 2) mhsa2_kernel(const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_free[s]);  // last read of S_j: the stream's next S MMA may start
       TR(3);
+      // only the P store and the O rescale need the stream's previous PV retired (P buffer free, O quiescent)
       if (t > 0) {
         wait_bar(&o_done[s], (t - 1) & 1, 20);
-        if (any_move) {  // rescale the TMEM-resident output row (warp-collective; factor = 1 for unmoved rows)
-          tc_fence_after();
-#pragma unroll 1
-          for (int cc = 0; cc < 8; ++cc) {
-            uint32_t o[8];
-            __syncwarp();
-            tmem_ld8(tO + cc * 8, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
-            tmem_st8(tO + cc * 8, o);
-          }
-          tmem_st_wait();
-        }
+        if (any0) rescale_o(factor0);
       }
       TR(4);
       if (row_active) {
@@ -351,6 +339,27 @@ __global__ void __launch_bounds__(kM2Threads, 2) mhsa2_kernel(const __grid_const
         for (int i = 0; i < 4; ++i)
           *reinterpret_cast<uint4*>(p_row + ((i ^ sw) * 16)) = *reinterpret_cast<uint4*>(&ph[4 * i]);
         if (second) {
+          const float pm = need_mask ? mhsa_max_chunk<true>(sc1, kv0 + 32, p.n_tokens, kv_limit)
+                                     : mhsa_max_chunk<false>(sc1, kv0 + 32, p.n_tokens, kv_limit);
+          float factor1;
+          if (move_offset(pm, factor1)) {  // rare: the first half of this tile was exponentiated against the old offset
+            l_run *= factor1;
+            l_tile *= factor1;
+            if (t > 0) rescale_o(factor1);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4* slot = reinterpret_cast<uint4*>(p_row + ((i ^ sw) * 16));
+              uint4 q = *slot;
+              __half2* h = reinterpret_cast<__half2*>(&q);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float2 f2 = __half22float2(h[u]);
+                h[u] = __floats2half2_rn(f2.x * factor1, f2.y * factor1);
+              }
+              *slot = q;
+            }
+          }
+          const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
           l_tile += need_mask ? mhsa_exp_chunk<true, POLY>(sc1, c, m_use, kv0 + 32, p.n_tokens, kv_limit, ph)
                               : mhsa_exp_chunk<false, POLY>(sc1, c, m_use, kv0 + 32, p.n_tokens, kv_limit, ph);
 #pragma unroll
