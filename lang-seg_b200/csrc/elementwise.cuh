@@ -220,50 +220,65 @@ static inline int launch_im2col_3x3_s2(const __half* x, __half* a, int B, int H,
 // ------------------------------------------------------------------------------------------
 // bilinear x2, align_corners=True, NHWC fp16 -> NHWC fp16 (fusion blocks, lseg_blocks.py:352-354).
 // src = dst * (in-1)/(out-1), computed like ATen (float scale, float product).
-// grid (ceil(Wo/8), Ho, B), 256 threads: 8 output pixels x 32 channel groups of 8.
+// grid (ceil(Wo/32), Ho, B), 256 threads: a warp produces 4 consecutive output pixels (32 channel groups of 8 per
+// pixel) with all 16 source loads in flight before the first use — one pixel per warp (4 loads, then a store) was
+// bound by the load round trip (1.6 TB/s of output at 240x240x256).
 // ------------------------------------------------------------------------------------------
 __global__ void upsample2x_nhwc_kernel(const __half* __restrict__ x, __half* __restrict__ y, int H, int W, int C) {
   griddep_launch_dependents();
   griddep_wait();
   const int Ho = 2 * H, Wo = 2 * W, c8 = C / 8;
   const int oy = blockIdx.y, b = blockIdx.z;
-  const int ox = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (ox >= Wo) return;
+  const int ox0 = blockIdx.x * 32 + (threadIdx.x >> 5) * 4;
+  if (ox0 >= Wo) return;
   const float sh = (Ho > 1) ? static_cast<float>(H - 1) / (Ho - 1) : 0.f;
   const float sw = (Wo > 1) ? static_cast<float>(W - 1) / (Wo - 1) : 0.f;
-  const float fy = sh * oy, fx = sw * ox;
-  const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
-  const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
-  const float ly = fy - y0, lx = fx - x0, hy = 1.f - ly, hx = 1.f - lx;
+  const float fy = sh * oy;
+  const int y0 = static_cast<int>(fy);
+  const int y1 = min(y0 + 1, H - 1);
+  const float ly = fy - y0, hy = 1.f - ly;
   const __half* base = x + static_cast<long long>(b) * H * W * C;
-  const __half* p00 = base + (static_cast<long long>(y0) * W + x0) * C;
-  const __half* p01 = base + (static_cast<long long>(y0) * W + x1) * C;
-  const __half* p10 = base + (static_cast<long long>(y1) * W + x0) * C;
-  const __half* p11 = base + (static_cast<long long>(y1) * W + x1) * C;
-  __half* dst = y + ((static_cast<long long>(b) * Ho + oy) * Wo + ox) * C;
+  const __half* row0 = base + static_cast<long long>(y0) * W * C;
+  const __half* row1 = base + static_cast<long long>(y1) * W * C;
+  __half* dst = y + ((static_cast<long long>(b) * Ho + oy) * Wo + ox0) * C;
   for (int c = threadIdx.x & 31; c < c8; c += 32) {
-    const uint4 q00 = reinterpret_cast<const uint4*>(p00)[c];
-    const uint4 q01 = reinterpret_cast<const uint4*>(p01)[c];
-    const uint4 q10 = reinterpret_cast<const uint4*>(p10)[c];
-    const uint4 q11 = reinterpret_cast<const uint4*>(p11)[c];
-    const __half2* a00 = reinterpret_cast<const __half2*>(&q00);
-    const __half2* a01 = reinterpret_cast<const __half2*>(&q01);
-    const __half2* a10 = reinterpret_cast<const __half2*>(&q10);
-    const __half2* a11 = reinterpret_cast<const __half2*>(&q11);
-    uint4 o;
-    __half2* oh = reinterpret_cast<__half2*>(&o);
+    uint4 q00[4], q01[4], q10[4], q11[4];
+    float lx[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const float2 f00 = __half22float2(a00[k]), f01 = __half22float2(a01[k]);
-      const float2 f10 = __half22float2(a10[k]), f11 = __half22float2(a11[k]);
-      oh[k] = __floats2half2_rn(hy * (hx * f00.x + lx * f01.x) + ly * (hx * f10.x + lx * f11.x),
-                                hy * (hx * f00.y + lx * f01.y) + ly * (hx * f10.y + lx * f11.y));
+      const int ox = min(ox0 + k, Wo - 1);  // clamped duplicates are computed but not stored
+      const float fx = sw * ox;
+      const int x0 = static_cast<int>(fx);
+      const int x1 = min(x0 + 1, W - 1);
+      lx[k] = fx - x0;
+      q00[k] = reinterpret_cast<const uint4*>(row0 + static_cast<long long>(x0) * C)[c];
+      q01[k] = reinterpret_cast<const uint4*>(row0 + static_cast<long long>(x1) * C)[c];
+      q10[k] = reinterpret_cast<const uint4*>(row1 + static_cast<long long>(x0) * C)[c];
+      q11[k] = reinterpret_cast<const uint4*>(row1 + static_cast<long long>(x1) * C)[c];
     }
-    reinterpret_cast<uint4*>(dst)[c] = o;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (ox0 + k >= Wo) break;
+      const float hx = 1.f - lx[k];
+      const __half2* a00 = reinterpret_cast<const __half2*>(&q00[k]);
+      const __half2* a01 = reinterpret_cast<const __half2*>(&q01[k]);
+      const __half2* a10 = reinterpret_cast<const __half2*>(&q10[k]);
+      const __half2* a11 = reinterpret_cast<const __half2*>(&q11[k]);
+      uint4 o;
+      __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f00 = __half22float2(a00[j]), f01 = __half22float2(a01[j]);
+        const float2 f10 = __half22float2(a10[j]), f11 = __half22float2(a11[j]);
+        oh[j] = __floats2half2_rn(hy * (hx * f00.x + lx[k] * f01.x) + ly * (hx * f10.x + lx[k] * f11.x),
+                                  hy * (hx * f00.y + lx[k] * f01.y) + ly * (hx * f10.y + lx[k] * f11.y));
+      }
+      reinterpret_cast<uint4*>(dst + static_cast<long long>(k) * C)[c] = o;
+    }
   }
 }
 static inline int launch_upsample2x_nhwc(const __half* x, __half* y, int B, int H, int W, int C, cudaStream_t s) {
-  launch_pdl(upsample2x_nhwc_kernel, dim3((2 * W + 7) / 8, 2 * H, B), dim3(256), 0, s, x, y, H, W, C);
+  launch_pdl(upsample2x_nhwc_kernel, dim3((2 * W + 31) / 32, 2 * H, B), dim3(256), 0, s, x, y, H, W, C);
   LSEG_LAUNCH_CHECK();
 }
 

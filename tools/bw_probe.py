@@ -32,6 +32,8 @@ out["copy_rw_GBs"] = 2 * y.numel() * 4 / out["copy_1.1GB_us"] / 1e3
 lr = torch.randn(8, 150, 240, 240, device="cuda").half()
 out["upsample_us"] = bench(lambda: ops.upsample2x_nchw(lr))
 out["upsample_write_GBs"] = y.numel() * 4 / out["upsample_us"] / 1e3
+xh = torch.randn(8, 120, 120, 256, device="cuda").half()
+out["upsample_nhwc_us"] = bench(lambda: ops.upsample2x_nhwc(xh), 20)
 x = torch.randn(7208, 1024, device="cuda")
 g = torch.ones(1024, device="cuda")
 out["layernorm_us"] = bench(lambda: ops.layernorm(x, g, g, 1e-6), 50)
