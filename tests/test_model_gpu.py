@@ -63,7 +63,10 @@ def test_text_encoder(net):
     assert d["rel_err"] < 1e-2 and d["min_cos"] > 0.9999
 
 
-@pytest.mark.parametrize("B,H,W,K", [(2, 64, 96, 5), (1, 480, 480, 150), (1, 480, 480, 2)])
+# configs[1] / configs[0] of BASELINE.json plus small, non-square and odd-label-count shapes (partial M / N tiles, token
+# grids that are not square, label counts that are not a multiple of 8)
+@pytest.mark.parametrize("B,H,W,K", [(2, 64, 96, 5), (1, 480, 480, 150), (1, 480, 480, 2), (2, 160, 224, 7),
+                                     (1, 320, 512, 33)])
 def test_forward_vs_oracle(net, B, H, W, K):
     labels = synth.ade20k_labels()[:K] if K != 2 else ["cat", "other"]
     tokens = synth.tokenize(labels)
