@@ -9,27 +9,34 @@
 //
 // Roles (one CTA per SM, persistent over a static round-robin tile list):
 //   warp 0   TMA producer       : fills the A/B smem ring (128B-swizzled, K-major)
-//   warp 1   MMA issuer         : one thread issues tcgen05.mma, commits to mbarriers
+//   warp 1   MMA issuer         : tcgen05.mma + commits to mbarriers
+//             (both warps run CONVERGED; one elect.sync lane predicates only the bulk-copy / MMA instructions,
+//              so descriptor arithmetic stays on the uniform datapath — a divergent `if (lane == 0)` region cost
+//              ~20 dependent instructions, ~130 clk, per tcgen05.mma)
 //   warp 2   TMEM allocator
-//   warps 4+ epilogue           : tcgen05.ld accumulator -> regs -> scale/bias/act/residual -> global
+//   warps 4+ epilogue (8 or 16) : tcgen05.ld accumulator -> regs -> scale/bias/act/residual -> global
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
 // the main loop of tile i+1.
 //
 // Kernels
-//   gemm_tc2_kernel<BN, EPI>  CTA pair (tcgen05 cta_group::2, UMMA 256 x BN x 16): default. Shared-memory
+//   gemm_tc2_kernel<BN, EPI, EW>  CTA pair (tcgen05 cta_group::2, UMMA 256 x BN x 16): default. Shared-memory
 //        bandwidth is the binding resource of an SS-mode UMMA main loop (every byte TMA writes is read back by
 //        the tensor core); the pair splits the weight tile, so each SM stages 32 KB per k-step instead of 48.
 //   gemm_tc_kernel<BN>        single CTA (LSEG_GEMM_1CTA=1), direct epilogue only; kept for A/B measurements.
 //
-// Epilogue modes (measured with tools/gemm_probe.py: the main loop alone runs at 1300-1400 TFLOP/s, so for
-// K <= 1024 the epilogue decides the speed):
+// Epilogue modes (measured with tools/gemm_probe.py / tools/gemm_trace.py: the main loop alone runs at
+// 1450-1500 TFLOP/s on the ViT shapes, so for K <= 1024 the epilogue decides the speed; with the tensor core
+// writing the other accumulator buffer a tcgen05.ld returns after ~700 clk):
 //   EPI_DIRECT   stores straight from registers, thread <-> accumulator row. Every 16 B access of a warp
 //                touches 32 different 128 B lines = 32 L1TEX wavefronts; fine for long-K tiles, 2-3x the
 //                main-loop time for K = 1024.
 //   EPI_TMA_F16  fp16 row-major outputs: each epilogue warp packs 32 rows x 64 columns into a private
-//                128B-swizzled smem tile and one lane issues a bulk tensor store (QKV 58 -> 42 us).
+//                128B-swizzled smem tile and one elected lane issues a bulk tensor store (QKV 58 -> 36 us);
+//                EW = 16 epilogue warps (64 columns each, one staging tile per warp) where K <= 512 or GELU.
 //   EPI_TMA_ADD  in-place fp32 residual stream (x += A W^T + b): the warp stages 32 x 32 fp32 results and
 //                issues a bulk tensor REDUCE-ADD, so the residual is never read by the SM at all.
+// Per-column constants (bias, folded-BN scale) live in registers per tile and are distributed by shuffle; the
+// TMEM hand-off back to the MMA warp is a relaxed cluster arrive (a release arrive drains the stores: 1.6k clk).
 // Rejected after measurement: a full smem transpose of the accumulator (competes with the main loop for smem
 // bandwidth: every GEMM 1.3-2.3x slower) and computing D^T so that lanes map to columns (4 B accesses: 4x
 // the LSU instructions, proj 39 -> 84 us).

@@ -10,8 +10,10 @@
 //   TMEM, its own P buffer in smem and its own (m, l) row state in registers, and four softmax warps
 //   (thread <-> query row). No exchange between streams until the end, where the two partial results are merged
 //   (O = O_A 2^(mA-M) + O_B 2^(mB-M), same for l). With 2 CTAs/SM an SM has four independent streams.
-//   * S is read from TMEM once into registers and released immediately, so the next S MMA of the stream runs
-//     under the exponentials of the current tile.
+//   * S is read from TMEM once, 32 columns at a time; the second half is fetched (which releases S for the
+//     stream's next S MMA) before the wait for the previous PV, so both hand-offs hide under exponentials.
+//   * the running offset is lazy and checked per 32-column chunk on the registers that feed the exponentials:
+//     no separate max pass (it cost a second trip to TMEM per tile).
 //   * the last key tile only computes ceil16(valid keys) columns (S MMA with N = 16.., PV with K = 16..):
 //     901 tokens = 14 tiles of 64 + 5 keys instead of 8 x 128 (11 % fewer exponentials and MMAs).
 //   * row groups of 32 that lie entirely beyond the sequence (the last query tile has 5 valid rows of 128)
