@@ -19,9 +19,10 @@
 //   * row groups of 32 that lie entirely beyond the sequence (the last query tile has 5 valid rows of 128)
 //     skip the softmax arithmetic: their P rows are garbage, which only reaches their own (unstored) O rows.
 //
-// Warps: 0 TMA producer (Q; K and V 64-key tiles through 4-deep rings; issuing a 64-row box costs the thread
-//        300-500 clk, which is why it is not folded into the MMA thread) + TMEM alloc; 1 MMA issuer: one thread
-//        multiplexes both streams by polling the hand-off barriers, PV first; 2..5 softmax stream A;
+// Warps: 0 TMA producer (Q; K and V 64-key tiles through 4-deep rings) + TMEM alloc; 1 MMA issuer: one warp
+//        multiplexes both streams by polling the hand-off barriers, PV first (both run converged with an elected
+//        issuing lane: from a divergent single lane a 64-row TMA box cost 300-500 clk to issue, a UMMA 130);
+//        2..5 softmax stream A;
 //        6..9 softmax stream B (warp & 3 = TMEM lane quarter).
 // TMEM (256 columns, 2 CTAs/SM): S_A [0,64) S_B [64,128) O_A [128,192) O_B [192,256).
 #pragma once
@@ -119,21 +120,31 @@ __global__ void __launch_bounds__(kM2Threads, 2) mhsa2_kernel(const __grid_const
   TR(0);
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      mbar_expect_tx(q_full, kM2QBytes);
-      tma_load_3d(sQ, &p.tma_t64, q_full, h * kMhsaDh, q0, b);
-      tma_load_3d(sQ + kM2QBytes / 2, &p.tma_t64, q_full, h * kMhsaDh, q0 + 64, b);
+    // ===================== TMA producer (converged warp, elected issuing lane) =====================
+    {
+      const bool leader = elect_one_sync();
+      if (leader) {
+        mbar_expect_tx(q_full, kM2QBytes);
+        tma_load_3d(sQ, &p.tma_t64, q_full, h * kMhsaDh, q0, b);
+        tma_load_3d(sQ + kM2QBytes / 2, &p.tma_t64, q_full, h * kMhsaDh, q0 + 64, b);
+      }
+      __syncwarp();
       for (int j = 0; j < nkt; ++j) {
         const int slot = j & (kM2Stages - 1);
         const uint32_t par = ((j / kM2Stages) & 1) ^ 1;
         wait_bar(&k_empty[slot], par, 11);
-        mbar_expect_tx(&k_full[slot], kM2KvBytes);
-        tma_load_3d(sK + slot * kM2KvBytes, &p.tma_t64, &k_full[slot], p.D + h * kMhsaDh, j * kM2KT, b);
+        if (leader) {
+          mbar_expect_tx(&k_full[slot], kM2KvBytes);
+          tma_load_3d(sK + slot * kM2KvBytes, &p.tma_t64, &k_full[slot], p.D + h * kMhsaDh, j * kM2KT, b);
+        }
+        __syncwarp();
         TR(20);
         wait_bar(&v_empty[slot], par, 12);
-        mbar_expect_tx(&v_full[slot], kM2KvBytes);
-        tma_load_3d(sV + slot * kM2KvBytes, &p.tma_t64, &v_full[slot], 2 * p.D + h * kMhsaDh, j * kM2KT, b);
+        if (leader) {
+          mbar_expect_tx(&v_full[slot], kM2KvBytes);
+          tma_load_3d(sV + slot * kM2KvBytes, &p.tma_t64, &v_full[slot], 2 * p.D + h * kMhsaDh, j * kM2KT, b);
+        }
+        __syncwarp();
         TR(21);
       }
     }
