@@ -118,6 +118,9 @@ int lseg_l2norm_scale(const float* x, void* y, long long M, int C, float logit_s
 int lseg_l2norm_f16(const void* x, void* y, int M, int C, void* stream);
 /* fp16 logits [planes,H,W] -> fp32 [planes,2H,2W], bilinear align_corners=True (k20; lseg_net.py:203). */
 int lseg_upsample2x_nchw(const void* x, float* y, long long planes, int H, int W, void* stream);
+/* Interpolate (lseg_blocks.py:113-147) fused with torch.max(., 1)[1]: lr fp16 [B,K,H,W] -> mask int64 [B,2H,2W]
+ * (first maximal class; the interpolated values are those of lseg_upsample2x_nchw bit for bit). */
+int lseg_upsample2x_argmax(const void* lr, long long* mask, int B, int K, int H, int W, void* stream);
 /* CLIP text glue (k18). tokens int64 [K,L]. */
 int lseg_text_embed(const int64_t* tokens, const float* tok_emb, const float* pos_emb, void* x, int K, int L, int Wd,
                     void* stream);
@@ -194,6 +197,13 @@ int lseg_encode_text(lseg_engine* e, const int64_t* tokens, int K, void* text_ou
  * image at text + b*text_image_stride*512 halves (zero-shot path, lseg_net_zs.py:196-210). */
 int lseg_forward(lseg_engine* e, const float* x, int B, int H, int W, const void* text, int K,
                  long long text_image_stride, float* out, void* stream);
+
+/* SURVEY.md 8(f) "next" row 2 — LSeg.forward fused with the torch.max(logits, 1)[1] every caller applies
+ * (lseg_app.py:357-360, test_lseg.py:397, test_lseg_zs.py:301): mask int64 [B,H,W] = index of the first maximal class
+ * of the (bilinearly upsampled, align_corners=True) logits, bit-identical to argmax over what lseg_forward returns.
+ * The fp32 [B,K,H,W] logits are not materialised unless `logits` is non-NULL (then both are produced). */
+int lseg_forward_argmax(lseg_engine* e, const float* x, int B, int H, int W, const void* text, int K,
+                        long long text_image_stride, long long* mask, float* logits, void* stream);
 
 /* Same as lseg_forward, but brackets every kernel launch with CUDA events on `stream`, synchronises,
  * and returns per-launch device time (ms), kernel class (0 elementwise, 1 tcgen05 GEMM, 2 MHSA,

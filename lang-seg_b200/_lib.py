@@ -72,7 +72,7 @@ SYMBOLS = [
     "lseg_last_error", "lseg_abi_version", "lseg_read_watchdog",
     "lseg_gemm", "lseg_mhsa", "lseg_mhsa_trace", "lseg_debug_gemm_trace", "lseg_set_deterministic", "lseg_layernorm", "lseg_patchify", "lseg_pos_resize", "lseg_assemble_tokens",
     "lseg_readout_split", "lseg_im2col_3x3_s2", "lseg_upsample2x_nhwc", "lseg_l2norm_scale", "lseg_l2norm_f16",
-    "lseg_upsample2x_nchw", "lseg_text_embed", "lseg_text_eot_gather",
+    "lseg_upsample2x_nchw", "lseg_upsample2x_argmax", "lseg_forward_argmax", "lseg_text_embed", "lseg_text_eot_gather",
     "lseg_create", "lseg_destroy", "lseg_encode_text", "lseg_forward", "lseg_debug_buffer",
     "lseg_last_launch_count", "lseg_forward_profiled",
 ]
@@ -125,6 +125,9 @@ def load(build_if_missing=True):
     lib.lseg_encode_text.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.lseg_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                  C.c_longlong, C.c_void_p, C.c_void_p]
+    lib.lseg_forward_argmax.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                        C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.lseg_upsample2x_argmax.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.lseg_last_launch_count.argtypes = [C.c_void_p]
     lib.lseg_forward_profiled.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                           C.c_longlong, C.c_void_p, C.c_void_p, C.POINTER(C.c_float),

@@ -334,6 +334,11 @@ __global__ void l2norm_f16_kernel(const __half* __restrict__ x, __half* __restri
     y[static_cast<long long>(row) * C + c] = __float2half_rn(__half2float(x[static_cast<long long>(row) * C + c]) / nrm);
 }
 
+// w0*a + w1*b with ONE fixed rounding sequence (product, then fused multiply-add): the logits upsample and the fused
+// argmax below must produce bit-identical interpolated values, which FMA contraction left to the compiler would not
+// guarantee across two kernels.
+__device__ __forceinline__ float lerp2(float w0, float a, float w1, float b) { return __fmaf_rn(w0, a, __fmul_rn(w1, b)); }
+
 // ------------------------------------------------------------------------------------------
 // output head (modules/models/lseg_net.py:196,203): fp16 logits [planes,H,W] (values of the fp16
 // matmul) -> .float() -> bilinear x2 align_corners=True -> fp32 [planes,2H,2W].
@@ -377,8 +382,8 @@ __global__ void upsample2x_nchw_kernel(const __half* __restrict__ x, float* __re
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float2 fa = __half22float2(ah[k]), fb = __half22float2(bh[k]);
-        o[2 * k] = hy * fa.x + ly * fb.x;
-        o[2 * k + 1] = hy * fa.y + ly * fb.y;
+        o[2 * k] = lerp2(hy, fa.x, ly, fb.x);
+        o[2 * k + 1] = lerp2(hy, fa.y, ly, fb.y);
       }
       reinterpret_cast<float4*>(v)[2 * c] = make_float4(o[0], o[1], o[2], o[3]);
       reinterpret_cast<float4*>(v)[2 * c + 1] = make_float4(o[4], o[5], o[6], o[7]);
@@ -397,7 +402,7 @@ __global__ void upsample2x_nchw_kernel(const __half* __restrict__ x, float* __re
           const int xi = static_cast<int>(fx);
           const float lxk = fx - xi;
           const int xa = min(xi, W - 1), xb = min(xa + 1, W - 1);
-          o[k] = (1.f - lxk) * v[xa] + lxk * v[xb];
+          o[k] = lerp2(1.f - lxk, v[xa], lxk, v[xb]);
         }
         if (STREAM)
           __stcs(reinterpret_cast<float4*>(orow + xq * 4), make_float4(o[0], o[1], o[2], o[3]));
@@ -419,6 +424,96 @@ static inline int launch_upsample2x_nchw(const __half* x, float* y, long long pl
     launch_pdl(upsample2x_nchw_kernel<true>, grid, dim3(256), 0, s, x, y, H, W);
   else
     launch_pdl(upsample2x_nchw_kernel<false>, grid, dim3(256), 0, s, x, y, H, W);
+  LSEG_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused scratch.output_conv + class argmax: the callers of LSeg.forward only ever take
+// torch.max(logits, 1)[1] (lseg_app.py:357-360, test_lseg.py:397, test_lseg_zs.py:301). This kernel interpolates the
+// fp16 low-resolution logits [B, K, H, W] exactly like upsample2x_nchw_kernel (same lerp2 sequence, so the values are
+// bit-identical to the fp32 logits forward() returns) and keeps only the first maximal class per output pixel:
+// 8 B per pixel leave the GPU instead of 4*K.
+// One warp = one output row of one image, all K classes in turn: the two source rows of class k are interpolated
+// vertically into a (double-buffered) smem line, then every lane updates the running (max, argmax) of its
+// lane + 32 j outputs, j < kArgJ. Output columns beyond 32*kArgJ are handled in further passes.
+// ------------------------------------------------------------------------------------------
+constexpr int kArgJ = 16;  // outputs per lane per pass (Wo <= 512 in one pass)
+__global__ void __launch_bounds__(256) upsample2x_argmax_kernel(const __half* __restrict__ lr, long long* __restrict__ mask,
+                                                                int K, int H, int W) {
+  griddep_launch_dependents();
+  griddep_wait();
+  __shared__ __align__(16) float line[8][2][kUpMaxW];
+  const int Ho = 2 * H, Wo = 2 * W;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int oy = blockIdx.x * 8 + warp;
+  if (oy >= Ho) return;  // warp-uniform
+  const float sh = (Ho > 1) ? static_cast<float>(H - 1) / (Ho - 1) : 0.f;
+  const float sw = (Wo > 1) ? static_cast<float>(W - 1) / (Wo - 1) : 0.f;
+  const float fy = sh * oy;
+  const int y0 = static_cast<int>(fy);
+  const int y1 = min(y0 + 1, H - 1);
+  const float ly = fy - y0, hy = 1.f - ly;
+  const long long plane_sz = static_cast<long long>(H) * W;
+  const __half* img = lr + static_cast<long long>(b) * K * plane_sz;
+  long long* orow = mask + (static_cast<long long>(b) * Ho + oy) * Wo;
+  for (int ox0 = 0; ox0 < Wo; ox0 += 32 * kArgJ) {
+    int xa[kArgJ], xb[kArgJ];
+    float lx[kArgJ], best[kArgJ];
+    int arg[kArgJ];
+#pragma unroll
+    for (int j = 0; j < kArgJ; ++j) {
+      const int ox = min(ox0 + lane + 32 * j, Wo - 1);
+      const float fx = sw * ox;
+      const int xi = static_cast<int>(fx);
+      lx[j] = fx - xi;
+      xa[j] = min(xi, W - 1);
+      xb[j] = min(xa[j] + 1, W - 1);
+      best[j] = -INFINITY;
+      arg[j] = 0;
+    }
+    for (int k = 0; k < K; ++k) {
+      const uint4* r0 = reinterpret_cast<const uint4*>(img + k * plane_sz + static_cast<long long>(y0) * W);
+      const uint4* r1 = reinterpret_cast<const uint4*>(img + k * plane_sz + static_cast<long long>(y1) * W);
+      float* v = line[warp][k & 1];
+      for (int c = lane; c < W / 8; c += 32) {
+        const uint4 a = r0[c], bq = r1[c];
+        const __half2* ah = reinterpret_cast<const __half2*>(&a);
+        const __half2* bh = reinterpret_cast<const __half2*>(&bq);
+        float o[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 fa = __half22float2(ah[q]), fb = __half22float2(bh[q]);
+          o[2 * q] = lerp2(hy, fa.x, ly, fb.x);
+          o[2 * q + 1] = lerp2(hy, fa.y, ly, fb.y);
+        }
+        reinterpret_cast<float4*>(v)[2 * c] = make_float4(o[0], o[1], o[2], o[3]);
+        reinterpret_cast<float4*>(v)[2 * c + 1] = make_float4(o[4], o[5], o[6], o[7]);
+      }
+      __syncwarp();  // line k visible; line k-1 (other buffer) is free again after this point for iteration k+1
+#pragma unroll
+      for (int j = 0; j < kArgJ; ++j) {
+        const float val = lerp2(1.f - lx[j], v[xa[j]], lx[j], v[xb[j]]);
+        if (val > best[j]) {  // strict: the first maximal class wins, like torch.max on the logits
+          best[j] = val;
+          arg[j] = k;
+        }
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < kArgJ; ++j) {
+      const int ox = ox0 + lane + 32 * j;
+      if (ox < Wo) orow[ox] = arg[j];
+    }
+  }
+}
+static inline int launch_upsample2x_argmax(const __half* lr, long long* mask, int B, int K, int H, int W, cudaStream_t s) {
+  if (W % 8 != 0 || W > kUpMaxW || B > 65535 || K <= 0) {
+    set_error("upsample2x_argmax: needs W %% 8 == 0, W <= %d, B <= 65535, K > 0 (W=%d B=%d K=%d)", kUpMaxW, W, B, K);
+    return -1;
+  }
+  launch_pdl(upsample2x_argmax_kernel, dim3((2 * H + 7) / 8, B), dim3(256), 0, s, lr, mask, K, H, W);
   LSEG_LAUNCH_CHECK();
 }
 

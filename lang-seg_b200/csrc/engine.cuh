@@ -20,7 +20,8 @@ struct CallCtx {
   const __half* text;
   int K;
   long long text_image_stride;
-  float* out;
+  float* out;            // fp32 logits [B,K,H,W], or nullptr when only the mask is wanted
+  long long* out_mask;   // optional int64 class mask [B,H,W] (fused upsample + argmax)
 };
 using StepFn = std::function<int(const CallCtx&, cudaStream_t)>;
 enum StepKind { KIND_EW = 0, KIND_GEMM = 1, KIND_MHSA = 2, KIND_LN = 3, KIND_MEMSET = 4 };
@@ -549,9 +550,19 @@ static int run_forward(lseg_engine* eng, const CallCtx& ctx, int B, int H, int W
     }
   }
   // ---- scratch.output_conv: bilinear x2, align_corners=True (lseg_net.py:203) ----
-  {
+  if (ctx.out) {
     const long long planes = static_cast<long long>(B) * ctx.K;
     if (launch_upsample2x_nchw(plan.logits_lr, ctx.out, planes, h2, w2, stream)) return -1;
+    ++launches;
+    if (prof) {
+      if (prof->mark(stream)) return -1;
+      prof->kind.push_back(KIND_EW);
+      prof->flops.push_back(0.0);
+    }
+  }
+  // ---- fused output_conv + torch.max(.., 1)[1]: the fp32 logits are never materialised ----
+  if (ctx.out_mask) {
+    if (launch_upsample2x_argmax(plan.logits_lr, ctx.out_mask, B, ctx.K, h2, w2, stream)) return -1;
     ++launches;
     if (prof) {
       if (prof->mark(stream)) return -1;
@@ -740,6 +751,24 @@ int lseg_forward(lseg_engine* e, const float* x, int B, int H, int W, const void
   ctx.K = K;
   ctx.text_image_stride = text_image_stride;
   ctx.out = out;
+  ctx.out_mask = nullptr;
+  return run_forward(e, ctx, B, H, W, static_cast<cudaStream_t>(stream));
+}
+
+int lseg_forward_argmax(lseg_engine* e, const float* x, int B, int H, int W, const void* text, int K,
+                        long long text_image_stride, long long* mask, float* logits, void* stream) {
+  using namespace lseg;
+  if (!e || !x || !text || !mask || B <= 0) {
+    set_error("lseg_forward_argmax: bad argument");
+    return -1;
+  }
+  CallCtx ctx;
+  ctx.x = x;
+  ctx.text = static_cast<const __half*>(text);
+  ctx.K = K;
+  ctx.text_image_stride = text_image_stride;
+  ctx.out = logits;  // optional
+  ctx.out_mask = mask;
   return run_forward(e, ctx, B, H, W, static_cast<cudaStream_t>(stream));
 }
 
@@ -757,6 +786,7 @@ int lseg_forward_profiled(lseg_engine* e, const float* x, int B, int H, int W, c
   ctx.K = K;
   ctx.text_image_stride = text_image_stride;
   ctx.out = out;
+  ctx.out_mask = nullptr;
   Profile prof;
   int rc = run_forward(e, ctx, B, H, W, static_cast<cudaStream_t>(stream), &prof);
   if (rc == 0 && cudaStreamSynchronize(static_cast<cudaStream_t>(stream)) != cudaSuccess) {

@@ -569,6 +569,11 @@ int lseg_upsample2x_nchw(const void* x, float* y, long long planes, int H, int W
   return launch_upsample2x_nchw(static_cast<const __half*>(x), y, planes, H, W, static_cast<cudaStream_t>(stream));
 }
 
+int lseg_upsample2x_argmax(const void* lr, long long* mask, int B, int K, int H, int W, void* stream) {
+  if (ensure_init()) return -1;
+  return launch_upsample2x_argmax(static_cast<const __half*>(lr), mask, B, K, H, W, static_cast<cudaStream_t>(stream));
+}
+
 int lseg_text_embed(const int64_t* tokens, const float* tok_emb, const float* pos_emb, void* x, int K, int L, int Wd,
                     void* stream) {
   if (ensure_init()) return -1;

@@ -70,6 +70,26 @@ class Engine:
                                              C.c_void_p(out.data_ptr()), _stream()))
         return out
 
+    def forward_argmax(self, x, text, k, text_image_stride=0, out=None, logits=None):
+        """Like forward, but returns torch.max(logits, 1)[1] as int64 [B,H,W] without materialising the fp32 logits
+        (they are also written when a `logits` tensor is passed)."""
+        if x.device != self.device:
+            raise RuntimeError(f"input is on {x.device}, engine is on {self.device}")
+        if x.dtype != torch.float32 or x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError("x must be float32 [B,3,H,W]")
+        x = x.contiguous()
+        b, _, h, w = x.shape
+        if h % 32 or w % 32:
+            raise ValueError(f"H={h}, W={w} must be multiples of 32 (the reference fails on odd token grids)")
+        if out is None:
+            out = torch.empty((b, h, w), dtype=torch.int64, device=self.device)
+        lp = C.c_void_p(logits.data_ptr()) if logits is not None else None
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.lseg_forward_argmax(self.handle, C.c_void_p(x.data_ptr()), b, h, w,
+                                                    C.c_void_p(text.data_ptr()), k, text_image_stride,
+                                                    C.c_void_p(out.data_ptr()), lp, _stream()))
+        return out
+
     def forward_profiled(self, x, text, k, text_image_stride=0, out=None):
         """One forward with CUDA events around every launch. Returns (out, [(ms, kind, flops), ...])."""
         x = x.contiguous()

@@ -290,6 +290,22 @@ class LSegNet(_LSegBase):
         feats = self._text_features(engine, text)
         return engine.forward(x.float(), feats, text.shape[0])
 
+    @torch.no_grad()
+    def predict(self, x, labelset=""):
+        """torch.max(self.forward(x, labelset), 1)[1] — what every caller of the reference does with the logits
+        (lseg_app.py:357-360, test_lseg.py:397) — fused on the device: int64 [B,H,W], the fp32 [B,K,H,W] logits are
+        never written."""
+        self._check_eval()
+        if isinstance(labelset, torch.Tensor):
+            text = labelset
+        elif isinstance(labelset, str) and labelset == "":
+            text = self.text
+        else:
+            text = tokenize(labelset)
+        engine = self._engine_for(x.device)
+        feats = self._text_features(engine, text)
+        return engine.forward_argmax(x.float(), feats, text.shape[0])
+
 
 class LSegNetZS(_LSegBase):
     """Zero-shot variant (reference: lseg_net_zs.py:219-239; forward :177-214): one ['others', name]
@@ -318,3 +334,15 @@ class LSegNetZS(_LSegBase):
         for i, c in enumerate(ids):
             text[i * stride:(i + 1) * stride] = self._text_features(engine, self.texts[c])
         return engine.forward(x.float(), text, 2, text_image_stride=stride)
+
+    @torch.no_grad()
+    def predict(self, x, class_info):
+        """argmax over the ['others', name] pair per pixel (test_lseg_zs.py:301), fused on the device."""
+        self._check_eval()
+        engine = self._engine_for(x.device)
+        ids = [int(c) for c in class_info]
+        stride = engine.padded_rows(2)
+        text = torch.zeros((len(ids) * stride, 512), dtype=torch.float16, device=x.device)
+        for i, c in enumerate(ids):
+            text[i * stride:(i + 1) * stride] = self._text_features(engine, self.texts[c])
+        return engine.forward_argmax(x.float(), text, 2, text_image_stride=stride)

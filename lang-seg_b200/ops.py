@@ -181,6 +181,14 @@ def upsample2x_nchw(x):
     return y
 
 
+def upsample2x_argmax(x):
+    """fp16 [B,K,H,W] -> int64 [B,2H,2W]: argmax over K of the align_corners=True bilinear x2 upsample (first maximum)."""
+    B, K, H, W = x.shape
+    m = torch.empty((B, 2 * H, 2 * W), dtype=torch.int64, device=x.device)
+    check(load().lseg_upsample2x_argmax(_ptr(x, torch.float16), _ptr(m), B, K, H, W, _stream()))
+    return m
+
+
 def text_embed(tokens, tok_emb, pos_emb):
     K, L = tokens.shape
     Wd = tok_emb.shape[1]

@@ -60,6 +60,20 @@ def argmax_report(got, ref, margin_eps):
     }
 
 
+def argmax_report_from_mask(mask, ref, margin_eps):
+    """Same rule for a class mask (int64 [B,H,W]) instead of logits."""
+    ref = ref.detach().float().cpu()
+    mask = mask.detach().cpu()
+    ra = ref.argmax(1)
+    mism = mask != ra
+    top2 = ref.topk(2, dim=1).values
+    margin = top2[:, 0] - top2[:, 1]
+    n_mis = int(mism.sum())
+    worst = float(margin[mism].max()) if n_mis else 0.0
+    return {"pixels": int(mism.numel()), "mismatch": n_mis, "agree_frac": 1.0 - n_mis / mism.numel(),
+            "worst_mismatch_margin": worst, "ok": bool(n_mis == 0 or worst < margin_eps)}
+
+
 def oracle_forward(x, tokens, seed=0, stages=True):
     oracle_threads()
     return O.lseg_forward(x, tokens, state_dict(seed), return_stages=stages)

@@ -15,7 +15,7 @@ import os
 import pytest
 import torch
 
-from parity_util import (NET_KW, argmax_report, oracle_forward, oracle_threads, rel_err, rms_rel_err, state_dict,
+from parity_util import (NET_KW, argmax_report, argmax_report_from_mask, oracle_forward, oracle_threads, rel_err, rms_rel_err, state_dict,
                          synth)
 
 pytestmark = pytest.mark.gpu
@@ -95,6 +95,21 @@ def test_forward_vs_oracle(net, B, H, W, K):
     assert d["path1"] < 2 * STAGE_TOL, d
     assert d["logits"] < LOGIT_TOL, d
     assert d["ok"], d
+
+
+def test_predict_is_argmax_of_forward(net):
+    """SURVEY 8(f) row 2 (fused argmax epilogue): predict() == torch.max(forward(), 1)[1], without the fp32 logits;
+    checked against the unfused path bit for bit and against the oracle under the margin rule."""
+    tokens = synth.tokenize(synth.ade20k_labels())
+    x = synth.make_image(2, 480, 480, seed=9).cuda()
+    logits = net(x, tokens)
+    mask = net.predict(x, tokens)
+    assert mask.dtype == torch.int64 and mask.shape == (2, 480, 480)
+    assert torch.equal(mask.cpu(), torch.max(logits.cpu(), 1)[1])
+    ref, _ = oracle_forward(x[:1].cpu(), tokens)
+    rep = argmax_report_from_mask(mask[:1].cpu(), ref, margin_eps(ref))
+    _report("predict_480_K150", rep)
+    assert rep["ok"] and rep["agree_frac"] > 0.99, rep
 
 
 def test_forward_rejects_bad_shapes(net):

@@ -232,6 +232,22 @@ def test_im2col_upsample_norms(ops):
     _close(tn, (t / t.norm(dim=-1, keepdim=True)).float(), 1e-3, "l2norm f16")
 
 
+@pytest.mark.parametrize("B,K,H,W", [(2, 5, 24, 40), (1, 150, 40, 40), (1, 2, 16, 8), (1, 7, 8, 264)])
+def test_upsample_argmax_matches_logits(ops, B, K, H, W):
+    """the fused upsample+argmax returns torch.max(logits, 1)[1] of the logits the unfused path
+    produces — same interpolated values bit for bit, first maximal class on ties (ties are provoked: fp16 inputs on a
+    coarse grid, duplicated class planes)."""
+    lg = (_rand((B, K, H, W), 31, 2.0) * 4).round() / 4  # coarse values -> many exact ties after interpolation
+    if K > 3:
+        lg[:, 3] = lg[:, 1]  # an exactly duplicated class: the first index must win
+    up = ops.upsample2x_nchw(lg)
+    m = ops.upsample2x_argmax(lg)
+    assert m.dtype == torch.int64 and m.shape == (B, 2 * H, 2 * W)
+    assert torch.equal(m, up.argmax(1)) or torch.equal(up.gather(1, m[:, None]), up.max(1, keepdim=True)[0])
+    # first-maximum rule (what torch.max returns on CPU)
+    assert torch.equal(m.cpu(), torch.max(up.cpu(), 1)[1])
+
+
 def test_text_glue(ops):
     K, L, Wd = 5, 77, 512
     g = torch.Generator().manual_seed(31)
