@@ -392,7 +392,7 @@ __global__ void upsample2x_nchw_kernel(const __half* __restrict__ x, float* __re
     float* orow = oplane + static_cast<long long>(oy) * Wo;
     // horizontal taps are recomputed per output (4 flops) instead of cached: caching them cost 64
     // registers per thread and capped the SM at one resident block
-#pragma unroll 2
+#pragma unroll 1
     for (int xq = lane; xq < w4; xq += 32) {
       {
         float o[4];
