@@ -86,3 +86,15 @@ def test_product_path_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_widened_api_surface():
+    """SURVEY 8(f) rows 1-2 are reachable through the package: fused-argmax predict() on both nets, the batched
+    multi-scale evaluator, and the deterministic switch."""
+    import lseg_b200  # noqa: F401
+    from lseg_b200 import ops
+    from lseg_b200.evaluator import MultiScaleEvaluator
+    from lseg_b200.lseg_net import LSegNet, LSegNetZS
+    assert callable(getattr(LSegNet, "predict")) and callable(getattr(LSegNetZS, "predict"))
+    assert callable(ops.set_deterministic) and callable(ops.upsample2x_argmax)
+    assert MultiScaleEvaluator(lambda x, l: x, base_size=64, crop_size=32).crop_size == 32
