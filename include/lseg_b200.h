@@ -82,6 +82,15 @@ int lseg_gemm(const lseg_gemm_args* args, void* stream);
 /* Fused MHSA, head_dim 64 (k5; timm Attention restated at lseg_vit.py:26-39; CLIP text MHA).
  * qkv fp16 [B, N, 3*heads*64] (q|k|v thirds) -> out fp16 [B*N, heads*64]. */
 int lseg_mhsa(const void* qkv, void* out, int B, int N, int heads, int causal, void* stream);
+/* Same contract as lseg_mhsa with an explicit kernel choice (A/B measurements, tools/op_bench.py; the engine runs
+ * variant 3 unless LSEG_MHSA_VARIANT overrides it): 0 = round-1 kernel (one polling MMA warp for both softmax streams);
+ * 1 = one blocking MMA warp per stream + per-role register budgets (setmaxnreg); 2 = 1 + packed-fp32 (FFMA2 / FADD2 /
+ * FMNMX3) softmax arithmetic; 3 = 2 + one of every four score pairs exponentiated on the FMA pipe; 4 = two of four. */
+int lseg_mhsa_variant(const void* qkv, void* out, int B, int N, int heads, int causal, int variant, void* stream);
+/* Causal attention of the CLIP text tower with the rounding points of torch's multi_head_attention_forward on fp16
+ * tensors (q*dh^-0.5, bmm -> fp16, softmax -> fp16 normalised, bmm -> fp16): CUDA cores, one
+ * CTA per (label, head). qkv fp16 [K, L, 3*heads*64] -> out fp16 [K*L, heads*64], L <= 80. */
+int lseg_text_attn(const void* qkv, void* out, int K, int L, int heads, void* stream);
 /* 1 (default): every floating-point sum is formed in a fixed order (bit-reproducible across runs and batch sizes).
  * 0 (or LSEG_SPLITK=1): the in-place residual GEMM of the MLP (fc2) may split a tile's K range over two CTA pairs whose
  * partial sums are reduce-added in arrival order (differences at the fp32 rounding level; fc2 55 -> 51 us in

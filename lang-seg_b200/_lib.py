@@ -70,7 +70,7 @@ class Weights(C.Structure):
 # every symbol include/lseg_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "lseg_last_error", "lseg_abi_version", "lseg_read_watchdog",
-    "lseg_gemm", "lseg_mhsa", "lseg_mhsa_trace", "lseg_debug_gemm_trace", "lseg_set_deterministic", "lseg_layernorm", "lseg_patchify", "lseg_pos_resize", "lseg_assemble_tokens",
+    "lseg_gemm", "lseg_mhsa", "lseg_mhsa_variant", "lseg_text_attn", "lseg_mhsa_trace", "lseg_debug_gemm_trace", "lseg_set_deterministic", "lseg_layernorm", "lseg_patchify", "lseg_pos_resize", "lseg_assemble_tokens",
     "lseg_readout_split", "lseg_im2col_3x3_s2", "lseg_upsample2x_nhwc", "lseg_l2norm_scale", "lseg_l2norm_f16",
     "lseg_upsample2x_nchw", "lseg_upsample2x_argmax", "lseg_forward_argmax", "lseg_text_embed", "lseg_text_eot_gather",
     "lseg_create", "lseg_destroy", "lseg_encode_text", "lseg_forward", "lseg_debug_buffer",
@@ -100,6 +100,8 @@ def load(build_if_missing=True):
     lib.lseg_debug_buffer.argtypes = [C.c_void_p, C.c_char_p]
     lib.lseg_gemm.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
     lib.lseg_mhsa.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.lseg_mhsa_variant.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.lseg_text_attn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.lseg_debug_gemm_trace.argtypes = [C.c_void_p]
     lib.lseg_set_deterministic.argtypes = [C.c_int]
     lib.lseg_mhsa_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]

@@ -624,18 +624,8 @@ static int build_text_plan(lseg_engine* eng, int K) {
       e.ldc = 3 * Wd;
       if (add_gemm(gsteps, txn, Wd, (int)M, (int)M, bw.in_proj, e)) return -1;
     }
-    {
-      MhsaDesc md;
-      md.qkv = tqkv;
-      md.out = tattn;
-      md.B = K;
-      md.N = L;
-      md.heads = 8;
-      md.causal = 1;
-      MhsaPlan mp;
-      if (mhsa_plan(md, &mp)) return -1;
-      gsteps.push_back([mp](const CallCtx&, cudaStream_t s) { return mhsa_run(mp, s); });
-    }
+    // causal attention with torch's fp16 rounding points (text_attn.cuh), not the flash kernel of the image trunk
+    gsteps.push_back([=](const CallCtx&, cudaStream_t s) { return launch_text_attn(tqkv, tattn, K, L, 8, s); });
     {
       GemmEpi e = epi_none();
       e.bias = bw.out_proj.b;

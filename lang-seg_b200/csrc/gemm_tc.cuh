@@ -22,7 +22,6 @@
 //   gemm_tc2_kernel<BN, EPI, EW>  CTA pair (tcgen05 cta_group::2, UMMA 256 x BN x 16): default. Shared-memory
 //        bandwidth is the binding resource of an SS-mode UMMA main loop (every byte TMA writes is read back by
 //        the tensor core); the pair splits the weight tile, so each SM stages 32 KB per k-step instead of 48.
-//   gemm_tc_kernel<BN>        single CTA (LSEG_GEMM_1CTA=1), direct epilogue only; kept for A/B measurements.
 //
 // Epilogue modes (measured with tools/gemm_probe.py / tools/gemm_trace.py: the main loop alone runs at
 // 1450-1500 TFLOP/s on the ViT shapes, so for K <= 1024 the epilogue decides the speed; with the tensor core
@@ -482,173 +481,6 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
       }
     }
     store_groups = groups;
-  }
-}
-
-// ==========================================================================================
-// single-CTA kernel (EPI_DIRECT only)
-// ==========================================================================================
-template <int BN>
-struct GemmCfg {
-  static constexpr int kABytes = kGemmBM * kGemmBK * 2;
-  static constexpr int kBBytes = BN * kGemmBK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
-  static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-};
-
-template <int BN>
-__global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BN>;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
-  uint64_t* full_bar = bars;                          // [kStages]
-  uint64_t* empty_bar = bars + Cfg::kStages;          // [kStages]
-  uint64_t* tmem_full = bars + 2 * Cfg::kStages;      // [2]
-  uint64_t* tmem_empty = bars + 2 * Cfg::kStages + 2; // [2]
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 4);
-
-  const int warp = warp_idx_sync();  // provably warp-uniform: role branches and their operands stay on the uniform datapath
-  const int lane = threadIdx.x & 31;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.tma_a);
-    tma_prefetch_desc(&p.tma_b);
-    for (int i = 0; i < Cfg::kStages; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 32 * kGemmEpiWarps);
-    }
-    mbar_fence_init();
-  }
-  griddep_launch_dependents();
-  if (warp == 2) tmem_alloc(tmem_base_slot, Cfg::kTmemCols);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_base_slot;
-  griddep_wait();  // everything above overlapped the previous kernel's tail; operands / outputs are touched below
-
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    // The warp stays converged and only the bulk-copy / tcgen05 instructions are predicated on one elected lane:
-    // inside an `if (lane == 0)` region every descriptor operand went through an ELECT + R2UR waterfall
-    // (~20 dependent instructions, ~130 clk per tcgen05.mma), which made the single-thread issue rate, not the
-    // tensor pipe, the limit of the mainloop.
-    {
-      const bool leader = elect_one_sync();
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_tile = tile % p.num_m_tiles;
-        const int n_tile = tile / p.num_m_tiles;
-        const int n0 = n_tile * BN;
-        int cb = 0, ch0 = 0, cw0 = 0;
-        if (p.conv) {
-          const int per_img = p.tiles_h * p.tiles_w;
-          cb = m_tile / per_img;
-          const int t = m_tile % per_img;
-          ch0 = (t / p.tiles_w) * kConvTH;
-          cw0 = (t % p.tiles_w) * kConvTW;
-        }
-        for (int kit = 0; kit < p.k_iters; ++kit) {
-          mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-          uint8_t* sa = smem + stage * Cfg::kStageBytes;
-          uint8_t* sb = sa + Cfg::kABytes;
-          int c0 = kit * kGemmBK, c1 = m_tile * kGemmBM, c2 = 0;
-          if (p.conv) {
-            const int tap = kit / p.k_chunks;
-            const int c = kit - tap * p.k_chunks;
-            const int dy = tap / p.kw, dx = tap - dy * p.kw;
-            c0 = c * kGemmBK;
-            c1 = cw0 + dx - p.pad;
-            c2 = ch0 + dy - p.pad;
-          }
-          if (leader) {
-            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-            if (p.conv)
-              tma_load_4d(sa, &p.tma_a, &full_bar[stage], c0, c1, c2, cb);
-            else
-              tma_load_2d(sa, &p.tma_a, &full_bar[stage], c0, c1);
-            tma_load_2d(sb, &p.tma_b, &full_bar[stage], kit * kGemmBK, n0);
-          }
-          __syncwarp();
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (converged warp, one elected issuing lane) =====================
-    {
-      const bool leader = elect_one_sync();
-      constexpr uint32_t idesc = umma_idesc_f16(kGemmBM, BN, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 2);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kit = 0; kit < p.k_iters; ++kit) {
-          mbar_wait(&full_bar[stage], phase, 3);
-          tc_fence_after();
-          const uint32_t a_base = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t b_base = a_base + Cfg::kABytes;
-          if (leader) {
-#pragma unroll
-            for (int k = 0; k < kGemmBK / 16; ++k) {
-              const uint64_t da = umma_desc_sw128(a_base + k * 32, 1024, 0);
-              const uint64_t db = umma_desc_sw128(b_base + k * 32, 1024, 0);
-              umma_f16_ss(d_tmem, da, db, idesc, (kit | k) != 0);
-            }
-            umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-          }
-          __syncwarp();
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
-        }
-        if (leader) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
-        __syncwarp();
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
-      }
-    }
-  } else if (warp >= 4) {
-    // ===================== Epilogue =====================
-    const int ew = warp - 4;
-    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
-    const int half = ew >> 2;                     // column half handled by this warp
-    constexpr int kColsPerWarp = BN / (kGemmEpiWarps / 4);
-    const int r = quarter * 32 + lane;            // row inside the 128-row tile
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    int unused_groups = 0;
-    GemmTrace tr;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_tile = tile % p.num_m_tiles;
-      const int n_tile = tile / p.num_m_tiles;
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * kColsPerWarp;
-      gemm_epilogue_tile<EPI_DIRECT, false>(p, t_row, n_tile * BN + half * kColsPerWarp, kColsPerWarp, m_tile, r,
-                                     [&]() { mbar_wait(&tmem_full[acc], acc_phase, 4); }, nullptr, unused_groups, tr);
-      tc_fence_before();
-      mbar_arrive(&tmem_empty[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 

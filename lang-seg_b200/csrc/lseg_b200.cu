@@ -15,6 +15,8 @@
 #include "gemm_tc.cuh"
 #include "mhsa.cuh"
 #include "mhsa2.cuh"
+#include "mhsa3.cuh"
+#include "text_attn.cuh"
 
 namespace lseg {
 
@@ -37,41 +39,55 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static PFN_encodeTiled g_encode = nullptr;
-static int g_num_sms = 0;
+static int g_num_sms = 0;        // SM count of the devices this process uses (all must agree: B200 = 148)
 static int g_gemm_two_cta = 1;
 static int g_deterministic = 1;  // 1 (default): fixed summation order; 0: split-K allowed (LSEG_SPLITK=1 / lseg_set_deterministic(0))
 static int g_plan_epoch = 0;     // bumped when an option that is baked into cached plans changes
 static unsigned long long* g_gemm_trace = nullptr;  // debug (lseg_debug_gemm_trace)
 static int g_gemm_probe = 0;
-static std::once_flag g_init_flag;
-static int g_init_status = -1;
+static int g_mhsa_variant = 3;   // kernel the engine's ViT attention runs (lseg_mhsa_variant documents the numbering)
+static std::mutex g_init_mutex;
+static bool g_global_init = false;
+constexpr int kMaxDevices = 64;
+static int g_dev_status[kMaxDevices];  // 0 = not initialised, 1 = ready, -1 = unusable
 
-static void init_once() {
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) {
-    set_error("lseg_b200: no CUDA device available (there is no CPU fallback)");
-    return;
-  }
-  cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
-    set_error("lseg_b200: cudaGetDeviceProperties failed");
-    return;
-  }
-  if (prop.major != 10) {
-    set_error("lseg_b200: device '%s' is sm_%d%d; this library contains sm_100a code only", prop.name, prop.major,
-              prop.minor);
-    return;
-  }
-  g_num_sms = prop.multiProcessorCount;
+// Process-wide part: driver entry point and environment switches.
+static int init_global() {
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
     set_error("lseg_b200: cuTensorMapEncodeTiled not available from the driver");
-    return;
+    return -1;
   }
   g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
-  cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256>::kSmemBytes);
-  cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::kSmemBytes);
+  if (getenv("LSEG_SPLITK")) g_deterministic = 0;
+  const char* pr = getenv("LSEG_GEMM_PROBE");  // measurement only, see GemmParams::probe
+  g_gemm_probe = pr ? atoi(pr) : 0;
+  const char* mv = getenv("LSEG_MHSA_VARIANT");
+  if (mv) g_mhsa_variant = atoi(mv);
+  return 0;
+}
+
+// Per-device part: architecture check and the function attributes (opt-in shared memory sizes are a property of
+// (function, device); a process that drives several GPUs — DataParallel replicas, additional_utils/models.py:183-248 —
+// must set them on each one).
+static int init_device(int dev) {
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+    set_error("lseg_b200: cudaGetDeviceProperties failed");
+    return -1;
+  }
+  if (prop.major != 10) {
+    set_error("lseg_b200: device '%s' is sm_%d%d; this library contains sm_100a code only", prop.name, prop.major,
+              prop.minor);
+    return -1;
+  }
+  if (g_num_sms != 0 && g_num_sms != prop.multiProcessorCount) {
+    set_error("lseg_b200: devices with different SM counts in one process (%d vs %d)", g_num_sms,
+              prop.multiProcessorCount);
+    return -1;
+  }
+  g_num_sms = prop.multiProcessorCount;
 #define LSEG_SET_SMEM_TC2(BN_, EPI_)                                                             \
   cudaFuncSetAttribute(gemm_tc2_kernel<BN_, EPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                        Gemm2Cfg<BN_, EPI_>::kSmemBytes)
@@ -84,31 +100,44 @@ static void init_once() {
 #undef LSEG_SET_SMEM_TC2
   cudaFuncSetAttribute(gemm_tc2_kernel<256, EPI_TMA_F16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        Gemm2Cfg<256, EPI_TMA_F16, 16>::kSmemBytes);
-  {  // LSEG_GEMM_1CTA=1 selects the single-CTA GEMM (A/B comparisons, debugging)
-    const char* env = getenv("LSEG_GEMM_1CTA");
-    g_gemm_two_cta = (env && env[0] == '1') ? 0 : 1;
-    if (getenv("LSEG_SPLITK")) g_deterministic = 0;
-    const char* pr = getenv("LSEG_GEMM_PROBE");  // measurement only, see GemmParams::probe
-    g_gemm_probe = pr ? atoi(pr) : 0;
-  }
-  cudaFuncSetAttribute(mhsa_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMhsaSmemBytes);
-  cudaFuncSetAttribute(mhsa_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-  cudaFuncSetAttribute(mhsa_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMhsaSmemBytes);
-  cudaFuncSetAttribute(mhsa_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
 #define LSEG_M2_ATTR(K)                                                                       \
   cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, kM2SmemBytes);          \
   cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, 100)
   LSEG_M2_ATTR((mhsa2_kernel<0, false>));
-  LSEG_M2_ATTR((mhsa2_kernel<2, false>));
-  LSEG_M2_ATTR((mhsa2_kernel<3, false>));
-  LSEG_M2_ATTR((mhsa2_kernel<4, false>));
   LSEG_M2_ATTR((mhsa2_kernel<kMhsaPolyDefault, true>));
+  LSEG_M2_ATTR((mhsa3_kernel<false, 0>));
+  LSEG_M2_ATTR((mhsa3_kernel<true, 0>));
+  LSEG_M2_ATTR((mhsa3_kernel<true, 1>));
+  LSEG_M2_ATTR((mhsa3_kernel<true, 2>));
 #undef LSEG_M2_ATTR
-  g_init_status = 0;
+  if (cudaGetLastError() != cudaSuccess) {
+    set_error("lseg_b200: cudaFuncSetAttribute failed on device %d", dev);
+    return -1;
+  }
+  return 0;
 }
+
+// Makes the CURRENT device usable (idempotent, thread-safe). Every entry point calls it after cudaSetDevice.
 static int ensure_init() {
-  std::call_once(g_init_flag, init_once);
-  return g_init_status;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    set_error("lseg_b200: no CUDA device available (there is no CPU fallback)");
+    return -1;
+  }
+  if (dev < 0 || dev >= kMaxDevices) {
+    set_error("lseg_b200: device index %d out of range", dev);
+    return -1;
+  }
+  if (g_dev_status[dev] == 1) return 0;
+  std::lock_guard<std::mutex> lock(g_init_mutex);
+  if (g_dev_status[dev] == 1) return 0;
+  if (!g_global_init) {
+    if (init_global()) return -1;
+    g_global_init = true;
+  }
+  if (init_device(dev)) return -1;
+  g_dev_status[dev] = 1;
+  return 0;
 }
 
 static int make_tmap(CUtensorMap* out, CUtensorMapDataType dtype, const void* base, int rank, const uint64_t* dims,
@@ -284,7 +313,7 @@ static int gemm_plan(const GemmDesc& d, GemmPlan* plan) {
 
 static int gemm_run(const GemmPlan& plan, cudaStream_t stream) {
   if (plan.grid <= 0) return 0;
-  if (plan.two_cta) {
+  {
 #define LSEG_LAUNCH_TC2(BN_, EPI_) \
   launch_pdl(gemm_tc2_kernel<BN_, EPI_>, dim3(plan.grid), dim3(Gemm2Cfg<BN_, EPI_>::kThreads), Gemm2Cfg<BN_, EPI_>::kSmemBytes, stream, plan.p)
     if (plan.bn == 256) {
@@ -303,12 +332,6 @@ static int gemm_run(const GemmPlan& plan, cudaStream_t stream) {
     LSEG_CHECK_CUDA(cudaGetLastError());
     return 0;
   }
-  if (plan.bn == 256)
-    launch_pdl(gemm_tc_kernel<256>, dim3(plan.grid), dim3(kGemmThreads), GemmCfg<256>::kSmemBytes, stream, plan.p);
-  else
-    launch_pdl(gemm_tc_kernel<128>, dim3(plan.grid), dim3(kGemmThreads), GemmCfg<128>::kSmemBytes, stream, plan.p);
-  LSEG_CHECK_CUDA(cudaGetLastError());
-  return 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -338,27 +361,21 @@ static int mhsa_plan(const MhsaDesc& d, MhsaPlan* plan) {
   plan->grid = dim3((d.N + kMhsaTile - 1) / kMhsaTile, d.B * d.heads, 1);
   return 0;
 }
-static int mhsa_run(const MhsaPlan& plan, cudaStream_t stream) {
-  static const bool spin = getenv("LSEG_MHSA_SPIN") != nullptr;
-  static const bool v3 = getenv("LSEG_MHSA_V3") != nullptr;  // A/B: the single-stream kernel of mhsa.cuh
-  if (!v3) {
-    static const int poly = getenv("LSEG_MHSA_POLY") ? atoi(getenv("LSEG_MHSA_POLY")) : kMhsaPolyDefault;
-    switch (poly) {
-      case 2: launch_pdl(mhsa2_kernel<2, false>, plan.grid, dim3(kM2Threads), kM2SmemBytes, stream, plan.p); break;
-      case 4: launch_pdl(mhsa2_kernel<4, false>, plan.grid, dim3(kM2Threads), kM2SmemBytes, stream, plan.p); break;
-      case 3: launch_pdl(mhsa2_kernel<3, false>, plan.grid, dim3(kM2Threads), kM2SmemBytes, stream, plan.p); break;
-      default: launch_pdl(mhsa2_kernel<0, false>, plan.grid, dim3(kM2Threads), kM2SmemBytes, stream, plan.p); break;
-    }
-    LSEG_CHECK_CUDA(cudaGetLastError());
-    return 0;
+// variant: 0 mhsa2 (round-1 kernel: one polling MMA warp); 1 mhsa3 (one blocking MMA warp per stream, setmaxnreg);
+// 2 = 1 + packed-fp32 softmax arithmetic; 3 = 2 + one of four score pairs on the FMA-pipe exp2 polynomial; 4 = two of four.
+static int mhsa_run_variant(const MhsaPlan& plan, int variant, cudaStream_t stream) {
+  switch (variant) {
+    case 0: launch_pdl(mhsa2_kernel<0, false>, plan.grid, dim3(kM2Threads), kM2SmemBytes, stream, plan.p); break;
+    case 1: launch_pdl(mhsa3_kernel<false, 0>, plan.grid, dim3(kM3Threads), kM2SmemBytes, stream, plan.p); break;
+    case 2: launch_pdl(mhsa3_kernel<true, 0>, plan.grid, dim3(kM3Threads), kM2SmemBytes, stream, plan.p); break;
+    case 3: launch_pdl(mhsa3_kernel<true, 1>, plan.grid, dim3(kM3Threads), kM2SmemBytes, stream, plan.p); break;
+    case 4: launch_pdl(mhsa3_kernel<true, 2>, plan.grid, dim3(kM3Threads), kM2SmemBytes, stream, plan.p); break;
+    default: set_error("mhsa: unknown kernel variant %d", variant); return -1;
   }
-  if (spin)
-    mhsa_kernel<true><<<plan.grid, kMhsaThreads, kMhsaSmemBytes, stream>>>(plan.p);
-  else
-    mhsa_kernel<false><<<plan.grid, kMhsaThreads, kMhsaSmemBytes, stream>>>(plan.p);
   LSEG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+static int mhsa_run(const MhsaPlan& plan, cudaStream_t stream) { return mhsa_run_variant(plan, g_mhsa_variant, stream); }
 
 // ------------------------------------------------------------------------------------------
 // elementwise launch helpers
@@ -462,6 +479,25 @@ int lseg_mhsa(const void* qkv, void* out, int B, int N, int heads, int causal, v
   MhsaPlan plan;
   if (mhsa_plan(d, &plan)) return -1;
   return mhsa_run(plan, static_cast<cudaStream_t>(stream));
+}
+
+int lseg_mhsa_variant(const void* qkv, void* out, int B, int N, int heads, int causal, int variant, void* stream) {
+  MhsaDesc d;
+  d.qkv = static_cast<const __half*>(qkv);
+  d.out = static_cast<__half*>(out);
+  d.B = B;
+  d.N = N;
+  d.heads = heads;
+  d.causal = causal;
+  MhsaPlan plan;
+  if (mhsa_plan(d, &plan)) return -1;
+  return mhsa_run_variant(plan, variant, static_cast<cudaStream_t>(stream));
+}
+
+int lseg_text_attn(const void* qkv, void* out, int K, int L, int heads, void* stream) {
+  if (ensure_init()) return -1;
+  return launch_text_attn(static_cast<const __half*>(qkv), static_cast<__half*>(out), K, L, heads,
+                          static_cast<cudaStream_t>(stream));
 }
 
 int lseg_set_deterministic(int on) {

@@ -155,6 +155,7 @@ class _LSegBase(nn.Module):
             self.scratch = _scratch_holder(self.out_c)
         self.logit_scale = torch.tensor(reference_logit_scale())
         self.clip_pretrained._owner = weakref.ref(self)
+        self._install_load_hooks()
         self._shared = {"engines": {}, "text_cache": {}, "lock": threading.Lock(), "master": weakref.ref(self)}
         self._fast_init()
 
@@ -215,11 +216,22 @@ class _LSegBase(nn.Module):
         self._invalidate()
         return out
 
-    def load_state_dict(self, state_dict, strict=True, **kw):
-        filtered = OrderedDict((k, v) for k, v in state_dict.items() if not k.startswith(_IGNORED_PREFIXES))
-        out = super().load_state_dict(filtered, strict=strict, **kw)
-        self._invalidate()
-        return out
+    # Checkpoint loading goes through torch's recursive _load_from_state_dict when this net is a CHILD of the module
+    # being loaded (Lightning's load_from_checkpoint loads `net.*` keys on the LightningModule), which never calls a
+    # child's load_state_dict override. So the two things that must happen on every load are hooks on this module:
+    #   pre : drop the entries of real checkpoints that have no holder here (CLIP visual tower, timm head) — they
+    #         would otherwise be 'unexpected keys' under strict=True;
+    #   post: drop the packed device weights / text-feature cache so the next forward re-packs.
+    def _install_load_hooks(self):
+        def pre(module, state_dict, prefix, *unused):
+            for k in [k for k in state_dict if k.startswith(prefix) and k[len(prefix):].startswith(_IGNORED_PREFIXES)]:
+                del state_dict[k]
+
+        def post(module, incompatible_keys):
+            module._invalidate()
+
+        self.register_load_state_dict_pre_hook(pre)
+        self.register_load_state_dict_post_hook(post)
 
     def load(self, path):
         """BaseModel.load (modules/models/lseg_net.py:81-92)."""

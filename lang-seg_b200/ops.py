@@ -87,9 +87,22 @@ def gemm(a, w, N=None, *, bias=None, bias_group_rows=0, scale=None, act=ACT_NONE
     check(load().lseg_gemm(C.byref(args), _stream()))
 
 
-def mhsa(qkv, B, N, heads, causal=False):
-    out = torch.empty((B * N, heads * 64), dtype=torch.float16, device=qkv.device)
-    check(load().lseg_mhsa(_ptr(qkv, torch.float16), _ptr(out), B, N, heads, int(causal), _stream()))
+def mhsa(qkv, B, N, heads, causal=False, variant=None, out=None):
+    """variant=None: the kernel the engine runs; 0..4: see lseg_mhsa_variant in include/lseg_b200.h."""
+    if out is None:
+        out = torch.empty((B * N, heads * 64), dtype=torch.float16, device=qkv.device)
+    if variant is None:
+        check(load().lseg_mhsa(_ptr(qkv, torch.float16), _ptr(out), B, N, heads, int(causal), _stream()))
+    else:
+        check(load().lseg_mhsa_variant(_ptr(qkv, torch.float16), _ptr(out), B, N, heads, int(causal), int(variant),
+                                       _stream()))
+    return out
+
+
+def text_attn(qkv, K, L, heads):
+    """Causal CLIP-text attention with torch's fp16 rounding points (include/lseg_b200.h lseg_text_attn)."""
+    out = torch.empty((K * L, heads * 64), dtype=torch.float16, device=qkv.device)
+    check(load().lseg_text_attn(_ptr(qkv, torch.float16), _ptr(out), K, L, heads, _stream()))
     return out
 
 

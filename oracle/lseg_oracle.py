@@ -172,13 +172,17 @@ def clip_text_weights_fp16(sd, dtype=torch.float16):
     return out
 
 
-def clip_encode_text(text, tw, heads=8, layers=12, dtype=torch.float16):
-    """CLIP.encode_text. text int64 [K,77] -> fp16 [K,512]."""
+def clip_encode_text(text, tw, heads=8, layers=12, dtype=torch.float16, layer_io=None):
+    """CLIP.encode_text. text int64 [K,77] -> fp16 [K,512].
+    layer_io: optional list that receives the residual stream [K,77,512] before block 0 and after every block
+    (teacher-forced per-block parity tests)."""
     x = tw["token_embedding.weight"][text].to(dtype)
     x = x + tw["positional_embedding"].to(dtype)
     K, L, Wd = x.shape
     mask = torch.full((L, L), float("-inf")).triu_(1).to(dtype)
     x = x.permute(1, 0, 2)  # LND
+    if layer_io is not None:
+        layer_io.append(x.permute(1, 0, 2).clone())
     for i in range(layers):
         b = f"transformer.resblocks.{i}."
         h = _ln_fp32(x, tw[b + "ln_1.weight"], tw[b + "ln_1.bias"])
@@ -200,6 +204,8 @@ def clip_encode_text(text, tw, heads=8, layers=12, dtype=torch.float16):
         h = h * torch.sigmoid(1.702 * h)  # QuickGELU
         h = F.linear(h, tw[b + "mlp.c_proj.weight"], tw[b + "mlp.c_proj.bias"])
         x = x + h
+        if layer_io is not None:
+            layer_io.append(x.permute(1, 0, 2).clone())
     x = x.permute(1, 0, 2)
     x = _ln_fp32(x, tw["ln_final.weight"], tw["ln_final.bias"]).to(dtype)
     x = x[torch.arange(x.shape[0]), text.argmax(dim=-1)] @ tw["text_projection"]

@@ -9,8 +9,9 @@ The reference depends on third-party packages that are not installed here (timm 
     fp32-computing LayerNorm), weights converted to fp16 like clip.load(device='cuda') does;
     `clip.tokenize` -> oracle.synth.tokenize (no BPE vocabulary offline);
   * inert stubs for encoding / pytorch_lightning / matplotlib so modules/lseg_module.py imports.
-It is used ONLY in this container (make_golden.py, tests that skip when /root/reference is absent);
-nothing here travels into the product path.
+Used by make_golden.py, by the tests that drive the unmodified reference (they skip when neither /root/reference nor
+the baseline/_ref copy made by oracle/make_ref.sh is present) and by bench.py --impl reference; nothing here is
+imported by the product path.
 """
 import os
 import sys
@@ -20,7 +21,22 @@ from collections import OrderedDict
 import torch
 import torch.nn as nn
 
-REFERENCE_ROOT = "/root/reference"
+def _find_reference_root():
+    """/root/reference in the build container; on the GPU box the byte-for-byte copy oracle/make_ref.sh installs under
+    baseline/_ref/ (git-ignored, travels with the gpurun snapshot)."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    for cand in (os.environ.get("LSEG_REFERENCE_ROOT"), "/root/reference",
+                 os.path.join(os.path.dirname(here), "baseline", "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "modules", "models")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference_root()
+
+
+def reference_available():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "modules", "models"))
 
 
 # ---------------------------------------------------------------------------------------------
@@ -204,8 +220,8 @@ def _clip_load(name, device="cpu", jit=False):
 
 def install(with_lightning_stack=True):
     """Register the stand-ins and put /root/reference on sys.path. Idempotent."""
-    if not os.path.isdir(REFERENCE_ROOT):
-        raise FileNotFoundError(f"{REFERENCE_ROOT} is not available (it only exists in the build container)")
+    if not reference_available():
+        raise FileNotFoundError(f"{REFERENCE_ROOT} is not available (run oracle/make_ref.sh in the build container)")
     here = os.path.dirname(os.path.abspath(__file__))
     sys.path.insert(0, os.path.dirname(here))
     from oracle import synth
@@ -279,3 +295,50 @@ def build_reference_net(state_dict, labels):
     assert not missing, f"state dict misses reference keys: {missing[:5]}"
     assert all(k.startswith("clip_pretrained.visual.") for k in unexpected), unexpected[:5]
     return net.eval()
+
+
+MODULE_KW = dict(data_path="", dataset="ade20k", batch_size=1, base_lr=0, max_epochs=0, backbone="clip_vitl16_384",
+                 num_features=256, aux=False, aux_weight=0, se_loss=False, se_weight=0, ignore_index=255, dropout=0.0,
+                 scale_inv=False, augment=False, no_batchnorm=False, widehead=False, widehead_hr=False, arch_option=0,
+                 block_depth=0, activation="lrelu")  # the keyword set of test_lseg.py:221-246
+
+
+def build_reference_module(state_dict=None, drop_in=False, **overrides):
+    """Construct the UNMODIFIED reference `LSegModule` (modules/lseg_module.py) the way test_lseg.py:221-246 does.
+
+    drop_in=False: with the reference's own `LSegNet` (modules/models/lseg_net.py) — the CPU baseline.
+    drop_in=True : the one-line import swap of INTEGRATION.md applied WITHOUT editing the file: the module name
+                   `modules.models.lseg_net` is pre-bound to a shim whose `LSegNet` is lseg_b200's, so
+                   `from .models.lseg_net import LSegNet` (modules/lseg_module.py:8) resolves to the B200 drop-in.
+    The label file is opened relative to the cwd (modules/lseg_module.py:99), hence the chdir."""
+    install()
+    for name in ("modules.lseg_module", "modules.lsegmentation_module", "modules.models.lseg_net"):
+        sys.modules.pop(name, None)
+    if drop_in:
+        import importlib
+        ours = importlib.import_module("lang-seg_b200.lseg_net")
+        shim = types.ModuleType("modules.models.lseg_net")
+        shim.LSegNet = ours.LSegNet
+        sys.modules["modules.models.lseg_net"] = shim
+    kw = dict(MODULE_KW)
+    kw.update(overrides)
+    cwd = os.getcwd()
+    os.chdir(REFERENCE_ROOT)
+    try:
+        from modules.lseg_module import LSegModule
+        module = LSegModule(**kw)
+    finally:
+        os.chdir(cwd)
+        sys.modules.pop("modules.models.lseg_net", None) if drop_in else None
+    if state_dict is not None:
+        missing, unexpected = module.net.load_state_dict(state_dict, strict=False)
+        missing = [k for k in missing if "num_batches_tracked" not in k]
+        assert not missing, f"state dict misses keys: {missing[:5]}"
+    return module.eval()
+
+
+def load_multi_eval_module():
+    """The unmodified `LSeg_MultiEvalModule` class (additional_utils/models.py)."""
+    install()
+    from additional_utils.models import LSeg_MultiEvalModule
+    return LSeg_MultiEvalModule

@@ -1,34 +1,57 @@
 """GPU parity of the whole forward path (through the drop-in LSegNet and the C ABI) against the CPU
 oracle on the same seeded weights and inputs.
 
-Tolerances (measured margins recorded in DESIGN.md):
-  * logits: max |got - ref| / max |ref| <= LOGIT_TOL. The trunk computes with fp16 operands and fp32
-    accumulation while the oracle's trunk is fp32, and the reference itself rounds the logits to fp16
-    (lseg_net.py:194), so the bar is the fp16 one BASELINE.json's north_star states (1e-3 relative), with
-    the fp16 quantum of the logits as a floor on the absolute error;
-  * argmax masks: identical, except pixels whose ORACLE top-2 margin is below MARGIN_EPS (near ties that
-    any fp16 pipeline may flip).
+Tolerance policy (DESIGN.md section 4 has the measurements behind every number):
+
+  * The contract (BASELINE.json north_star / BASELINE.md section 3) is "<= 1e-3 relative fp16 tolerance, argmax masks
+    identical", metric max|got - ref| / max|ref|. It is asserted AS WRITTEN on everything that is a deterministic
+    function of well-conditioned arithmetic: the four ViT taps (STAGE_TOL), the decoder output path_1 (PATH1_TOL) and
+    the logits of the image path + head + pixel x text + upsample when the text features are TEACHER-FORCED, i.e. the
+    oracle's own fp16 text features are fed to lseg_forward (LOGIT_TOL).
+  * The CLIP text tower is a 12-layer fp16 network: with the seeded random weights it amplifies 1-ulp differences of
+    the fp32 summation order to ~1.7e-3 of the feature scale at its output. That is a property of the reference, not of
+    this implementation: the reference's own two executions of it — torch's nn.MultiheadAttention fast path (the
+    unmodified reference modules, committed as tests/golden/ref_480_k150.npz::text_features) and the step-by-step
+    multi_head_attention_forward recipe the oracle restates — differ by 1.75e-3 (features), 2.0e-3 (logits) and agree
+    on only 98.1 % of the argmax pixels (tests/test_oracle.py::test_text_tower_reference_floor, CPU). So the text tower
+    is held to (a) bit-level parity PER BLOCK with teacher-forced inputs (every op follows the reference's rounding
+    points; allowed: 2 fp16 ulp, >= 90 % of the outputs bit-identical) and (b) end to end no further from the oracle
+    than TEXT_FLOOR_FACTOR x the distance between the reference's own two executions; the full-pipeline logits
+    (own text tower) are held to FULL_LOGIT_TOL, the teacher-forced ones to the contract's 1e-3.
+  * argmax masks: identical, except pixels whose ORACLE top-2 margin is below MARGIN_QUANTA fp16 quanta of the logit
+    magnitude (the reference's matmul result is an fp16 tensor, lseg_net.py:194: margins below its quantum are ties
+    that any other summation order may break differently).
 """
 import json
+import math
 import os
 
+import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
-from parity_util import (NET_KW, argmax_report, argmax_report_from_mask, oracle_forward, oracle_threads, rel_err, rms_rel_err, state_dict,
-                         synth)
+from parity_util import (NET_KW, argmax_report, argmax_report_from_mask, oracle_forward, oracle_threads, rel_err,
+                         rms_rel_err, state_dict, synth)
 
 pytestmark = pytest.mark.gpu
 oracle_threads()
 
-LOGIT_TOL = 4e-3      # max-abs error relative to max |logit|
-STAGE_TOL = 4e-3      # same metric on intermediate activations
+STAGE_TOL = 1.0e-3       # taps of blocks 5/11/17/23 (fp32 residual stream)
+PATH1_TOL = 1.2e-3       # decoder output (fp16 NHWC in HBM: + one fp16 rounding of the stored value)
+LOGIT_TOL = 1.0e-3       # logits with teacher-forced text features: the contract's bar
+FULL_LOGIT_TOL = 3.0e-3  # logits with the GPU text tower: reference-vs-reference floor is 2.0e-3 (see module docstring)
+TEXT_FLOOR_FACTOR = 1.5  # GPU text features vs oracle <= 1.5 x (reference fast path vs oracle) = 2.6e-3
+MARGIN_QUANTA = 4        # flips allowed only where the oracle's top-2 margin < 4 fp16 quanta of max|logit|
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def fp16_quantum(v):
+    return 2.0 ** (math.floor(math.log2(max(float(v), 2.0 ** -14))) - 10)
 
 
 def margin_eps(ref):
-    """A flip is legitimate only if the oracle's top-2 margin is below twice the logit tolerance
-    (both competing logits off by LOGIT_TOL * max|logit| in opposite directions)."""
-    return 2 * LOGIT_TOL * float(ref.abs().max())
+    return MARGIN_QUANTA * fp16_quantum(ref.abs().max())
 
 
 @pytest.fixture(scope="module")
@@ -49,32 +72,103 @@ def _report(name, d):
             f.write(json.dumps({"case": name, **d}) + "\n")
 
 
-def test_text_encoder(net):
+def _padded_text(eng, feats):
+    """oracle fp16 text features [K,512] -> the engine's operand layout (rows padded to 128, zero rows)."""
+    k = feats.shape[0]
+    t = torch.zeros((eng.padded_rows(k), 512), dtype=torch.float16, device="cuda")
+    t[:k] = feats.half().cuda()
+    return t
+
+
+# ------------------------------------------------------------------------------------------------
+# CLIP text tower
+# ------------------------------------------------------------------------------------------------
+def test_text_encoder_end_to_end(net):
+    from oracle import lseg_oracle as O
     tokens = synth.tokenize(synth.ade20k_labels())
     eng = net._engine_for(torch.device("cuda"))
-    got = eng.encode_text(tokens)[:150]
-    from oracle import lseg_oracle as O
+    got = eng.encode_text(tokens)[:150].float().cpu()
     tw = O.clip_text_weights_fp16(state_dict(0))
-    ref = O.clip_encode_text(tokens, tw)
+    ref = O.clip_encode_text(tokens, tw).float()
     ref = ref / ref.norm(dim=-1, keepdim=True)
-    cos = torch.nn.functional.cosine_similarity(got.float().cpu(), ref.float(), dim=-1)
-    d = {"rel_err": rel_err(got, ref), "rms_rel": rms_rel_err(got, ref), "min_cos": cos.min().item()}
+    gold = torch.from_numpy(np.load(os.path.join(GOLD, "ref_480_k150.npz"))["text_features"]).float()
+    floor = rel_err(gold, ref)  # the reference's own two executions of this tower
+    cos = F.cosine_similarity(got, ref, dim=-1)
+    d = {"vs_oracle": rel_err(got, ref), "vs_reference_golden": rel_err(got, gold), "reference_vs_oracle_floor": floor,
+         "rms_vs_oracle": rms_rel_err(got, ref), "min_cos": cos.min().item()}
     _report("text_encoder_k150", d)
-    assert d["rel_err"] < 1e-2 and d["min_cos"] > 0.9999
+    assert 1.0e-3 < floor < 2.5e-3, floor  # the fixture still shows the floor this policy rests on
+    assert d["vs_oracle"] <= TEXT_FLOOR_FACTOR * floor, d
+    assert d["vs_reference_golden"] <= TEXT_FLOOR_FACTOR * floor, d
+    assert d["min_cos"] > 0.99999, d
 
 
-# configs[1] / configs[0] of BASELINE.json plus small, non-square and odd-label-count shapes (partial M / N tiles, token
-# grids that are not square, label counts that are not a multiple of 8)
+def test_text_blocks_teacher_forced():
+    """Every ResidualAttentionBlock on the oracle's own fp16 input: the GPU block (LayerNorm -> in_proj GEMM ->
+    lseg_text_attn -> out_proj GEMM + fp16 residual -> LayerNorm -> c_fc GEMM + QuickGELU -> c_proj GEMM + fp16 residual,
+    all through the C ABI stage ops) must reproduce the oracle's output to the fp16 ulp."""
+    from lseg_b200 import ops
+    from oracle import lseg_oracle as O
+    sd = state_dict(0)
+    tw = O.clip_text_weights_fp16(sd)
+    tokens = synth.tokenize(synth.ade20k_labels()[:40])
+    K, L, Wd = tokens.shape[0], 77, 512
+    io = []
+    O.clip_encode_text(tokens, tw, layer_io=io)
+    assert len(io) == 13
+    worst_ulp, worst_exact = 0.0, 1.0
+    for i in range(12):
+        b = f"transformer.resblocks.{i}."
+
+        def wt(name):
+            return ops.pad_rows(tw[b + name].half().cuda())
+
+        w_in, b_in = wt("attn.in_proj_weight"), tw[b + "attn.in_proj_bias"].float().cuda()
+        w_out, b_out = wt("attn.out_proj.weight"), tw[b + "attn.out_proj.bias"].float().cuda()
+        w_fc, b_fc = wt("mlp.c_fc.weight"), tw[b + "mlp.c_fc.bias"].float().cuda()
+        w_pr, b_pr = wt("mlp.c_proj.weight"), tw[b + "mlp.c_proj.bias"].float().cuda()
+        x = ops.pad_rows(io[i].reshape(K * L, Wd).half().cuda())  # rows padded for the TMA boxes
+        M = K * L
+        h = ops.layernorm(x, tw[b + "ln_1.weight"].cuda(), tw[b + "ln_1.bias"].cuda(), 1e-5)
+        qkv = torch.empty((x.shape[0], 3 * Wd), dtype=torch.float16, device="cuda")
+        ops.gemm(h, w_in, 3 * Wd, M=M, bias=b_in, out_f16=qkv)
+        a = ops.pad_rows(ops.text_attn(qkv[:M].contiguous().view(K, L, 3 * Wd), K, L, 8))
+        x1 = torch.zeros_like(x)
+        ops.gemm(a, w_out, Wd, M=M, bias=b_out, res_f16=x, out_f16=x1)
+        h = ops.layernorm(x1, tw[b + "ln_2.weight"].cuda(), tw[b + "ln_2.bias"].cuda(), 1e-5)
+        g = torch.empty((x.shape[0], 4 * Wd), dtype=torch.float16, device="cuda")
+        ops.gemm(h, w_fc, 4 * Wd, M=M, bias=b_fc, act=ops.ACT_QUICKGELU, out_f16=g)
+        x2 = torch.zeros_like(x)
+        ops.gemm(g, w_pr, Wd, M=M, bias=b_pr, res_f16=x1, out_f16=x2)
+        got = x2[:M].float().cpu()
+        ref = io[i + 1].reshape(M, Wd).float()
+        diff = (got - ref).abs()
+        ulp = torch.clamp(ref.abs(), min=2.0 ** -14).log2().floor().exp2() * 2.0 ** -10
+        # a near-zero output is the difference of O(1) residual-stream values: measure its error in ulps of that scale
+        ulp = torch.maximum(ulp, torch.full_like(ulp, fp16_quantum(0.05)))
+        worst_ulp = max(worst_ulp, (diff / ulp).max().item())
+        worst_exact = min(worst_exact, (diff == 0).float().mean().item())
+    d = {"worst_ulp": worst_ulp, "min_bit_identical_frac": worst_exact}
+    _report("text_blocks_teacher_forced", d)
+    assert worst_ulp <= 2.0, d
+    assert worst_exact >= 0.90, d
+
+
+# ------------------------------------------------------------------------------------------------
+# image path
+# ------------------------------------------------------------------------------------------------
+# configs[1] (B=8 and B=1) / configs[0] of BASELINE.json plus small, non-square and odd-label-count shapes (partial M / N
+# tiles, token grids that are not square, label counts that are not a multiple of 8)
 @pytest.mark.parametrize("B,H,W,K", [(2, 64, 96, 5), (1, 480, 480, 150), (1, 480, 480, 2), (2, 160, 224, 7),
-                                     (1, 320, 512, 33)])
+                                     (1, 320, 512, 33), (8, 480, 480, 150)])
 def test_forward_vs_oracle(net, B, H, W, K):
     labels = synth.ade20k_labels()[:K] if K != 2 else ["cat", "other"]
     tokens = synth.tokenize(labels)
     x = synth.make_image(B, H, W, seed=B * 1000 + H)
     ref, st = oracle_forward(x, tokens)
-    got = net(x.cuda(), tokens)
-    assert got.shape == ref.shape and got.dtype == torch.float32 and got.is_contiguous()
     eng = net._engine_for(torch.device("cuda"))
+    # (1) teacher-forced text features: everything but the text tower, at the contract's tolerance
+    got_tf = eng.forward(x.cuda(), _padded_text(eng, st["text_features"]), K)
     N = (H // 16) * (W // 16) + 1
     d = {"launches": eng.last_launch_count()}
     for k in range(4):
@@ -82,19 +176,51 @@ def test_forward_vs_oracle(net, B, H, W, K):
         d[f"tap{k}"] = rel_err(tap, st["taps"][k])
     p1 = eng.debug_tensor("path1", (B, H // 2, W // 2, 256), torch.float16)
     d["path1"] = rel_err(p1.permute(0, 3, 1, 2), st["path_1"])
-    lr = eng.debug_tensor("logits_lr", (B, K, H // 2, W // 2), torch.float16)
-    d["logits_lr"] = rel_err(lr, st["logits_lr"])
+    d["logits_teacher_forced"] = rel_err(got_tf, ref)
+    d["max_abs_logit"] = ref.abs().max().item()
+    tf = argmax_report(got_tf, ref, margin_eps(ref))
+    d.update({"tf_" + k: v for k, v in tf.items()})
+    # (2) the public call: own text tower
+    got = net(x.cuda(), tokens)
+    assert got.shape == ref.shape and got.dtype == torch.float32 and got.is_contiguous()
     d["logits"] = rel_err(got, ref)
     d["logits_rms"] = rms_rel_err(got, ref)
-    d["max_abs_logit"] = ref.abs().max().item()
-    d.update(argmax_report(got, ref, margin_eps(ref)))
+    full = argmax_report(got, ref, margin_eps(ref))
+    d.update(full)
     _report(f"forward_B{B}_{H}x{W}_K{K}", d)
-    assert torch.isfinite(got).all()
+    assert torch.isfinite(got).all() and torch.isfinite(got_tf).all()
     for k in range(4):
-        assert d[f"tap{k}"] < STAGE_TOL, d
-    assert d["path1"] < 2 * STAGE_TOL, d
-    assert d["logits"] < LOGIT_TOL, d
-    assert d["ok"], d
+        assert d[f"tap{k}"] <= STAGE_TOL, d
+    assert d["path1"] <= PATH1_TOL, d
+    assert d["logits_teacher_forced"] <= LOGIT_TOL, d
+    assert tf["ok"], d
+    assert d["logits"] <= FULL_LOGIT_TOL, d
+    assert full["ok"], d
+    if K == 2:  # configs[0]: real margins -> the mask is bit-identical
+        assert tf["mismatch"] == 0 and full["mismatch"] == 0, d
+
+
+def test_against_reference_golden(net):
+    """The committed outputs of the UNMODIFIED reference modules (oracle/make_golden.py) at 480x480, K=150 and K=2:
+    logits on the stride-8 lattice, full argmax mask, margins."""
+    for tag, labels in (("k150", synth.ade20k_labels()), ("k2", ["cat", "other"])):
+        g = np.load(os.path.join(GOLD, f"ref_480_{tag}.npz"))
+        x = synth.make_image(1, 480, 480, seed=1480)
+        got = net(x.cuda(), synth.tokenize(labels)).cpu()
+        lat = torch.from_numpy(g["logits_lattice"])
+        d = {"logits_lattice": rel_err(got[:, :, ::8, ::8], lat)}
+        mask = torch.from_numpy(g["argmax"].astype(np.int64))
+        margin = torch.from_numpy(g["margin_f16"].astype(np.float32))
+        mism = got.argmax(1) != mask
+        eps = MARGIN_QUANTA * fp16_quantum(lat.abs().max())
+        d["mismatch"] = int(mism.sum())
+        d["worst_mismatch_margin"] = float(margin[mism].max()) if d["mismatch"] else 0.0
+        d["margin_eps"] = eps
+        _report(f"reference_golden_480_{tag}", d)
+        assert d["logits_lattice"] <= FULL_LOGIT_TOL, d
+        assert d["mismatch"] == 0 or d["worst_mismatch_margin"] < eps, d
+        if tag == "k2":
+            assert d["mismatch"] == 0, d
 
 
 def test_predict_is_argmax_of_forward(net):
@@ -119,11 +245,17 @@ def test_forward_rejects_bad_shapes(net):
         net(torch.zeros(1, 3, 64, 64))  # CPU tensor: no fallback
 
 
-def test_zero_shot_path():
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs[3]: zero-shot path, PASCAL-5i / COCO-20i label files, 473x473
+# ------------------------------------------------------------------------------------------------
+def _label_file(name):
+    return [line.strip() for line in open(os.path.join(GOLD, name)) if line.strip()]
+
+
+def test_zero_shot_small():
     from lseg_b200.lseg_net import LSegNetZS
     from oracle import lseg_oracle as O
-    names = [line.strip() for line in open(os.path.join(os.path.dirname(__file__), "golden", "fewshot_pascal.txt"))
-             if line.strip()]
+    names = _label_file("fewshot_pascal.txt")
     zs = LSegNetZS(label_list=names, **NET_KW)
     zs.load_state_dict(state_dict(0))
     zs = zs.cuda().eval()
@@ -135,9 +267,71 @@ def test_zero_shot_path():
     got = zs(x.cuda(), class_info.cuda())
     d = {"logits": rel_err(got, ref)}
     d.update(argmax_report(got, ref, margin_eps(ref)))
+    gold = np.load(os.path.join(GOLD, "ref_zs.npz"))  # the unmodified reference LSegNetZS on the same inputs
+    d["logits_vs_reference_golden"] = rel_err(got, torch.from_numpy(gold["logits"]))
     _report("zero_shot_B3_96", d)
     assert got.shape == (B, 2, H, W)
-    assert d["logits"] < LOGIT_TOL and d["ok"], d
+    assert d["logits"] <= FULL_LOGIT_TOL and d["ok"], d
+    assert d["logits_vs_reference_golden"] <= FULL_LOGIT_TOL, d
+
+
+@pytest.mark.parametrize("label_file", ["fewshot_pascal.txt", "fewshot_coco.txt"])
+def test_zero_shot_config4(label_file):
+    """configs[3]: B=8 images of 473x473. 473 is not runnable by the reference ViT path (token grid 29.56; the reference's
+    own ZS script evaluates at 480, test_lseg_zs.py:268-270), so the input is padded to 480 with the normalised zero
+    value -1 exactly like pad_image (additional_utils/models.py:145-156) and the output is cropped back — on both sides."""
+    from lseg_b200.lseg_net import LSegNetZS
+    from oracle import lseg_oracle as O
+    names = _label_file(label_file)
+    zs = LSegNetZS(label_list=names, **NET_KW)
+    zs.load_state_dict(state_dict(0))
+    zs = zs.cuda().eval()
+    B = 8
+    x473 = synth.make_image(B, 473, 473, seed=473)
+    x = F.pad(x473, (0, 7, 0, 7), value=-1.0)
+    g = torch.Generator().manual_seed(4)
+    class_info = torch.randint(0, len(names), (B,), generator=g)
+    texts = [synth.tokenize(["others", n]) for n in names]
+    ref = O.lseg_forward_zs(x, class_info, texts, state_dict(0))[:, :, :473, :473]
+    got = zs(x.cuda(), class_info.cuda())[:, :, :473, :473]
+    mask = zs.predict(x.cuda(), class_info.cuda())[:, :473, :473]
+    d = {"logits": rel_err(got, ref), "n_classes": len(names)}
+    d.update(argmax_report(got, ref, margin_eps(ref)))
+    _report(f"zero_shot_cfg4_{label_file.split('.')[0]}", d)
+    assert got.shape == (B, 2, 473, 473)
+    assert torch.equal(mask.cpu(), got.argmax(1).cpu())
+    assert d["logits"] <= FULL_LOGIT_TOL and d["ok"], d
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs[4]: open-vocabulary stress, 720x720, 512 synthetic prompts
+# ------------------------------------------------------------------------------------------------
+def test_open_vocab_config5(net):
+    """configs[4] at B=1: 720 is not runnable (odd 45-token grid: the reference raises a 46-vs-45 size mismatch), so the
+    image is padded to 736 with -1 (pad_image) and the logits are cropped back to 720 — stated, and done on both sides.
+    N = 2117 tokens (34 key tiles, 17 query tiles of the attention kernel), K = 512 = 4 weight tiles of the pixel x text
+    GEMM, 135 424 pixels."""
+    tokens = synth.synthetic_prompts(512, seed=0)
+    x720 = synth.make_image(1, 720, 720, seed=720)
+    x = F.pad(x720, (0, 16, 0, 16), value=-1.0)
+    ref, st = oracle_forward(x, tokens)
+    eng = net._engine_for(torch.device("cuda"))
+    got_tf = eng.forward(x.cuda(), _padded_text(eng, st["text_features"]), 512)[:, :, :720, :720]
+    got = net(x.cuda(), tokens)[:, :, :720, :720]
+    ref = ref[:, :, :720, :720]
+    d = {"logits_teacher_forced": rel_err(got_tf, ref), "logits": rel_err(got, ref),
+         "max_abs_logit": ref.abs().max().item()}
+    tf = argmax_report(got_tf, ref, margin_eps(ref))
+    d.update({"tf_" + k: v for k, v in tf.items()})
+    d.update(argmax_report(got, ref, margin_eps(ref)))
+    N = 46 * 46 + 1
+    for k in range(4):
+        d[f"tap{k}"] = rel_err(eng.debug_tensor(f"tap{k}", (1, N, 1024), torch.float32), st["taps"][k])
+    _report("open_vocab_cfg5_736_K512", d)
+    for k in range(4):
+        assert d[f"tap{k}"] <= STAGE_TOL, d
+    assert d["logits_teacher_forced"] <= LOGIT_TOL and tf["ok"], d
+    assert d["logits"] <= FULL_LOGIT_TOL and d["ok"], d
 
 
 def test_argmax_planted_prototypes(net):
@@ -146,7 +340,6 @@ def test_argmax_planted_prototypes(net):
     normalised pixel embeddings at seeded pixel positions are used as 'text features'. Every pixel then has
     a clear winner, and the image trunk + head + correlation + upsample must reproduce the oracle's mask."""
     from oracle import lseg_oracle as O
-    import torch.nn.functional as F
     sd = state_dict(0)
     B, H, W, K = 1, 480, 480, 150
     x = synth.make_image(B, H, W, seed=1480)
@@ -162,14 +355,12 @@ def test_argmax_planted_prototypes(net):
     protos = (protos / protos.norm(dim=-1, keepdim=True)).half()
     ref = O.output_conv(O.correlation_head(path_1, protos, sd))
     eng = net._engine_for(torch.device("cuda"))
-    text = torch.zeros((eng.padded_rows(K), 512), dtype=torch.float16, device="cuda")
-    text[:K] = protos.cuda()
-    got = eng.forward(x.cuda(), text, K)
+    got = eng.forward(x.cuda(), _padded_text(eng, protos), K)
     d = {"logits": rel_err(got, ref), "max_abs_logit": ref.abs().max().item()}
     d.update(argmax_report(got, ref, margin_eps(ref)))
     _report("planted_prototypes_480_K150", d)
-    assert d["logits"] < LOGIT_TOL, d
-    assert d["ok"] and d["agree_frac"] > 0.999, d
+    assert d["logits"] <= LOGIT_TOL, d
+    assert d["ok"] and d["agree_frac"] > 0.9999, d
 
 
 def test_batch_consistency(net):

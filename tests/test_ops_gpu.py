@@ -161,22 +161,59 @@ def test_deferred_row_normalisation(ops):
     _close(out, ref, 2e-3, "deferred normalisation vs reference recipe")
 
 
-@pytest.mark.parametrize("B,N,heads,causal,amp", [
-    (2, 901, 16, False, 1.0), (3, 77, 8, True, 1.0), (1, 37, 16, False, 1.0), (1, 300, 2, True, 1.0),
-    # tile-boundary cases of the 64-key two-stream kernel: one tile only (second stream empty), exact multiples,
-    # 1..2 keys in the tail tile, odd/even tile counts; amp 3 makes the running-max offset move (O rescale path)
-    (1, 64, 1, False, 1.0), (1, 65, 1, True, 1.0), (1, 128, 2, False, 1.0), (1, 130, 2, False, 3.0),
-    (1, 1025, 2, False, 1.0), (2, 300, 2, False, 3.0), (1, 193, 1, True, 3.0)])
-def test_mhsa(ops, B, N, heads, causal, amp):
+def _mhsa_ref(qkv, B, N, heads, causal):
     D = heads * 64
-    qkv = _rand((B, N, 3 * D), 19, amp)
-    out = ops.mhsa(qkv, B, N, heads, causal)
     q, k, v = qkv.float().view(B, N, 3, heads, 64).permute(2, 0, 3, 1, 4)
     s = (q @ k.transpose(-1, -2)) * 0.125
     if causal:
         s = s + torch.full((N, N), float("-inf"), device="cuda").triu_(1)
-    ref = (s.softmax(-1) @ v).transpose(1, 2).reshape(B * N, D)
-    _close(out, ref, 2e-3, "mhsa")
+    return (s.softmax(-1) @ v).transpose(1, 2).reshape(B * N, D)
+
+
+MHSA_SHAPES = [
+    (2, 901, 16, False, 1.0), (3, 77, 8, True, 1.0), (1, 37, 16, False, 1.0), (1, 300, 2, True, 1.0),
+    # tile-boundary cases of the 64-key two-stream kernels: one tile only (second stream empty), exact multiples,
+    # 1..2 keys in the tail tile, odd/even tile counts; amp 3 makes the running-max offset move (O rescale path)
+    (1, 64, 1, False, 1.0), (1, 65, 1, True, 1.0), (1, 128, 2, False, 1.0), (1, 130, 2, False, 3.0),
+    (1, 1025, 2, False, 1.0), (2, 300, 2, False, 3.0), (1, 193, 1, True, 3.0),
+    # token counts of BASELINE.json configs[4]: 704^2 -> 1937, 736^2 -> 2117 (34 key tiles; 17 query tiles)
+    (1, 1937, 4, False, 1.0), (1, 2117, 3, False, 1.0), (1, 2117, 1, False, 3.0)]
+
+
+# variant None = the kernel the engine runs; 0 = round-1 kernel, 1..4 = mhsa3 instantiations (include/lseg_b200.h)
+@pytest.mark.parametrize("variant", [None, 0, 1, 2, 3, 4])
+@pytest.mark.parametrize("B,N,heads,causal,amp", MHSA_SHAPES)
+def test_mhsa(ops, B, N, heads, causal, amp, variant):
+    D = heads * 64
+    qkv = _rand((B, N, 3 * D), 19, amp)
+    out = ops.mhsa(qkv, B, N, heads, causal, variant=variant)
+    _close(out, _mhsa_ref(qkv, B, N, heads, causal), 2e-3, f"mhsa variant {variant}")
+
+
+def test_text_attn_rounding_points(ops):
+    """lseg_text_attn follows torch's multi_head_attention_forward on fp16 tensors step by step (q scaled in fp16, bmm ->
+    fp16, softmax -> fp16 normalised, bmm -> fp16): against that recipe evaluated with the same rounding points the result
+    is bit-identical except where an fp32 sum formed in another order lands on the other side of an fp16 rounding
+    boundary (rare 1-ulp differences)."""
+    K, L, heads = 23, 77, 8
+    D = heads * 64
+    qkv = _rand((K, L, 3 * D), 31, 1.5)
+    got = ops.text_attn(qkv, K, L, heads).float()
+
+    def r16(t):
+        return t.half().float()
+    q, k, v = qkv.float().view(K, L, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    mask = torch.full((L, L), float("-inf"), device="cuda").triu_(1)
+    s = r16(r16(q * 0.125) @ k.transpose(-1, -2)) + mask
+    p = r16(torch.softmax(s, dim=-1))
+    ref = r16(p @ v).transpose(1, 2).reshape(K * L, D)
+    diff = (got - ref).abs()
+    ulp = torch.maximum(ref.abs(), torch.tensor(2.0 ** -14, device="cuda")).log2().floor().exp2() * 2.0 ** -10
+    assert (diff <= 2 * ulp).all(), f"text_attn: {int((diff > 2 * ulp).sum())} elements off by more than 2 fp16 ulp"
+    frac_exact = (diff == 0).float().mean().item()
+    assert frac_exact > 0.97, f"text_attn: only {frac_exact:.4f} of the outputs bit-identical to the fp16-step recipe"
+    # and it agrees with the flash kernel to fp16 accuracy (different rounding points, same function)
+    _close(ops.mhsa(qkv, K, L, heads, True), ref, 3e-3, "mhsa vs fp16-step recipe")
 
 
 def test_layernorm(ops):

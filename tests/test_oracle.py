@@ -56,6 +56,33 @@ def test_480_golden_matches_oracle(tag, labels):
     mism = out.argmax(1) != ref_mask
     eps = 2 * TEXT_FP16_TOL * float(lat.abs().max())
     assert not (mism & (margin > eps)).any(), "argmax flipped on a pixel that is not a near tie"
+    if tag == "k150":
+        _text_tower_reference_floor(out, st, z, tf, lat, ref_mask)
+
+
+def _text_tower_reference_floor(out, st, z, tf, lat, ref_mask):
+    """The floor every GPU tolerance on the text tower rests on (tests/test_model_gpu.py docstring): the reference's own
+    two executions of its fp16 CLIP text tower — torch's nn.MultiheadAttention fast path inside the unmodified
+    reference modules (the golden fixture) and the step-by-step multi_head_attention_forward recipe (the oracle) —
+    sit ~1.7e-3 apart in the features, ~2e-3 in the logits, and disagree on ~2 % of the argmax pixels, although every
+    single op agrees to the fp16 ulp (tools/text_tower_floor.py reproduces the per-op and end-to-end numbers)."""
+    feat = rel_err(st["text_features"], tf)
+    logit = rel_err(out[:, :, ::8, ::8], lat)
+    agree = (out.argmax(1) == ref_mask).float().mean().item()
+    print(f"reference-vs-oracle floor: text features {feat:.3e}, logits {logit:.3e}, argmax agreement {agree:.4f}")
+    assert 1.0e-3 < feat < 2.5e-3, feat
+    assert 1.0e-3 < logit < 3.0e-3, logit
+    assert 0.97 < agree < 0.995, agree
+
+
+def test_text_tower_reference_floor():
+    """Alias so the floor shows up under its own name (the work is done inside the k150 golden test)."""
+    z = np.load(os.path.join(GOLD, "ref_480_k150.npz"))
+    tw = O.clip_text_weights_fp16(state_dict(0))
+    ref = O.clip_encode_text(synth.tokenize(synth.ade20k_labels()), tw).float()
+    ref = ref / ref.norm(dim=-1, keepdim=True)
+    feat = rel_err(ref, torch.from_numpy(z["text_features"]).float())
+    assert 1.0e-3 < feat < 2.5e-3, feat
 
 
 def test_zero_shot_golden_matches_oracle():
@@ -164,6 +191,30 @@ def test_reference_key_contract():
     net.load_state_dict(sd)
     assert net.text.shape == (2, 77) and net.text.dtype == torch.int64
     assert abs(float(net.logit_scale) - 14.2857) < 1e-3
+
+
+def test_checkpoint_load_through_parent_module():
+    """Lightning's load_from_checkpoint loads `net.`-prefixed keys on the PARENT module; torch then recurses with
+    _load_from_state_dict and never calls a child's load_state_dict override. strict=True must still accept real-checkpoint
+    extras and the packed weights must be invalidated (hooks on the net, not an override)."""
+    import lseg_b200  # noqa: F401
+    from lseg_b200.lseg_net import LSegNet
+    from parity_util import NET_KW
+
+    class Parent(torch.nn.Module):
+        def __init__(self, net):
+            super().__init__()
+            self.net = net
+
+    net = LSegNet(labels=["a", "b"], **NET_KW)
+    parent = Parent(net)
+    net._shared["text_cache"]["sentinel"] = 1
+    sd = {"net." + k: v for k, v in synth.make_state_dict(0, with_clip_visual_stub=True).items()}
+    sd["net.pretrained.model.head.weight"] = torch.zeros(1000, 1024)
+    res = parent.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert "sentinel" not in net._shared["text_cache"], "load through the parent did not invalidate the engine state"
+    assert torch.equal(net.scratch.head1.bias, sd["net.scratch.head1.bias"])
 
 
 def test_tokenizer_contract():
