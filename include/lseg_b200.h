@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LSEG_B200_ABI_VERSION 1
+#define LSEG_B200_ABI_VERSION 2
 
 /* ---- error / info ------------------------------------------------------------------------------ */
 const char* lseg_last_error(void);
@@ -68,6 +68,9 @@ typedef struct lseg_gemm_args {
   int store;
   int d2s_s, d2s_cout, d2s_h, d2s_w;
   int nchw_p, nchw_k;
+  int nchw_group;       /* LSEG_STORE_NCHW_T, > 0: the N columns are per-image blocks of nchw_group columns; a row of image
+                         * b stores only columns [b*nchw_group, b*nchw_group + nchw_k) as channels 0..nchw_k-1 (the
+                         * zero-shot path's per-image label pair, lseg_net_zs.py:196-210, as ONE GEMM) */
   /* deferred row normalisation (head1 -> pixel x text, lseg_net.py:185-194): a GEMM can write the partial
    * squared norms of its result rows, out_row_sumsq[row, n/32] = sum over that 32-column chunk (fp32, no
    * atomics: deterministic), and an LSEG_STORE_NCHW_T GEMM can scale each row by
@@ -202,10 +205,20 @@ int lseg_encode_text(lseg_engine* e, const int64_t* tokens, int K, void* text_ou
 
 /* LSeg.forward after tokenisation (lseg_net.py:166-205).
  * x fp32 NCHW [B,3,H,W] (H, W multiples of 32) -> out fp32 NCHW [B,K,H,W].
- * text fp16 [rows_padded(K),512] shared by all images (text_image_stride = 0), or one such block per
- * image at text + b*text_image_stride*512 halves (zero-shot path, lseg_net_zs.py:196-210). */
+ * text fp16 [rows_padded(K),512] shared by all images (text_image_stride = 0), or one K-row block per
+ * image at text + b*text_image_stride*512 halves, text_image_stride >= K, total rows padded to a multiple of 128
+ * (zero-shot path, lseg_net_zs.py:196-210). */
 int lseg_forward(lseg_engine* e, const float* x, int B, int H, int W, const void* text, int K,
                  long long text_image_stride, float* out, void* stream);
+
+/* LSeg.forward up to the fp16 matmul result (lseg_net.py:194-196): logits_lr fp16 [B,K,H/2,W/2] is written to the CALLER's
+ * buffer, which may be PEER memory of another GPU (an address obtained with lseg_p2p_open): the pixel x text GEMM's
+ * epilogue then stores straight into the gathering rank's buffer over NVLink — the one collective of the path
+ *  fused into the kernel that produces the data. `out` (fp32 [B,K,H,W]) is optional (NULL: the
+ * x2 upsample, lseg_net.py:203, is left to the gathering rank: lseg_upsample2x_nchw on the gathered planes is bit-identical).
+ * text_image_stride > 0: rows [b*stride, b*stride + K) of `text` are image b's label block (stride >= K; any value). */
+int lseg_forward_lowres(lseg_engine* e, const float* x, int B, int H, int W, const void* text, int K,
+                        long long text_image_stride, void* logits_lr, float* out, void* stream);
 
 /* SURVEY.md 8(f) "next" row 2 — LSeg.forward fused with the torch.max(logits, 1)[1] every caller applies
  * (lseg_app.py:357-360, test_lseg.py:397, test_lseg_zs.py:301): mask int64 [B,H,W] = index of the first maximal class

@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "liblseg_b200.so")
 
 VIT_DEPTH = 24
 TEXT_DEPTH = 12
+ABI_VERSION = 2  # == LSEG_B200_ABI_VERSION of include/lseg_b200.h; the struct mirrors below follow that layout
 
 ACT_NONE, ACT_GELU, ACT_QUICKGELU, ACT_RELU = 0, 1, 2, 3
 STORE_ROWMAJOR, STORE_D2S, STORE_NCHW_T = 0, 1, 2
@@ -28,7 +29,7 @@ class GemmArgs(C.Structure):
         ("out_f32", C.c_void_p), ("out_f16", C.c_void_p), ("out_f16_relu", C.c_void_p),
         ("ldc", C.c_longlong), ("store", C.c_int),
         ("d2s_s", C.c_int), ("d2s_cout", C.c_int), ("d2s_h", C.c_int), ("d2s_w", C.c_int),
-        ("nchw_p", C.c_int), ("nchw_k", C.c_int),
+        ("nchw_p", C.c_int), ("nchw_k", C.c_int), ("nchw_group", C.c_int),
         ("row_sumsq", C.c_void_p), ("row_sumsq_parts", C.c_int), ("row_scale", C.c_float),
         ("out_row_sumsq", C.c_void_p),
     ]
@@ -73,7 +74,7 @@ SYMBOLS = [
     "lseg_gemm", "lseg_mhsa", "lseg_mhsa_variant", "lseg_text_attn", "lseg_mhsa_trace", "lseg_debug_gemm_trace", "lseg_set_deterministic", "lseg_layernorm", "lseg_patchify", "lseg_pos_resize", "lseg_assemble_tokens",
     "lseg_readout_split", "lseg_im2col_3x3_s2", "lseg_upsample2x_nhwc", "lseg_l2norm_scale", "lseg_l2norm_f16",
     "lseg_upsample2x_nchw", "lseg_upsample2x_argmax", "lseg_forward_argmax", "lseg_text_embed", "lseg_text_eot_gather",
-    "lseg_create", "lseg_destroy", "lseg_encode_text", "lseg_forward", "lseg_debug_buffer",
+    "lseg_create", "lseg_destroy", "lseg_encode_text", "lseg_forward", "lseg_forward_lowres", "lseg_debug_buffer",
     "lseg_last_launch_count", "lseg_forward_profiled",
 ]
 
@@ -87,14 +88,22 @@ def load(build_if_missing=True):
         return _lib
     if build_if_missing:
         from . import build as _build
+        stale = _build.needs_build()
         try:
             _build.build()
-        except Exception:
+        except Exception as e:
+            # a stale library may have another lseg_weights / lseg_gemm_args layout: never load it silently
+            if stale and os.path.exists(LIB_PATH) and not os.environ.get("LSEG_ALLOW_STALE_LIB"):
+                raise ImportError(f"liblseg_b200.so is older than its sources and rebuilding failed ({e}); refusing to "
+                                  f"load a possibly ABI-incompatible library (LSEG_ALLOW_STALE_LIB=1 overrides)") from e
             if not os.path.exists(LIB_PATH):
                 raise
     if not os.path.exists(LIB_PATH):
         raise ImportError("liblseg_b200.so is missing and could not be built; lseg_b200 has no CPU fallback")
     lib = C.CDLL(LIB_PATH)
+    if lib.lseg_abi_version() != ABI_VERSION:
+        raise ImportError(f"liblseg_b200.so has ABI version {lib.lseg_abi_version()}, this binding expects {ABI_VERSION}: "
+                          f"rebuild with `python -m lang-seg_b200.build --force`")
     lib.lseg_last_error.restype = C.c_char_p
     lib.lseg_debug_buffer.restype = C.c_void_p
     lib.lseg_debug_buffer.argtypes = [C.c_void_p, C.c_char_p]
@@ -127,6 +136,8 @@ def load(build_if_missing=True):
     lib.lseg_encode_text.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.lseg_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                  C.c_longlong, C.c_void_p, C.c_void_p]
+    lib.lseg_forward_lowres.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                        C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.lseg_forward_argmax.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                         C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.lseg_upsample2x_argmax.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]

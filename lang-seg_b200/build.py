@@ -33,25 +33,41 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
+    """Compile into a temporary file and rename it over the library (atomic: a peer process that dlopens the path sees
+    either the old or the new file, never a partial one), under an exclusive file lock so that N torchrun ranks finding
+    a stale library build it once, not N times into the same path."""
+    import fcntl
     if not force and not needs_build():
         return LIB
-    cmd = [
-        nvcc_path(),
-        "-gencode", "arch=compute_100a,code=sm_100a",
-        "-O3", "-std=c++17", "-lineinfo",
-        "-shared", "-Xcompiler", "-fPIC",
-        "-cudart", "static",
-        "-o", LIB,
-    ]
-    if verbose:
-        cmd += ["-Xptxas", "-v"]
-    cmd += [os.path.join(CSRC, s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed building liblseg_b200.so")
-    if verbose:
-        sys.stderr.write(res.stdout + res.stderr)
+    lock_path = LIB + ".lock"
+    with open(lock_path, "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():  # a peer built it while we waited
+                return LIB
+            tmp = f"{LIB}.tmp{os.getpid()}"
+            cmd = [
+                nvcc_path(),
+                "-gencode", "arch=compute_100a,code=sm_100a",
+                "-O3", "-std=c++17", "-lineinfo",
+                "-shared", "-Xcompiler", "-fPIC",
+                "-cudart", "static",
+                "-o", tmp,
+            ]
+            if verbose:
+                cmd += ["-Xptxas", "-v"]
+            cmd += [os.path.join(CSRC, s) for s in SOURCES]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                sys.stderr.write(res.stdout + res.stderr)
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed building liblseg_b200.so")
+            if verbose:
+                sys.stderr.write(res.stdout + res.stderr)
+            os.replace(tmp, LIB)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 

@@ -12,6 +12,7 @@
 #include <functional>
 #include <map>
 #include <memory>
+#include <tuple>
 
 namespace lseg {
 
@@ -20,8 +21,11 @@ struct CallCtx {
   const __half* text;
   int K;
   long long text_image_stride;
-  float* out;            // fp32 logits [B,K,H,W], or nullptr when only the mask is wanted
+  float* out;            // fp32 logits [B,K,H,W], or nullptr when only the mask / the low-res logits are wanted
   long long* out_mask;   // optional int64 class mask [B,H,W] (fused upsample + argmax)
+  __half* out_lr;        // optional target of the fp16 low-res logits [B,K,H/2,W/2] (the exact result of the reference's
+                         // fp16 matmul, lseg_net.py:194-196) instead of the plan's own buffer; may be PEER memory — the
+                         // pixel x text GEMM then stores straight into another GPU's gather buffer over NVLink
 };
 using StepFn = std::function<int(const CallCtx&, cudaStream_t)>;
 enum StepKind { KIND_EW = 0, KIND_GEMM = 1, KIND_MHSA = 2, KIND_LN = 3, KIND_MEMSET = 4 };
@@ -38,21 +42,39 @@ struct Step {
 };
 
 struct Arena {
-  uint8_t* base = nullptr;
-  size_t cap = 0;
-  size_t off = 0;
-  std::vector<void*> owned;
-  // Simple bump allocator over cudaMalloc'd slabs (256-byte aligned blocks).
+  // Bump allocator over a few large cudaMalloc'd slabs: a plan makes ~60 allocations, which as individual
+  // cudaMalloc / cudaFree calls cost a device-wide synchronisation each when a plan is rebuilt.
+  static constexpr size_t kSlab = size_t(512) << 20;
+  std::vector<void*> slabs;
+  uint8_t* cur = nullptr;
+  size_t left = 0;
+  size_t total = 0;
   void* alloc(size_t bytes) {
-    bytes = (bytes + 1023) & ~size_t(1023);
-    void* p = nullptr;
-    if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
-    owned.push_back(p);
-    return p;
+    bytes = (bytes + 1023) & ~size_t(1023);  // 1024 B: swizzled TMA tiles / tensor-map bases stay aligned
+    if (bytes > left) {
+      const size_t want = bytes > kSlab ? bytes : kSlab;
+      void* p = nullptr;
+      if (cudaMalloc(&p, want) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+      }
+      slabs.push_back(p);
+      total += want;
+      if (bytes > kSlab) return p;  // oversized request: its own slab, the current one keeps its remainder
+      cur = static_cast<uint8_t*>(p);
+      left = want;
+    }
+    void* r = cur;
+    cur += bytes;
+    left -= bytes;
+    return r;
   }
   void release() {
-    for (void* p : owned) cudaFree(p);
-    owned.clear();
+    for (void* p : slabs) cudaFree(p);
+    slabs.clear();
+    cur = nullptr;
+    left = 0;
+    total = 0;
   }
 };
 
@@ -65,9 +87,24 @@ struct ImagePlan {
   // head buffers needed by the per-call tail
   __half* featn = nullptr;
   float* feat_sumsq = nullptr;
-  __half* logits_lr = nullptr;
+  __half* logits_lr = nullptr;  // own cudaMalloc (grows with K), not part of the arena
   size_t logits_cap_k = 0;
-  ~ImagePlan() { arena.release(); }
+  // pixel x text GEMM plans (host-encoded tensor maps) keyed by (text pointer, K, per-image stride, output pointer)
+  struct CorrKey {
+    const void* text;
+    int K;
+    long long stride;
+    const void* out;
+    bool operator<(const CorrKey& o) const {
+      return std::tie(text, K, stride, out) < std::tie(o.text, o.K, o.stride, o.out);
+    }
+  };
+  std::map<CorrKey, std::vector<std::pair<GemmPlan, double>>> corr;
+  unsigned long long last_use = 0;
+  ~ImagePlan() {
+    arena.release();
+    if (logits_lr) cudaFree(logits_lr);
+  }
 };
 
 struct TextPlan {
@@ -82,7 +119,12 @@ struct TextPlan {
 struct lseg_engine {
   lseg_weights w;
   int device = 0;
-  std::unique_ptr<lseg::ImagePlan> img;
+  // a few image plans, least-recently-used eviction: the multi-scale evaluator alternates between its full batch and
+  // the last partial one, the zero-shot and the ADE nets share an engine, ...
+  static constexpr int kMaxImagePlans = 3;
+  std::vector<std::unique_ptr<lseg::ImagePlan>> plans;
+  lseg::ImagePlan* img = nullptr;  // the plan of the last forward (debug buffers)
+  unsigned long long use_counter = 0;
   std::unique_ptr<lseg::TextPlan> txt;
   std::map<std::pair<int, int>, float*> pos_cache;
   int last_launches = 0;
@@ -456,7 +498,15 @@ static int build_image_plan(lseg_engine* eng, int B, int H, int W, cudaStream_t 
   }
   plan->featn = featn;
   plan->feat_sumsq = feat_sumsq;
-  eng->img = std::move(plan);
+  if (static_cast<int>(eng->plans.size()) >= lseg_engine::kMaxImagePlans) {
+    size_t victim = 0;
+    for (size_t i = 1; i < eng->plans.size(); ++i)
+      if (eng->plans[i]->last_use < eng->plans[victim]->last_use) victim = i;
+    LSEG_CHECK_CUDA(cudaStreamSynchronize(stream));  // the victim's buffers may still be in use by queued work
+    eng->plans.erase(eng->plans.begin() + victim);
+  }
+  eng->plans.push_back(std::move(plan));
+  eng->img = eng->plans.back().get();
   return 0;
 }
 
@@ -488,23 +538,41 @@ static int run_forward(lseg_engine* eng, const CallCtx& ctx, int B, int H, int W
     return -1;
   }
   LSEG_CHECK_CUDA(cudaSetDevice(eng->device));
-  if (!eng->img || eng->img->B != B || eng->img->H != H || eng->img->W != W || eng->img->epoch != g_plan_epoch) {
-    eng->img.reset();
-    if (build_image_plan(eng, B, H, W, stream)) return -1;
+  if (ensure_init()) return -1;
+  eng->img = nullptr;
+  for (size_t i = 0; i < eng->plans.size();) {
+    ImagePlan* pl = eng->plans[i].get();
+    if (pl->epoch != g_plan_epoch) {  // an option baked into the GEMM plans changed
+      LSEG_CHECK_CUDA(cudaStreamSynchronize(stream));
+      eng->plans.erase(eng->plans.begin() + i);
+      continue;
+    }
+    if (pl->B == B && pl->H == H && pl->W == W) eng->img = pl;
+    ++i;
   }
+  if (!eng->img && build_image_plan(eng, B, H, W, stream)) return -1;
   ImagePlan& plan = *eng->img;
+  plan.last_use = ++eng->use_counter;
   const int h2 = H / 2, w2 = W / 2;
   const long long P = static_cast<long long>(h2) * w2;
-  if (!plan.logits_lr || plan.logits_cap_k < (size_t)ctx.K) {
-    void* p = plan.arena.alloc(sizeof(__half) * (size_t)B * ctx.K * P);
-    if (!p) {
+  if (!ctx.out_lr && (!plan.logits_lr || plan.logits_cap_k < (size_t)ctx.K)) {
+    if (plan.logits_lr) {
+      LSEG_CHECK_CUDA(cudaStreamSynchronize(stream));
+      LSEG_CHECK_CUDA(cudaFree(plan.logits_lr));
+      plan.logits_lr = nullptr;
+      plan.corr.clear();
+    }
+    void* p = nullptr;
+    if (cudaMalloc(&p, sizeof(__half) * (size_t)B * ctx.K * P) != cudaSuccess) {
+      cudaGetLastError();
       set_error("logits workspace allocation failed");
       return -1;
     }
     plan.logits_lr = static_cast<__half*>(p);
     plan.logits_cap_k = ctx.K;
-    plan.debug["logits_lr"] = p;
   }
+  __half* lr = ctx.out_lr ? ctx.out_lr : plan.logits_lr;
+  plan.debug["logits_lr"] = lr;
   int launches = 0;
   if (prof && prof->mark(stream)) return -1;
   for (auto& st : plan.steps) {
@@ -517,42 +585,63 @@ static int run_forward(lseg_engine* eng, const CallCtx& ctx, int B, int H, int W
     }
   }
   // ---- pixel x text correlation (lseg_net.py:194-196): fp16 GEMM, fp16 result, NCHW store ----
-  const int kpad = ((ctx.K + 127) / 128) * 128;
-  const int groups = ctx.text_image_stride > 0 ? B : 1;
-  for (int g = 0; g < groups; ++g) {
-    GemmDesc d;
-    memset(&d, 0, sizeof(d));
-    const long long rows = (groups == 1) ? static_cast<long long>(B) * P : P;
-    d.a = plan.featn + static_cast<long long>(g) * P * 512;
-    d.lda = 512;
-    d.a_rows = (int)rows;
-    d.w = ctx.text + static_cast<long long>(g) * ctx.text_image_stride * 512;
-    d.w_rows = kpad;
-    d.M = (int)rows;
-    d.N = ctx.K;
-    d.K = 512;
-    d.e = epi_none();
-    d.e.out_f16 = plan.logits_lr + static_cast<long long>(g) * ctx.K * P;
-    d.e.store = STORE_NCHW_T;
-    d.e.nchw_p = (int)P;
-    d.e.nchw_k = ctx.K;
-    d.e.row_sumsq = plan.feat_sumsq + static_cast<long long>(g) * P * 16;
-    d.e.row_sumsq_parts = 16;
-    d.e.row_scale = eng->w.logit_scale;
-    GemmPlan gp;
-    if (gemm_plan(d, &gp)) return -1;
-    if (gemm_run(gp, stream)) return -1;
-    ++launches;
-    if (prof) {
-      if (prof->mark(stream)) return -1;
-      prof->kind.push_back(KIND_GEMM);
-      prof->flops.push_back(2.0 * rows * ctx.K * 512.0);
+  // One label set for all images (text_image_stride == 0): one GEMM over all B*P pixel rows.
+  // One label block per image (zero-shot path, lseg_net_zs.py:196-210; rows [b*stride, b*stride + K) of `text`):
+  // still ONE GEMM, against all B*stride text rows at once — each pixel row keeps only the K columns of its own
+  // image's block (nchw_group), the other columns are computed and dropped. For K = 2 the N tile is 128 wide anyway,
+  // so this costs the same tile as one image's block and replaces B launches by one. Falls back to one launch per
+  // image when B*stride exceeds one 256-column tile.
+  {
+    ImagePlan::CorrKey key{ctx.text, ctx.K, ctx.text_image_stride, lr};
+    auto it = plan.corr.find(key);
+    if (it == plan.corr.end()) {
+      if (plan.corr.size() > 16) plan.corr.clear();
+      std::vector<std::pair<GemmPlan, double>> plans;
+      const long long stride = ctx.text_image_stride;
+      const bool grouped = stride > 0 && static_cast<long long>(B) * stride <= 256;
+      const int groups = (stride > 0 && !grouped) ? B : 1;
+      for (int g = 0; g < groups; ++g) {
+        GemmDesc d;
+        memset(&d, 0, sizeof(d));
+        const long long rows = (groups == 1) ? static_cast<long long>(B) * P : P;
+        const int n_cols = grouped ? static_cast<int>(B * stride) : ctx.K;
+        d.a = plan.featn + static_cast<long long>(g) * P * 512;
+        d.lda = 512;
+        d.a_rows = (int)rows;
+        d.w = ctx.text + static_cast<long long>(g) * stride * 512;
+        d.w_rows = ((n_cols + 127) / 128) * 128;
+        d.M = (int)rows;
+        d.N = n_cols;
+        d.K = 512;
+        d.e = epi_none();
+        d.e.out_f16 = lr + static_cast<long long>(g) * ctx.K * P;
+        d.e.store = STORE_NCHW_T;
+        d.e.nchw_p = (int)P;
+        d.e.nchw_k = ctx.K;
+        d.e.nchw_group = grouped ? (int)stride : 0;
+        d.e.row_sumsq = plan.feat_sumsq + static_cast<long long>(g) * P * 16;
+        d.e.row_sumsq_parts = 16;
+        d.e.row_scale = eng->w.logit_scale;
+        GemmPlan gp;
+        if (gemm_plan(d, &gp)) return -1;
+        plans.emplace_back(gp, 2.0 * rows * n_cols * 512.0);
+      }
+      it = plan.corr.emplace(key, std::move(plans)).first;
+    }
+    for (auto& pr : it->second) {
+      if (gemm_run(pr.first, stream)) return -1;
+      ++launches;
+      if (prof) {
+        if (prof->mark(stream)) return -1;
+        prof->kind.push_back(KIND_GEMM);
+        prof->flops.push_back(pr.second);
+      }
     }
   }
   // ---- scratch.output_conv: bilinear x2, align_corners=True (lseg_net.py:203) ----
   if (ctx.out) {
     const long long planes = static_cast<long long>(B) * ctx.K;
-    if (launch_upsample2x_nchw(plan.logits_lr, ctx.out, planes, h2, w2, stream)) return -1;
+    if (launch_upsample2x_nchw(lr, ctx.out, planes, h2, w2, stream)) return -1;
     ++launches;
     if (prof) {
       if (prof->mark(stream)) return -1;
@@ -562,7 +651,7 @@ static int run_forward(lseg_engine* eng, const CallCtx& ctx, int B, int H, int W
   }
   // ---- fused output_conv + torch.max(.., 1)[1]: the fp32 logits are never materialised ----
   if (ctx.out_mask) {
-    if (launch_upsample2x_argmax(plan.logits_lr, ctx.out_mask, B, ctx.K, h2, w2, stream)) return -1;
+    if (launch_upsample2x_argmax(lr, ctx.out_mask, B, ctx.K, h2, w2, stream)) return -1;
     ++launches;
     if (prof) {
       if (prof->mark(stream)) return -1;
@@ -699,7 +788,9 @@ int lseg_create(const lseg_weights* w, int device, lseg_engine** out) {
 void lseg_destroy(lseg_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
-  e->img.reset();
+  cudaDeviceSynchronize();
+  e->plans.clear();
+  e->img = nullptr;
   e->txt.reset();
   for (auto& kv : e->pos_cache) cudaFree(kv.second);
   delete e;
@@ -742,6 +833,25 @@ int lseg_forward(lseg_engine* e, const float* x, int B, int H, int W, const void
   ctx.text_image_stride = text_image_stride;
   ctx.out = out;
   ctx.out_mask = nullptr;
+  ctx.out_lr = nullptr;
+  return run_forward(e, ctx, B, H, W, static_cast<cudaStream_t>(stream));
+}
+
+int lseg_forward_lowres(lseg_engine* e, const float* x, int B, int H, int W, const void* text, int K,
+                        long long text_image_stride, void* logits_lr, float* out, void* stream) {
+  using namespace lseg;
+  if (!e || !x || !text || !logits_lr || B <= 0) {
+    set_error("lseg_forward_lowres: bad argument");
+    return -1;
+  }
+  CallCtx ctx;
+  ctx.x = x;
+  ctx.text = static_cast<const __half*>(text);
+  ctx.K = K;
+  ctx.text_image_stride = text_image_stride;
+  ctx.out = out;  // optional
+  ctx.out_mask = nullptr;
+  ctx.out_lr = static_cast<__half*>(logits_lr);
   return run_forward(e, ctx, B, H, W, static_cast<cudaStream_t>(stream));
 }
 
@@ -759,6 +869,7 @@ int lseg_forward_argmax(lseg_engine* e, const float* x, int B, int H, int W, con
   ctx.text_image_stride = text_image_stride;
   ctx.out = logits;  // optional
   ctx.out_mask = mask;
+  ctx.out_lr = nullptr;
   return run_forward(e, ctx, B, H, W, static_cast<cudaStream_t>(stream));
 }
 
@@ -777,6 +888,7 @@ int lseg_forward_profiled(lseg_engine* e, const float* x, int B, int H, int W, c
   ctx.text_image_stride = text_image_stride;
   ctx.out = out;
   ctx.out_mask = nullptr;
+  ctx.out_lr = nullptr;
   Profile prof;
   int rc = run_forward(e, ctx, B, H, W, static_cast<cudaStream_t>(stream), &prof);
   if (rc == 0 && cudaStreamSynchronize(static_cast<cudaStream_t>(stream)) != cudaSuccess) {

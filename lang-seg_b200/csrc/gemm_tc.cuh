@@ -70,6 +70,8 @@ struct GemmEpi {
   int store;               // GemmStore
   int d2s_s, d2s_cout, d2s_h, d2s_w;  // depth-to-space: input grid h x w, upscale s, cout channels
   int nchw_p, nchw_k;      // STORE_NCHW_T: pixels per image, channel count (n < nchw_k stored)
+  int nchw_group;          // STORE_NCHW_T, > 0: the N columns are per-image blocks of `nchw_group` columns; a row of image
+                           // b stores only columns [b*group, b*group + nchw_k) as channels 0..nchw_k-1 (zero-shot path)
   const float* row_sumsq;  // STORE_NCHW_T only, nullable: [rows, row_sumsq_parts] partial squared norms;
   int row_sumsq_parts;     //   result *= row_scale * rsqrt(sum of the row's parts)
   float row_scale;
@@ -308,10 +310,13 @@ __device__ __forceinline__ void gemm_epilogue_store(const GemmEpi& e, int N, flo
   } else {  // STORE_NCHW_T : out[(b*K + n)*P + p], fp16 (lanes = consecutive pixels -> coalesced)
     const int b = static_cast<int>(grow / e.nchw_p);
     const int pix = static_cast<int>(grow - static_cast<long long>(b) * e.nchw_p);
-    __half* op = e.out_f16 + (static_cast<long long>(b) * e.nchw_k + n0) * e.nchw_p + pix;
+    const int c_lo = e.nchw_group > 0 ? b * e.nchw_group : 0;  // first column of this row's image block
+    __half* op = e.out_f16 + (static_cast<long long>(b) * e.nchw_k + (n0 - c_lo)) * e.nchw_p + pix;
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (n0 + i < e.nchw_k) op[static_cast<long long>(i) * e.nchw_p] = __float2half_rn(f[i]);
+    for (int i = 0; i < 32; ++i) {
+      const int ch = n0 + i - c_lo;
+      if (ch >= 0 && ch < e.nchw_k && n0 + i < N) op[static_cast<long long>(i) * e.nchw_p] = __float2half_rn(f[i]);
+    }
   }
 }
 

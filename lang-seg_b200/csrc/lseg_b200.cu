@@ -435,6 +435,7 @@ static void fill_epi(const lseg_gemm_args* a, GemmEpi* e) {
   e->d2s_w = a->d2s_w;
   e->nchw_p = a->nchw_p;
   e->nchw_k = a->nchw_k;
+  e->nchw_group = a->nchw_group;
   e->row_sumsq = a->row_sumsq;
   e->row_sumsq_parts = a->row_sumsq_parts;
   e->row_scale = a->row_scale;

@@ -70,6 +70,32 @@ class Engine:
                                              C.c_void_p(out.data_ptr()), _stream()))
         return out
 
+    def forward_lowres(self, x, text, k, text_image_stride=0, logits_lr=None, out=None):
+        """LSeg.forward up to the reference's fp16 matmul result: fp16 [B,K,H/2,W/2]. `logits_lr` may be a tensor of
+        this device or a raw device address (int) — e.g. a peer GPU's gather slot opened with lseg_p2p_open: the
+        pixel x text GEMM then stores straight over NVLink. `out` (fp32 [B,K,H,W]) is optional."""
+        self._check_input(x)
+        x = x.contiguous()
+        b, _, h, w = x.shape
+        if logits_lr is None:
+            logits_lr = torch.empty((b, k, h // 2, w // 2), dtype=torch.float16, device=self.device)
+        lr_ptr = logits_lr if isinstance(logits_lr, int) else logits_lr.data_ptr()
+        op = C.c_void_p(out.data_ptr()) if out is not None else None
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.lseg_forward_lowres(self.handle, C.c_void_p(x.data_ptr()), b, h, w,
+                                                    C.c_void_p(text.data_ptr()), k, text_image_stride,
+                                                    C.c_void_p(lr_ptr), op, _stream()))
+        return logits_lr
+
+    def _check_input(self, x):
+        if x.device != self.device:
+            raise RuntimeError(f"input is on {x.device}, engine is on {self.device}")
+        if x.dtype != torch.float32 or x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError("x must be float32 [B,3,H,W]")
+        if x.shape[2] % 32 or x.shape[3] % 32:
+            raise ValueError(f"H={x.shape[2]}, W={x.shape[3]} must be multiples of 32 (the reference fails on odd token "
+                             f"grids)")
+
     def forward_argmax(self, x, text, k, text_image_stride=0, out=None, logits=None):
         """Like forward, but returns torch.max(logits, 1)[1] as int64 [B,H,W] without materialising the fp32 logits
         (they are also written when a `logits` tensor is passed)."""

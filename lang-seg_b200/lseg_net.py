@@ -336,25 +336,36 @@ class LSegNetZS(_LSegBase):
         if path is not None:
             self.load(path)
 
+    def _pair_features(self, engine):
+        """L2-normalised fp16 features of every ['others', name] pair, [2 * n_labels, 512], encoded in ONE text-tower
+        call per device (the reference re-encodes the pair of every image on every forward, lseg_net_zs.py:196)."""
+        tokens = torch.cat(self.texts, 0)
+        return self._text_features(engine, tokens)
+
+    def _image_text(self, engine, class_info, device):
+        """text operand of the zero-shot forward: image b's pair at rows [2b, 2b+2) (text_image_stride = 2), rows padded
+        to a multiple of 128 — one gather, no per-image Python loop."""
+        ids = torch.as_tensor(class_info).to(device=device, dtype=torch.int64).reshape(-1)
+        if ids.numel() and (int(ids.min()) < 0 or int(ids.max()) >= len(self.label_list)):
+            raise IndexError("class_info out of range")
+        pairs = self._pair_features(engine)
+        rows = torch.stack((2 * ids, 2 * ids + 1), 1).reshape(-1)
+        # > 256 text rows: the engine falls back to one 128-row weight tile per image starting at that image's
+        # block, so the last blocks need 128 readable rows behind them
+        extra = 128 if rows.numel() > 256 else 0
+        text = torch.zeros((engine.padded_rows(rows.numel()) + extra, 512), dtype=torch.float16, device=device)
+        text[: rows.numel()] = pairs.index_select(0, rows)
+        return text
+
     @torch.no_grad()
     def forward(self, x, class_info):
         self._check_eval()
         engine = self._engine_for(x.device)
-        ids = [int(c) for c in class_info]
-        stride = engine.padded_rows(2)
-        text = torch.zeros((len(ids) * stride, 512), dtype=torch.float16, device=x.device)
-        for i, c in enumerate(ids):
-            text[i * stride:(i + 1) * stride] = self._text_features(engine, self.texts[c])
-        return engine.forward(x.float(), text, 2, text_image_stride=stride)
+        return engine.forward(x.float(), self._image_text(engine, class_info, x.device), 2, text_image_stride=2)
 
     @torch.no_grad()
     def predict(self, x, class_info):
         """argmax over the ['others', name] pair per pixel (test_lseg_zs.py:301), fused on the device."""
         self._check_eval()
         engine = self._engine_for(x.device)
-        ids = [int(c) for c in class_info]
-        stride = engine.padded_rows(2)
-        text = torch.zeros((len(ids) * stride, 512), dtype=torch.float16, device=x.device)
-        for i, c in enumerate(ids):
-            text[i * stride:(i + 1) * stride] = self._text_features(engine, self.texts[c])
-        return engine.forward_argmax(x.float(), text, 2, text_image_stride=stride)
+        return engine.forward_argmax(x.float(), self._image_text(engine, class_info, x.device), 2, text_image_stride=2)

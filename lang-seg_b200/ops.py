@@ -79,7 +79,8 @@ def gemm(a, w, N=None, *, bias=None, bias_group_rows=0, scale=None, act=ACT_NONE
     if d2s is not None:
         args.d2s_s, args.d2s_cout, args.d2s_h, args.d2s_w = d2s
     if nchw is not None:
-        args.nchw_p, args.nchw_k = nchw
+        args.nchw_p, args.nchw_k = nchw[0], nchw[1]
+        args.nchw_group = nchw[2] if len(nchw) > 2 else 0
     args.row_sumsq = _ptr(row_sumsq, torch.float32)
     args.row_sumsq_parts = int(row_sumsq.shape[1]) if row_sumsq is not None else 0
     args.row_scale = float(row_scale)
