@@ -9,8 +9,11 @@
 //     as S_j has been read and K_{j+2} has landed, then P_j V_j) with BLOCKING mbarrier waits. mhsa2 multiplexed both
 //     streams from one warp by polling four barriers with test_wait (~150 clk each): a hand-off was noticed half a
 //     polling round (~300 clk) late, twice per tile.
-//   * register budget by role (setmaxnreg): the control warpgroup (TMA producer, 2 MMA warps) drops to 40 registers,
-//     the two softmax warpgroups rise to 96 — 12 warps fit where 10 did.
+//   * 12 warps instead of 10: the launch bound (384 threads x 2 CTAs/SM) is 80 registers per thread, and by role
+//     (setmaxnreg) the control warpgroup (TMA producer, 2 MMA warps) drops to 40 while the two softmax warpgroups may
+//     rise to 96. With that head-room ptxas allocates the softmax code without a single spill (and in 78 registers);
+//     under a flat 80-register cap it spills 12-16 bytes in two instantiations, which is ruinous here (the shared-memory
+//     carve-out leaves almost no L1 for local memory).
 //   * PACK: the softmax arithmetic uses the sm_100 packed-fp32 instructions (FFMA2 / FADD2: two lanes of fp32 per
 //     issue slot) and the 3-input FMNMX3 for the row maximum: 6 issue slots per pair of scores instead of 9. The
 //     softmax warps are issue-bound as much as MUFU-bound (4 softmax warps per SM sub-partition share one issue port
@@ -29,7 +32,7 @@
 namespace lseg {
 
 constexpr int kM3Threads = 384;
-constexpr int kM3CtrlRegs = 40;
+constexpr int kM3CtrlRegs = 40;     // pool arithmetic per CTA: 128 x (80 - 40) = 5120 released >= 256 x (96 - 80) = 4096 claimed
 constexpr int kM3SoftmaxRegs = 96;
 
 template <int N>
