@@ -138,6 +138,24 @@ int lseg_text_embed(const int64_t* tokens, const float* tok_emb, const float* po
                     void* stream);
 int lseg_text_eot_gather(const int64_t* tokens, const void* x, void* out, int K, int L, int Wd, void* stream);
 
+/* ---- peer memory: the logits gather, one process per GPU over NVLink 5 / NVSwitch ----------
+ * Replaces the thread-per-GPU DataParallel gather of additional_utils/models.py:35-53. A rank allocates a buffer its peers
+ * can map (CUDA IPC; the 64-byte handle travels through any host channel, e.g. torch.distributed.all_gather_object);
+ * peers either let lseg_forward_lowres store into the mapping or push with the copy engines (lseg_p2p_copy), then
+ * publish completion with a system-scope release flag that the gathering rank's stream acquires — all enqueued on CUDA
+ * streams, no host synchronisation and no NCCL call on the data path. */
+int lseg_p2p_alloc(unsigned long long bytes, void** dptr, unsigned char* handle64);  /* zero-initialised; synchronises */
+int lseg_p2p_open(const unsigned char* handle64, void** dptr);   /* maps a peer's buffer into this process */
+int lseg_p2p_close(void* dptr);
+int lseg_p2p_free(void* dptr);
+int lseg_p2p_copy(void* dst, const void* src, unsigned long long bytes, void* stream);  /* async, either side may be peer */
+/* *flag = value with release semantics at system scope after all earlier work of `stream` (flag: own or peer memory) */
+int lseg_p2p_signal(unsigned long long* flag, unsigned long long value, void* stream);
+/* blocks `stream` (a one-thread kernel) until flags[i*stride] >= value for all i < n; after timeout_ms the device
+ * watchdog records tag 77 (lseg_read_watchdog) and the stream continues */
+int lseg_p2p_wait(const unsigned long long* flags, int n, int stride, unsigned long long value, unsigned int timeout_ms,
+                  void* stream);
+
 /* ---- whole-model engine -------------------------------------------------------------------------- */
 
 typedef struct lseg_linear_w {

@@ -76,6 +76,8 @@ SYMBOLS = [
     "lseg_upsample2x_nchw", "lseg_upsample2x_argmax", "lseg_forward_argmax", "lseg_text_embed", "lseg_text_eot_gather",
     "lseg_create", "lseg_destroy", "lseg_encode_text", "lseg_forward", "lseg_forward_lowres", "lseg_debug_buffer",
     "lseg_last_launch_count", "lseg_forward_profiled",
+    "lseg_p2p_alloc", "lseg_p2p_open", "lseg_p2p_close", "lseg_p2p_free", "lseg_p2p_copy", "lseg_p2p_signal",
+    "lseg_p2p_wait",
 ]
 
 _lib = None
@@ -141,6 +143,13 @@ def load(build_if_missing=True):
     lib.lseg_forward_argmax.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                         C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.lseg_upsample2x_argmax.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.lseg_p2p_alloc.argtypes = [C.c_ulonglong, C.POINTER(C.c_void_p), C.c_char_p]
+    lib.lseg_p2p_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.lseg_p2p_close.argtypes = [C.c_void_p]
+    lib.lseg_p2p_free.argtypes = [C.c_void_p]
+    lib.lseg_p2p_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_ulonglong, C.c_void_p]
+    lib.lseg_p2p_signal.argtypes = [C.c_void_p, C.c_ulonglong, C.c_void_p]
+    lib.lseg_p2p_wait.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_ulonglong, C.c_uint, C.c_void_p]
     lib.lseg_last_launch_count.argtypes = [C.c_void_p]
     lib.lseg_forward_profiled.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                           C.c_longlong, C.c_void_p, C.c_void_p, C.POINTER(C.c_float),

@@ -17,6 +17,7 @@
 #include "mhsa2.cuh"
 #include "mhsa3.cuh"
 #include "text_attn.cuh"
+#include "p2p.cuh"
 
 namespace lseg {
 
@@ -499,6 +500,83 @@ int lseg_text_attn(const void* qkv, void* out, int K, int L, int heads, void* st
   if (ensure_init()) return -1;
   return launch_text_attn(static_cast<const __half*>(qkv), static_cast<__half*>(out), K, L, heads,
                           static_cast<cudaStream_t>(stream));
+}
+
+// ---- peer memory (the logits gather) ----
+int lseg_p2p_alloc(unsigned long long bytes, void** dptr, unsigned char* handle64) {
+  if (ensure_init()) return -1;
+  if (!dptr || !handle64 || bytes == 0) {
+    set_error("lseg_p2p_alloc: bad argument");
+    return -1;
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  void* p = nullptr;
+  LSEG_CHECK_CUDA(cudaMalloc(&p, bytes));
+  LSEG_CHECK_CUDA(cudaMemset(p, 0, bytes));
+  LSEG_CHECK_CUDA(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  cudaError_t err = cudaIpcGetMemHandle(&h, p);
+  if (err != cudaSuccess) {
+    cudaFree(p);
+    set_error("lseg_p2p_alloc: cudaIpcGetMemHandle failed: %s", cudaGetErrorString(err));
+    return -1;
+  }
+  memcpy(handle64, &h, 64);
+  *dptr = p;
+  return 0;
+}
+
+int lseg_p2p_open(const unsigned char* handle64, void** dptr) {
+  if (ensure_init()) return -1;
+  if (!dptr || !handle64) {
+    set_error("lseg_p2p_open: bad argument");
+    return -1;
+  }
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  cudaError_t err = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (err != cudaSuccess) {
+    cudaGetLastError();
+    set_error("lseg_p2p_open: cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(err));
+    return -1;
+  }
+  *dptr = p;
+  return 0;
+}
+
+int lseg_p2p_close(void* dptr) {
+  if (!dptr) return 0;
+  LSEG_CHECK_CUDA(cudaIpcCloseMemHandle(dptr));
+  return 0;
+}
+
+int lseg_p2p_free(void* dptr) {
+  if (!dptr) return 0;
+  LSEG_CHECK_CUDA(cudaFree(dptr));
+  return 0;
+}
+
+int lseg_p2p_copy(void* dst, const void* src, unsigned long long bytes, void* stream) {
+  LSEG_CHECK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int lseg_p2p_signal(unsigned long long* flag, unsigned long long value, void* stream) {
+  if (ensure_init()) return -1;
+  p2p_signal_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(flag, value);
+  LSEG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int lseg_p2p_wait(const unsigned long long* flags, int n, int stride, unsigned long long value, unsigned int timeout_ms,
+                  void* stream) {
+  if (ensure_init()) return -1;
+  if (n <= 0) return 0;
+  p2p_wait_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(flags, n, stride, value,
+                                                                  static_cast<unsigned long long>(timeout_ms) * 1000000ull);
+  LSEG_CHECK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 int lseg_set_deterministic(int on) {

@@ -325,16 +325,23 @@ __global__ void __launch_bounds__(kM2Threads, 2) mhsa2_kernel(const __grid_const
         __syncwarp();
         tmem_ld32(tS, sc0);
         tmem_ld_wait();
+        TR(40);
         const float pm = need_mask ? mhsa_max_chunk<true>(sc0, kv0, p.n_tokens, kv_limit)
                                    : mhsa_max_chunk<false>(sc0, kv0, p.n_tokens, kv_limit);
         any0 = move_offset(pm, factor0);
         if (any0) l_run *= factor0;
+        TR(41);
         const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
         l_tile = need_mask ? mhsa_exp_chunk<true, POLY>(sc0, c, m_use, kv0, p.n_tokens, kv_limit, ph)
                            : mhsa_exp_chunk<false, POLY>(sc0, c, m_use, kv0, p.n_tokens, kv_limit, ph);
+        if (TRACE) {  // make the stamp wait for the exponentials (the packed halves are consumed much later)
+          asm volatile("" ::"r"(*reinterpret_cast<uint32_t*>(&ph[15])) : "memory");
+        }
+        TR(42);
         __syncwarp();
         tmem_ld32(tS + 32, sc1);  // unconditional (columns beyond a short tail tile are stale but allocated)
         tmem_ld_wait();
+        TR(43);
       }
       tc_fence_before();
       __syncwarp();

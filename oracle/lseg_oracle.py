@@ -172,10 +172,11 @@ def clip_text_weights_fp16(sd, dtype=torch.float16):
     return out
 
 
-def clip_encode_text(text, tw, heads=8, layers=12, dtype=torch.float16, layer_io=None):
+def clip_encode_text(text, tw, heads=8, layers=12, dtype=torch.float16, layer_io=None, op_trace=None):
     """CLIP.encode_text. text int64 [K,77] -> fp16 [K,512].
     layer_io: optional list that receives the residual stream [K,77,512] before block 0 and after every block
-    (teacher-forced per-block parity tests)."""
+    (teacher-forced per-block parity tests). op_trace: optional dict {block index: {}} that receives, for those blocks,
+    the output of every op of the block ([K,77,*] layout): ln1, qkv, attn (heads merged), x1, ln2, gelu, x2."""
     x = tw["token_embedding.weight"][text].to(dtype)
     x = x + tw["positional_embedding"].to(dtype)
     K, L, Wd = x.shape
@@ -185,9 +186,12 @@ def clip_encode_text(text, tw, heads=8, layers=12, dtype=torch.float16, layer_io
         layer_io.append(x.permute(1, 0, 2).clone())
     for i in range(layers):
         b = f"transformer.resblocks.{i}."
+        tr = op_trace.get(i) if op_trace is not None else None
         h = _ln_fp32(x, tw[b + "ln_1.weight"], tw[b + "ln_1.bias"])
         # nn.MultiheadAttention (torch 1.9 multi_head_attention_forward)
         qkv = F.linear(h, tw[b + "attn.in_proj_weight"], tw[b + "attn.in_proj_bias"])
+        if tr is not None:
+            tr["ln1"], tr["qkv"] = h.permute(1, 0, 2).clone(), qkv.permute(1, 0, 2).clone()
         q, k, v = qkv.chunk(3, dim=-1)
         hd = Wd // heads
         q = q * (float(hd) ** -0.5)
@@ -197,13 +201,21 @@ def clip_encode_text(text, tw, heads=8, layers=12, dtype=torch.float16, layer_io
         attn = torch.bmm(q, k.transpose(1, 2)) + mask
         attn = F.softmax(attn, dim=-1)
         o = torch.bmm(attn, v).transpose(0, 1).contiguous().view(L, K, Wd)
+        if tr is not None:
+            tr["attn"] = o.permute(1, 0, 2).clone()
         o = F.linear(o, tw[b + "attn.out_proj.weight"], tw[b + "attn.out_proj.bias"])
         x = x + o
         h = _ln_fp32(x, tw[b + "ln_2.weight"], tw[b + "ln_2.bias"])
+        if tr is not None:
+            tr["x1"], tr["ln2"] = x.permute(1, 0, 2).clone(), h.permute(1, 0, 2).clone()
         h = F.linear(h, tw[b + "mlp.c_fc.weight"], tw[b + "mlp.c_fc.bias"])
         h = h * torch.sigmoid(1.702 * h)  # QuickGELU
+        if tr is not None:
+            tr["gelu"] = h.permute(1, 0, 2).clone()
         h = F.linear(h, tw[b + "mlp.c_proj.weight"], tw[b + "mlp.c_proj.bias"])
         x = x + h
+        if tr is not None:
+            tr["x2"] = x.permute(1, 0, 2).clone()
         if layer_io is not None:
             layer_io.append(x.permute(1, 0, 2).clone())
     x = x.permute(1, 0, 2)

@@ -316,6 +316,7 @@ def build_reference_module(state_dict=None, drop_in=False, **overrides):
         sys.modules.pop(name, None)
     if drop_in:
         import importlib
+        importlib.import_module("lang-seg_b200.tokenizer").enable_stand_in()  # synthetic weights, no BPE vocabulary
         ours = importlib.import_module("lang-seg_b200.lseg_net")
         shim = types.ModuleType("modules.models.lseg_net")
         shim.LSegNet = ours.LSegNet

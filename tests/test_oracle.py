@@ -69,7 +69,13 @@ def _text_tower_reference_floor(out, st, z, tf, lat, ref_mask):
     feat = rel_err(st["text_features"], tf)
     logit = rel_err(out[:, :, ::8, ::8], lat)
     agree = (out.argmax(1) == ref_mask).float().mean().item()
-    print(f"reference-vs-oracle floor: text features {feat:.3e}, logits {logit:.3e}, argmax agreement {agree:.4f}")
+    top2 = out.topk(2, dim=1).values
+    flips = out.argmax(1) != ref_mask
+    quantum = 2.0 ** (int(np.floor(np.log2(float(out.abs().max())))) - 10)
+    worst_quanta = float((top2[:, 0] - top2[:, 1])[flips].max()) / quantum
+    print(f"reference-vs-oracle floor: text features {feat:.3e}, logits {logit:.3e}, argmax agreement {agree:.4f}, "
+          f"worst flipped margin {worst_quanta:.2f} fp16 quanta")
+    assert 3.0 < worst_quanta < 6.0, worst_quanta  # the GPU tests allow 6 quanta with the GPU text tower
     assert 1.0e-3 < feat < 2.5e-3, feat
     assert 1.0e-3 < logit < 3.0e-3, logit
     assert 0.97 < agree < 0.995, agree

@@ -12,7 +12,7 @@ import pytest
 import torch
 
 from parity_util import oracle_forward, oracle_threads, rel_err, state_dict, synth
-from test_model_gpu import FULL_LOGIT_TOL, _report, margin_eps
+from test_model_gpu import FULL_LOGIT_REL, _report, logit_tolerance, margin_eps
 from parity_util import argmax_report
 
 pytestmark = pytest.mark.gpu
@@ -50,13 +50,13 @@ def test_evaluate_random_and_forward_match_oracle(module):
     d = {"logits": rel_err(got, ref)}
     d.update(argmax_report(got, ref, margin_eps(ref)))
     _report("reference_caller_evaluate_random", d)
-    assert d["logits"] <= FULL_LOGIT_TOL and d["ok"], d
+    assert d["logits"] <= logit_tolerance(ref, FULL_LOGIT_REL) and d["ok"], d
     ref150, _ = oracle_forward(x[:1], synth.tokenize(synth.ade20k_labels()))
     with torch.no_grad():
         a = module(x[:1].cuda())            # LightningModule.forward -> self.net(x) with the constructor's 150 labels
         b = module.evaluate(x[:1].cuda())   # -> self.net.forward(x)
     assert torch.equal(a, b)
-    assert rel_err(a, ref150) <= FULL_LOGIT_TOL
+    assert rel_err(a, ref150) <= logit_tolerance(ref150, FULL_LOGIT_REL)
 
 
 @needs_ref
