@@ -130,9 +130,18 @@ int lseg_l2norm_scale(const float* x, void* y, long long M, int C, float logit_s
 int lseg_l2norm_f16(const void* x, void* y, int M, int C, void* stream);
 /* fp16 logits [planes,H,W] -> fp32 [planes,2H,2W], bilinear align_corners=True (k20; lseg_net.py:203). */
 int lseg_upsample2x_nchw(const void* x, float* y, long long planes, int H, int W, void* stream);
+/* same from fp32 planes (after the arch_option 1 / 2 head blocks) */
+int lseg_upsample2x_nchw_f32(const float* x, float* y, long long planes, int H, int W, void* stream);
 /* Interpolate (lseg_blocks.py:113-147) fused with torch.max(., 1)[1]: lr fp16 [B,K,H,W] -> mask int64 [B,2H,2W]
  * (first maximal class; the interpolated values are those of lseg_upsample2x_nchw bit for bit). */
 int lseg_upsample2x_argmax(const void* lr, long long* mask, int B, int K, int H, int W, void* stream);
+/* One application of scratch.head_block (arch_option 1 / 2, lseg_net.py:29-79): the SAME 3x3 kernel w9 (+ bias) over every
+ * class plane of x [B,K,h,w] (fp16 if in_f16 else fp32), mode 1 adds the per-pixel maximum over the K classes of the
+ * INPUT (bottleneck_block), then the activation (LSEG_HEAD_ACT_*; the reference skips it on the last application).
+ * y fp32 [B,K,h,w]; cmax_ws fp32 [B,h,w] workspace (mode 1). */
+enum { LSEG_HEAD_ACT_NONE = 0, LSEG_HEAD_ACT_RELU = 1, LSEG_HEAD_ACT_LRELU = 2, LSEG_HEAD_ACT_TANH = 3 };
+int lseg_head_block(const void* x, int in_f16, float* cmax_ws, float* y, int B, int K, int h, int w, const float* w9_host,
+                    float bias, int mode, int act, void* stream);
 /* CLIP text glue (k18). tokens int64 [K,L]. */
 int lseg_text_embed(const int64_t* tokens, const float* tok_emb, const float* pos_emb, void* x, int K, int L, int Wd,
                     void* stream);
@@ -209,6 +218,12 @@ typedef struct lseg_weights {
   lseg_text_block_w text_blocks[LSEG_TEXT_DEPTH];
   const float *lnf_g, *lnf_b;
   lseg_linear_w text_proj;                 /* text_projection^T as [512(out), 512(in)], no bias */
+  /* optional head blocks over the class planes (lseg_net.py:29-79,148-154,198-201) */
+  int arch_option;                         /* 0 none (default), 1 bottleneck_block, 2 depthwise_block */
+  int block_depth;                         /* the block runs max(block_depth, 1) times, activation on all but the last */
+  int head_act;                            /* LSEG_HEAD_ACT_* of kwargs["activation"] */
+  float head_block_w[9];                   /* scratch.head_block.depthwise.depthwise.weight [1,1,3,3] */
+  float head_block_b;                      /* ... .bias [1] */
 } lseg_weights;
 
 typedef struct lseg_engine lseg_engine;

@@ -350,8 +350,24 @@ __device__ __forceinline__ float lerp2(float w0, float a, float w1, float b) { r
 // ------------------------------------------------------------------------------------------
 constexpr int kUpRows = 4;      // output rows per warp
 constexpr int kUpMaxW = 512;    // widest source row (smem line)
-template <bool STREAM>  // STREAM: st.global.cs stores (A/B switch LSEG_UPSAMPLE_CS=1; default plain stores)
-__global__ void upsample2x_nchw_kernel(const __half* __restrict__ x, float* __restrict__ y, int H, int W) {
+// 8 consecutive source values as fp32 (TIn = __half: one 16-byte load; float: two)
+__device__ __forceinline__ void load8_f32(const __half* p, float (&o)[8]) {
+  const uint4 a = *reinterpret_cast<const uint4*>(p);
+  const __half2* ah = reinterpret_cast<const __half2*>(&a);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 f = __half22float2(ah[k]);
+    o[2 * k] = f.x;
+    o[2 * k + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void load8_f32(const float* p, float (&o)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+// TIn = __half: the fp16 matmul result (arch_option 0); float: the output of the arch_option 1/2 head blocks
+template <bool STREAM, typename TIn = __half>  // STREAM: st.global.cs stores (A/B switch LSEG_UPSAMPLE_CS=1; default plain stores)
+__global__ void upsample2x_nchw_kernel(const TIn* __restrict__ x, float* __restrict__ y, int H, int W) {
   griddep_launch_dependents();
   griddep_wait();
   __shared__ __align__(16) float line[8][kUpMaxW];
@@ -360,7 +376,7 @@ __global__ void upsample2x_nchw_kernel(const __half* __restrict__ x, float* __re
   const long long pl = blockIdx.y;
   const float sh = (Ho > 1) ? static_cast<float>(H - 1) / (Ho - 1) : 0.f;
   const float sw = (Wo > 1) ? static_cast<float>(W - 1) / (Wo - 1) : 0.f;
-  const __half* plane = x + pl * H * W;
+  const TIn* plane = x + pl * H * W;
   float* oplane = y + pl * Ho * Wo;
   float* v = line[warp];
   const int oy0 = (blockIdx.x * 8 + warp) * kUpRows;
@@ -371,20 +387,15 @@ __global__ void upsample2x_nchw_kernel(const __half* __restrict__ x, float* __re
     const int y0 = static_cast<int>(fy);
     const int y1 = min(y0 + 1, H - 1);
     const float ly = fy - y0, hy = 1.f - ly;
-    const uint4* r0 = reinterpret_cast<const uint4*>(plane + y0 * W);
-    const uint4* r1 = reinterpret_cast<const uint4*>(plane + y1 * W);
+    const TIn* r0 = plane + y0 * W;
+    const TIn* r1 = plane + y1 * W;
     __syncwarp();
     for (int c = lane; c < W / 8; c += 32) {
-      const uint4 a = r0[c], b = r1[c];
-      const __half2* ah = reinterpret_cast<const __half2*>(&a);
-      const __half2* bh = reinterpret_cast<const __half2*>(&b);
-      float o[8];
+      float fa[8], fb[8], o[8];
+      load8_f32(r0 + 8 * c, fa);
+      load8_f32(r1 + 8 * c, fb);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 fa = __half22float2(ah[k]), fb = __half22float2(bh[k]);
-        o[2 * k] = lerp2(hy, fa.x, ly, fb.x);
-        o[2 * k + 1] = lerp2(hy, fa.y, ly, fb.y);
-      }
+      for (int k = 0; k < 8; ++k) o[k] = lerp2(hy, fa[k], ly, fb[k]);
       reinterpret_cast<float4*>(v)[2 * c] = make_float4(o[0], o[1], o[2], o[3]);
       reinterpret_cast<float4*>(v)[2 * c + 1] = make_float4(o[4], o[5], o[6], o[7]);
     }
@@ -412,7 +423,8 @@ __global__ void upsample2x_nchw_kernel(const __half* __restrict__ x, float* __re
     }
   }
 }
-static inline int launch_upsample2x_nchw(const __half* x, float* y, long long planes, int H, int W, cudaStream_t s) {
+template <typename TIn>
+static inline int launch_upsample2x_nchw(const TIn* x, float* y, long long planes, int H, int W, cudaStream_t s) {
   if (W % 8 != 0 || W > kUpMaxW || planes > 65535) {
     set_error("upsample2x_nchw: needs W %% 8 == 0, W <= %d, planes <= 65535 (W=%d planes=%lld)", kUpMaxW, W, planes);
     return -1;
@@ -421,9 +433,9 @@ static inline int launch_upsample2x_nchw(const __half* x, float* y, long long pl
   static const bool stream_stores = getenv("LSEG_UPSAMPLE_CS") != nullptr;
   const dim3 grid((2 * H + rows_per_block - 1) / rows_per_block, static_cast<unsigned>(planes));
   if (stream_stores)
-    launch_pdl(upsample2x_nchw_kernel<true>, grid, dim3(256), 0, s, x, y, H, W);
+    launch_pdl(upsample2x_nchw_kernel<true, TIn>, grid, dim3(256), 0, s, x, y, H, W);
   else
-    launch_pdl(upsample2x_nchw_kernel<false>, grid, dim3(256), 0, s, x, y, H, W);
+    launch_pdl(upsample2x_nchw_kernel<false, TIn>, grid, dim3(256), 0, s, x, y, H, W);
   LSEG_LAUNCH_CHECK();
 }
 
@@ -438,7 +450,8 @@ static inline int launch_upsample2x_nchw(const __half* x, float* y, long long pl
 // lane + 32 j outputs, j < kArgJ. Output columns beyond 32*kArgJ are handled in further passes.
 // ------------------------------------------------------------------------------------------
 constexpr int kArgJ = 16;  // outputs per lane per pass (Wo <= 512 in one pass)
-__global__ void __launch_bounds__(256) upsample2x_argmax_kernel(const __half* __restrict__ lr, long long* __restrict__ mask,
+template <typename TIn>
+__global__ void __launch_bounds__(256) upsample2x_argmax_kernel(const TIn* __restrict__ lr, long long* __restrict__ mask,
                                                                 int K, int H, int W) {
   griddep_launch_dependents();
   griddep_wait();
@@ -455,7 +468,7 @@ __global__ void __launch_bounds__(256) upsample2x_argmax_kernel(const __half* __
   const int y1 = min(y0 + 1, H - 1);
   const float ly = fy - y0, hy = 1.f - ly;
   const long long plane_sz = static_cast<long long>(H) * W;
-  const __half* img = lr + static_cast<long long>(b) * K * plane_sz;
+  const TIn* img = lr + static_cast<long long>(b) * K * plane_sz;
   long long* orow = mask + (static_cast<long long>(b) * Ho + oy) * Wo;
   for (int ox0 = 0; ox0 < Wo; ox0 += 32 * kArgJ) {
     int xa[kArgJ], xb[kArgJ];
@@ -473,20 +486,15 @@ __global__ void __launch_bounds__(256) upsample2x_argmax_kernel(const __half* __
       arg[j] = 0;
     }
     for (int k = 0; k < K; ++k) {
-      const uint4* r0 = reinterpret_cast<const uint4*>(img + k * plane_sz + static_cast<long long>(y0) * W);
-      const uint4* r1 = reinterpret_cast<const uint4*>(img + k * plane_sz + static_cast<long long>(y1) * W);
+      const TIn* r0 = img + k * plane_sz + static_cast<long long>(y0) * W;
+      const TIn* r1 = img + k * plane_sz + static_cast<long long>(y1) * W;
       float* v = line[warp][k & 1];
       for (int c = lane; c < W / 8; c += 32) {
-        const uint4 a = r0[c], bq = r1[c];
-        const __half2* ah = reinterpret_cast<const __half2*>(&a);
-        const __half2* bh = reinterpret_cast<const __half2*>(&bq);
-        float o[8];
+        float fa[8], fb[8], o[8];
+        load8_f32(r0 + 8 * c, fa);
+        load8_f32(r1 + 8 * c, fb);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float2 fa = __half22float2(ah[q]), fb = __half22float2(bh[q]);
-          o[2 * q] = lerp2(hy, fa.x, ly, fb.x);
-          o[2 * q + 1] = lerp2(hy, fa.y, ly, fb.y);
-        }
+        for (int q = 0; q < 8; ++q) o[q] = lerp2(hy, fa[q], ly, fb[q]);
         reinterpret_cast<float4*>(v)[2 * c] = make_float4(o[0], o[1], o[2], o[3]);
         reinterpret_cast<float4*>(v)[2 * c + 1] = make_float4(o[4], o[5], o[6], o[7]);
       }
@@ -508,12 +516,89 @@ __global__ void __launch_bounds__(256) upsample2x_argmax_kernel(const __half* __
     }
   }
 }
-static inline int launch_upsample2x_argmax(const __half* lr, long long* mask, int B, int K, int H, int W, cudaStream_t s) {
+template <typename TIn>
+static inline int launch_upsample2x_argmax(const TIn* lr, long long* mask, int B, int K, int H, int W, cudaStream_t s) {
   if (W % 8 != 0 || W > kUpMaxW || B > 65535 || K <= 0) {
     set_error("upsample2x_argmax: needs W %% 8 == 0, W <= %d, B <= 65535, K > 0 (W=%d B=%d K=%d)", kUpMaxW, W, B, K);
     return -1;
   }
-  launch_pdl(upsample2x_argmax_kernel, dim3((2 * H + 7) / 8, B), dim3(256), 0, s, lr, mask, K, H, W);
+  launch_pdl(upsample2x_argmax_kernel<TIn>, dim3((2 * H + 7) / 8, B), dim3(256), 0, s, lr, mask, K, H, W);
+  LSEG_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------
+// arch_option 1 / 2 head blocks (modules/models/lseg_net.py:29-79, applied at :198-201 to the fp32 view of the
+// low-resolution logits [B,K,h,w]): ONE 3x3 convolution kernel (Conv2d(1,1,3,padding=1), weight [1,1,3,3] + bias)
+// shared by every class plane (`depthwise_conv` reshapes the classes into the batch), optionally plus the per-pixel
+// maximum over the classes (`bottleneck_block`: x.max(dim=1) skip), optionally an activation. fp32 arithmetic.
+// ------------------------------------------------------------------------------------------
+enum HeadAct { HEAD_ACT_NONE = 0, HEAD_ACT_RELU = 1, HEAD_ACT_LRELU = 2, HEAD_ACT_TANH = 3 };
+struct HeadBlockW {
+  float w[9];
+  float bias;
+};
+__device__ __forceinline__ float ld_f32(const __half* p) { return __half2float(*p); }
+__device__ __forceinline__ float ld_f32(const float* p) { return *p; }
+
+// cmax[b, y, x] = max_k x[b, k, y, x]; grid (ceil(h*w/256), B)
+template <typename TIn>
+__global__ void channel_max_kernel(const TIn* __restrict__ x, float* __restrict__ cmax, int K, int P) {
+  griddep_launch_dependents();
+  griddep_wait();
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= P) return;
+  const TIn* src = x + static_cast<long long>(blockIdx.y) * K * P + pix;
+  float m = -INFINITY;
+  for (int k = 0; k < K; ++k) m = fmaxf(m, ld_f32(src + static_cast<long long>(k) * P));
+  cmax[static_cast<long long>(blockIdx.y) * P + pix] = m;
+}
+
+// y[plane, i, j] = act( bias + sum_{a,b} w[a][b] x[plane, i+a-1, j+b-1] (+ cmax[b, i, j]) ), zero padding.
+// grid (ceil(w/32), ceil(h/8), B*K), block (32, 8)
+template <typename TIn>
+__global__ void head_block_kernel(const TIn* __restrict__ x, const float* __restrict__ cmax, float* __restrict__ y, int K,
+                                  int h, int w, HeadBlockW hw, int act) {
+  griddep_launch_dependents();
+  griddep_wait();
+  const int j = blockIdx.x * 32 + threadIdx.x, i = blockIdx.y * 8 + threadIdx.y;
+  if (i >= h || j >= w) return;
+  const long long plane = blockIdx.z;
+  const TIn* src = x + plane * h * w;
+  float acc = 0.f;  // torch accumulates the taps first and adds the bias last
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const int ii = i + a - 1;
+    if (ii < 0 || ii >= h) continue;
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      const int jj = j + b - 1;
+      if (jj < 0 || jj >= w) continue;
+      acc = fmaf(hw.w[a * 3 + b], ld_f32(src + static_cast<long long>(ii) * w + jj), acc);
+    }
+  }
+  acc += hw.bias;
+  if (cmax) acc += cmax[(plane / K) * static_cast<long long>(h) * w + static_cast<long long>(i) * w + j];
+  if (act == HEAD_ACT_RELU) acc = fmaxf(acc, 0.f);
+  else if (act == HEAD_ACT_LRELU) acc = acc > 0.f ? acc : 0.01f * acc;
+  else if (act == HEAD_ACT_TANH) acc = tanhf(acc);
+  y[plane * h * w + static_cast<long long>(i) * w + j] = acc;
+}
+
+// one application of scratch.head_block; mode 1 = bottleneck_block (channel-max skip), 2 = depthwise_block
+template <typename TIn>
+static inline int launch_head_block(const TIn* x, float* cmax_ws, float* y, int B, int K, int h, int w, const HeadBlockW& hw,
+                                    int mode, int act, cudaStream_t s) {
+  const int P = h * w;
+  if (static_cast<long long>(B) * K > 65535) {
+    set_error("head_block: B*K = %lld planes exceed 65535", static_cast<long long>(B) * K);
+    return -1;
+  }
+  if (mode == 1) {
+    launch_pdl(channel_max_kernel<TIn>, dim3((P + 255) / 256, B), dim3(256), 0, s, x, cmax_ws, K, P);
+    LSEG_CHECK_CUDA(cudaGetLastError());
+  }
+  launch_pdl(head_block_kernel<TIn>, dim3((w + 31) / 32, (h + 7) / 8, B * K), dim3(32, 8), 0, s, x,
+             static_cast<const float*>(mode == 1 ? cmax_ws : nullptr), y, K, h, w, hw, act);
   LSEG_LAUNCH_CHECK();
 }
 

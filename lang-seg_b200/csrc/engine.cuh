@@ -89,6 +89,9 @@ struct ImagePlan {
   float* feat_sumsq = nullptr;
   __half* logits_lr = nullptr;  // own cudaMalloc (grows with K), not part of the arena
   size_t logits_cap_k = 0;
+  float* head_ws[2] = {nullptr, nullptr};  // arch_option 1/2: fp32 [B,K,h,w] ping-pong (own cudaMalloc, grows with K)
+  float* head_cmax = nullptr;              // [B,h,w]
+  size_t head_cap_k = 0;
   // pixel x text GEMM plans (host-encoded tensor maps) keyed by (text pointer, K, per-image stride, output pointer)
   struct CorrKey {
     const void* text;
@@ -104,6 +107,9 @@ struct ImagePlan {
   ~ImagePlan() {
     arena.release();
     if (logits_lr) cudaFree(logits_lr);
+    for (float* p : head_ws)
+      if (p) cudaFree(p);
+    if (head_cmax) cudaFree(head_cmax);
   }
 };
 
@@ -638,10 +644,50 @@ static int run_forward(lseg_engine* eng, const CallCtx& ctx, int B, int H, int W
       }
     }
   }
+  // ---- optional head blocks on the fp32 view of the low-res logits (arch_option 1 / 2, lseg_net.py:198-201) ----
+  const float* lr32 = nullptr;
+  const int arch = eng->w.arch_option;
+  if (arch == 1 || arch == 2) {
+    if (ctx.out_lr) {
+      set_error("lseg_forward_lowres: the fp16 low-res logits are not the network output when arch_option is %d", arch);
+      return -1;
+    }
+    if (!plan.head_ws[0] || plan.head_cap_k < (size_t)ctx.K) {
+      LSEG_CHECK_CUDA(cudaStreamSynchronize(stream));
+      for (int i = 0; i < 2; ++i) {
+        if (plan.head_ws[i]) cudaFree(plan.head_ws[i]);
+        plan.head_ws[i] = nullptr;
+        LSEG_CHECK_CUDA(cudaMalloc(&plan.head_ws[i], sizeof(float) * (size_t)B * ctx.K * P));
+      }
+      if (!plan.head_cmax) LSEG_CHECK_CUDA(cudaMalloc(&plan.head_cmax, sizeof(float) * (size_t)B * P));
+      plan.head_cap_k = ctx.K;
+    }
+    HeadBlockW hw;
+    for (int i = 0; i < 9; ++i) hw.w[i] = eng->w.head_block_w[i];
+    hw.bias = eng->w.head_block_b;
+    const int depth = eng->w.block_depth > 1 ? eng->w.block_depth : 1;  // range(block_depth - 1) + the final call
+    for (int dpt = 0; dpt < depth; ++dpt) {
+      const int act = (dpt + 1 < depth) ? eng->w.head_act : HEAD_ACT_NONE;
+      float* dst = plan.head_ws[dpt & 1];
+      int rc = (dpt == 0) ? launch_head_block(lr, plan.head_cmax, dst, B, ctx.K, h2, w2, hw, arch, act, stream)
+                          : launch_head_block(static_cast<const float*>(plan.head_ws[(dpt - 1) & 1]), plan.head_cmax, dst,
+                                              B, ctx.K, h2, w2, hw, arch, act, stream);
+      if (rc) return -1;
+      launches += (arch == 1) ? 2 : 1;
+      if (prof) {
+        if (prof->mark(stream)) return -1;
+        prof->kind.push_back(KIND_EW);
+        prof->flops.push_back(0.0);
+      }
+      lr32 = dst;
+    }
+  }
   // ---- scratch.output_conv: bilinear x2, align_corners=True (lseg_net.py:203) ----
   if (ctx.out) {
     const long long planes = static_cast<long long>(B) * ctx.K;
-    if (launch_upsample2x_nchw(lr, ctx.out, planes, h2, w2, stream)) return -1;
+    if (lr32 ? launch_upsample2x_nchw(lr32, ctx.out, planes, h2, w2, stream)
+             : launch_upsample2x_nchw(lr, ctx.out, planes, h2, w2, stream))
+      return -1;
     ++launches;
     if (prof) {
       if (prof->mark(stream)) return -1;
@@ -651,7 +697,9 @@ static int run_forward(lseg_engine* eng, const CallCtx& ctx, int B, int H, int W
   }
   // ---- fused output_conv + torch.max(.., 1)[1]: the fp32 logits are never materialised ----
   if (ctx.out_mask) {
-    if (launch_upsample2x_argmax(lr, ctx.out_mask, B, ctx.K, h2, w2, stream)) return -1;
+    if (lr32 ? launch_upsample2x_argmax(lr32, ctx.out_mask, B, ctx.K, h2, w2, stream)
+             : launch_upsample2x_argmax(lr, ctx.out_mask, B, ctx.K, h2, w2, stream))
+      return -1;
     ++launches;
     if (prof) {
       if (prof->mark(stream)) return -1;

@@ -684,6 +684,32 @@ int lseg_upsample2x_nchw(const void* x, float* y, long long planes, int H, int W
   return launch_upsample2x_nchw(static_cast<const __half*>(x), y, planes, H, W, static_cast<cudaStream_t>(stream));
 }
 
+int lseg_upsample2x_nchw_f32(const float* x, float* y, long long planes, int H, int W, void* stream) {
+  if (ensure_init()) return -1;
+  if ((2 * W) % 4 != 0) {
+    set_error("upsample2x_nchw: output width must be a multiple of 4");
+    return -1;
+  }
+  return launch_upsample2x_nchw(x, y, planes, H, W, static_cast<cudaStream_t>(stream));
+}
+
+int lseg_head_block(const void* x, int in_f16, float* cmax_ws, float* y, int B, int K, int h, int w, const float* w9_host,
+                    float bias, int mode, int act, void* stream) {
+  if (ensure_init()) return -1;
+  if (!x || !y || !w9_host || (mode != 1 && mode != 2) || (mode == 1 && !cmax_ws)) {
+    set_error("lseg_head_block: bad argument");
+    return -1;
+  }
+  HeadBlockW hw;
+  for (int i = 0; i < 9; ++i) hw.w[i] = w9_host[i];
+  hw.bias = bias;
+  if (in_f16)
+    return launch_head_block(static_cast<const __half*>(x), cmax_ws, y, B, K, h, w, hw, mode, act,
+                             static_cast<cudaStream_t>(stream));
+  return launch_head_block(static_cast<const float*>(x), cmax_ws, y, B, K, h, w, hw, mode, act,
+                           static_cast<cudaStream_t>(stream));
+}
+
 int lseg_upsample2x_argmax(const void* lr, long long* mask, int B, int K, int H, int W, void* stream) {
   if (ensure_init()) return -1;
   return launch_upsample2x_argmax(static_cast<const __half*>(lr), mask, B, K, H, W, static_cast<cudaStream_t>(stream));

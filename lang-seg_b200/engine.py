@@ -14,14 +14,15 @@ def _stream():
 class Engine:
     """Owns the packed weights and the native engine for one CUDA device."""
 
-    def __init__(self, state_dict, device):
+    def __init__(self, state_dict, device, arch_option=0, block_depth=0, activation="lrelu"):
         device = torch.device(device)
         if device.type != "cuda":
             raise RuntimeError("lseg_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
         self.device = device
         self.lib = _lib.load()
         with torch.cuda.device(device):
-            self.weights = PackedWeights(state_dict, device)
+            self.weights = PackedWeights(state_dict, device, arch_option=arch_option, block_depth=block_depth,
+                                         activation=activation)
             torch.cuda.synchronize()
             handle = C.c_void_p()
             idx = device.index if device.index is not None else torch.cuda.current_device()

@@ -142,9 +142,14 @@ class _LSegBase(nn.Module):
             # same failure mode as lseg_blocks.py:53-55; other backbones are out of scope
             print(f"Backbone '{backbone}' not implemented")
             assert False
-        self.arch_option = kwargs.get("arch_option", 0)
-        if self.arch_option not in (0, None):
-            raise NotImplementedError("arch_option 1/2 head blocks are not part of the B200 hot path yet")
+        self.arch_option = kwargs.get("arch_option", 0) or 0
+        if self.arch_option not in (0, 1, 2):
+            raise ValueError(f"arch_option {self.arch_option}: the reference defines 0, 1 (bottleneck_block) and 2 "
+                             f"(depthwise_block) (lseg_net.py:148-154)")
+        self.block_depth = kwargs.get("block_depth", 0) or 0
+        self.activation = kwargs.get("activation", "lrelu")
+        if self.arch_option and self.activation not in ("relu", "lrelu", "tanh"):
+            raise ValueError(f"activation '{self.activation}': relu, lrelu or tanh (lseg_net.py:45-50)")
         self.channels_last = False
         self.out_c = 512
         # holders are built on the meta device (no per-module default init: 400 M parameters would take
@@ -153,6 +158,11 @@ class _LSegBase(nn.Module):
             self.clip_pretrained = _ClipTextHolder()
             self.pretrained = _pretrained_holder()
             self.scratch = _scratch_holder(self.out_c)
+            if self.arch_option in (1, 2):  # scratch.head_block.depthwise.depthwise = Conv2d(1, 1, 3, padding=1)
+                hb = nn.Module()
+                hb.depthwise = nn.Module()
+                hb.depthwise.depthwise = nn.Conv2d(1, 1, kernel_size=3, stride=1, padding=1)
+                self.scratch.head_block = hb
         self.logit_scale = torch.tensor(reference_logit_scale())
         self.clip_pretrained._owner = weakref.ref(self)
         self._install_load_hooks()
@@ -255,7 +265,8 @@ class _LSegBase(nn.Module):
                 if not sd:  # DataParallel replica: parameters live on the master copy
                     master = shared["master"]()
                     sd = master.state_dict() if master is not None else sd
-                eng = Engine(sd, device)
+                eng = Engine(sd, device, arch_option=self.arch_option, block_depth=self.block_depth,
+                             activation=self.activation)
                 shared["engines"][device] = eng
             return eng
 

@@ -107,6 +107,25 @@ def text_attn(qkv, K, L, heads):
     return out
 
 
+def head_block(x, weight9, bias, mode, act):
+    """One application of scratch.head_block on x [B,K,h,w] (fp16 or fp32) -> fp32 (include/lseg_b200.h lseg_head_block)."""
+    B, K, h, w = x.shape
+    y = torch.empty((B, K, h, w), dtype=torch.float32, device=x.device)
+    cmax = torch.empty((B, h, w), dtype=torch.float32, device=x.device)
+    w9 = (C.c_float * 9)(*[float(v) for v in weight9])
+    check(load().lseg_head_block(_ptr(x), int(x.dtype == torch.float16), _ptr(cmax), _ptr(y), B, K, h, w, w9, float(bias),
+                                 int(mode), int(act), _stream()))
+    return y
+
+
+def upsample2x_nchw_f32(x):
+    planes = x.numel() // (x.shape[-1] * x.shape[-2])
+    H, W = x.shape[-2:]
+    y = torch.empty(tuple(x.shape[:-2]) + (2 * H, 2 * W), dtype=torch.float32, device=x.device)
+    check(load().lseg_upsample2x_nchw_f32(_ptr(x, torch.float32), _ptr(y), planes, H, W, _stream()))
+    return y
+
+
 def set_deterministic(on):
     """True (default): fixed summation order everywhere (bit-reproducible); False: the in-place residual GEMMs may
     split K across CTA pairs (include/lseg_b200.h lseg_set_deterministic)."""

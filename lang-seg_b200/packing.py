@@ -63,11 +63,19 @@ def reference_logit_scale():
 class PackedWeights:
     """Owns the packed tensors and the ctypes descriptor that points into them."""
 
-    def __init__(self, state_dict, device):
+    def __init__(self, state_dict, device, arch_option=0, block_depth=0, activation="lrelu"):
         self.device = torch.device(device)
         self._keep = []
         self.desc = _lib.Weights()
         self._pack(state_dict)
+        d = self.desc
+        d.arch_option, d.block_depth = int(arch_option or 0), int(block_depth or 0)
+        d.head_act = _lib.HEAD_ACT[activation] if d.arch_option else 0
+        if d.arch_option in (1, 2):  # scratch.head_block (lseg_net.py:148-154): one shared 3x3 kernel + bias
+            w = state_dict["scratch.head_block.depthwise.depthwise.weight"].detach().float().reshape(9).tolist()
+            for i in range(9):
+                d.head_block_w[i] = w[i]
+            d.head_block_b = float(state_dict["scratch.head_block.depthwise.depthwise.bias"].detach().float().reshape(-1)[0])
 
     # -- helpers -------------------------------------------------------------------------------
     def _f32(self, t):

@@ -241,14 +241,36 @@ def correlation_head(path_1, text_features, sd):
     return logits_per_image.float().view(imshape[0], imshape[2], imshape[3], -1).permute(0, 3, 1, 2)
 
 
+def head_block(out, sd, arch_option, block_depth, activation):
+    """scratch.head_block applied as lseg_net.py:198-201 does: `block_depth - 1` times with the activation, once without.
+    depthwise_conv (lseg_net.py:29-42) folds the classes into the batch and runs ONE Conv2d(1,1,3,padding=1) over every
+    class plane; bottleneck_block (:62-79) adds the per-pixel max over the classes of its input; depthwise_block (:45-60)
+    does not."""
+    w = sd["scratch.head_block.depthwise.depthwise.weight"]
+    b = sd["scratch.head_block.depthwise.depthwise.bias"]
+    act = {"relu": F.relu, "lrelu": lambda t: F.leaky_relu(t, 0.01), "tanh": torch.tanh}[activation]
+
+    def block(x, use_act):
+        B, C, H, W = x.shape
+        y = F.conv2d(x.reshape(-1, 1, H, W), w, b, padding=1).view(-1, C, H, W)
+        if arch_option == 1:
+            y = y + x.max(dim=1, keepdim=True)[0]
+        return act(y) if use_act else y
+
+    for _ in range(block_depth - 1):
+        out = block(out, True)
+    return block(out, False)
+
+
 def output_conv(out):
     """scratch.output_conv = Interpolate(x2, bilinear, align_corners=True) (lseg_net.py:203,219-221)."""
     return F.interpolate(out, scale_factor=2, mode="bilinear", align_corners=True)
 
 
 @torch.no_grad()
-def lseg_forward(x, tokens, sd, text_weights=None, return_stages=False):
-    """LSeg.forward (modules/models/lseg_net.py:160-205, arch_option 0). x fp32 [B,3,H,W], tokens int64 [K,77]."""
+def lseg_forward(x, tokens, sd, text_weights=None, return_stages=False, arch_option=0, block_depth=0,
+                 activation="lrelu"):
+    """LSeg.forward (modules/models/lseg_net.py:160-205). x fp32 [B,3,H,W], tokens int64 [K,77]."""
     if x.shape[2] % 32 or x.shape[3] % 32:
         raise ValueError("H and W must be multiples of 32 (even token grid)")
     tw = text_weights if text_weights is not None else clip_text_weights_fp16(sd)
@@ -257,6 +279,8 @@ def lseg_forward(x, tokens, sd, text_weights=None, return_stages=False):
     path_1 = decoder(layers, sd)
     text_features = clip_encode_text(tokens, tw)
     low = correlation_head(path_1, text_features, sd)
+    if arch_option in (1, 2):
+        low = head_block(low, sd, arch_option, block_depth, activation)
     out = output_conv(low)
     if return_stages:
         tf = text_features / text_features.norm(dim=-1, keepdim=True)

@@ -279,15 +279,15 @@ def install(with_lightning_stack=True):
         sys.path.insert(0, REFERENCE_ROOT)
 
 
-def build_reference_net(state_dict, labels):
+def build_reference_net(state_dict, labels, arch_option=0, block_depth=0, activation="lrelu"):
     """Construct the UNMODIFIED reference LSegNet (modules/models/lseg_net.py:208-226) on CPU and load `state_dict`."""
     install()
     cwd = os.getcwd()
     os.chdir(REFERENCE_ROOT)
     try:
         from modules.models.lseg_net import LSegNet
-        net = LSegNet(labels=labels, backbone="clip_vitl16_384", features=256, crop_size=480, arch_option=0,
-                      block_depth=0, activation="lrelu")
+        net = LSegNet(labels=labels, backbone="clip_vitl16_384", features=256, crop_size=480, arch_option=arch_option,
+                      block_depth=block_depth, activation=activation)
     finally:
         os.chdir(cwd)
     missing, unexpected = net.load_state_dict(state_dict, strict=False)

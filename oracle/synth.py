@@ -43,7 +43,7 @@ class _Gen:
         return self.uniform(shape, -b, b)
 
 
-def make_state_dict(seed=0, with_clip_visual_stub=False):
+def make_state_dict(seed=0, with_clip_visual_stub=False, head_block=False):
     """fp32 state dict of LSegNet(backbone='clip_vitl16_384') — keys per SURVEY.md Appendix C."""
     g = _Gen(seed)
     sd = {}
@@ -123,6 +123,9 @@ def make_state_dict(seed=0, with_clip_visual_stub=False):
     sd[c + "ln_final.bias"] = g.normal((Wd,), 0.05)
     if with_clip_visual_stub:  # real checkpoints also carry the (unused) CLIP visual tower
         sd[c + "visual.conv1.weight"] = g.normal((8, 3, 32, 32), 0.02)
+    if head_block:  # arch_option 1 / 2 (lseg_net.py:148-154); drawn last so every other tensor keeps its value
+        sd["scratch.head_block.depthwise.depthwise.weight"] = g.uniform((1, 1, 3, 3), -0.4, 0.4)
+        sd["scratch.head_block.depthwise.depthwise.bias"] = g.uniform((1,), -0.2, 0.2)
     return sd
 
 

@@ -142,10 +142,12 @@ def test_text_ops_teacher_forced():
     def dev(t, cols):  # oracle activation [K,77,cols] -> padded fp16 rows on the GPU (TMA boxes never exceed the tensor)
         return ops.pad_rows(t.reshape(M, cols).half().cuda())
 
-    def check(name, got, ref, max_ulp, floor):
+    def check(name, got, ref, max_ulp):
+        # error in fp16 ulps of the element, but never finer than the ulp at 1/8 of the tensor's largest magnitude: an
+        # output that is small by cancellation (a dot product near zero) carries the rounding of its O(max) terms
         got, ref = got[:M].float().cpu(), ref.reshape(M, -1).float()
         diff = (got - ref).abs()
-        worst = (diff / _ulp16(ref, floor)).max().item()
+        worst = (diff / _ulp16(ref, float(ref.abs().max()) / 8)).max().item()
         exact = (diff == 0).float().mean().item()
         report[name] = (round(worst, 2), round(exact, 4))
         assert worst <= max_ulp, (name, worst, exact)
@@ -162,29 +164,28 @@ def test_text_ops_teacher_forced():
 
         x0 = dev(io[i], Wd)
         scale = float(io[i + 1].abs().max())
-        tiny = fp16_quantum(scale) * 2.0 ** 10 / 64  # ulp floor: 1/64 of the stream scale
         # -- each op on the oracle's input of that op --
         h = ops.layernorm(x0, tw[b + "ln_1.weight"].cuda(), tw[b + "ln_1.bias"].cuda(), 1e-5)
-        check(f"b{i}.ln1", h, t["ln1"], 1.0, tiny)
+        check(f"b{i}.ln1", h, t["ln1"], 1.0)
         qkv = torch.empty((x0.shape[0], 3 * Wd), dtype=torch.float16, device="cuda")
         ops.gemm(dev(t["ln1"], Wd), wt("attn.in_proj_weight"), 3 * Wd, M=M, bias=bias("attn.in_proj_bias"), out_f16=qkv)
-        check(f"b{i}.in_proj", qkv, t["qkv"], 1.0, tiny)
+        check(f"b{i}.in_proj", qkv, t["qkv"], 1.0)
         a = ops.text_attn(t["qkv"].half().cuda().contiguous(), K, L, 8)
-        check(f"b{i}.attn", a, t["attn"], 1.0, tiny)
+        check(f"b{i}.attn", a, t["attn"], 1.0)
         x1 = torch.zeros_like(x0)
         ops.gemm(dev(t["attn"], Wd), wt("attn.out_proj.weight"), Wd, M=M, bias=bias("attn.out_proj.bias"), res_f16=x0,
                  out_f16=x1)
-        check(f"b{i}.out_proj+res", x1, t["x1"], 2.0, scale / 4)
+        check(f"b{i}.out_proj+res", x1, t["x1"], 2.0)
         h2 = ops.layernorm(dev(t["x1"], Wd), tw[b + "ln_2.weight"].cuda(), tw[b + "ln_2.bias"].cuda(), 1e-5)
-        check(f"b{i}.ln2", h2, t["ln2"], 1.0, tiny)
+        check(f"b{i}.ln2", h2, t["ln2"], 1.0)
         g = torch.empty((x0.shape[0], 4 * Wd), dtype=torch.float16, device="cuda")
         ops.gemm(dev(t["ln2"], Wd), wt("mlp.c_fc.weight"), 4 * Wd, M=M, bias=bias("mlp.c_fc.bias"), act=ops.ACT_QUICKGELU,
                  out_f16=g)
-        check(f"b{i}.c_fc+quickgelu", g, t["gelu"], 1.0, tiny)
+        check(f"b{i}.c_fc+quickgelu", g, t["gelu"], 1.0)
         x2 = torch.zeros_like(x0)
         ops.gemm(dev(t["gelu"], 4 * Wd), wt("mlp.c_proj.weight"), Wd, M=M, bias=bias("mlp.c_proj.bias"),
                  res_f16=dev(t["x1"], Wd), out_f16=x2)
-        check(f"b{i}.c_proj+res", x2, t["x2"], 2.0, scale / 4)
+        check(f"b{i}.c_proj+res", x2, t["x2"], 2.0)
         # -- the whole block chained on the GPU from the oracle's block input --
         ops.gemm(h, wt("attn.in_proj_weight"), 3 * Wd, M=M, bias=bias("attn.in_proj_bias"), out_f16=qkv)
         a = ops.pad_rows(ops.text_attn(qkv[:M].contiguous(), K, L, 8))
@@ -378,6 +379,40 @@ def test_open_vocab_config5(net):
         assert d[f"tap{k}"] <= STAGE_TOL, d
     assert d["logits_teacher_forced"] <= logit_tolerance(ref, LOGIT_REL) and tf["ok"], d
     assert d["logits"] <= logit_tolerance(ref, FULL_LOGIT_REL) and d["ok"], d
+
+
+@pytest.mark.parametrize("tag,kw", [("opt1", dict(arch_option=1, block_depth=2, activation="lrelu")),
+                                    ("opt2", dict(arch_option=2, block_depth=3, activation="tanh"))])
+def test_arch_option_head_blocks(tag, kw):
+    """arch_option 1 / 2 (lseg_net.py:148-154,198-201) against the oracle AND against the committed
+    output of the unmodified reference LSegNet (oracle/make_golden_arch.py). The blocks themselves are exact to 2e-6
+    (tests/test_ops_gpu.py::test_head_block, tests/test_oracle.py bit-level vs the reference module); what this case
+    measures end to end is how much they AMPLIFY the upstream differences (shared 3x3 taps up to 0.4 and a channel max,
+    applied block_depth times: x3-4 per application), hence the wider bar."""
+    from lseg_b200.lseg_net import LSegNet
+    from oracle import lseg_oracle as O
+    sd = synth.make_state_dict(0, head_block=True)
+    labels = synth.ade20k_labels()[:5]
+    nk = dict(NET_KW)
+    nk.update(kw)
+    n = LSegNet(labels=labels, **nk)
+    n.load_state_dict(sd)
+    n = n.cuda().eval()
+    x = synth.make_image(2, 64, 96, seed=2064)
+    tokens = synth.tokenize(labels)
+    ref, st = O.lseg_forward(x, tokens, sd, return_stages=True, **kw)
+    eng = n._engine_for(torch.device("cuda"))
+    got_tf = eng.forward(x.cuda(), _padded_text(eng, st["text_features"]), 5)
+    got = n(x.cuda(), tokens)
+    mask = n.predict(x.cuda(), tokens)
+    gold = np.load(os.path.join(GOLD, "ref_arch.npz"))
+    d = {"logits_teacher_forced": rel_err(got_tf, ref), "logits": rel_err(got, ref),
+         "logits_vs_reference_golden": rel_err(got, torch.from_numpy(gold[f"{tag}_logits"])),
+         "max_abs_logit": ref.abs().max().item()}
+    _report(f"arch_option_{tag}", d)
+    assert torch.equal(mask.cpu(), got.argmax(1).cpu())  # fused argmax reads the same fp32 block output
+    assert d["logits_teacher_forced"] <= 6e-3, d
+    assert d["logits"] <= 2e-2 and d["logits_vs_reference_golden"] <= 2e-2, d
 
 
 def test_argmax_planted_prototypes(net):

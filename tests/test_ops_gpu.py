@@ -285,6 +285,26 @@ def test_upsample_argmax_matches_logits(ops, B, K, H, W):
     assert torch.equal(m.cpu(), torch.max(up.cpu(), 1)[1])
 
 
+@pytest.mark.parametrize("mode,act,in_f16", [(1, "lrelu", True), (1, "none", False), (2, "tanh", True), (2, "relu", False)])
+def test_head_block(ops, mode, act, in_f16):
+    """scratch.head_block (arch_option 1 = bottleneck_block, 2 = depthwise_block; lseg_net.py:29-79): one shared 3x3 kernel
+    over every class plane, optional channel-max skip, optional activation — against torch's own conv2d / max."""
+    from lseg_b200 import _lib
+    B, K, h, w = 2, 7, 37, 52
+    x = _rand((B, K, h, w), 61, 1.5, torch.float16 if in_f16 else torch.float32)
+    wt = _rand((1, 1, 3, 3), 62, 0.3, torch.float32)
+    bias = 0.17
+    got = ops.head_block(x, wt.flatten().tolist(), bias, mode, _lib.HEAD_ACT[act])
+    xf = x.float()
+    ref = F.conv2d(xf.reshape(-1, 1, h, w), wt, torch.tensor([bias], device="cuda"), padding=1).view(B, K, h, w)
+    if mode == 1:
+        ref = ref + xf.max(dim=1, keepdim=True)[0]
+    ref = {"none": lambda t: t, "relu": F.relu, "lrelu": lambda t: F.leaky_relu(t, 0.01), "tanh": torch.tanh}[act](ref)
+    _close(got, ref, 2e-6, f"head_block mode {mode} {act}")
+    up = ops.upsample2x_nchw_f32(got)
+    _close(up, F.interpolate(got, scale_factor=2, mode="bilinear", align_corners=True), 1e-6, "fp32-input upsample")
+
+
 def test_text_glue(ops):
     K, L, Wd = 5, 77, 512
     g = torch.Generator().manual_seed(31)

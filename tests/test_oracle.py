@@ -100,6 +100,22 @@ def test_zero_shot_golden_matches_oracle():
     assert rel_err(out, torch.from_numpy(z["logits"])) < TEXT_FP16_TOL
 
 
+def test_head_block_golden():
+    """arch_option 1 / 2: the oracle's head_block on the reference's own pre-block logits reproduces the reference module
+    bit for bit (fixture generated by oracle/make_golden_arch.py from the unmodified bottleneck_block / depthwise_block)."""
+    z = np.load(os.path.join(GOLD, "ref_arch.npz"))
+    sd = synth.make_state_dict(0, head_block=True)
+    for tag, kw in (("opt1", dict(arch_option=1, block_depth=2, activation="lrelu")),
+                    ("opt2", dict(arch_option=2, block_depth=3, activation="tanh"))):
+        got = O.head_block(torch.from_numpy(z[f"{tag}_pre_block"]), sd, **kw)
+        assert torch.equal(got, torch.from_numpy(z[f"{tag}_post_block"]))
+    # the extra keys are the only difference to the plain state dict
+    base = state_dict(0)
+    assert all(torch.equal(sd[k], v) for k, v in base.items())
+    assert set(sd) - set(base) == {"scratch.head_block.depthwise.depthwise.weight",
+                                   "scratch.head_block.depthwise.depthwise.bias"}
+
+
 def test_text_tower_vs_transformers():
     """Restated CLIP encode_text (fp32 variant) vs transformers.CLIPTextModelWithProjection."""
     tr = pytest.importorskip("transformers")
