@@ -16,6 +16,7 @@
 #include "mhsa.cuh"
 #include "mhsa2.cuh"
 #include "mhsa3.cuh"
+#include "mhsa4.cuh"
 #include "text_attn.cuh"
 #include "p2p.cuh"
 
@@ -111,6 +112,14 @@ static int init_device(int dev) {
   LSEG_M2_ATTR((mhsa3_kernel<true, 1>));
   LSEG_M2_ATTR((mhsa3_kernel<true, 2>));
 #undef LSEG_M2_ATTR
+#define LSEG_M4_ATTR(K)                                                                       \
+  cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, kM4SmemBytes);          \
+  cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, 100)
+  LSEG_M4_ATTR((mhsa4_kernel<false, 0>));
+  LSEG_M4_ATTR((mhsa4_kernel<true, 0>));
+  LSEG_M4_ATTR((mhsa4_kernel<true, 1>));
+  LSEG_M4_ATTR((mhsa4_kernel<true, 2>));
+#undef LSEG_M4_ATTR
   if (cudaGetLastError() != cudaSuccess) {
     set_error("lseg_b200: cudaFuncSetAttribute failed on device %d", dev);
     return -1;
@@ -363,7 +372,8 @@ static int mhsa_plan(const MhsaDesc& d, MhsaPlan* plan) {
   return 0;
 }
 // variant: 0 mhsa2 (round-1 kernel: one polling MMA warp); 1 mhsa3 (one blocking MMA warp per stream, setmaxnreg);
-// 2 = 1 + packed-fp32 softmax arithmetic; 3 = 2 + one of four score pairs on the FMA-pipe exp2 polynomial; 4 = two of four.
+// 2 = 1 + packed-fp32 softmax arithmetic; 3 = 2 + one of four score pairs on the FMA-pipe exp2 polynomial; 4 = two of four;
+// 5..8 mhsa4 (P in tensor memory, TS-form PV MMA): 5 scalar arithmetic, 6 packed, 7 packed + 1/4 polynomial, 8 + 2/4.
 static int mhsa_run_variant(const MhsaPlan& plan, int variant, cudaStream_t stream) {
   switch (variant) {
     case 0: launch_pdl(mhsa2_kernel<0, false>, plan.grid, dim3(kM2Threads), kM2SmemBytes, stream, plan.p); break;
@@ -371,6 +381,10 @@ static int mhsa_run_variant(const MhsaPlan& plan, int variant, cudaStream_t stre
     case 2: launch_pdl(mhsa3_kernel<true, 0>, plan.grid, dim3(kM3Threads), kM2SmemBytes, stream, plan.p); break;
     case 3: launch_pdl(mhsa3_kernel<true, 1>, plan.grid, dim3(kM3Threads), kM2SmemBytes, stream, plan.p); break;
     case 4: launch_pdl(mhsa3_kernel<true, 2>, plan.grid, dim3(kM3Threads), kM2SmemBytes, stream, plan.p); break;
+    case 5: launch_pdl(mhsa4_kernel<false, 0>, plan.grid, dim3(kM3Threads), kM4SmemBytes, stream, plan.p); break;
+    case 6: launch_pdl(mhsa4_kernel<true, 0>, plan.grid, dim3(kM3Threads), kM4SmemBytes, stream, plan.p); break;
+    case 7: launch_pdl(mhsa4_kernel<true, 1>, plan.grid, dim3(kM3Threads), kM4SmemBytes, stream, plan.p); break;
+    case 8: launch_pdl(mhsa4_kernel<true, 2>, plan.grid, dim3(kM3Threads), kM4SmemBytes, stream, plan.p); break;
     default: set_error("mhsa: unknown kernel variant %d", variant); return -1;
   }
   LSEG_CHECK_CUDA(cudaGetLastError());
