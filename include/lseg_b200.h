@@ -149,6 +149,32 @@ int lseg_text_embed(const int64_t* tokens, const float* tok_emb, const float* po
                     void* stream);
 int lseg_text_eot_gather(const int64_t* tokens, const void* x, void* out, int K, int L, int Wd, void* stream);
 
+/* ---- multi-scale / flip / sliding-window evaluator glue ------------------------------------
+ * Device side of LSeg_MultiEvalModule.forward (additional_utils/models.py:55-140): the chain of interpolate / pad / slice /
+ * flip calls that builds every network input and the inverse chain over every network output, as three gather kernels.
+ * Window geometry (which windows exist for which scale) is integer host logic and stays in lang-seg_b200/evaluator.py. */
+typedef struct lseg_eval_window {
+  int height, width;  /* the scale's resized image (int(h * long_size / w + 0.5) etc., models.py:69-80) */
+  int h0, w0;         /* window origin in the padded resized image (idh * stride, idw * stride, models.py:113-114) */
+  int flip;           /* this network input is the horizontally flipped crop (flip_image, models.py:161-165) */
+  int out_index;      /* its position in the crop batch and of its output in the logits batch */
+} lseg_eval_window;
+/* img fp32 [3,h,w] -> crops fp32 [n_inputs,3,crop,crop]: pixel = bilinear(align_corners=True) sample of img at the
+ * scale's coordinates, or pad3_host[c] (= -mean/std, pad_image models.py:145-156) outside the resized image. wins: DEVICE. */
+int lseg_eval_make_crops(const float* img, float* crops, const lseg_eval_window* wins, int n_inputs, int h, int w, int crop,
+                         const float* pad3_host, void* stream);
+/* outs fp32 [n,K,crop,crop] (network outputs; a window's flipped input is the entry after its plain one when flip != 0)
+ * -> canvas fp32 [K,height,width]: per pixel the (plain + flipped-back) outputs of the covering windows summed in list
+ * order and divided by their count (models.py:117-132); whole != 0: single padded window, no division (models.py:82-89). */
+int lseg_eval_canvas(const float* outs, float* canvas, const lseg_eval_window* wins, int n_win, int K, int crop, int height,
+                     int width, int flip, int whole, void* stream);
+/* scores fp32 [K,h,w] += bilinear(canvas [K,height,width] -> (h,w), align_corners=True) (models.py:133-136) */
+int lseg_eval_resize_add(const float* canvas, float* scores, int K, int height, int width, int h, int w, void* stream);
+/* ToTensor + Normalize + Resize([Ho,Wo]) (+ constant pad to [Hp,Wp]) of an 8-bit HWC image -> fp32 [3,Hp,Wp]
+ * (lseg_app.py:328-334, modules/lseg_module.py:42-53). img: DEVICE u8 [h,w,3]. */
+int lseg_preprocess(const unsigned char* img_hwc, float* out, int h, int w, int Ho, int Wo, int Hp, int Wp,
+                    const float* mean3_host, const float* std3_host, const float* pad3_host, void* stream);
+
 /* ---- peer memory: the logits gather, one process per GPU over NVLink 5 / NVSwitch ----------
  * Replaces the thread-per-GPU DataParallel gather of additional_utils/models.py:35-53. A rank allocates a buffer its peers
  * can map (CUDA IPC; the 64-byte handle travels through any host channel, e.g. torch.distributed.all_gather_object);

@@ -19,6 +19,7 @@
 #include "mhsa4.cuh"
 #include "text_attn.cuh"
 #include "p2p.cuh"
+#include "evaluator.cuh"
 
 namespace lseg {
 
@@ -514,6 +515,63 @@ int lseg_text_attn(const void* qkv, void* out, int K, int L, int heads, void* st
   if (ensure_init()) return -1;
   return launch_text_attn(static_cast<const __half*>(qkv), static_cast<__half*>(out), K, L, heads,
                           static_cast<cudaStream_t>(stream));
+}
+
+// ---- multi-scale evaluator glue + preprocessing ----
+static_assert(sizeof(lseg_eval_window) == sizeof(EvalWindow), "lseg_eval_window layout");
+
+int lseg_eval_make_crops(const float* img, float* crops, const lseg_eval_window* wins, int n_inputs, int h, int w, int crop,
+                         const float* pad3_host, void* stream) {
+  if (ensure_init()) return -1;
+  if (!img || !crops || !wins || !pad3_host || n_inputs <= 0 || n_inputs > 65535 || crop <= 0) {
+    set_error("lseg_eval_make_crops: bad argument");
+    return -1;
+  }
+  eval_make_crops_kernel<<<dim3((crop + 31) / 32, (crop + 7) / 8, n_inputs), dim3(32, 8), 0,
+                           static_cast<cudaStream_t>(stream)>>>(img, crops, reinterpret_cast<const EvalWindow*>(wins), h, w,
+                                                                crop, pad3_host[0], pad3_host[1], pad3_host[2]);
+  LSEG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int lseg_eval_canvas(const float* outs, float* canvas, const lseg_eval_window* wins, int n_win, int K, int crop, int height,
+                     int width, int flip, int whole, void* stream) {
+  if (ensure_init()) return -1;
+  if (!outs || !canvas || !wins || n_win <= 0 || K <= 0 || K > 65535) {
+    set_error("lseg_eval_canvas: bad argument");
+    return -1;
+  }
+  eval_canvas_kernel<<<dim3((width + 31) / 32, (height + 7) / 8, K), dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
+      outs, canvas, reinterpret_cast<const EvalWindow*>(wins), n_win, K, crop, height, width, flip, whole);
+  LSEG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int lseg_eval_resize_add(const float* canvas, float* scores, int K, int height, int width, int h, int w, void* stream) {
+  if (ensure_init()) return -1;
+  if (!canvas || !scores || K <= 0 || K > 65535) {
+    set_error("lseg_eval_resize_add: bad argument");
+    return -1;
+  }
+  eval_resize_add_kernel<<<dim3((w + 31) / 32, (h + 7) / 8, K), dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
+      canvas, scores, height, width, h, w);
+  LSEG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int lseg_preprocess(const unsigned char* img_hwc, float* out, int h, int w, int Ho, int Wo, int Hp, int Wp,
+                    const float* mean3_host, const float* std3_host, const float* pad3_host, void* stream) {
+  if (ensure_init()) return -1;
+  if (!img_hwc || !out || !mean3_host || !std3_host || !pad3_host || h <= 0 || w <= 0 || Ho <= 0 || Wo <= 0 || Hp < Ho ||
+      Wp < Wo) {
+    set_error("lseg_preprocess: bad argument");
+    return -1;
+  }
+  preprocess_kernel<<<dim3((Wp + 31) / 32, (Hp + 7) / 8), dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
+      img_hwc, out, h, w, Ho, Wo, Hp, Wp, mean3_host[0], mean3_host[1], mean3_host[2], std3_host[0], std3_host[1],
+      std3_host[2], pad3_host[0], pad3_host[1], pad3_host[2]);
+  LSEG_CHECK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 // ---- peer memory (the logits gather) ----

@@ -13,9 +13,16 @@ only then are the reference's accumulations replayed, in the reference's order, 
 batch-invariant network (lseg_b200 in its default deterministic mode) the result is bit-identical to the sequential
 algorithm; `tests/test_evaluator_cpu.py` checks that against the unmodified reference class on CPU.
 
-The glue ops (resize, pad, flip, accumulate) are torch calls on the image's device; the hot path is `net(batch,
-label_set)` = `LSegNet.forward`. One process per GPU handles its own images (lang-seg_b200/parallel.py) instead of
-the reference's thread-per-GPU `parallel_forward` (`additional_utils/models.py:35-53`).
+Two implementations of the glue around `net(batch, label_set)` = `LSegNet.forward`:
+  * `fused=True` (default on a CUDA image): three gather kernels of liblseg_b200.so (csrc/evaluator.cuh) — every network
+    input of a scale is sampled straight from the original image (resize + pad + slice + pad + flip in one launch), the
+    window outputs are overlap-averaged into the scale's canvas and the canvas is resized back and added to the scores;
+    the resized / padded images and the per-window torch slices never exist;
+  * `fused=False`: the same algorithm as torch calls (runs on CPU too: tests/test_evaluator_cpu.py pins it bit for bit
+    against the unmodified reference class).
+Both keep the reference's order of floating-point operations. One process per GPU handles its own images
+(lang-seg_b200/parallel.py) instead of the reference's thread-per-GPU `parallel_forward`
+(`additional_utils/models.py:35-53`).
 """
 import math
 
@@ -52,7 +59,7 @@ class MultiScaleEvaluator:
     """
 
     def __init__(self, net, base_size=520, crop_size=480, mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5), flip=True,
-                 scales=(0.5, 0.75, 1.0, 1.25, 1.5, 1.75), up_kwargs=None, max_batch=16):
+                 scales=(0.5, 0.75, 1.0, 1.25, 1.5, 1.75), up_kwargs=None, max_batch=16, fused=None):
         self.net = net
         self.base_size = base_size
         self.crop_size = crop_size
@@ -62,6 +69,73 @@ class MultiScaleEvaluator:
         self.scales = list(scales)
         self.up_kwargs = dict(UP_KWARGS if up_kwargs is None else up_kwargs)
         self.max_batch = max_batch
+        self.fused = fused  # None: fused kernels whenever the image is on a CUDA device
+
+    # ---- integer geometry of one scale (additional_utils/models.py:67-114), shared by both implementations ----
+    def _geometry(self, h, w, scale):
+        crop = self.crop_size
+        stride = int(crop * (2.0 / 3.0))
+        long_size = int(math.ceil(self.base_size * scale))
+        if h > w:
+            height = long_size
+            width = int(1.0 * w * long_size / h + 0.5)
+            short_size = width
+        else:
+            width = long_size
+            height = int(1.0 * h * long_size / w + 0.5)
+            short_size = height
+        if long_size <= crop:
+            return {"height": height, "width": width, "whole": True, "origins": [(0, 0)]}
+        ph = max(height, crop) if short_size < crop else height
+        pw = max(width, crop) if short_size < crop else width
+        h_grids = int(math.ceil(1.0 * (ph - crop) / stride)) + 1
+        w_grids = int(math.ceil(1.0 * (pw - crop) / stride)) + 1
+        origins = [(idh * stride, idw * stride) for idh in range(h_grids) for idw in range(w_grids)]
+        return {"height": height, "width": width, "whole": False, "origins": origins}
+
+    # ---- fused device path: csrc/evaluator.cuh through the C ABI ----
+    @torch.no_grad()
+    def _forward_fused(self, image, label_set):
+        import ctypes as C
+        from . import _lib
+        lib = _lib.load()
+        dev = image.device
+        _, _, h, w = image.shape
+        crop = self.crop_size
+        img = image[0].contiguous().float()
+        pad = (C.c_float * 3)(*[-float(m) / float(s) for m, s in zip(self.mean, self.std)])
+        per = 2 if self.flip else 1
+        scores = None
+
+        def stream():
+            return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+        with torch.cuda.device(dev):
+            for scale in self.scales:
+                g = self._geometry(h, w, scale)
+                n_win = len(g["origins"])
+                rows = []
+                for i, (h0, w0) in enumerate(g["origins"]):
+                    rows.append([g["height"], g["width"], h0, w0, 0, per * i])
+                    if self.flip:
+                        rows.append([g["height"], g["width"], h0, w0, 1, per * i + 1])
+                wins = torch.tensor(rows, dtype=torch.int32).to(dev)           # every network input of the scale
+                plain = wins[::per].contiguous()                                # one entry per window (canvas pass)
+                crops = torch.empty((len(rows), 3, crop, crop), dtype=torch.float32, device=dev)
+                _lib.check(lib.lseg_eval_make_crops(C.c_void_p(img.data_ptr()), C.c_void_p(crops.data_ptr()),
+                                                    C.c_void_p(wins.data_ptr()), len(rows), h, w, crop, pad, stream()))
+                outs = torch.cat([self.net(crops[i:i + self.max_batch], label_set).float()
+                                  for i in range(0, len(rows), self.max_batch)], 0).contiguous()
+                K = outs.shape[1]
+                if scores is None:
+                    scores = torch.zeros((1, K, h, w), dtype=torch.float32, device=dev)
+                canvas = torch.empty((K, g["height"], g["width"]), dtype=torch.float32, device=dev)
+                _lib.check(lib.lseg_eval_canvas(C.c_void_p(outs.data_ptr()), C.c_void_p(canvas.data_ptr()),
+                                                C.c_void_p(plain.data_ptr()), n_win, K, crop, g["height"], g["width"],
+                                                int(self.flip), int(g["whole"]), stream()))
+                _lib.check(lib.lseg_eval_resize_add(C.c_void_p(canvas.data_ptr()), C.c_void_p(scores.data_ptr()), K,
+                                                    g["height"], g["width"], h, w, stream()))
+        return scores
 
     # ---- phase 1: geometry + windows of one scale (additional_utils/models.py:67-123, no network calls) ----
     def _plan_scale(self, image, scale):
@@ -122,6 +196,11 @@ class MultiScaleEvaluator:
     def forward(self, image, label_set=""):
         batch, _, h, w = image.shape
         assert batch == 1, "only single image is supported for evaluation (additional_utils/models.py:62)"
+        fused = image.is_cuda if self.fused is None else self.fused
+        if fused:
+            if not image.is_cuda:
+                raise RuntimeError("the fused evaluator kernels need a CUDA image (fused=False runs the torch glue)")
+            return self._forward_fused(image, label_set)
         plans = [self._plan_scale(image, s) for s in self.scales]
         windows = [win[4] for p in plans for win in p["windows"]]
         outs = self._run_windows(windows, label_set)

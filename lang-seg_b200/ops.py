@@ -126,6 +126,23 @@ def upsample2x_nchw_f32(x):
     return y
 
 
+def preprocess(img_u8, size, pad_to=None, mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5)):
+    """uint8 HWC image on the GPU -> fp32 [1,3,Hp,Wp]: ToTensor + Normalize + Resize(size) (bilinear, align_corners=False,
+    no antialias: torchvision's tensor resize of the reference's era) + constant pad with -mean/std (pad_image) to
+    `pad_to`. One kernel (include/lseg_b200.h lseg_preprocess; lseg_app.py:328-334)."""
+    if img_u8.dtype != torch.uint8 or img_u8.dim() != 3 or img_u8.shape[2] != 3:
+        raise ValueError("img_u8 must be uint8 [H,W,3]")
+    h, w = img_u8.shape[:2]
+    Ho, Wo = size
+    Hp, Wp = pad_to if pad_to is not None else (Ho, Wo)
+    out = torch.empty((1, 3, Hp, Wp), dtype=torch.float32, device=img_u8.device)
+    m3 = (C.c_float * 3)(*[float(v) for v in mean])
+    s3 = (C.c_float * 3)(*[float(v) for v in std])
+    p3 = (C.c_float * 3)(*[-float(a) / float(b) for a, b in zip(mean, std)])
+    check(load().lseg_preprocess(_ptr(img_u8), _ptr(out), h, w, Ho, Wo, Hp, Wp, m3, s3, p3, _stream()))
+    return out
+
+
 def set_deterministic(on):
     """True (default): fixed summation order everywhere (bit-reproducible); False: the in-place residual GEMMs may
     split K across CTA pairs (include/lseg_b200.h lseg_set_deterministic)."""
