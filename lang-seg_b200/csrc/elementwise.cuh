@@ -102,63 +102,73 @@ static inline int launch_assemble_tokens(const float* patch, const float* cls, c
 // ------------------------------------------------------------------------------------------
 // LayerNorm over the last dim, one warp per row, fp32 statistics (two-pass in registers), fp16 out.
 // timm: eps 1e-6 on the fp32 residual stream; CLIP: eps 1e-5 on the fp16 stream computed in fp32
-// (SURVEY.md Appendix A.1/A.2). C must be a multiple of 128 and <= 1024.
+// (SURVEY.md Appendix A.1/A.2). C in {512, 1024} is a template constant (fully unrolled, no predicates).
+// HBM-bound: 6 B per element. A lane owns chunks of 8 consecutive elements (32 B loads in, one 16 B store out per
+// chunk); gamma / beta are staged in shared memory by the whole block while the row loads are in flight, so the
+// normalisation does not wait for a second round trip after the statistics (round 1: 12.5 us for 44 MB, r02: see
+// profiles/r02_layernorm.md).
 // ------------------------------------------------------------------------------------------
-template <typename TIn>
-__global__ void layernorm_kernel(const TIn* __restrict__ x, const float* __restrict__ gamma,
-                                 const float* __restrict__ beta, __half* __restrict__ y, long long M, int C,
-                                 float eps) {
+template <typename TIn, int C>
+__global__ void __launch_bounds__(256) layernorm_kernel(const TIn* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, __half* __restrict__ y,
+                                                        long long M, float eps) {
+  constexpr int kChunks = C / 256;  // 8-element chunks per lane
+  __shared__ __align__(16) float sg[C];
+  __shared__ __align__(16) float sb[C];
   griddep_launch_dependents();
+  for (int i = threadIdx.x; i < C / 4; i += blockDim.x) {  // weights: not produced by the previous kernel
+    reinterpret_cast<float4*>(sg)[i] = __ldg(reinterpret_cast<const float4*>(gamma) + i);
+    reinterpret_cast<float4*>(sb)[i] = __ldg(reinterpret_cast<const float4*>(beta) + i);
+  }
   griddep_wait();
   const int lane = threadIdx.x & 31;
   const long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= M) return;
-  const int nv = C / 128;  // float4 groups per lane
-  float v[32];
-  float s = 0.f;
+  float v[8 * kChunks];
+  if (row < M) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    if (i < nv) {
-      const int col = (i * 32 + lane) * 4;
+    for (int i = 0; i < kChunks; ++i) {
+      const int col = (i * 32 + lane) * 8;
       if constexpr (sizeof(TIn) == 4) {
-        const float4 q = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + row * C + col);
-        v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+        const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + row * C + col);
+        const float4 q0 = p[0], q1 = p[1];
+        v[8 * i] = q0.x; v[8 * i + 1] = q0.y; v[8 * i + 2] = q0.z; v[8 * i + 3] = q0.w;
+        v[8 * i + 4] = q1.x; v[8 * i + 5] = q1.y; v[8 * i + 6] = q1.z; v[8 * i + 7] = q1.w;
       } else {
-        const uint2 q = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(x) + row * C + col);
-        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&q.x));
-        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
-        v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = b.x; v[4 * i + 3] = b.y;
+        const uint4 q = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(x) + row * C + col);
+        const __half2* qh = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __half22float2(qh[k]);
+          v[8 * i + 2 * k] = f.x;
+          v[8 * i + 2 * k + 1] = f.y;
+        }
       }
-      s += v[4 * i] + v[4 * i + 1] + v[4 * i + 2] + v[4 * i + 3];
     }
   }
+  __syncthreads();  // gamma / beta staged (all threads reach this, also those of rows beyond M)
+  if (row >= M) return;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8 * kChunks; ++i) s += v[i];
   const float mean = warp_sum(s) / C;
   float ss = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    if (i < nv) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float d = v[4 * i + j] - mean;
-        ss += d * d;
-      }
-    }
+  for (int i = 0; i < 8 * kChunks; ++i) {
+    const float d = v[i] - mean;
+    ss += d * d;
   }
   const float rstd = rsqrtf(warp_sum(ss) / C + eps);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    if (i < nv) {
-      const int col = (i * 32 + lane) * 4;
-      const float4 g = *reinterpret_cast<const float4*>(gamma + col);
-      const float4 bb = *reinterpret_cast<const float4*>(beta + col);
-      __half2 h0 = __floats2half2_rn((v[4 * i] - mean) * rstd * g.x + bb.x, (v[4 * i + 1] - mean) * rstd * g.y + bb.y);
-      __half2 h1 =
-          __floats2half2_rn((v[4 * i + 2] - mean) * rstd * g.z + bb.z, (v[4 * i + 3] - mean) * rstd * g.w + bb.w);
-      uint2 o;
-      o.x = *reinterpret_cast<uint32_t*>(&h0);
-      o.y = *reinterpret_cast<uint32_t*>(&h1);
-      *reinterpret_cast<uint2*>(y + row * C + col) = o;
-    }
+  for (int i = 0; i < kChunks; ++i) {
+    const int col = (i * 32 + lane) * 8;
+    const float4 g0 = *reinterpret_cast<const float4*>(sg + col), g1 = *reinterpret_cast<const float4*>(sg + col + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(sb + col), b1 = *reinterpret_cast<const float4*>(sb + col + 4);
+    __half2 h[4];
+    h[0] = __floats2half2_rn((v[8 * i] - mean) * rstd * g0.x + b0.x, (v[8 * i + 1] - mean) * rstd * g0.y + b0.y);
+    h[1] = __floats2half2_rn((v[8 * i + 2] - mean) * rstd * g0.z + b0.z, (v[8 * i + 3] - mean) * rstd * g0.w + b0.w);
+    h[2] = __floats2half2_rn((v[8 * i + 4] - mean) * rstd * g1.x + b1.x, (v[8 * i + 5] - mean) * rstd * g1.y + b1.y);
+    h[3] = __floats2half2_rn((v[8 * i + 6] - mean) * rstd * g1.z + b1.z, (v[8 * i + 7] - mean) * rstd * g1.w + b1.w);
+    *reinterpret_cast<uint4*>(y + row * C + col) = *reinterpret_cast<uint4*>(h);
   }
 }
 

@@ -513,8 +513,13 @@ struct Gemm2Cfg {
   static constexpr int kEpiBufBytes = (kEpiWarps == 16) ? 4096 : kEpiStageBytes;
   // stages | per-warp TMA-epilogue staging (1024 B aligned) | mbarriers
   static constexpr int kStageOutBytes = (EPI == EPI_DIRECT) ? 0 : kEpiWarps * kEpiBufBytes;
-  static constexpr int kStages = (BN == 256) ? ((EPI == EPI_DIRECT) ? 6 : 5) : ((EPI == EPI_DIRECT) ? 8 : 6);
-  static constexpr int kTmemCols = 2 * BN;
+  // BN = 224 (in-place residual GEMMs with N = 1024: 5 tiles of 224 make 145 pair tiles = 1.96 waves of 74 CTA pairs
+  // where 4 tiles of 256 make 116 = 1.57 -> 2 waves of wider tiles) shares the BN = 256 pipeline depth.
+  static constexpr int kStages = (BN >= 224) ? ((EPI == EPI_DIRECT) ? 6 : 5) : ((EPI == EPI_DIRECT) ? 8 : 6);
+  static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;  // tcgen05.alloc takes powers of two
+  // columns of the 8-warp epilogue's first column half (a multiple of 32); the second half takes the rest
+  static constexpr int kColsHalf0 = ((BN / 2 + 31) / 32) * 32;
+  static_assert(BN % 32 == 0 && BN % 16 == 0 && BN <= 256, "tile width");
   static constexpr int kSmemBytes = kStages * kStageBytes + kStageOutBytes + 1024 + 256;
 };
 
@@ -706,7 +711,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((Gemm2Cfg<BN, EPI, E
     const int ew = warp - 4;
     const int quarter = warp & 3;
     const int half = ew >> 2;
+    // 8 warps: two column halves (kColsHalf0 | BN - kColsHalf0); 16 warps: four quarters of BN / 4
     constexpr int kColsPerWarp = BN / (Cfg::kEpiWarps / 4);
+    const int col0 = (Cfg::kEpiWarps == 16) ? half * kColsPerWarp : half * Cfg::kColsHalf0;
+    const int ncols = (Cfg::kEpiWarps == 16) ? kColsPerWarp : (half == 0 ? Cfg::kColsHalf0 : BN - Cfg::kColsHalf0);
     const int r = quarter * 32 + lane;
     uint8_t* stage_buf = stage_out + ew * Cfg::kEpiBufBytes;
     int store_groups = 0;
@@ -721,8 +729,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((Gemm2Cfg<BN, EPI, E
     while (sc.next(tile, k_begin, k_end)) {
       const int m_tile = (tile % m_pairs) * 2 + static_cast<int>(rank);
       const int n_tile = tile / m_pairs;
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * kColsPerWarp;
-      gemm_epilogue_tile<EPI, Cfg::kEpiWarps == 16>(p, t_row, n_tile * BN + half * kColsPerWarp, kColsPerWarp, m_tile, r,
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + col0;
+      gemm_epilogue_tile<EPI, Cfg::kEpiWarps == 16>(p, t_row, n_tile * BN + col0, ncols, m_tile, r,
                               [&]() { mbar_wait(&tmem_full[acc], acc_phase, 24); }, stage_buf, store_groups, tr,
                               k_begin == 0);
       tc_fence_before();

@@ -57,6 +57,20 @@ def test_gemm_bias_f32_f16(ops, M, N, K):
     _close(out16, ref, 1e-3, "fp16 out")
 
 
+@pytest.mark.parametrize("M,N,K", [(7208, 1024, 1024), (7208, 1024, 4096), (8468, 1024, 1024), (300, 1024, 512)])
+def test_gemm_inplace_residual_tile_widths(ops, M, N, K):
+    """x += A W^T + b through the bulk reduce-add epilogue at the ViT shapes: B=8 480^2 (29 row pairs -> the planner picks
+    224-wide tiles: 145 pair tiles = 1.96 waves), B=4 736^2 (34 row pairs -> 256-wide), and a single-wave case. The column
+    split of the 224-wide tile (128 | 96 per epilogue warp pair, last tile 128 valid columns) must cover every column."""
+    a = _rand((M, K), 41, 0.5)
+    w = _rand((N, K), 42, 0.03)
+    bias = _rand((N,), 43, 0.5, torch.float32)
+    res = _rand((M, N), 44, 1.0, torch.float32)
+    x = res.clone()
+    ops.gemm(ops.pad_rows(a), ops.pad_rows(w), N, M=M, bias=bias, res_f32=x, out_f32=x)
+    _close(x, a.float() @ w.float().t() + bias + res, 2e-4, f"in-place residual {M}x{N}x{K}")
+
+
 def test_gemm_gelu_residual_relu(ops):
     M, N, K = 901 * 2, 1024, 1024
     a = _rand((M, K), 4)
