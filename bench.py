@@ -233,6 +233,7 @@ def main():
                     choices=["p2p_copy", "p2p_store", "nccl"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-eval", action="store_true", help="skip the multi-scale evaluator line (SURVEY 8(f) row 1)")
     ap.add_argument("--dump-profile", default=None, help="write the per-launch profile of one step to this JSON file")
     args = ap.parse_args()
     cfg = make_config(args)
@@ -391,7 +392,7 @@ def main():
                     "timing_note": "per-launch events serialise the programmatic-dependent-launch overlap of consecutive "
                                    "kernels: the breakdown sums to more than ms_per_step"}
         ach_m = m_fl / (m_ms / 1e3) / 1e12 if m_ms > 0 else 0.0
-        mhsa_roof = {"kernel": "mhsa3_kernel" if os.environ.get("LSEG_MHSA_VARIANT", "3") != "0" else "mhsa2_kernel",
+        mhsa_roof = {"kernel": "mhsa2_kernel (lseg_mhsa_variant %s)" % os.environ.get("LSEG_MHSA_VARIANT", "0"),
                      "bound": "tensor", "achieved": ach_m, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_m / peak_tf,
                      "frac_of_burst_peak": ach_m / peak_burst, "launches": m_n, "traffic": traffic_m,
                      "avg_launch_ms": m_ms / max(m_n, 1), "share_of_step": m_ms / tot}
@@ -458,6 +459,34 @@ def main():
                       "what": "LSegNet.predict (forward fused with torch.max(.,1)[1]) from pinned host images to a pinned "
                               "host int64 mask"}
 
+    # ---- the ADE20K evaluation workload — one 512x683 image, 6 scales, flip, sliding 480x480 windows
+    # (test_lseg.py:308-317,383; additional_utils/models.py:55-140): the reference issues one batch-1 forward per window
+    # and flip; here the fused evaluator batches every network input of a scale and keeps the glue in three gather kernels.
+    evaluator = None
+    if rank == 0 and world == 1 and not args.no_eval and cfg["tokens"] is None:
+        from lseg_b200.evaluator import MultiScaleEvaluator
+        ev = MultiScaleEvaluator(net, base_size=520, crop_size=480, max_batch=16)
+        img = torch.randn(1, 3, 512, 683, device=dev).clamp_(-1, 1)
+        n_fwd = ev.num_forwards(img)[0]
+
+        def run_eval(fused):
+            ev.fused = fused
+            ev(img, labels)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                ev(img, labels)
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t0) / 3
+
+        t_fused, t_glue = run_eval(True), run_eval(False)
+        evaluator = {"value": 1.0 / t_fused, "unit": "images/sec", "ms_per_image": t_fused * 1e3,
+                     "ms_per_image_torch_glue": t_glue * 1e3, "network_inputs_per_image": n_fwd,
+                     "workload": "one 512x683 image, scales 0.5..1.75, flip, 480x480 windows with stride 320, K=%d" % K,
+                     "reference_forwards_per_image": n_fwd,
+                     "what": "MultiScaleEvaluator (fused gather kernels + batched LSegNet.forward), wall clock incl. host "
+                             "planning; the reference runs the same %d crops as batch-1 forwards" % n_fwd}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_rate(3, 1, labels if cfg["tokens"] is None else labels[:K], S) if cfg["tokens"] is None else None
@@ -483,8 +512,13 @@ def main():
             "wall_s": t_wall, "clocks": clocks, "gpu_launches": launches_per_step * Ksteps,
             "launches_per_step": launches_per_step,
             "roofline": roofline, "roofline_mhsa": mhsa_roof, "step_breakdown_ms": breakdown,
-            "cpu_baseline": cpu_baseline, "e2e": e2e, "e2e_argmax": e2e_argmax,
+            "cpu_baseline": cpu_baseline, "e2e": e2e, "e2e_argmax": e2e_argmax, "evaluator": evaluator,
         }
+        if evaluator is not None and cpu_baseline is not None:
+            evaluator["reference_cpu_estimate"] = {
+                "value": 1.0 / (evaluator["reference_forwards_per_image"] / cpu_baseline["value"]), "unit": "images/sec",
+                "what": "forwards per image x the measured per-forward time of the reference CPU path above (not run: "
+                        "%d forwards of ~%.1f s)" % (evaluator["reference_forwards_per_image"], 1.0 / cpu_baseline["value"])}
         if gather_info is not None:
             line["gather"] = gather_info
         print(json.dumps(line))

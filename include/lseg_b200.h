@@ -86,7 +86,7 @@ int lseg_gemm(const lseg_gemm_args* args, void* stream);
  * qkv fp16 [B, N, 3*heads*64] (q|k|v thirds) -> out fp16 [B*N, heads*64]. */
 int lseg_mhsa(const void* qkv, void* out, int B, int N, int heads, int causal, void* stream);
 /* Same contract as lseg_mhsa with an explicit kernel choice (A/B measurements, tools/op_bench.py; the engine runs
- * variant 3 unless LSEG_MHSA_VARIANT overrides it): 0 = round-1 kernel (one polling MMA warp for both softmax streams);
+ * variant 0 unless LSEG_MHSA_VARIANT overrides it — round 2 measured 1..8 within +-3 % of it, profiles/r02_mhsa_analysis.md): 0 = round-1 kernel (one polling MMA warp for both softmax streams);
  * 1 = one blocking MMA warp per stream + per-role register budgets (setmaxnreg); 2 = 1 + packed-fp32 (FFMA2 / FADD2 /
  * FMNMX3) softmax arithmetic; 3 = 2 + one of every four score pairs exponentiated on the FMA pipe; 4 = two of four;
  * 5..8 = the probabilities stay in tensor memory (tcgen05.st over the S tile, PV MMA with its A operand from TMEM):

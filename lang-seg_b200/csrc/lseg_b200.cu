@@ -48,7 +48,8 @@ static int g_deterministic = 1;  // 1 (default): fixed summation order; 0: split
 static int g_plan_epoch = 0;     // bumped when an option that is baked into cached plans changes
 static unsigned long long* g_gemm_trace = nullptr;  // debug (lseg_debug_gemm_trace)
 static int g_gemm_probe = 0;
-static int g_mhsa_variant = 3;   // kernel the engine's ViT attention runs (lseg_mhsa_variant documents the numbering)
+static int g_mhsa_variant = 0;   // kernel the engine's ViT attention runs (lseg_mhsa_variant documents the numbering;
+                                 // 1..8 measured within +-3 % of 0 in the step, profiles/r02_mhsa_analysis.md)
 static std::mutex g_init_mutex;
 static bool g_global_init = false;
 constexpr int kMaxDevices = 64;

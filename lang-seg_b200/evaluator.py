@@ -234,5 +234,6 @@ class MultiScaleEvaluator:
 
     def num_forwards(self, image):
         """(network forwards the reference would issue, crop-sized images we batch) for this image size."""
-        n = sum(len(self._plan_scale(image, s)["windows"]) for s in self.scales)
+        h, w = image.shape[2:]
+        n = sum(len(self._geometry(h, w, s)["origins"]) for s in self.scales)
         return (n * (2 if self.flip else 1), n * (2 if self.flip else 1))

@@ -30,11 +30,27 @@ def test_fused_matches_torch_glue_and_is_batch_invariant(net, h, w, base, crop, 
     img = synth.make_image(1, h, w, seed=h + w).cuda()
     labels = ["cat", "other", "tree"]
     kw = dict(base_size=base, crop_size=crop, scales=scales, flip=True)
+    # (1) the network inputs: every crop the fused kernel builds equals the torch chain (interpolate, pad, slice, pad,
+    #     flip) to fp32 rounding — recorded through a network stand-in that just remembers what it is given
+    seen = {}
+
+    def recorder(tag):
+        def f(x, label_set):
+            seen.setdefault(tag, []).append(x.clone())
+            return torch.zeros((x.shape[0], 1) + tuple(x.shape[2:]), device=x.device)
+        return f
+    MultiScaleEvaluator(recorder("glue"), fused=False, max_batch=1 << 30, **kw)(img, labels)
+    MultiScaleEvaluator(recorder("fused"), fused=True, max_batch=1 << 30, **kw)(img, labels)
+    a, b = torch.cat(seen["glue"], 0), torch.cat(seen["fused"], 0)
+    assert a.shape == b.shape
+    assert (a - b).abs().max().item() < 2e-6, (a - b).abs().max().item()
+    # (2) end to end on the real network. Geometry / accumulation are exact (stand-in golden test below, 2e-5); here the
+    #     network itself quantises its input to fp16, so inputs that differ by 1e-7 flip the rounding of a few hundred
+    #     pixels per crop and the logits move like two evaluations of the fp16 pipeline do
     glue = MultiScaleEvaluator(net, fused=False, **kw)(img, labels)
     fused = MultiScaleEvaluator(net, fused=True, max_batch=16, **kw)(img, labels)
     assert fused.shape == glue.shape == (1, 3, h, w)
-    # same algorithm, same order of adds; the bilinear blends differ from torch's kernels by FMA contraction only
-    assert rel_err(fused, glue) < 2e-5, rel_err(fused, glue)
+    assert rel_err(fused, glue) < 3e-3, rel_err(fused, glue)
     # the batched evaluation equals the sequential (one network input at a time) algorithm bit for bit
     seq = MultiScaleEvaluator(net, fused=True, max_batch=1, **kw)(img, labels)
     assert torch.equal(fused, seq)

@@ -181,7 +181,9 @@ def test_text_ops_teacher_forced():
         g = torch.empty((x0.shape[0], 4 * Wd), dtype=torch.float16, device="cuda")
         ops.gemm(dev(t["ln2"], Wd), wt("mlp.c_fc.weight"), 4 * Wd, M=M, bias=bias("mlp.c_fc.bias"), act=ops.ACT_QUICKGELU,
                  out_f16=g)
-        check(f"b{i}.c_fc+quickgelu", g, t["gelu"], 1.0)
+        # a 1-ulp flip of the pre-activation h (summation order) moves x*sigmoid(1.702x) by up to ~3 of ITS ulps where the
+        # output is much smaller than h (negative h): allow 4
+        check(f"b{i}.c_fc+quickgelu", g, t["gelu"], 4.0)
         x2 = torch.zeros_like(x0)
         ops.gemm(dev(t["gelu"], 4 * Wd), wt("mlp.c_proj.weight"), Wd, M=M, bias=bias("mlp.c_proj.bias"),
                  res_f16=dev(t["x1"], Wd), out_f16=x2)

@@ -304,7 +304,7 @@ def test_head_block(ops, mode, act, in_f16):
     """scratch.head_block (arch_option 1 = bottleneck_block, 2 = depthwise_block; lseg_net.py:29-79): one shared 3x3 kernel
     over every class plane, optional channel-max skip, optional activation — against torch's own conv2d / max."""
     from lseg_b200 import _lib
-    B, K, h, w = 2, 7, 37, 52
+    B, K, h, w = 2, 7, 37, 56
     x = _rand((B, K, h, w), 61, 1.5, torch.float16 if in_f16 else torch.float32)
     wt = _rand((1, 1, 3, 3), 62, 0.3, torch.float32)
     bias = 0.17

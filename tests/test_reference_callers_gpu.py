@@ -94,5 +94,7 @@ def test_multi_eval_module_threads_and_replicas(module):
                                flip=True, fused=False)(img, labels)
     assert torch.equal(glue, seq), f"batched evaluator differs from the reference class: {rel_err(glue, seq):.3e}"
     fused = MultiScaleEvaluator(module.net, base_size=module.base_size, crop_size=module.crop_size, scales=scales,
-                                flip=True)(img, labels)  # gather kernels instead of the torch glue: fp32 rounding only
-    assert rel_err(fused, seq) < 2e-5, rel_err(fused, seq)
+                                flip=True)(img, labels)
+    # gather kernels instead of the torch glue: the network inputs agree to fp32 rounding (tests/test_evaluator_gpu.py), but
+    # the network quantises its input to fp16, so a 1e-7 difference flips the rounding of a few hundred input pixels per crop
+    assert rel_err(fused, seq) < logit_tolerance(seq, FULL_LOGIT_REL), rel_err(fused, seq)

@@ -4,7 +4,7 @@
 set -u
 R=${1:-r01}
 mkdir -p gpurun_out
-BENCH="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e"
+BENCH="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-eval"
 # (1) launch list of the bench command: per-launch durations, cold-cache and serialised -> compare SHARES
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv \
   --log-file gpurun_out/launches_${R}.csv $BENCH > gpurun_out/ncu_launches_${R}.log 2>&1
@@ -18,4 +18,6 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:mhsa
   -f -o gpurun_out/prof_mhsa_${R} $BENCH > gpurun_out/ncu_mhsa_${R}.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:upsample2x_nchw --launch-skip 2 -c 1 \
   -f -o gpurun_out/prof_upsample_${R} $BENCH > gpurun_out/ncu_upsample_${R}.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:layernorm --launch-skip 20 -c 1 \
+  -f -o gpurun_out/prof_ln_${R} $BENCH > gpurun_out/ncu_ln_${R}.log 2>&1
 ls -la gpurun_out | tail -12
