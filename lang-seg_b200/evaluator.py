@@ -105,30 +105,40 @@ class MultiScaleEvaluator:
         img = image[0].contiguous().float()
         pad = (C.c_float * 3)(*[-float(m) / float(s) for m, s in zip(self.mean, self.std)])
         per = 2 if self.flip else 1
-        scores = None
 
         def stream():
             return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
         with torch.cuda.device(dev):
-            for scale in self.scales:
-                g = self._geometry(h, w, scale)
-                n_win = len(g["origins"])
-                rows = []
-                for i, (h0, w0) in enumerate(g["origins"]):
-                    rows.append([g["height"], g["width"], h0, w0, 0, per * i])
+            # every network input of every scale, built by ONE launch, and evaluated in fixed-size batches (the engine
+            # caches one launch plan per batch shape: per-scale batches of 2, 2, 8, 12, ... would rebuild it every time)
+            geo = [self._geometry(h, w, scale) for scale in self.scales]
+            rows, first = [], []
+            for g in geo:
+                first.append(len(rows))
+                for (h0, w0) in g["origins"]:
+                    rows.append([g["height"], g["width"], h0, w0, 0, len(rows)])
                     if self.flip:
-                        rows.append([g["height"], g["width"], h0, w0, 1, per * i + 1])
-                wins = torch.tensor(rows, dtype=torch.int32).to(dev)           # every network input of the scale
-                plain = wins[::per].contiguous()                                # one entry per window (canvas pass)
-                crops = torch.empty((len(rows), 3, crop, crop), dtype=torch.float32, device=dev)
-                _lib.check(lib.lseg_eval_make_crops(C.c_void_p(img.data_ptr()), C.c_void_p(crops.data_ptr()),
-                                                    C.c_void_p(wins.data_ptr()), len(rows), h, w, crop, pad, stream()))
-                outs = torch.cat([self.net(crops[i:i + self.max_batch], label_set).float()
-                                  for i in range(0, len(rows), self.max_batch)], 0).contiguous()
-                K = outs.shape[1]
-                if scores is None:
-                    scores = torch.zeros((1, K, h, w), dtype=torch.float32, device=dev)
+                        rows.append([g["height"], g["width"], h0, w0, 1, len(rows)])
+            wins = torch.tensor(rows, dtype=torch.int32).to(dev)
+            crops = torch.empty((len(rows), 3, crop, crop), dtype=torch.float32, device=dev)
+            _lib.check(lib.lseg_eval_make_crops(C.c_void_p(img.data_ptr()), C.c_void_p(crops.data_ptr()),
+                                                C.c_void_p(wins.data_ptr()), len(rows), h, w, crop, pad, stream()))
+            outs = None
+            direct = getattr(self.net, "supports_out", False)  # LSegNet writes straight into the output batch
+            for i in range(0, len(rows), self.max_batch):
+                if direct and outs is not None:
+                    self.net(crops[i:i + self.max_batch], label_set, out=outs[i:i + self.max_batch])
+                    continue
+                o = self.net(crops[i:i + self.max_batch], label_set).float()
+                if outs is None:
+                    outs = torch.empty((len(rows),) + tuple(o.shape[1:]), dtype=torch.float32, device=dev)
+                outs[i:i + o.shape[0]] = o
+            K = outs.shape[1]
+            scores = torch.zeros((1, K, h, w), dtype=torch.float32, device=dev)
+            for g, f0 in zip(geo, first):
+                n_win = len(g["origins"])
+                plain = wins[f0:f0 + per * n_win:per].contiguous()  # one entry per window of this scale
                 canvas = torch.empty((K, g["height"], g["width"]), dtype=torch.float32, device=dev)
                 _lib.check(lib.lseg_eval_canvas(C.c_void_p(outs.data_ptr()), C.c_void_p(canvas.data_ptr()),
                                                 C.c_void_p(plain.data_ptr()), n_win, K, crop, g["height"], g["width"],

@@ -300,8 +300,11 @@ class LSegNet(_LSegBase):
         if path is not None:
             self.load(path)
 
+    supports_out = True  # forward(..., out=) writes into a caller tensor (the evaluator's output batch)
+
     @torch.no_grad()
-    def forward(self, x, labelset=""):
+    def forward(self, x, labelset="", out=None):
+        """`out` (optional, beyond the reference signature): a contiguous fp32 [B,K,H,W] CUDA tensor to write into."""
         self._check_eval()
         if isinstance(labelset, torch.Tensor):
             text = labelset
@@ -311,7 +314,10 @@ class LSegNet(_LSegBase):
             text = tokenize(labelset)
         engine = self._engine_for(x.device)
         feats = self._text_features(engine, text)
-        return engine.forward(x.float(), feats, text.shape[0])
+        if out is not None and (out.dtype != torch.float32 or not out.is_contiguous() or
+                                tuple(out.shape) != (x.shape[0], text.shape[0], x.shape[2], x.shape[3])):
+            raise ValueError("out must be a contiguous float32 [B,K,H,W] tensor")
+        return engine.forward(x.float(), feats, text.shape[0], out=out)
 
     @torch.no_grad()
     def predict(self, x, labelset=""):
