@@ -90,9 +90,7 @@ int lseg_mhsa(const void* qkv, void* out, int B, int N, int heads, int causal, v
  * 1 = one blocking MMA warp per stream + per-role register budgets (setmaxnreg); 2 = 1 + packed-fp32 (FFMA2 / FADD2 /
  * FMNMX3) softmax arithmetic; 3 = 2 + one of every four score pairs exponentiated on the FMA pipe; 4 = two of four;
  * 5..8 = the probabilities stay in tensor memory (tcgen05.st over the S tile, PV MMA with its A operand from TMEM):
- * 5 scalar softmax arithmetic, 6 packed, 7 packed + one of four pairs on the FMA pipe, 8 two of four;
- * 9..12 = one CTA per SM owning two 128-row query tiles, 128-key tiles, P in its own TMEM region (non-causal only):
- * 9 packed arithmetic, 10 + one of four pairs on the FMA pipe, 11 two of four, 12 scalar arithmetic. */
+ * 5 scalar softmax arithmetic, 6 packed, 7 packed + one of four pairs on the FMA pipe, 8 two of four. */
 int lseg_mhsa_variant(const void* qkv, void* out, int B, int N, int heads, int causal, int variant, void* stream);
 /* Causal attention of the CLIP text tower with the rounding points of torch's multi_head_attention_forward on fp16
  * tensors (q*dh^-0.5, bmm -> fp16, softmax -> fp16 normalised, bmm -> fp16): CUDA cores, one

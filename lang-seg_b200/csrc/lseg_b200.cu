@@ -17,7 +17,6 @@
 #include "mhsa2.cuh"
 #include "mhsa3.cuh"
 #include "mhsa4.cuh"
-#include "mhsa5.cuh"
 #include "text_attn.cuh"
 #include "p2p.cuh"
 #include "evaluator.cuh"
@@ -124,14 +123,6 @@ static int init_device(int dev) {
   LSEG_M4_ATTR((mhsa4_kernel<true, 1>));
   LSEG_M4_ATTR((mhsa4_kernel<true, 2>));
 #undef LSEG_M4_ATTR
-#define LSEG_M5_ATTR(K)                                                                       \
-  cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, kM5SmemBytes);          \
-  cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, 100)
-  LSEG_M5_ATTR((mhsa5_kernel<false, 0>));
-  LSEG_M5_ATTR((mhsa5_kernel<true, 0>));
-  LSEG_M5_ATTR((mhsa5_kernel<true, 1>));
-  LSEG_M5_ATTR((mhsa5_kernel<true, 2>));
-#undef LSEG_M5_ATTR
   if (cudaGetLastError() != cudaSuccess) {
     set_error("lseg_b200: cudaFuncSetAttribute failed on device %d", dev);
     return -1;
@@ -406,8 +397,6 @@ static int mhsa_plan(const MhsaDesc& d, MhsaPlan* plan) {
 // variant: 0 mhsa2 (round-1 kernel: one polling MMA warp); 1 mhsa3 (one blocking MMA warp per stream, setmaxnreg);
 // 2 = 1 + packed-fp32 softmax arithmetic; 3 = 2 + one of four score pairs on the FMA-pipe exp2 polynomial; 4 = two of four;
 // 5..8 mhsa4 (P in tensor memory, TS-form PV MMA): 5 scalar arithmetic, 6 packed, 7 packed + 1/4 polynomial, 8 + 2/4.
-// 9..12 mhsa5 (one CTA per SM, two 128-row query tiles, 128-key tiles, P in its own TMEM region; non-causal):
-// 9 packed, 10 packed + 1/4 polynomial, 11 + 2/4, 12 scalar arithmetic.
 static int mhsa_run_variant(const MhsaPlan& plan, int variant, cudaStream_t stream) {
   switch (variant) {
     case 0: launch_pdl(mhsa2_kernel<0, false>, plan.grid, dim3(kM2Threads), kM2SmemBytes, stream, plan.p); break;
@@ -419,18 +408,6 @@ static int mhsa_run_variant(const MhsaPlan& plan, int variant, cudaStream_t stre
     case 6: launch_pdl(mhsa4_kernel<true, 0>, plan.grid, dim3(kM3Threads), kM4SmemBytes, stream, plan.p); break;
     case 7: launch_pdl(mhsa4_kernel<true, 1>, plan.grid, dim3(kM3Threads), kM4SmemBytes, stream, plan.p); break;
     case 8: launch_pdl(mhsa4_kernel<true, 2>, plan.grid, dim3(kM3Threads), kM4SmemBytes, stream, plan.p); break;
-    case 9: case 10: case 11: case 12: {
-      if (plan.p.causal) {
-        set_error("mhsa: kernel variant %d (two query tiles per CTA) is non-causal only", variant);
-        return -1;
-      }
-      const dim3 grid2((plan.grid.x + 1) / 2, plan.grid.y, 1);
-      if (variant == 9) launch_pdl(mhsa5_kernel<true, 0>, grid2, dim3(kM5Threads), kM5SmemBytes, stream, plan.p);
-      else if (variant == 10) launch_pdl(mhsa5_kernel<true, 1>, grid2, dim3(kM5Threads), kM5SmemBytes, stream, plan.p);
-      else if (variant == 11) launch_pdl(mhsa5_kernel<true, 2>, grid2, dim3(kM5Threads), kM5SmemBytes, stream, plan.p);
-      else launch_pdl(mhsa5_kernel<false, 0>, grid2, dim3(kM5Threads), kM5SmemBytes, stream, plan.p);
-      break;
-    }
     default: set_error("mhsa: unknown kernel variant %d", variant); return -1;
   }
   LSEG_CHECK_CUDA(cudaGetLastError());
