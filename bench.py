@@ -231,6 +231,9 @@ def main():
     ap.add_argument("--size", type=int, default=480)
     ap.add_argument("--gather", default=os.environ.get("LSEG_GATHER_MODE", "p2p_copy"),
                     choices=["p2p_copy", "p2p_store", "nccl"])
+    ap.add_argument("--backbone", default="clip_vitl16_384",
+                    choices=["clip_vitl16_384", "clipRN50x16_vitl16_384", "clip_vitb32_384"],
+                    help="BASELINE.json's metric is quoted on the default; the others are extra lines (config.backbone)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-eval", action="store_true", help="skip the multi-scale evaluator line (SURVEY 8(f) row 1)")
@@ -264,7 +267,7 @@ def main():
     K = len(labels)
     B, S = cfg["batch"], cfg["size"]
     torch.manual_seed(1234 + rank)
-    net = LSegNet(labels=labels if cfg["tokens"] is None else ["x"], **NET_KW).eval().to(dev)
+    net = LSegNet(labels=labels if cfg["tokens"] is None else ["x"], **{**NET_KW, "backbone": args.backbone}).eval().to(dev)
     tokens = cfg["tokens"] if cfg["tokens"] is not None else tokenizer.tokenize(labels)
     if cfg["tokens"] is not None:
         net.text = tokens  # the constructor's label set, pre-tokenised (the public call `net(x)` uses it)
@@ -319,25 +322,30 @@ def main():
     value, total_ms = compute_value, compute_ms
     if dist is not None:
         del out
-        g = LogitsGather(eng, B, K, S, S, root=0, mode=args.gather)
-        for _ in range(W):
-            g.forward(x, text)
-        g.sync()
-        barrier()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        t_wall0 = time.perf_counter()
-        e0.record()
-        for i in range(Ksteps):
-            full = g.forward(x, text)
-        g.sync()
-        e1.record()
-        barrier()
-        t_wall = time.perf_counter() - t_wall0
-        clocks = sampler.summary()
-        total_ms = max_over_ranks(e0.elapsed_time(e1))
+        def run_gather(materialize):
+            g = LogitsGather(eng, B, K, S, S, root=0, mode=args.gather, materialize=materialize)
+            for _ in range(W):
+                g.forward(x, text)
+            g.sync()
+            barrier()
+            smp = ClockSampler(local_rank)
+            smp.start()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            t0 = time.perf_counter()
+            e0.record()
+            for i in range(Ksteps):
+                full = g.forward(x, text)
+            g.sync()
+            e1.record()
+            barrier()
+            wall = time.perf_counter() - t0
+            return g, full, max_over_ranks(e0.elapsed_time(e1)), wall, smp.summary()
+
+        g0, _, lowres_ms, _, _ = run_gather(False)   # exchange only: root keeps the fp16 low-res logits of all shards
+        g0.close()
+        del g0
+        g, full, total_ms, t_wall, clocks = run_gather(True)
         value = world * B * Ksteps / (total_ms / 1e3)
         wd = ops.read_watchdog()
         check = None
@@ -351,6 +359,11 @@ def main():
                        "what": "fp16 low-res logits (the reference's fp16 matmul result, 1/8 of the fp32 bytes it determines) "
                                "pushed into rank 0's buffer over NVLink by the copy engines, release/acquire flags, rank 0 "
                                "upsamples all shards to fp32 [N*B,K,H,W] on a side stream (overlaps the next step)",
+                       "lowres_only": {"value": world * B * Ksteps / (lowres_ms / 1e3), "ms_per_step": lowres_ms / Ksteps,
+                                       "what": "the same steps with the exchange but without rank 0's fp32 expansion: all "
+                                               "shards' fp16 low-res logits resident on rank 0 (the difference to `value` is "
+                                               "rank 0 writing N*B*K*H*W*4 bytes of fp32 logits per step, which cannot "
+                                               "overlap kernels that own every SM's shared memory)"},
                        "compute_only": {"value": compute_value, "ms_per_step": compute_ms / Ksteps,
                                         "what": "the same K steps without the gather (round-1 definition of value)"}}
         g.close()
@@ -505,7 +518,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": Ksteps, "warmup": W,
             "ms_per_step": total_ms / Ksteps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "fp16 operands, fp32 accumulate (fp32 residual stream)", "data": "synthetic",
-            "config": dict(cfg["config"], global_batch=B * world, parallelism=par,
+            "config": dict(cfg["config"], backbone=args.backbone, global_batch=B * world, parallelism=par,
                            weights="random init of the architecture", text_features="cached per label set",
                            l2="N=1: 256 MiB flush (untimed) between timed steps; N>1: back-to-back steps, per-step "
                               "working set ~3.7 GB >> 126 MB L2"),

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LSEG_B200_ABI_VERSION 2
+#define LSEG_B200_ABI_VERSION 3
 
 /* ---- error / info ------------------------------------------------------------------------------ */
 const char* lseg_last_error(void);
@@ -113,8 +113,8 @@ int lseg_mhsa_trace(const void* qkv, void* out, int B, int N, int heads, int cau
 int lseg_layernorm(const void* x, int in_f16, const float* gamma, const float* beta, void* y, long long M, int C,
                    float eps, void* stream);
 
-/* x fp32 NCHW [B,3,H,W] -> fp16 [B*(H/16)*(W/16), 768] patch rows (k1 operand). */
-int lseg_patchify(const float* x, void* a, int B, int H, int W, void* stream);
+/* x fp32 NCHW [B,3,H,W] -> fp16 [B*(H/P)*(W/P), 3*P*P] patch rows (k1 operand), P = patch in {16, 32}. */
+int lseg_patchify(const float* x, void* a, int B, int H, int W, int patch, void* stream);
 /* bilinear (align_corners=False) resize of pos_embed [1+g0*g0, D] -> [1+gh*gw, D] (k2; lseg_vit.py:149-163). */
 int lseg_pos_resize(const float* pos, float* out, int g0, int gh, int gw, int D, void* stream);
 /* x[b] = cat(cls, patch[b]) + pos (lseg_vit.py:188-193); fp32. */
@@ -220,32 +220,42 @@ typedef struct lseg_text_block_w {         /* CLIP ResidualAttentionBlock (Appen
 #define LSEG_TEXT_DEPTH 12
 
 typedef struct lseg_weights {
-  /* image trunk: timm vit_large_patch16_384 driven by forward_flex (lseg_vit.py:166-201) */
-  lseg_linear_w patch;                     /* [1024, 768] */
-  const float* cls_token;                  /* [1024] */
-  const float* pos_embed;                  /* [1+pos_grid^2, 1024] */
-  int pos_grid;                            /* 24 */
-  lseg_vit_block_w blocks[LSEG_VIT_DEPTH];
-  int hooks[4];                            /* 5, 11, 17, 23 (lseg_net.py:119-123) */
-  /* reassemble (lseg_vit.py:442-522) */
-  lseg_linear_w readout_tok[4];            /* W[:, :1024]  */
-  lseg_linear_w readout_cls[4];            /* W[:, 1024:] with the bias */
-  lseg_linear_w post_conv1x1[4];           /* 1024 -> {256,512,1024,1024} */
-  lseg_linear_w post1_deconv;              /* ConvT k4 s4: [(i*4+j)*256+co, ci], bias expanded [4096] */
-  lseg_linear_w post2_deconv;              /* ConvT k2 s2: [(i*2+j)*512+co, ci], bias expanded [2048] */
-  lseg_linear_w post4_conv;                /* 3x3 s2: [1024, 9*1024] tap-major */
+  /* image trunk: a timm VisionTransformer driven by forward_flex (lseg_vit.py:166-201). The geometry travels with
+   * the weights: backbone "clip_vitl16_384" = vit_large_patch16_384 (D 1024, 24 blocks, 16 heads, patch 16, hooks
+   * 5/11/17/23, lseg_vit.py:442-522), "clip_vitb32_384" = vit_base_patch32_384 (D 768, 12 blocks, 12 heads, patch 32,
+   * hooks 2/5/8/11, lseg_vit.py:525-589). Head dim is 64 in both. */
+  int vit_dim, vit_depth, vit_heads, patch_size;
+  lseg_linear_w patch;                     /* [D, 3*patch^2] */
+  const float* cls_token;                  /* [D] */
+  const float* pos_embed;                  /* [1+pos_grid^2, D] */
+  int pos_grid;                            /* 384 / patch: 24 | 12 */
+  lseg_vit_block_w blocks[LSEG_VIT_DEPTH]; /* the first vit_depth entries */
+  int hooks[4];                            /* lseg_net.py:119-123 */
+  /* reassemble (lseg_vit.py:442-589) */
+  lseg_linear_w readout_tok[4];            /* W[:, :D]  */
+  lseg_linear_w readout_cls[4];            /* W[:, D:] with the bias */
+  lseg_linear_w post_conv1x1[4];           /* D -> post_channels[k] */
+  int post_channels[4];                    /* STORED widths, multiples of 64: {256,512,1024,1024} | {128,192,384,768}
+                                              (the reference's 96 is padded to 128 with zero weights / bias) */
+  int post_resample[4];                    /* s > 0: ConvTranspose2d(k=s, stride=s); 0: none; -2: Conv2d 3x3 stride 2.
+                                              {4,2,0,-2} | {8,4,2,0} */
+  lseg_linear_w post_resample_w[4];        /* ConvT: [(i*s+j)*C+co, ci], bias expanded [s*s*C]; conv: [C, 9*C] tap-major;
+                                              unused (w NULL) where post_resample == 0 */
   /* decoder (lseg_blocks.py:60-110, 222-358) */
-  lseg_linear_w layer_rn[4];               /* [256, 9*Cin] tap-major, no bias */
+  lseg_linear_w layer_rn[4];               /* [256, 9*post_channels[k]] tap-major, no bias */
   lseg_rcu_w rcu1[4], rcu2[4];             /* index i = refinenet(i+1); rcu1[3] is dead (lseg_net.py:176) */
   lseg_linear_w out_conv[4];               /* [256,256] + bias */
-  lseg_linear_w head1;                     /* [512,256] + bias */
+  lseg_linear_w head1;                     /* [out_c,256] + bias */
   float logit_scale;                       /* exp(log(1/0.07)) (lseg_net.py:141) */
-  /* CLIP ViT-B/32 text tower */
-  const float* tok_emb;                    /* [49408, 512] fp32 */
-  const float* text_pos;                   /* [77, 512] fp32 */
+  /* CLIP text tower: ViT-B/32's (width 512, 8 heads, embedding 512) for clip_vitl16_384 / clip_vitb32_384, RN50x16's
+   * (width 768, 12 heads, embedding 768) for clipRN50x16_vitl16_384 (lseg_vit.py:221-257, lseg_net.py:142-146).
+   * out_c = embedding width = rows of head1 = K dim of the pixel x text product. Head dim 64. */
+  int text_width, text_heads, out_c;
+  const float* tok_emb;                    /* [49408, text_width] fp32 */
+  const float* text_pos;                   /* [77, text_width] fp32 */
   lseg_text_block_w text_blocks[LSEG_TEXT_DEPTH];
   const float *lnf_g, *lnf_b;
-  lseg_linear_w text_proj;                 /* text_projection^T as [512(out), 512(in)], no bias */
+  lseg_linear_w text_proj;                 /* text_projection^T as [out_c(out), text_width(in)], no bias */
   /* optional head blocks over the class planes (lseg_net.py:29-79,148-154,198-201) */
   int arch_option;                         /* 0 none (default), 1 bottleneck_block, 2 depthwise_block */
   int block_depth;                         /* the block runs max(block_depth, 1) times, activation on all but the last */

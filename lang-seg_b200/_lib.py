@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "liblseg_b200.so")
 
 VIT_DEPTH = 24
 TEXT_DEPTH = 12
-ABI_VERSION = 2  # == LSEG_B200_ABI_VERSION of include/lseg_b200.h; the struct mirrors below follow that layout
+ABI_VERSION = 3  # == LSEG_B200_ABI_VERSION of include/lseg_b200.h; the struct mirrors below follow that layout
 
 ACT_NONE, ACT_GELU, ACT_QUICKGELU, ACT_RELU = 0, 1, 2, 3
 HEAD_ACT = {"none": 0, "relu": 1, "lrelu": 2, "tanh": 3}
@@ -58,12 +58,14 @@ class TextBlockW(C.Structure):
 
 class Weights(C.Structure):
     _fields_ = [
+        ("vit_dim", C.c_int), ("vit_depth", C.c_int), ("vit_heads", C.c_int), ("patch_size", C.c_int),
         ("patch", LinearW), ("cls_token", C.c_void_p), ("pos_embed", C.c_void_p), ("pos_grid", C.c_int),
         ("blocks", VitBlockW * VIT_DEPTH), ("hooks", C.c_int * 4),
         ("readout_tok", LinearW * 4), ("readout_cls", LinearW * 4), ("post_conv1x1", LinearW * 4),
-        ("post1_deconv", LinearW), ("post2_deconv", LinearW), ("post4_conv", LinearW),
+        ("post_channels", C.c_int * 4), ("post_resample", C.c_int * 4), ("post_resample_w", LinearW * 4),
         ("layer_rn", LinearW * 4), ("rcu1", RcuW * 4), ("rcu2", RcuW * 4), ("out_conv", LinearW * 4),
         ("head1", LinearW), ("logit_scale", C.c_float),
+        ("text_width", C.c_int), ("text_heads", C.c_int), ("out_c", C.c_int),
         ("tok_emb", C.c_void_p), ("text_pos", C.c_void_p), ("text_blocks", TextBlockW * TEXT_DEPTH),
         ("lnf_g", C.c_void_p), ("lnf_b", C.c_void_p), ("text_proj", LinearW),
         ("arch_option", C.c_int), ("block_depth", C.c_int), ("head_act", C.c_int),
@@ -122,7 +124,7 @@ def load(build_if_missing=True):
     lib.lseg_mhsa_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.lseg_layernorm.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int,
                                    C.c_float, C.c_void_p]
-    lib.lseg_patchify.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.lseg_patchify.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.lseg_pos_resize.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.lseg_assemble_tokens.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                          C.c_void_p]

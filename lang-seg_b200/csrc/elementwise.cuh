@@ -15,34 +15,44 @@ namespace lseg {
   } while (0)
 
 // ------------------------------------------------------------------------------------------
-// patchify: x fp32 NCHW [B,3,H,W] -> A fp16 [B*gh*gw, 768], column = c*256 + py*16 + px, which is
-// the flattening of the patch-embed Conv2d(3,1024,k16,s16) weight (modules/models/lseg_vit.py:179),
-// so the conv becomes one GEMM with the weight used as stored.
-// grid (ceil(gw*192/256), B*gh): one thread = 4 pixels of one patch row.
+// patchify: x fp32 NCHW [B,3,H,W] -> A fp16 [B*gh*gw, 3*P*P], column = c*P*P + py*P + px, which is
+// the flattening of the patch-embed Conv2d(3,D,kP,sP) weight (modules/models/lseg_vit.py:179; P = 16 for
+// vit_large_patch16_384, 32 for vit_base_patch32_384), so the conv becomes one GEMM with the weight used as stored.
+// grid (ceil(gw*3*P*P/4 / 256), B*gh): one thread = 4 pixels of one patch row.
 // ------------------------------------------------------------------------------------------
+template <int P>
 __global__ void patchify_kernel(const float* __restrict__ x, __half* __restrict__ a, int H, int W) {
   griddep_launch_dependents();
   griddep_wait();
-  const int gh = H / 16, gw = W / 16;
+  constexpr int kQuads = P / 4;           // float4 groups per patch row
+  constexpr int kPerPatchCh = P * kQuads;  // threads per (patch, channel)
+  const int gh = H / P, gw = W / P;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= gw * 192) return;
+  if (i >= gw * 3 * kPerPatchCh) return;
   const int b = blockIdx.y / gh, gy = blockIdx.y - b * gh;
-  const int px4 = i & 3, py = (i >> 2) & 15;
-  const int rest = i >> 6;  // gx*3 + c
+  const int px4 = i % kQuads, py = (i / kQuads) % P;
+  const int rest = i / kPerPatchCh;  // gx*3 + c
   const int gx = rest / 3, c = rest - gx * 3;
   const float4 v = *reinterpret_cast<const float4*>(
-      x + ((static_cast<long long>(b) * 3 + c) * H + gy * 16 + py) * W + gx * 16 + px4 * 4);
+      x + ((static_cast<long long>(b) * 3 + c) * H + gy * P + py) * W + gx * P + px4 * 4);
   __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
   uint2 o;
   o.x = *reinterpret_cast<uint32_t*>(&h0);
   o.y = *reinterpret_cast<uint32_t*>(&h1);
-  __half* dst = a + (static_cast<long long>(blockIdx.y) * gw + gx) * 768 + c * 256 + py * 16 + px4 * 4;
+  __half* dst = a + (static_cast<long long>(blockIdx.y) * gw + gx) * (3 * P * P) + c * P * P + py * P + px4 * 4;
   *reinterpret_cast<uint2*>(dst) = o;
 }
-static inline int launch_patchify(const float* x, __half* a, int B, int H, int W, cudaStream_t s) {
-  const int gw = W / 16, gh = H / 16;
-  dim3 grid((gw * 192 + 255) / 256, B * gh);
-  launch_pdl(patchify_kernel, grid, dim3(256), 0, s, x, a, H, W);
+static inline int launch_patchify(const float* x, __half* a, int B, int H, int W, int P, cudaStream_t s) {
+  if ((P != 16 && P != 32) || H % P != 0 || W % P != 0) {
+    set_error("patchify: patch size %d (16 or 32) must divide H=%d and W=%d", P, H, W);
+    return -1;
+  }
+  const int gw = W / P, gh = H / P;
+  dim3 grid((gw * 3 * P * (P / 4) + 255) / 256, B * gh);
+  if (P == 16)
+    launch_pdl(patchify_kernel<16>, grid, dim3(256), 0, s, x, a, H, W);
+  else
+    launch_pdl(patchify_kernel<32>, grid, dim3(256), 0, s, x, a, H, W);
   LSEG_LAUNCH_CHECK();
 }
 
@@ -354,7 +364,7 @@ __device__ __forceinline__ float lerp2(float w0, float a, float w1, float b) { r
 // matmul) -> .float() -> bilinear x2 align_corners=True -> fp32 [planes,2H,2W].
 // HBM-write-bound (K*H*W*4 B per image). Separable: a WARP owns kUpRows consecutive output rows of one
 // plane; per row it (1) blends the two source rows vertically into a private smem line (16 B loads,
-// coalesced), (2) blends horizontally from that line — 2 LDS + 2 FMA per output — and streams float4
+// coalesced; stored split by column parity), (2) blends horizontally from that line — 2 LDS + 2 FMA per output — and streams float4
 // stores (512 B contiguous per warp instruction). The horizontal taps/weights live in registers and are
 // reused for all of the warp's rows. grid (ceil(Ho / (8 warps * kUpRows)), planes), W % 8 == 0, W <= 512.
 // ------------------------------------------------------------------------------------------
@@ -406,8 +416,11 @@ __global__ void upsample2x_nchw_kernel(const TIn* __restrict__ x, float* __restr
       load8_f32(r1 + 8 * c, fb);
 #pragma unroll
       for (int k = 0; k < 8; ++k) o[k] = lerp2(hy, fa[k], ly, fb[k]);
-      reinterpret_cast<float4*>(v)[2 * c] = make_float4(o[0], o[1], o[2], o[3]);
-      reinterpret_cast<float4*>(v)[2 * c + 1] = make_float4(o[4], o[5], o[6], o[7]);
+      // de-interleaved line: even source columns in v[0..), odd ones in v[kUpMaxW/2..). The horizontal pass of a
+      // lane reads columns ~2*xq + const, i.e. a stride of two words across the warp: interleaved that is a 2-way bank
+      // conflict on every LDS (the kernel is LSU-bound), split by parity it is one conflict-free wavefront
+      reinterpret_cast<float4*>(v)[c] = make_float4(o[0], o[2], o[4], o[6]);
+      reinterpret_cast<float4*>(v + kUpMaxW / 2)[c] = make_float4(o[1], o[3], o[5], o[7]);
     }
     __syncwarp();
     float* orow = oplane + static_cast<long long>(oy) * Wo;
@@ -423,7 +436,7 @@ __global__ void upsample2x_nchw_kernel(const TIn* __restrict__ x, float* __restr
           const int xi = static_cast<int>(fx);
           const float lxk = fx - xi;
           const int xa = min(xi, W - 1), xb = min(xa + 1, W - 1);
-          o[k] = lerp2(1.f - lxk, v[xa], lxk, v[xb]);
+          o[k] = lerp2(1.f - lxk, v[(xa & 1) * (kUpMaxW / 2) + (xa >> 1)], lxk, v[(xb & 1) * (kUpMaxW / 2) + (xb >> 1)]);
         }
         if (STREAM)
           __stcs(reinterpret_cast<float4*>(orow + xq * 4), make_float4(o[0], o[1], o[2], o[3]));

@@ -236,8 +236,9 @@ static int get_pos_embed(lseg_engine* eng, int gh, int gw, cudaStream_t stream, 
     return 0;
   }
   float* buf = nullptr;
-  LSEG_CHECK_CUDA(cudaMalloc(&buf, sizeof(float) * (1 + (size_t)gh * gw) * 1024));
-  pos_resize_kernel<<<1 + gh * gw, 256, 0, stream>>>(eng->w.pos_embed, buf, eng->w.pos_grid, gh, gw, 1024);
+  const int D = eng->w.vit_dim;
+  LSEG_CHECK_CUDA(cudaMalloc(&buf, sizeof(float) * (1 + (size_t)gh * gw) * D));
+  pos_resize_kernel<<<1 + gh * gw, 256, 0, stream>>>(eng->w.pos_embed, buf, eng->w.pos_grid, gh, gw, D);
   LSEG_CHECK_CUDA(cudaGetLastError());
   eng->pos_cache[key] = buf;
   *out = buf;
@@ -253,8 +254,11 @@ static int build_image_plan(lseg_engine* eng, int B, int H, int W, cudaStream_t 
   plan->epoch = g_plan_epoch;
   Arena& arena = plan->arena;
   std::vector<Step>& steps = plan->steps;
-  const int gh = H / 16, gw = W / 16, T = gh * gw, N = T + 1;
-  const int D = 1024;
+  // backbone geometry (lseg_vit.py:442-522 _make_pretrained_clip_vitl16_384 / _vitb32_384): token width, depth, heads,
+  // patch size and the per-level reassemble recipe come with the weights
+  const int P = w.patch_size, D = w.vit_dim, heads = w.vit_heads;
+  const int gh = H / P, gw = W / P, T = gh * gw, N = T + 1;
+  const int patch_k = 3 * P * P;
   const long long M = static_cast<long long>(B) * N;
   const long long BT = static_cast<long long>(B) * T;
 
@@ -262,7 +266,7 @@ static int build_image_plan(lseg_engine* eng, int B, int H, int W, cudaStream_t 
   if (get_pos_embed(eng, gh, gw, stream, &pos)) return -1;
 
   // ---- ViT trunk (modules/models/lseg_vit.py:166-201) ----
-  LSEG_ALLOC(patch_a, __half, BT * 768);
+  LSEG_ALLOC(patch_a, __half, BT * patch_k);
   LSEG_ALLOC(patch_out, float, BT * D);
   LSEG_ALLOC(xbuf, float, M * D);
   LSEG_ALLOC(xn, __half, M * D);
@@ -279,14 +283,14 @@ static int build_image_plan(lseg_engine* eng, int B, int H, int W, cudaStream_t 
   }
 
   steps.push_back([=](const CallCtx& c, cudaStream_t s) {
-    return launch_patchify(c.x, patch_a, B, H, W, s);
+    return launch_patchify(c.x, patch_a, B, H, W, P, s);
   });
   {
     GemmEpi e = epi_none();
     e.bias = w.patch.b;
     e.out_f32 = patch_out;
     e.ldc = D;
-    if (add_gemm(steps, patch_a, 768, (int)BT, (int)BT, w.patch, e)) return -1;
+    if (add_gemm(steps, patch_a, patch_k, (int)BT, (int)BT, w.patch, e)) return -1;
   }
   {
     const float* cls = w.cls_token;
@@ -294,7 +298,7 @@ static int build_image_plan(lseg_engine* eng, int B, int H, int W, cudaStream_t 
       return launch_assemble_tokens(patch_out, cls, pos, xbuf, B, T, D, s);
     });
   }
-  for (int i = 0; i < LSEG_VIT_DEPTH; ++i) {
+  for (int i = 0; i < w.vit_depth; ++i) {
     const lseg_vit_block_w& bw = w.blocks[i];
     // The residual stream lives in xbuf and both branch outputs are accumulated IN PLACE (x += proj(..),
     // x += fc2(..)): that lets the GEMM epilogue use a bulk tensor reduce-add and never read x. A hooked
@@ -314,12 +318,12 @@ static int build_image_plan(lseg_engine* eng, int B, int H, int W, cudaStream_t 
       md.out = attn;
       md.B = B;
       md.N = N;
-      md.heads = 16;
+      md.heads = heads;
       md.causal = 0;
       MhsaPlan mp;
       if (mhsa_plan(md, &mp)) return -1;
       steps.emplace_back([mp](const CallCtx&, cudaStream_t s) { return mhsa_run(mp, s); }, KIND_MHSA,
-                         4.0 * B * 16 * static_cast<double>(N) * N * 64);
+                         4.0 * B * heads * static_cast<double>(N) * N * 64);
     }
     {
       GemmEpi e = epi_none();
@@ -360,7 +364,26 @@ static int build_image_plan(lseg_engine* eng, int B, int H, int W, cudaStream_t 
   // final self.norm is dead code in the reference (glob unused, lseg_vit.py:108,199) -> skipped.
 
   // ---- readout + reassemble (lseg_vit.py:79-90, 104-146, 442-522) ----
-  const int c_post[4] = {256, 512, 1024, 1024};
+  // Level k: 1x1 conv D -> post_channels[k], then ConvTranspose (k = s, stride s), nothing, or a 3x3 stride-2 conv
+  // (lseg_vit.py:465-520 for ViT-L/16: x4, x2, -, /2; 531-586 for ViT-B/32: x8, x4, x2, -). post_channels are the
+  // STORED widths: reference counts rounded up to a multiple of 64 with zero weights in the pad (96 -> 128).
+  int c_post[4], lh[4], lw[4];
+  for (int k = 0; k < 4; ++k) {
+    c_post[k] = w.post_channels[k];
+    const int r = w.post_resample[k];
+    if (c_post[k] <= 0 || c_post[k] % 64 != 0 || !(r == -2 || r == 0 || r == 2 || r == 4 || r == 8)) {
+      set_error("reassemble level %d: post_channels=%d (multiple of 64), post_resample=%d (8, 4, 2, 0, -2)", k, c_post[k], r);
+      return -1;
+    }
+    lh[k] = (r > 0) ? gh * r : (r == 0 ? gh : gh / 2);
+    lw[k] = (r > 0) ? gw * r : (r == 0 ? gw : gw / 2);
+  }
+  for (int k = 0; k < 3; ++k)
+    if (lh[k] != 2 * lh[k + 1] || lw[k] != 2 * lw[k + 1]) {
+      set_error("reassemble: level %d (%dx%d) is not twice level %d (%dx%d) — the fusion decoder needs a x2 pyramid "
+                "(H, W multiples of 32)", k, lh[k], lw[k], k + 1, lh[k + 1], lw[k + 1]);
+      return -1;
+    }
   LSEG_ALLOC(tok, __half, BT * D);
   const int cls_rows = ((B + 127) / 128) * 128;
   LSEG_ALLOC(cls16, __half, (size_t)cls_rows * D);
@@ -368,21 +391,19 @@ static int build_image_plan(lseg_engine* eng, int B, int H, int W, cudaStream_t 
   LSEG_ALLOC(clsb, float, (size_t)B * D);
   LSEG_ALLOC(ro, __half, BT * D);
   __half* layer_in[4];  // NHWC fp16 inputs of scratch.layerN_rn
-  const int lh[4] = {4 * gh, 2 * gh, gh, gh / 2};
-  const int lw[4] = {4 * gw, 2 * gw, gw, gw / 2};
   for (int k = 0; k < 4; ++k) {
     const float* tap = taps[k];
     steps.push_back([=](const CallCtx&, cudaStream_t s) {
       return launch_readout_split(tap, tok, cls16, B, T, D, s);
     });
-    {  // per-image half of the readout projection: cls * W[:,1024:]^T + b
+    {  // per-image half of the readout projection: cls * W[:,D:]^T + b
       GemmEpi e = epi_none();
       e.bias = w.readout_cls[k].b;
       e.out_f32 = clsb;
       e.ldc = D;
       if (add_gemm(steps, cls16, D, cls_rows, B, w.readout_cls[k], e)) return -1;
     }
-    {  // tok * W[:,:1024]^T + (per-image row) -> GELU
+    {  // tok * W[:,:D]^T + (per-image row) -> GELU
       GemmEpi e = epi_none();
       e.bias = clsb;
       e.bias_group_rows = T;
@@ -399,36 +420,43 @@ static int build_image_plan(lseg_engine* eng, int B, int H, int W, cudaStream_t 
       e.ldc = c_post[k];
       if (add_gemm(steps, ro, D, (int)BT, (int)BT, w.post_conv1x1[k], e)) return -1;
     }
-    if (k == 0 || k == 1) {
-      const int s_up = (k == 0) ? 4 : 2;
-      const lseg_linear_w& dw = (k == 0) ? w.post1_deconv : w.post2_deconv;
-      LSEG_ALLOC(lk, __half, BT * s_up * s_up * c_post[k]);
+    const int r = w.post_resample[k];
+    const lseg_linear_w& rw = w.post_resample_w[k];
+    if (r > 0) {
+      LSEG_ALLOC(lk, __half, BT * r * r * c_post[k]);
       GemmEpi e = epi_none();
-      e.bias = dw.b;
+      e.bias = rw.b;
       e.out_f16 = lk;
       e.store = STORE_D2S;
-      e.d2s_s = s_up;
+      e.d2s_s = r;
       e.d2s_cout = c_post[k];
       e.d2s_h = gh;
       e.d2s_w = gw;
-      if (add_gemm(steps, pk, c_post[k], (int)BT, (int)BT, dw, e)) return -1;
+      if (add_gemm(steps, pk, c_post[k], (int)BT, (int)BT, rw, e)) return -1;
       layer_in[k] = lk;
-    } else if (k == 2) {
+    } else if (r == 0) {
       layer_in[k] = pk;
     } else {
-      const long long rows4 = static_cast<long long>(B) * lh[3] * lw[3];
-      LSEG_ALLOC(a4, __half, rows4 * 9 * 1024);
-      LSEG_ALLOC(l4, __half, rows4 * 1024);
+      const int ck = c_post[k];
+      const long long rows4 = static_cast<long long>(B) * lh[k] * lw[k];
+      LSEG_ALLOC(a4, __half, rows4 * 9 * ck);
+      LSEG_ALLOC(l4, __half, rows4 * ck);
       steps.push_back([=](const CallCtx&, cudaStream_t s) {
-        return launch_im2col_3x3_s2(pk, a4, B, gh, gw, 1024, s);
+        return launch_im2col_3x3_s2(pk, a4, B, gh, gw, ck, s);
       });
       GemmEpi e = epi_none();
-      e.bias = w.post4_conv.b;
+      e.bias = rw.b;
       e.out_f16 = l4;
-      e.ldc = 1024;
-      if (add_gemm(steps, a4, 9 * 1024, (int)rows4, (int)rows4, w.post4_conv, e)) return -1;
+      e.ldc = ck;
+      if (add_gemm(steps, a4, 9 * ck, (int)rows4, (int)rows4, rw, e)) return -1;
       layer_in[k] = l4;
     }
+  }
+
+  for (int k = 0; k < 4; ++k) {
+    char name[12];
+    snprintf(name, sizeof(name), "layer%d", k);
+    plan->debug[name] = layer_in[k];  // NHWC fp16 [B, lh, lw, post_channels[k]]
   }
 
   // ---- scratch.layerN_rn (lseg_blocks.py:73-108; lseg_net.py:171-174) ----
@@ -492,14 +520,15 @@ static int build_image_plan(lseg_engine* eng, int B, int H, int W, cudaStream_t 
   // norm (accumulated from the fp32 accumulators); the pixel x text GEMM applies logit_scale / ||row|| in
   // its epilogue. Same quantity as the reference's normalise -> half -> scale -> matmul up to where the
   // fp16 roundings fall, without the 118 MB/img fp32 feature round trip and the separate norm pass.
-  LSEG_ALLOC(featn, __half, BP * 512);
-  LSEG_ALLOC(feat_sumsq, float, BP * 16);  // [row, 512/32] partial squared norms
+  const int OC = w.out_c;
+  LSEG_ALLOC(featn, __half, BP * OC);
+  LSEG_ALLOC(feat_sumsq, float, BP * (OC / 32));  // [row, out_c/32] partial squared norms
   {
     GemmEpi e = epi_none();
     e.bias = w.head1.b;
     e.out_f16 = featn;
     e.out_row_sumsq = feat_sumsq;
-    e.ldc = 512;
+    e.ldc = OC;
     if (add_gemm(steps, path1_f16, 256, (int)BP, (int)BP, w.head1, e)) return -1;
   }
   plan->featn = featn;
@@ -611,26 +640,27 @@ static int run_forward(lseg_engine* eng, const CallCtx& ctx, int B, int H, int W
         memset(&d, 0, sizeof(d));
         const long long rows = (groups == 1) ? static_cast<long long>(B) * P : P;
         const int n_cols = grouped ? static_cast<int>(B * stride) : ctx.K;
-        d.a = plan.featn + static_cast<long long>(g) * P * 512;
-        d.lda = 512;
+        const int OC = eng->w.out_c;
+        d.a = plan.featn + static_cast<long long>(g) * P * OC;
+        d.lda = OC;
         d.a_rows = (int)rows;
-        d.w = ctx.text + static_cast<long long>(g) * stride * 512;
+        d.w = ctx.text + static_cast<long long>(g) * stride * OC;
         d.w_rows = ((n_cols + 127) / 128) * 128;
         d.M = (int)rows;
         d.N = n_cols;
-        d.K = 512;
+        d.K = OC;
         d.e = epi_none();
         d.e.out_f16 = lr + static_cast<long long>(g) * ctx.K * P;
         d.e.store = STORE_NCHW_T;
         d.e.nchw_p = (int)P;
         d.e.nchw_k = ctx.K;
         d.e.nchw_group = grouped ? (int)stride : 0;
-        d.e.row_sumsq = plan.feat_sumsq + static_cast<long long>(g) * P * 16;
-        d.e.row_sumsq_parts = 16;
+        d.e.row_sumsq = plan.feat_sumsq + static_cast<long long>(g) * P * (OC / 32);
+        d.e.row_sumsq_parts = OC / 32;
         d.e.row_scale = eng->w.logit_scale;
         GemmPlan gp;
         if (gemm_plan(d, &gp)) return -1;
-        plans.emplace_back(gp, 2.0 * rows * n_cols * 512.0);
+        plans.emplace_back(gp, 2.0 * rows * n_cols * static_cast<double>(OC));
       }
       it = plan.corr.emplace(key, std::move(plans)).first;
     }
@@ -719,7 +749,7 @@ static int build_text_plan(lseg_engine* eng, int K) {
   std::unique_ptr<TextPlan> plan(new TextPlan());
   plan->K = K;
   Arena& arena = plan->arena;
-  const int L = 77, Wd = 512;
+  const int L = 77, Wd = w.text_width, OC = w.out_c, theads = w.text_heads;
   const long long M = static_cast<long long>(K) * L;
   const int kpad = ((K + 127) / 128) * 128;
   LSEG_ALLOC(tx, __half, M * Wd);
@@ -728,7 +758,7 @@ static int build_text_plan(lseg_engine* eng, int K) {
   LSEG_ALLOC(tattn, __half, M * Wd);
   LSEG_ALLOC(th, __half, M * 4 * Wd);
   LSEG_ALLOC(teot, __half, (size_t)kpad * Wd);
-  LSEG_ALLOC(tfeat, __half, (size_t)kpad * Wd);
+  LSEG_ALLOC(tfeat, __half, (size_t)kpad * OC);
   LSEG_CHECK_CUDA(cudaMemset(teot, 0, sizeof(__half) * (size_t)kpad * Wd));
 
   std::vector<Step> gsteps;  // reuse the image-side builders, then adapt
@@ -762,7 +792,7 @@ static int build_text_plan(lseg_engine* eng, int K) {
       if (add_gemm(gsteps, txn, Wd, (int)M, (int)M, bw.in_proj, e)) return -1;
     }
     // causal attention with torch's fp16 rounding points (text_attn.cuh), not the flash kernel of the image trunk
-    gsteps.push_back([=](const CallCtx&, cudaStream_t s) { return launch_text_attn(tqkv, tattn, K, L, 8, s); });
+    gsteps.push_back([=](const CallCtx&, cudaStream_t s) { return launch_text_attn(tqkv, tattn, K, L, theads, s); });
     {
       GemmEpi e = epi_none();
       e.bias = bw.out_proj.b;
@@ -800,13 +830,13 @@ static int build_text_plan(lseg_engine* eng, int K) {
   {
     GemmEpi e = epi_none();
     e.out_f16 = tfeat;
-    e.ldc = Wd;
+    e.ldc = OC;
     if (add_gemm(gsteps, teot, Wd, kpad, K, w.text_proj, e)) return -1;
     wrap(gsteps);
   }
   steps.push_back([=](const long long*, __half* out, cudaStream_t s) {
-    LSEG_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(__half) * (size_t)kpad * Wd, s));
-    l2norm_f16_kernel<<<(K + 7) / 8, 256, 0, s>>>(tfeat, out, K, Wd);
+    LSEG_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(__half) * (size_t)kpad * OC, s));
+    l2norm_f16_kernel<<<(K + 7) / 8, 256, 0, s>>>(tfeat, out, K, OC);
     LSEG_CHECK_CUDA(cudaGetLastError());
     return 0;
   });
@@ -824,6 +854,25 @@ int lseg_create(const lseg_weights* w, int device, lseg_engine** out) {
     set_error("lseg_create: null argument");
     return -1;
   }
+  if (w->vit_heads <= 0 || w->vit_dim != 64 * w->vit_heads || (w->vit_dim != 768 && w->vit_dim != 1024) ||
+      w->vit_depth <= 0 || w->vit_depth > LSEG_VIT_DEPTH || (w->patch_size != 16 && w->patch_size != 32) ||
+      w->pos_grid <= 0) {
+    set_error("lseg_create: backbone geometry dim=%d depth=%d heads=%d patch=%d pos_grid=%d (dim = 64*heads in {768, "
+              "1024}, depth <= %d, patch 16 | 32)", w->vit_dim, w->vit_depth, w->vit_heads, w->patch_size, w->pos_grid,
+              LSEG_VIT_DEPTH);
+    return -1;
+  }
+  if ((w->text_width != 512 && w->text_width != 768) || w->text_width != 64 * w->text_heads ||
+      (w->out_c != 512 && w->out_c != 768)) {
+    set_error("lseg_create: text tower width=%d heads=%d out_c=%d (width = 64*heads in {512, 768}, out_c in {512, 768})",
+              w->text_width, w->text_heads, w->out_c);
+    return -1;
+  }
+  for (int k = 0; k < 4; ++k)
+    if (w->hooks[k] < 0 || w->hooks[k] >= w->vit_depth || (k && w->hooks[k] <= w->hooks[k - 1])) {
+      set_error("lseg_create: hooks must be increasing block indices below depth %d", w->vit_depth);
+      return -1;
+    }
   LSEG_CHECK_CUDA(cudaSetDevice(device));
   if (ensure_init()) return -1;
   lseg_engine* e = new lseg_engine();

@@ -420,24 +420,25 @@ static int mhsa_run(const MhsaPlan& plan, cudaStream_t stream) { return mhsa_run
 // ------------------------------------------------------------------------------------------
 static int run_layernorm(const void* x, int in_f16, const float* g, const float* b, __half* y, long long M, int C,
                          float eps, cudaStream_t s) {
-  if (C != 512 && C != 1024) {
-    set_error("layernorm: C=%d (the path has 512 — CLIP text — and 1024 — ViT-L)", C);
-    return -1;
-  }
   const int rows_per_block = 8;
   const int grid = static_cast<int>((M + rows_per_block - 1) / rows_per_block);
   const dim3 blk(rows_per_block * 32);
-  if (in_f16) {
-    if (C == 512)
-      launch_pdl(layernorm_kernel<__half, 512>, dim3(grid), blk, 0, s, static_cast<const __half*>(x), g, b, y, M, eps);
-    else
-      launch_pdl(layernorm_kernel<__half, 1024>, dim3(grid), blk, 0, s, static_cast<const __half*>(x), g, b, y, M, eps);
-  } else {
-    if (C == 512)
-      launch_pdl(layernorm_kernel<float, 512>, dim3(grid), blk, 0, s, static_cast<const float*>(x), g, b, y, M, eps);
-    else
-      launch_pdl(layernorm_kernel<float, 1024>, dim3(grid), blk, 0, s, static_cast<const float*>(x), g, b, y, M, eps);
+#define LSEG_LN_CASE(CC)                                                                                            \
+  case CC:                                                                                                          \
+    if (in_f16)                                                                                                     \
+      launch_pdl(layernorm_kernel<__half, CC>, dim3(grid), blk, 0, s, static_cast<const __half*>(x), g, b, y, M, eps); \
+    else                                                                                                            \
+      launch_pdl(layernorm_kernel<float, CC>, dim3(grid), blk, 0, s, static_cast<const float*>(x), g, b, y, M, eps);   \
+    break;
+  switch (C) {
+    LSEG_LN_CASE(512)
+    LSEG_LN_CASE(768)
+    LSEG_LN_CASE(1024)
+    default:
+      set_error("layernorm: C=%d (the path has 512 — CLIP text —, 768 — ViT-B — and 1024 — ViT-L)", C);
+      return -1;
   }
+#undef LSEG_LN_CASE
   LSEG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -716,13 +717,9 @@ int lseg_layernorm(const void* x, int in_f16, const float* gamma, const float* b
   return run_layernorm(x, in_f16, gamma, beta, static_cast<__half*>(y), M, C, eps, static_cast<cudaStream_t>(stream));
 }
 
-int lseg_patchify(const float* x, void* a, int B, int H, int W, void* stream) {
+int lseg_patchify(const float* x, void* a, int B, int H, int W, int patch, void* stream) {
   if (ensure_init()) return -1;
-  if (H % 16 || W % 16) {
-    set_error("patchify: H, W must be multiples of 16");
-    return -1;
-  }
-  return launch_patchify(x, static_cast<__half*>(a), B, H, W, static_cast<cudaStream_t>(stream));
+  return launch_patchify(x, static_cast<__half*>(a), B, H, W, patch, static_cast<cudaStream_t>(stream));
 }
 
 int lseg_pos_resize(const float* pos, float* out, int g0, int gh, int gw, int D, void* stream) {

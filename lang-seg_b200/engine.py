@@ -14,7 +14,7 @@ def _stream():
 class Engine:
     """Owns the packed weights and the native engine for one CUDA device."""
 
-    def __init__(self, state_dict, device, arch_option=0, block_depth=0, activation="lrelu"):
+    def __init__(self, state_dict, device, arch_option=0, block_depth=0, activation="lrelu", backbone="clip_vitl16_384"):
         device = torch.device(device)
         if device.type != "cuda":
             raise RuntimeError("lseg_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
@@ -22,7 +22,8 @@ class Engine:
         self.lib = _lib.load()
         with torch.cuda.device(device):
             self.weights = PackedWeights(state_dict, device, arch_option=arch_option, block_depth=block_depth,
-                                         activation=activation)
+                                         activation=activation, backbone=backbone)
+            self.out_c = int(self.weights.desc.out_c)
             torch.cuda.synchronize()
             handle = C.c_void_p()
             idx = device.index if device.index is not None else torch.cuda.current_device()
@@ -42,19 +43,19 @@ class Engine:
         return (k + 127) // 128 * 128
 
     def encode_text(self, tokens):
-        """tokens int64 [K,77] (any device) -> L2-normalised text features fp16 [rows_padded(K), 512]."""
+        """tokens int64 [K,77] (any device) -> L2-normalised text features fp16 [rows_padded(K), out_c]."""
         tokens = tokens.to(self.device, torch.int64).contiguous()
         k = tokens.shape[0]
         if tokens.dim() != 2 or tokens.shape[1] != 77:
             raise ValueError("tokens must be int64 [K, 77]")
-        out = torch.empty((self.padded_rows(k), 512), dtype=torch.float16, device=self.device)
+        out = torch.empty((self.padded_rows(k), self.out_c), dtype=torch.float16, device=self.device)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.lseg_encode_text(self.handle, C.c_void_p(tokens.data_ptr()), k,
                                                  C.c_void_p(out.data_ptr()), _stream()))
         return out
 
     def forward(self, x, text, k, text_image_stride=0, out=None):
-        """x fp32 [B,3,H,W] cuda; text fp16 [rows,512] (or [B*stride,512] per-image blocks) -> fp32 [B,K,H,W]."""
+        """x fp32 [B,3,H,W] cuda; text fp16 [rows,out_c] (or [B*stride,out_c] per-image blocks) -> fp32 [B,K,H,W]."""
         if x.device != self.device:
             raise RuntimeError(f"input is on {x.device}, engine is on {self.device}")
         if x.dtype != torch.float32 or x.dim() != 4 or x.shape[1] != 3:

@@ -19,58 +19,64 @@ from collections import OrderedDict
 import torch
 import torch.nn as nn
 
-from .packing import reference_logit_scale
+from .packing import BACKBONES, reference_logit_scale
 from .tokenizer import tokenize
 
 
 # ---------------------------------------------------------------------------------------------
 # parameter holders (names == reference / timm / CLIP module names)
 # ---------------------------------------------------------------------------------------------
-def _vit_large_holder():
+def _vit_holder(cfg):
+    """timm VisionTransformer parameter holder (vit_large_patch16_384 / vit_base_patch32_384)."""
+    D, P, depth, heads = cfg["dim"], cfg["patch"], cfg["depth"], cfg["heads"]
     m = nn.Module()
     m.patch_embed = nn.Module()
-    m.patch_embed.proj = nn.Conv2d(3, 1024, kernel_size=16, stride=16)
+    m.patch_embed.proj = nn.Conv2d(3, D, kernel_size=P, stride=P)
     m.patch_embed.img_size = (384, 384)
-    m.cls_token = nn.Parameter(torch.zeros(1, 1, 1024))
-    m.pos_embed = nn.Parameter(torch.zeros(1, 577, 1024))
+    m.cls_token = nn.Parameter(torch.zeros(1, 1, D))
+    m.pos_embed = nn.Parameter(torch.zeros(1, 1 + (384 // P) ** 2, D))
     nn.init.normal_(m.cls_token, std=0.02)
     nn.init.normal_(m.pos_embed, std=0.02)
     blocks = []
-    for _ in range(24):
+    for _ in range(depth):
         b = nn.Module()
-        b.norm1 = nn.LayerNorm(1024, eps=1e-6)
+        b.norm1 = nn.LayerNorm(D, eps=1e-6)
         b.attn = nn.Module()
-        b.attn.qkv = nn.Linear(1024, 3072)
-        b.attn.proj = nn.Linear(1024, 1024)
-        b.attn.num_heads = 16
-        b.norm2 = nn.LayerNorm(1024, eps=1e-6)
+        b.attn.qkv = nn.Linear(D, 3 * D)
+        b.attn.proj = nn.Linear(D, D)
+        b.attn.num_heads = heads
+        b.norm2 = nn.LayerNorm(D, eps=1e-6)
         b.mlp = nn.Module()
-        b.mlp.fc1 = nn.Linear(1024, 4096)
-        b.mlp.fc2 = nn.Linear(4096, 1024)
+        b.mlp.fc1 = nn.Linear(D, 4 * D)
+        b.mlp.fc2 = nn.Linear(4 * D, D)
         blocks.append(b)
     m.blocks = nn.ModuleList(blocks)
-    m.norm = nn.LayerNorm(1024, eps=1e-6)  # present in checkpoints; dead in forward (lseg_vit.py:108,199)
-    m.patch_size = [16, 16]
+    m.norm = nn.LayerNorm(D, eps=1e-6)  # present in checkpoints; dead in forward (lseg_vit.py:108,199)
+    m.patch_size = [P, P]
     m.start_index = 1
     return m
 
 
-def _readout_holder():
+def _readout_holder(D):
     r = nn.Module()
-    r.project = nn.Sequential(nn.Linear(2048, 1024), nn.GELU())
+    r.project = nn.Sequential(nn.Linear(2 * D, D), nn.GELU())
     return r
 
 
-def _pretrained_holder():
+def _pretrained_holder(cfg):
+    """act_postprocess1..4 with the reference's Sequential indices (0 readout, 3 the 1x1 conv, 4 the resampling op;
+    lseg_vit.py:309-398 for ViT-B/32, :445-520 for ViT-L/16)."""
+    D = cfg["dim"]
     p = nn.Module()
-    p.model = _vit_large_holder()
-    p.act_postprocess1 = nn.Sequential(_readout_holder(), nn.Identity(), nn.Identity(), nn.Conv2d(1024, 256, 1),
-                                       nn.ConvTranspose2d(256, 256, 4, stride=4))
-    p.act_postprocess2 = nn.Sequential(_readout_holder(), nn.Identity(), nn.Identity(), nn.Conv2d(1024, 512, 1),
-                                       nn.ConvTranspose2d(512, 512, 2, stride=2))
-    p.act_postprocess3 = nn.Sequential(_readout_holder(), nn.Identity(), nn.Identity(), nn.Conv2d(1024, 1024, 1))
-    p.act_postprocess4 = nn.Sequential(_readout_holder(), nn.Identity(), nn.Identity(), nn.Conv2d(1024, 1024, 1),
-                                       nn.Conv2d(1024, 1024, 3, stride=2, padding=1))
+    p.model = _vit_holder(cfg)
+    for k in range(4):
+        c, r = cfg["features"][k], cfg["resample"][k]
+        mods = [_readout_holder(D), nn.Identity(), nn.Identity(), nn.Conv2d(D, c, 1)]
+        if r > 0:
+            mods.append(nn.ConvTranspose2d(c, c, r, stride=r))
+        elif r == -2:
+            mods.append(nn.Conv2d(c, c, 3, stride=2, padding=1))
+        setattr(p, f"act_postprocess{k + 1}", nn.Sequential(*mods))
     return p
 
 
@@ -83,9 +89,9 @@ def _rcu_holder():
     return u
 
 
-def _scratch_holder(out_c):
+def _scratch_holder(out_c, features=(256, 512, 1024, 1024)):
     s = nn.Module()
-    for k, cin in enumerate((256, 512, 1024, 1024)):
+    for k, cin in enumerate(features):
         setattr(s, f"layer{k + 1}_rn", nn.Conv2d(cin, 256, 3, padding=1, bias=False))
     for k in range(1, 5):
         f = nn.Module()
@@ -99,27 +105,28 @@ def _scratch_holder(out_c):
 
 
 class _ClipTextHolder(nn.Module):
-    """CLIP ViT-B/32 text tower parameters; `encode_text` runs on the engine of the owning net."""
+    """CLIP text tower parameters (ViT-B/32: width 512, 8 heads, embedding 512; RN50x16: 768, 12, 768); `encode_text` runs
+    on the engine of the owning net."""
 
-    def __init__(self):
+    def __init__(self, width=512, heads=8, embed_dim=512):
         super().__init__()
-        self.positional_embedding = nn.Parameter(torch.empty(77, 512).normal_(std=0.01))
-        self.text_projection = nn.Parameter(torch.empty(512, 512).normal_(std=512 ** -0.5))
+        self.positional_embedding = nn.Parameter(torch.empty(77, width).normal_(std=0.01))
+        self.text_projection = nn.Parameter(torch.empty(width, embed_dim).normal_(std=width ** -0.5))
         self.logit_scale = nn.Parameter(torch.ones([]) * 2.6592600)
-        self.token_embedding = nn.Embedding(49408, 512)
+        self.token_embedding = nn.Embedding(49408, width)
         nn.init.normal_(self.token_embedding.weight, std=0.02)
         blocks = []
         for _ in range(12):
             b = nn.Module()
-            b.attn = nn.MultiheadAttention(512, 8)
-            b.ln_1 = nn.LayerNorm(512)
-            b.mlp = nn.Sequential(OrderedDict([("c_fc", nn.Linear(512, 2048)), ("gelu", nn.Identity()),
-                                               ("c_proj", nn.Linear(2048, 512))]))
-            b.ln_2 = nn.LayerNorm(512)
+            b.attn = nn.MultiheadAttention(width, heads)
+            b.ln_1 = nn.LayerNorm(width)
+            b.mlp = nn.Sequential(OrderedDict([("c_fc", nn.Linear(width, 4 * width)), ("gelu", nn.Identity()),
+                                               ("c_proj", nn.Linear(4 * width, width))]))
+            b.ln_2 = nn.LayerNorm(width)
             blocks.append(b)
         self.transformer = nn.Module()
         self.transformer.resblocks = nn.Sequential(*blocks)
-        self.ln_final = nn.LayerNorm(512)
+        self.ln_final = nn.LayerNorm(width)
         self._owner = None
 
     def encode_text(self, text):
@@ -138,10 +145,13 @@ _IGNORED_PREFIXES = ("clip_pretrained.visual.", "pretrained.model.head.", "pretr
 class _LSegBase(nn.Module):
     def _init_common(self, **kwargs):
         backbone = kwargs.get("backbone", "clip_vitl16_384")
-        if backbone != "clip_vitl16_384":
-            # same failure mode as lseg_blocks.py:53-55; other backbones are out of scope
+        if backbone not in BACKBONES:
+            # same failure mode as lseg_blocks.py:53-55. Built here: the three backbones of lseg_net.py:119-123
+            # (clip_vitl16_384, clipRN50x16_vitl16_384, clip_vitb32_384); clip_resnet101 (lseg_blocks.py:46-52) is not.
             print(f"Backbone '{backbone}' not implemented")
             assert False
+        self.backbone = backbone
+        cfg = BACKBONES[backbone]
         self.arch_option = kwargs.get("arch_option", 0) or 0
         if self.arch_option not in (0, 1, 2):
             raise ValueError(f"arch_option {self.arch_option}: the reference defines 0, 1 (bottleneck_block) and 2 "
@@ -151,13 +161,13 @@ class _LSegBase(nn.Module):
         if self.arch_option and self.activation not in ("relu", "lrelu", "tanh"):
             raise ValueError(f"activation '{self.activation}': relu, lrelu or tanh (lseg_net.py:45-50)")
         self.channels_last = False
-        self.out_c = 512
+        self.out_c = cfg["text"][2]  # lseg_net.py:142-146: 768 with the RN50x16 text tower, else 512
         # holders are built on the meta device (no per-module default init: 400 M parameters would take
         # ~11 s of single-threaded CPU RNG) and then materialised with one cheap pass, see _fast_init
         with torch.device("meta"):
-            self.clip_pretrained = _ClipTextHolder()
-            self.pretrained = _pretrained_holder()
-            self.scratch = _scratch_holder(self.out_c)
+            self.clip_pretrained = _ClipTextHolder(*cfg["text"])
+            self.pretrained = _pretrained_holder(cfg)
+            self.scratch = _scratch_holder(self.out_c, cfg["features"])
             if self.arch_option in (1, 2):  # scratch.head_block.depthwise.depthwise = Conv2d(1, 1, 3, padding=1)
                 hb = nn.Module()
                 hb.depthwise = nn.Module()
@@ -266,7 +276,7 @@ class _LSegBase(nn.Module):
                     master = shared["master"]()
                     sd = master.state_dict() if master is not None else sd
                 eng = Engine(sd, device, arch_option=self.arch_option, block_depth=self.block_depth,
-                             activation=self.activation)
+                             activation=self.activation, backbone=self.backbone)
                 shared["engines"][device] = eng
             return eng
 
@@ -354,7 +364,7 @@ class LSegNetZS(_LSegBase):
             self.load(path)
 
     def _pair_features(self, engine):
-        """L2-normalised fp16 features of every ['others', name] pair, [2 * n_labels, 512], encoded in ONE text-tower
+        """L2-normalised fp16 features of every ['others', name] pair, [2 * n_labels, out_c], encoded in ONE text-tower
         call per device (the reference re-encodes the pair of every image on every forward, lseg_net_zs.py:196)."""
         tokens = torch.cat(self.texts, 0)
         return self._text_features(engine, tokens)
@@ -370,7 +380,7 @@ class LSegNetZS(_LSegBase):
         # > 256 text rows: the engine falls back to one 128-row weight tile per image starting at that image's
         # block, so the last blocks need 128 readable rows behind them
         extra = 128 if rows.numel() > 256 else 0
-        text = torch.zeros((engine.padded_rows(rows.numel()) + extra, 512), dtype=torch.float16, device=device)
+        text = torch.zeros((engine.padded_rows(rows.numel()) + extra, self.out_c), dtype=torch.float16, device=device)
         text[: rows.numel()] = pairs.index_select(0, rows)
         return text
 

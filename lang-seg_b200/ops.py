@@ -165,10 +165,10 @@ def layernorm(x, gamma, beta, eps):
     return y
 
 
-def patchify(x):
+def patchify(x, patch=16):
     B, _, H, W = x.shape
-    a = torch.empty((B * (H // 16) * (W // 16), 768), dtype=torch.float16, device=x.device)
-    check(load().lseg_patchify(_ptr(x, torch.float32), _ptr(a), B, H, W, _stream()))
+    a = torch.empty((B * (H // patch) * (W // patch), 3 * patch * patch), dtype=torch.float16, device=x.device)
+    check(load().lseg_patchify(_ptr(x, torch.float32), _ptr(a), B, H, W, patch, _stream()))
     return a
 
 

@@ -9,8 +9,8 @@ Layouts
   * 3x3 convs are tap-major: [N, (ky, kx, c)]  (the implicit-GEMM K loop walks taps, then channels);
   * ConvTranspose2d with kernel == stride becomes a GEMM with N = (i, j, co) and a depth-to-space
     store; its bias is expanded to [s*s*cout];
-  * ProjectReadout's Linear(2048->1024) is split into the token half W[:, :1024] and the cls half
-    W[:, 1024:] (+bias) — exact up to summation order (SURVEY.md section 2b k10);
+  * ProjectReadout's Linear(2D->D) is split into the token half W[:, :D] and the cls half
+    W[:, D:] (+bias) — exact up to summation order (SURVEY.md section 2b k10);
   * eval-mode BatchNorm is folded to per-channel (scale, shift) applied in the GEMM epilogue in fp32.
 """
 import math
@@ -22,7 +22,39 @@ from . import _lib
 
 VIT_DEPTH = _lib.VIT_DEPTH
 TEXT_DEPTH = _lib.TEXT_DEPTH
-HOOKS = (5, 11, 17, 23)  # modules/models/lseg_net.py:119-123
+HOOKS = (5, 11, 17, 23)  # modules/models/lseg_net.py:119-123 (clip_vitl16_384)
+
+# Image backbones of LSeg.__init__ (lseg_net.py:119-123) and how modules/models/lseg_vit.py builds them:
+# _make_pretrained_clip_vitl16_384 (:221-238 + _make_vit_b16_backbone :408-532) and _make_pretrained_clip_vitb32_384
+# (:259-273 + _make_vit_b32_backbone :275-405). `resample` per level: s > 0 ConvTranspose2d(k=s, stride=s), 0 nothing,
+# -2 Conv2d 3x3 stride 2. Both use the CLIP ViT-B/32 text tower.
+# `text`: (transformer_width, heads, embed_dim) of the CLIP model whose text tower is used — ViT-B/32 or RN50x16
+# (lseg_vit.py:224, 243, 260); embed_dim is LSeg's out_c (lseg_net.py:142-146).
+BACKBONES = {
+    "clip_vitl16_384": dict(dim=1024, depth=24, heads=16, patch=16, hooks=(5, 11, 17, 23),
+                            features=(256, 512, 1024, 1024), resample=(4, 2, 0, -2), timm="vit_large_patch16_384",
+                            clip="ViT-B/32", text=(512, 8, 512)),
+    "clipRN50x16_vitl16_384": dict(dim=1024, depth=24, heads=16, patch=16, hooks=(5, 11, 17, 23),
+                                   features=(256, 512, 1024, 1024), resample=(4, 2, 0, -2), timm="vit_large_patch16_384",
+                                   clip="RN50x16", text=(768, 12, 768)),
+    "clip_vitb32_384": dict(dim=768, depth=12, heads=12, patch=32, hooks=(2, 5, 8, 11),
+                            features=(96, 192, 384, 768), resample=(8, 4, 2, 0), timm="vit_base_patch32_384",
+                            clip="ViT-B/32", text=(512, 8, 512)),
+}
+
+
+def stored_channels(c):
+    """Channel count as the engine stores it: the next multiple of 64 (TMA boxes of the implicit-GEMM convs and the K
+    loop work in 64-channel chunks); the pad carries zero weights and zero bias, so it stays exactly zero."""
+    return (c + 63) // 64 * 64
+
+
+def _pad_to(t, dim, n):
+    if t.shape[dim] == n:
+        return t
+    shape = list(t.shape)
+    shape[dim] = n - t.shape[dim]
+    return torch.cat([t, torch.zeros(shape, dtype=t.dtype, device=t.device)], dim=dim)
 
 
 def _pad_rows(w, mult=128):
@@ -63,11 +95,14 @@ def reference_logit_scale():
 class PackedWeights:
     """Owns the packed tensors and the ctypes descriptor that points into them."""
 
-    def __init__(self, state_dict, device, arch_option=0, block_depth=0, activation="lrelu"):
+    def __init__(self, state_dict, device, arch_option=0, block_depth=0, activation="lrelu", backbone="clip_vitl16_384"):
+        if backbone not in BACKBONES:
+            raise ValueError(f"backbone {backbone!r}: this engine builds {sorted(BACKBONES)}")
         self.device = torch.device(device)
+        self.backbone = backbone
         self._keep = []
         self.desc = _lib.Weights()
-        self._pack(state_dict)
+        self._pack(state_dict, BACKBONES[backbone])
         d = self.desc
         d.arch_option, d.block_depth = int(arch_option or 0), int(block_depth or 0)
         d.head_act = _lib.HEAD_ACT[activation] if d.arch_option else 0
@@ -102,15 +137,20 @@ class PackedWeights:
             slot.b = None
 
     # -- packing -------------------------------------------------------------------------------
-    def _pack(self, sd):
+    def _pack(self, sd, cfg):
         d = self.desc
         p = "pretrained.model."
-        self._linear(d.patch, sd[p + "patch_embed.proj.weight"].reshape(1024, 768), sd[p + "patch_embed.proj.bias"])
-        d.cls_token = self._f32(sd[p + "cls_token"].reshape(1024))
-        pos = sd[p + "pos_embed"].reshape(-1, 1024)
+        D, P = cfg["dim"], cfg["patch"]
+        d.vit_dim, d.vit_depth, d.vit_heads, d.patch_size = D, cfg["depth"], cfg["heads"], P
+        pw = sd[p + "patch_embed.proj.weight"]
+        if tuple(pw.shape) != (D, 3, P, P):
+            raise ValueError(f"{self.backbone}: patch_embed.proj.weight is {tuple(pw.shape)}, expected {(D, 3, P, P)}")
+        self._linear(d.patch, pw.reshape(D, 3 * P * P), sd[p + "patch_embed.proj.bias"])
+        d.cls_token = self._f32(sd[p + "cls_token"].reshape(D))
+        pos = sd[p + "pos_embed"].reshape(-1, D)
         d.pos_embed = self._f32(pos)
         d.pos_grid = int(round(math.sqrt(pos.shape[0] - 1)))
-        for i in range(VIT_DEPTH):
+        for i in range(cfg["depth"]):
             b = f"{p}blocks.{i}."
             blk = d.blocks[i]
             blk.ln1_g, blk.ln1_b = self._f32(sd[b + "norm1.weight"]), self._f32(sd[b + "norm1.bias"])
@@ -120,21 +160,27 @@ class PackedWeights:
             self._linear(blk.fc1, sd[b + "mlp.fc1.weight"], sd[b + "mlp.fc1.bias"])
             self._linear(blk.fc2, sd[b + "mlp.fc2.weight"], sd[b + "mlp.fc2.bias"])
         for k in range(4):
-            d.hooks[k] = HOOKS[k]
+            d.hooks[k] = cfg["hooks"][k]
             q = f"pretrained.act_postprocess{k + 1}."
             w = sd[q + "0.project.0.weight"]
-            self._linear(d.readout_tok[k], w[:, :1024], None)
-            self._linear(d.readout_cls[k], w[:, 1024:], sd[q + "0.project.0.bias"])
-            c = sd[q + "3.weight"]
-            self._linear(d.post_conv1x1[k], c.reshape(c.shape[0], c.shape[1]), sd[q + "3.bias"])
-        w = sd["pretrained.act_postprocess1.4.weight"]
-        self._linear(d.post1_deconv, deconv_to_gemm(w), sd["pretrained.act_postprocess1.4.bias"].repeat(16))
-        w = sd["pretrained.act_postprocess2.4.weight"]
-        self._linear(d.post2_deconv, deconv_to_gemm(w), sd["pretrained.act_postprocess2.4.bias"].repeat(4))
-        self._linear(d.post4_conv, conv3x3_to_gemm(sd["pretrained.act_postprocess4.4.weight"]),
-                     sd["pretrained.act_postprocess4.4.bias"])
+            self._linear(d.readout_tok[k], w[:, :D], None)
+            self._linear(d.readout_cls[k], w[:, D:], sd[q + "0.project.0.bias"])
+            c, cp = cfg["features"][k], stored_channels(cfg["features"][k])
+            d.post_channels[k], d.post_resample[k] = cp, cfg["resample"][k]
+            cw = sd[q + "3.weight"]
+            if cw.shape[0] != c:
+                raise ValueError(f"{self.backbone}: act_postprocess{k + 1}.3 has {cw.shape[0]} channels, expected {c}")
+            self._linear(d.post_conv1x1[k], _pad_to(cw.reshape(c, D), 0, cp), _pad_to(sd[q + "3.bias"], 0, cp))
+            r = cfg["resample"][k]
+            if r > 0:    # ConvTranspose2d [cin, cout, r, r]
+                w = _pad_to(_pad_to(sd[q + "4.weight"], 0, cp), 1, cp)
+                self._linear(d.post_resample_w[k], deconv_to_gemm(w), _pad_to(sd[q + "4.bias"], 0, cp).repeat(r * r))
+            elif r == -2:  # Conv2d 3x3 stride 2 [cout, cin, 3, 3]
+                w = _pad_to(_pad_to(sd[q + "4.weight"], 0, cp), 1, cp)
+                self._linear(d.post_resample_w[k], conv3x3_to_gemm(w), _pad_to(sd[q + "4.bias"], 0, cp))
         for k in range(4):
-            self._linear(d.layer_rn[k], conv3x3_to_gemm(sd[f"scratch.layer{k + 1}_rn.weight"]), None)
+            self._linear(d.layer_rn[k], conv3x3_to_gemm(_pad_to(sd[f"scratch.layer{k + 1}_rn.weight"], 1,
+                                                                stored_channels(cfg["features"][k]))), None)
             q = f"scratch.refinenet{k + 1}."
             for slot, unit in ((d.rcu1[k], "resConfUnit1."), (d.rcu2[k], "resConfUnit2.")):
                 self._linear(slot.conv1, conv3x3_to_gemm(sd[q + unit + "conv1.weight"]), None)
@@ -146,6 +192,11 @@ class PackedWeights:
             oc = sd[q + "out_conv.weight"]
             self._linear(d.out_conv[k], oc.reshape(oc.shape[0], oc.shape[1]), sd[q + "out_conv.bias"])
         h1 = sd["scratch.head1.weight"]
+        d.text_width, d.text_heads, d.out_c = cfg["text"]
+        if h1.shape[0] != d.out_c or tuple(sd["clip_pretrained.text_projection"].shape) != (d.text_width, d.out_c):
+            raise ValueError(f"{self.backbone}: head1 has {h1.shape[0]} channels / text_projection is "
+                             f"{tuple(sd['clip_pretrained.text_projection'].shape)}, expected out_c {d.out_c}, "
+                             f"text width {d.text_width} (CLIP {cfg['clip']})")
         self._linear(d.head1, h1.reshape(h1.shape[0], h1.shape[1]), sd["scratch.head1.bias"])
         d.logit_scale = reference_logit_scale()
         # CLIP text tower: Linear / MHA weights are fp16 in the reference (clip.load on cuda)

@@ -86,8 +86,11 @@ class LogitsGather:
     available; also what the gloo CPU tests exercise).
     """
 
-    def __init__(self, engine, B, K, H, W, root=0, mode="p2p_copy", group=None, timeout_ms=30000):
+    def __init__(self, engine, B, K, H, W, root=0, mode="p2p_copy", group=None, timeout_ms=30000, materialize=True):
         self.engine, self.B, self.K, self.H, self.W = engine, B, K, H, W
+        # materialize=False: root keeps the gathered fp16 low-res logits (`lowres()`), the exact information content of
+        # the step, and does not expand them to fp32 — what a consumer that takes the argmax / a crop would want
+        self.materialize = materialize
         self.group, self.root, self.timeout_ms = group, root, timeout_ms
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -101,7 +104,7 @@ class LogitsGather:
         self.mode = mode if self.world > 1 else "single"
         self.fallback_reason = None
         self.out = None
-        if self.rank == root or self.world == 1:
+        if (self.rank == root or self.world == 1) and materialize:
             self.out = torch.empty((self.world * B, K, H, W), dtype=torch.float32, device=self.device)
         if self.mode.startswith("p2p"):
             try:
@@ -252,6 +255,9 @@ class LogitsGather:
     def _upsample(self, lr_ptr):
         import ctypes as C
         from . import _lib
+        self.lr_ptr = lr_ptr
+        if not self.materialize:
+            return
         lib = _lib.load()
         _lib.check(lib.lseg_upsample2x_nchw(C.c_void_p(lr_ptr), C.c_void_p(self.out.data_ptr()),
                                             self.world * self.B * self.K, self.h2, self.w2,

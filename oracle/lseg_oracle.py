@@ -23,6 +23,16 @@ import torch.nn.functional as F
 
 VIT_HOOKS = (5, 11, 17, 23)  # modules/models/lseg_net.py:119-123
 
+# backbone -> (hooks, heads, per-level resampling after the 1x1 conv). lseg_net.py:119-123 (hooks),
+# lseg_vit.py:221-238 + 408-532 (ViT-L/16: ConvT x4, ConvT x2, -, Conv 3x3 stride 2),
+# lseg_vit.py:259-405 (ViT-B/32: ConvT x8, ConvT x4, ConvT x2, -). Patch size / width / depth are read off the weights.
+# text_heads: heads of the CLIP text tower in use (ViT-B/32: 8; RN50x16: 12 — width 768, lseg_vit.py:243).
+BACKBONES = {
+    "clip_vitl16_384": dict(hooks=(5, 11, 17, 23), heads=16, resample=(4, 2, 0, -2), text_heads=8),
+    "clipRN50x16_vitl16_384": dict(hooks=(5, 11, 17, 23), heads=16, resample=(4, 2, 0, -2), text_heads=12),
+    "clip_vitb32_384": dict(hooks=(2, 5, 8, 11), heads=12, resample=(8, 4, 2, 0), text_heads=8),
+}
+
 
 # ------------------------------------------------------------------------------------------------
 # image trunk
@@ -49,10 +59,10 @@ def vit_attention(x, sd, prefix, num_heads=16):
     return F.linear(x, sd[prefix + "proj.weight"], sd[prefix + "proj.bias"])
 
 
-def vit_block(x, sd, prefix):
+def vit_block(x, sd, prefix, num_heads=16):
     """timm 0.4.12 Block.forward: x + Attn(LN1(x)); x + Mlp(LN2(x)); LN eps 1e-6, exact-erf GELU."""
     h = F.layer_norm(x, (x.shape[-1],), sd[prefix + "norm1.weight"], sd[prefix + "norm1.bias"], 1e-6)
-    x = x + vit_attention(h, sd, prefix + "attn.")
+    x = x + vit_attention(h, sd, prefix + "attn.", num_heads)
     h = F.layer_norm(x, (x.shape[-1],), sd[prefix + "norm2.weight"], sd[prefix + "norm2.bias"], 1e-6)
     h = F.linear(h, sd[prefix + "mlp.fc1.weight"], sd[prefix + "mlp.fc1.bias"])
     h = F.gelu(h)
@@ -60,21 +70,22 @@ def vit_block(x, sd, prefix):
     return x + h
 
 
-def vit_forward_flex(x, sd, hooks=VIT_HOOKS, depth=24):
+def vit_forward_flex(x, sd, hooks=VIT_HOOKS, depth=24, num_heads=16):
     """modules/models/lseg_vit.py:166-201 + the forward hooks of :421-426. Returns the four taps
     (outputs of blocks `hooks`, i.e. the un-normed residual stream). The final self.norm (:199) only
     feeds `glob`, which forward_vit discards (:108), so it is not computed."""
     p = "pretrained.model."
     b, c, h, w = x.shape
-    pos_embed = resize_pos_embed(sd[p + "pos_embed"], h // 16, w // 16)
-    x = F.conv2d(x, sd[p + "patch_embed.proj.weight"], sd[p + "patch_embed.proj.bias"], stride=16)
+    patch = sd[p + "patch_embed.proj.weight"].shape[-1]  # model.patch_size (lseg_vit.py:295 / :526)
+    pos_embed = resize_pos_embed(sd[p + "pos_embed"], h // patch, w // patch)
+    x = F.conv2d(x, sd[p + "patch_embed.proj.weight"], sd[p + "patch_embed.proj.bias"], stride=patch)
     x = x.flatten(2).transpose(1, 2)
     cls_tokens = sd[p + "cls_token"].expand(b, -1, -1)
     x = torch.cat((cls_tokens, x), dim=1)
     x = x + pos_embed
     taps = []
     for i in range(depth):
-        x = vit_block(x, sd, f"{p}blocks.{i}.")
+        x = vit_block(x, sd, f"{p}blocks.{i}.", num_heads)
         if i in hooks:
             taps.append(x)
         if i == max(hooks):
@@ -89,23 +100,24 @@ def project_readout(x, sd, prefix):
     return F.gelu(F.linear(features, sd[prefix + "project.0.weight"], sd[prefix + "project.0.bias"]))
 
 
-def forward_vit(x, sd, taps_out=None):
-    """modules/models/lseg_vit.py:104-146 with the act_postprocess stacks of :442-522."""
+def forward_vit(x, sd, taps_out=None, backbone="clip_vitl16_384"):
+    """modules/models/lseg_vit.py:104-146 with the act_postprocess stacks of :442-522 (ViT-L/16) / :309-398 (ViT-B/32)."""
+    cfg = BACKBONES[backbone]
     b, c, h, w = x.shape
-    taps = vit_forward_flex(x, sd)
+    patch = sd["pretrained.model.patch_embed.proj.weight"].shape[-1]
+    taps = vit_forward_flex(x, sd, cfg["hooks"], max(cfg["hooks"]) + 1, cfg["heads"])
     if taps_out is not None:
         taps_out.extend(taps)
     layers = []
     for k, tap in enumerate(taps):
         q = f"pretrained.act_postprocess{k + 1}."
         y = project_readout(tap, sd, q + "0.").transpose(1, 2)
-        y = y.unflatten(2, (h // 16, w // 16))
+        y = y.unflatten(2, (h // patch, w // patch))
         y = F.conv2d(y, sd[q + "3.weight"], sd[q + "3.bias"])
-        if k == 0:
-            y = F.conv_transpose2d(y, sd[q + "4.weight"], sd[q + "4.bias"], stride=4)
-        elif k == 1:
-            y = F.conv_transpose2d(y, sd[q + "4.weight"], sd[q + "4.bias"], stride=2)
-        elif k == 3:
+        r = cfg["resample"][k]
+        if r > 0:
+            y = F.conv_transpose2d(y, sd[q + "4.weight"], sd[q + "4.bias"], stride=r)
+        elif r == -2:
             y = F.conv2d(y, sd[q + "4.weight"], sd[q + "4.bias"], stride=2, padding=1)
         layers.append(y)
     return layers
@@ -269,15 +281,15 @@ def output_conv(out):
 
 @torch.no_grad()
 def lseg_forward(x, tokens, sd, text_weights=None, return_stages=False, arch_option=0, block_depth=0,
-                 activation="lrelu"):
+                 activation="lrelu", backbone="clip_vitl16_384"):
     """LSeg.forward (modules/models/lseg_net.py:160-205). x fp32 [B,3,H,W], tokens int64 [K,77]."""
     if x.shape[2] % 32 or x.shape[3] % 32:
         raise ValueError("H and W must be multiples of 32 (even token grid)")
     tw = text_weights if text_weights is not None else clip_text_weights_fp16(sd)
     taps = []
-    layers = forward_vit(x, sd, taps)
+    layers = forward_vit(x, sd, taps, backbone)
     path_1 = decoder(layers, sd)
-    text_features = clip_encode_text(tokens, tw)
+    text_features = clip_encode_text(tokens, tw, heads=BACKBONES[backbone]["text_heads"])
     low = correlation_head(path_1, text_features, sd)
     if arch_option in (1, 2):
         low = head_block(low, sd, arch_option, block_depth, activation)

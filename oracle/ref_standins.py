@@ -111,9 +111,11 @@ class VisionTransformer(nn.Module):
 
 
 def _timm_create_model(name, pretrained=False, **kw):
-    if name != "vit_large_patch16_384":
-        raise NotImplementedError(name)
-    return VisionTransformer()
+    if name == "vit_large_patch16_384":
+        return VisionTransformer()
+    if name == "vit_base_patch32_384":  # timm 0.4.12 vision_transformer.py: patch 32, dim 768, depth 12, 12 heads
+        return VisionTransformer(patch=32, dim=768, depth=12, heads=12)
+    raise NotImplementedError(name)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -211,9 +213,12 @@ def _convert_weights(model):
 
 
 def _clip_load(name, device="cpu", jit=False):
-    if name != "ViT-B/32":
+    if name == "ViT-B/32":
+        model = ClipTextOnly()
+    elif name == "RN50x16":  # CLIP model card: embed_dim 768, transformer_width 768, 12 heads, 12 layers
+        model = ClipTextOnly(embed_dim=768, width=768, heads=12)
+    else:
         raise NotImplementedError(name)
-    model = ClipTextOnly()
     _convert_weights(model)  # what clip.load(device='cuda') leaves behind (lseg_vit.py:224)
     return model.eval(), None
 
@@ -279,14 +284,14 @@ def install(with_lightning_stack=True):
         sys.path.insert(0, REFERENCE_ROOT)
 
 
-def build_reference_net(state_dict, labels, arch_option=0, block_depth=0, activation="lrelu"):
+def build_reference_net(state_dict, labels, arch_option=0, block_depth=0, activation="lrelu", backbone="clip_vitl16_384"):
     """Construct the UNMODIFIED reference LSegNet (modules/models/lseg_net.py:208-226) on CPU and load `state_dict`."""
     install()
     cwd = os.getcwd()
     os.chdir(REFERENCE_ROOT)
     try:
         from modules.models.lseg_net import LSegNet
-        net = LSegNet(labels=labels, backbone="clip_vitl16_384", features=256, crop_size=480, arch_option=arch_option,
+        net = LSegNet(labels=labels, backbone=backbone, features=256, crop_size=480, arch_option=arch_option,
                       block_depth=block_depth, activation=activation)
     finally:
         os.chdir(cwd)

@@ -43,17 +43,32 @@ class _Gen:
         return self.uniform(shape, -b, b)
 
 
-def make_state_dict(seed=0, with_clip_visual_stub=False, head_block=False):
-    """fp32 state dict of LSegNet(backbone='clip_vitl16_384') — keys per SURVEY.md Appendix C."""
+# image backbones (modules/models/lseg_vit.py:221-238 + 408-532; 259-405): trunk geometry, reassemble channels and
+# the resampling op behind each 1x1 conv (s > 0 ConvTranspose2d k=s stride=s, -2 Conv2d 3x3 stride 2, 0 none)
+# `text`: (transformer_width, embed_dim) of the CLIP text tower — ViT-B/32's or RN50x16's (lseg_vit.py:224, 243, 260)
+BACKBONE_SHAPES = {
+    "clip_vitl16_384": dict(dim=1024, depth=24, patch=16, feats=(256, 512, 1024, 1024), resample=(4, 2, 0, -2),
+                            text=(512, 512)),
+    "clipRN50x16_vitl16_384": dict(dim=1024, depth=24, patch=16, feats=(256, 512, 1024, 1024), resample=(4, 2, 0, -2),
+                                   text=(768, 768)),
+    "clip_vitb32_384": dict(dim=768, depth=12, patch=32, feats=(96, 192, 384, 768), resample=(8, 4, 2, 0),
+                            text=(512, 512)),
+}
+
+
+def make_state_dict(seed=0, with_clip_visual_stub=False, head_block=False, backbone="clip_vitl16_384"):
+    """fp32 state dict of LSegNet(backbone=...) — keys per SURVEY.md Appendix C. The draw order for the default
+    backbone is frozen (the committed golden fixtures were generated from it)."""
     g = _Gen(seed)
     sd = {}
-    D = VIT_DIM
+    shp = BACKBONE_SHAPES[backbone]
+    D, P, depth = shp["dim"], shp["patch"], shp["depth"]
     p = "pretrained.model."
     sd[p + "cls_token"] = g.normal((1, 1, D), 0.02)
-    sd[p + "pos_embed"] = g.normal((1, 577, D), 0.02)
-    sd[p + "patch_embed.proj.weight"] = g.normal((D, 3, 16, 16), 0.02)
+    sd[p + "pos_embed"] = g.normal((1, 1 + (384 // P) ** 2, D), 0.02)
+    sd[p + "patch_embed.proj.weight"] = g.normal((D, 3, P, P), 0.02)
     sd[p + "patch_embed.proj.bias"] = g.normal((D,), 0.02)
-    for i in range(VIT_DEPTH):
+    for i in range(depth):
         b = f"{p}blocks.{i}."
         for n in ("norm1", "norm2"):
             sd[b + n + ".weight"] = g.normal((D,), 0.1, 1.0)
@@ -68,19 +83,22 @@ def make_state_dict(seed=0, with_clip_visual_stub=False, head_block=False):
         sd[b + "mlp.fc2.bias"] = g.normal((D,), 0.02)
     sd[p + "norm.weight"] = g.normal((D,), 0.1, 1.0)
     sd[p + "norm.bias"] = g.normal((D,), 0.05)
-    feats = [256, 512, 1024, 1024]
+    feats = list(shp["feats"])
     for k in range(4):
         q = f"pretrained.act_postprocess{k + 1}."
         sd[q + "0.project.0.weight"] = g.kaiming((D, 2 * D))
         sd[q + "0.project.0.bias"] = g.uniform((D,), -0.02, 0.02)
         sd[q + "3.weight"] = g.kaiming((feats[k], D, 1, 1))
         sd[q + "3.bias"] = g.uniform((feats[k],), -0.03, 0.03)
-    sd["pretrained.act_postprocess1.4.weight"] = g.kaiming((256, 256, 4, 4))
-    sd["pretrained.act_postprocess1.4.bias"] = g.uniform((256,), -0.03, 0.03)
-    sd["pretrained.act_postprocess2.4.weight"] = g.kaiming((512, 512, 2, 2))
-    sd["pretrained.act_postprocess2.4.bias"] = g.uniform((512,), -0.03, 0.03)
-    sd["pretrained.act_postprocess4.4.weight"] = g.kaiming((1024, 1024, 3, 3))
-    sd["pretrained.act_postprocess4.4.bias"] = g.uniform((1024,), -0.01, 0.01)
+    for k in range(4):
+        r, c = shp["resample"][k], feats[k]
+        q = f"pretrained.act_postprocess{k + 1}.4."
+        if r > 0:
+            sd[q + "weight"] = g.kaiming((c, c, r, r))
+            sd[q + "bias"] = g.uniform((c,), -0.03, 0.03)
+        elif r == -2:
+            sd[q + "weight"] = g.kaiming((c, c, 3, 3))
+            sd[q + "bias"] = g.uniform((c,), -0.01, 0.01)
     for k in range(4):
         sd[f"scratch.layer{k + 1}_rn.weight"] = g.kaiming((256, feats[k], 3, 3))
     for k in range(1, 5):
@@ -95,13 +113,13 @@ def make_state_dict(seed=0, with_clip_visual_stub=False, head_block=False):
                 sd[f"{q}{u}.bn{c}.running_mean"] = g.normal((256,), 0.1)
                 sd[f"{q}{u}.bn{c}.running_var"] = g.uniform((256,), 0.5, 1.5)
                 sd[f"{q}{u}.bn{c}.num_batches_tracked"] = torch.tensor(100, dtype=torch.int64)
-    sd["scratch.head1.weight"] = g.kaiming((512, 256, 1, 1))
-    sd["scratch.head1.bias"] = g.uniform((512,), -0.06, 0.06)
+    Wd, out_c = shp["text"]
+    sd["scratch.head1.weight"] = g.kaiming((out_c, 256, 1, 1))
+    sd["scratch.head1.bias"] = g.uniform((out_c,), -0.06, 0.06)
     # CLIP ViT-B/32 text tower (CLIP.initialize_parameters scales)
     c = "clip_pretrained."
-    Wd = TEXT_WIDTH
     sd[c + "positional_embedding"] = g.normal((CONTEXT, Wd), 0.01)
-    sd[c + "text_projection"] = g.normal((Wd, 512), Wd ** -0.5)
+    sd[c + "text_projection"] = g.normal((Wd, out_c), Wd ** -0.5)
     sd[c + "logit_scale"] = torch.tensor(float(np.log(1 / 0.07)))
     sd[c + "token_embedding.weight"] = g.normal((VOCAB, Wd), 0.02)
     proj_std = (Wd ** -0.5) * ((2 * TEXT_DEPTH) ** -0.5)

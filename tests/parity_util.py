@@ -17,10 +17,11 @@ NET_KW = dict(backbone="clip_vitl16_384", features=256, crop_size=480, arch_opti
 _STATE = {}
 
 
-def state_dict(seed=0):
-    if seed not in _STATE:
-        _STATE[seed] = synth.make_state_dict(seed)
-    return _STATE[seed]
+def state_dict(seed=0, backbone="clip_vitl16_384"):
+    key = seed if backbone == "clip_vitl16_384" else (seed, backbone)
+    if key not in _STATE:
+        _STATE[key] = synth.make_state_dict(seed, backbone=backbone)
+    return _STATE[key]
 
 
 def rel_err(got, ref):

@@ -30,7 +30,7 @@ def test_header_symbols_exported(lib):
     missing = [s for s in declared if not hasattr(lib, s)]
     assert not missing, f"declared in include/lseg_b200.h but not exported: {missing}"
     assert sorted(_lib.SYMBOLS) == declared, "ctypes binding list out of sync with the header"
-    assert lib.lseg_abi_version() == _lib.ABI_VERSION == 2
+    assert lib.lseg_abi_version() == _lib.ABI_VERSION == 3
 
 
 def test_no_torch_types_in_signatures():
@@ -46,16 +46,29 @@ def test_library_has_no_libcuda_or_torch_dependency():
     assert "libtorch" not in out and "libcuda.so" not in out and "libc10" not in out
 
 
-def test_struct_layout_matches_header():
-    """The ctypes mirrors must have the C layout of the header structs (spot-check sizes/offsets)."""
+def test_struct_layout_matches_header(tmp_path):
+    """The ctypes mirrors must have the C layout of the header structs: a C program compiled against include/lseg_b200.h
+    prints sizeof / offsetof of every lseg_weights member, compared with the ctypes fields one by one."""
+    import subprocess
     from lseg_b200 import _lib
     assert C.sizeof(_lib.LinearW) == 32
     assert C.sizeof(_lib.VitBlockW) == 4 * 8 + 4 * 32
     assert C.sizeof(_lib.RcuW) == 2 * 32 + 4 * 8
     assert _lib.GemmArgs.lda.offset == 8 and _lib.GemmArgs.w.offset == 24
-    # lseg_weights: first member patch (32 B), then two pointers, int pos_grid (+pad), 24 blocks ...
-    assert _lib.Weights.blocks.offset == 32 + 8 + 8 + 8
-    assert _lib.Weights.hooks.offset == _lib.Weights.blocks.offset + 24 * 160
+    cname = {"in_": "in"}
+    fields = [f[0] for f in _lib.Weights._fields_]
+    prog = ['#include <stdio.h>', '#include <stddef.h>', '#include "lseg_b200.h"', 'int main(void) {',
+            '  printf("sizeof %zu\\n", sizeof(lseg_weights));']
+    prog += [f'  printf("{f} %zu\\n", offsetof(lseg_weights, {cname.get(f, f)}));' for f in fields]
+    prog += ['  printf("eval_window %zu\\n", sizeof(lseg_eval_window));', '  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(prog))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    assert int(out["sizeof"]) == C.sizeof(_lib.Weights)
+    for f in fields:
+        assert int(out[f]) == getattr(_lib.Weights, f).offset, f
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

@@ -89,7 +89,7 @@ def _report(name, d):
 def _padded_text(eng, feats):
     """oracle fp16 text features [K,512] -> the engine's operand layout (rows padded to 128, zero rows)."""
     k = feats.shape[0]
-    t = torch.zeros((eng.padded_rows(k), 512), dtype=torch.float16, device="cuda")
+    t = torch.zeros((eng.padded_rows(k), feats.shape[1]), dtype=torch.float16, device="cuda")
     t[:k] = feats.half().cuda()
     return t
 
@@ -247,6 +247,106 @@ def test_forward_vs_oracle(net, B, H, W, K):
     assert full["ok"], d
     if K == 2:  # configs[0]: real margins -> the mask is bit-identical
         assert tf["mismatch"] == 0 and full["mismatch"] == 0, d
+
+
+# ------------------------------------------------------------------------------------------------
+# the other backbones of lseg_net.py:119-123
+#   clip_vitb32_384 (lseg_vit.py:259-405): ViT-B/32 trunk (D 768, 12 blocks, 12 heads, patch 32, hooks 2/5/8/11),
+#     reassemble to 96/192/384/768 channels (stored 128/192/384/768) with ConvT x8 / x4 / x2 / none
+#   clipRN50x16_vitl16_384 (lseg_vit.py:240-257): the ViT-L/16 trunk with CLIP RN50x16's text tower (width 768, 12 heads),
+#     out_c = 768 (lseg_net.py:142-146)
+# ------------------------------------------------------------------------------------------------
+OTHER = {"b32": dict(backbone="clip_vitb32_384", D=768, patch=32, stored=(128, 192, 384, 768)),
+         "rn50x16": dict(backbone="clipRN50x16_vitl16_384", D=1024, patch=16, stored=(256, 512, 1024, 1024))}
+_OTHER_NETS = {}
+
+
+def other_net(tag):
+    if tag not in _OTHER_NETS:
+        import lseg_b200  # noqa: F401
+        from lseg_b200.lseg_net import LSegNet
+        bb = OTHER[tag]["backbone"]
+        n = LSegNet(labels=synth.ade20k_labels(), **{**NET_KW, "backbone": bb})
+        n.load_state_dict(state_dict(0, bb))
+        _OTHER_NETS.clear()  # one extra engine resident at a time (weights + plans ~ 3 GB each)
+        _OTHER_NETS[tag] = n.cuda().eval()
+    return _OTHER_NETS[tag]
+
+
+@pytest.mark.parametrize("tag,B,H,W,K", [("b32", 2, 64, 96, 5), ("b32", 1, 480, 480, 150), ("b32", 3, 160, 224, 7),
+                                         ("b32", 8, 480, 480, 150), ("rn50x16", 2, 64, 96, 5),
+                                         ("rn50x16", 1, 480, 480, 150), ("rn50x16", 8, 480, 480, 150)])
+def test_other_backbone_forward_vs_oracle(tag, B, H, W, K):
+    from oracle import lseg_oracle as O
+    cfg = OTHER[tag]
+    bb, D, P = cfg["backbone"], cfg["D"], cfg["patch"]
+    net_o = other_net(tag)
+    labels = synth.ade20k_labels()[:K]
+    tokens = synth.tokenize(labels)
+    x = synth.make_image(B, H, W, seed=B * 1000 + H + 32)
+    ref, st = O.lseg_forward(x, tokens, state_dict(0, bb), return_stages=True, backbone=bb)
+    eng = net_o._engine_for(torch.device("cuda"))
+    assert st["text_features"].shape[1] == eng.out_c == net_o.out_c
+    got_tf = eng.forward(x.cuda(), _padded_text(eng, st["text_features"]), K)
+    N = (H // P) * (W // P) + 1
+    d = {"launches": eng.last_launch_count()}
+    for k in range(4):
+        tap = eng.debug_tensor(f"tap{k}", (B, N, D), torch.float32)
+        d[f"tap{k}"] = rel_err(tap, st["taps"][k])
+        lay = st["layers"][k]
+        c, lh, lw = lay.shape[1], lay.shape[2], lay.shape[3]
+        got_l = eng.debug_tensor(f"layer{k}", (B, lh, lw, cfg["stored"][k]), torch.float16).permute(0, 3, 1, 2).float()
+        d[f"layer{k}"] = rel_err(got_l[:, :c], lay)
+        d[f"layer{k}_pad_max"] = float(got_l[:, c:].abs().max()) if cfg["stored"][k] > c else 0.0
+    p1 = eng.debug_tensor("path1", (B, H // 2, W // 2, 256), torch.float16)
+    d["path1"] = rel_err(p1.permute(0, 3, 1, 2), st["path_1"])
+    d["logits_teacher_forced"] = rel_err(got_tf, ref)
+    d["logit_tol_tf"] = logit_tolerance(ref, LOGIT_REL)
+    tf = argmax_report(got_tf, ref, margin_eps(ref, MARGIN_QUANTA_TF))
+    d.update({"tf_" + k: v for k, v in tf.items()})
+    got = net_o(x.cuda(), tokens)
+    d["logits"] = rel_err(got, ref)
+    d["logit_tol_full"] = logit_tolerance(ref, FULL_LOGIT_REL)
+    full = argmax_report(got, ref, margin_eps(ref))
+    d.update(full)
+    _report(f"{tag}_forward_B{B}_{H}x{W}_K{K}", d)
+    assert torch.isfinite(got).all()
+    for k in range(4):
+        assert d[f"tap{k}"] <= STAGE_TOL and d[f"layer{k}"] <= STAGE_TOL, d
+        assert d[f"layer{k}_pad_max"] == 0.0, d  # the channel pad (96 -> 128) carries zero weights: exactly zero
+    assert d["path1"] <= STAGE_TOL, d
+    assert d["logits_teacher_forced"] <= d["logit_tol_tf"], d
+    assert tf["ok"], d
+    assert d["logits"] <= d["logit_tol_full"], d
+    assert full["ok"], d
+
+
+@pytest.mark.parametrize("tag", ["b32", "rn50x16"])
+def test_other_backbone_against_reference_golden(tag):
+    """Outputs of the UNMODIFIED reference LSegNet with that backbone (oracle/make_golden_backbones.py)."""
+    net_o = other_net(tag)
+    g = np.load(os.path.join(GOLD, f"ref_{tag}.npz"))
+    labels = [str(s) for s in g["small_labels"]]
+    x = synth.make_image(2, 64, 96, seed=2064)
+    got = net_o(x.cuda(), synth.tokenize(labels)).cpu()
+    ref = torch.from_numpy(g["small_logits"])
+    d = {"small_logits": rel_err(got, ref), "small_tol": logit_tolerance(ref, FULL_LOGIT_REL)}
+    rep = argmax_report(got, ref, margin_eps(ref))
+    x = synth.make_image(1, 480, 480, seed=1480)
+    got = net_o(x.cuda(), synth.tokenize(synth.ade20k_labels())).cpu()
+    lat = torch.from_numpy(g["k150_logits_lattice"])
+    d["k150_lattice"] = rel_err(got[:, :, ::8, ::8], lat)
+    mask = torch.from_numpy(g["k150_argmax"].astype(np.int64))
+    margin = torch.from_numpy(g["k150_margin_f16"].astype(np.float32))
+    mism = got.argmax(1) != mask
+    eps = MARGIN_QUANTA_FULL * fp16_quantum(lat.abs().max())
+    d["k150_mismatch"] = int(mism.sum())
+    d["k150_worst_mismatch_margin"] = float(margin[mism].max()) if d["k150_mismatch"] else 0.0
+    d["margin_eps"] = eps
+    _report(f"{tag}_reference_golden", d)
+    assert d["small_logits"] <= d["small_tol"] and rep["ok"], (d, rep)
+    assert d["k150_lattice"] <= logit_tolerance(lat, FULL_LOGIT_REL), d
+    assert d["k150_mismatch"] == 0 or d["k150_worst_mismatch_margin"] < eps, d
 
 
 def test_against_reference_golden(net):

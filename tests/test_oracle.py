@@ -215,6 +215,38 @@ def test_reference_key_contract():
     assert abs(float(net.logit_scale) - 14.2857) < 1e-3
 
 
+@pytest.mark.parametrize("tag,backbone,layer_shapes", [
+    ("b32", "clip_vitb32_384", [(96, 16, 24), (192, 8, 12), (384, 4, 6), (768, 2, 3)]),
+    ("rn50x16", "clipRN50x16_vitl16_384", [(256, 16, 24), (512, 8, 12), (1024, 4, 6), (1024, 2, 3)])])
+def test_other_backbone_golden_and_key_contract(tag, backbone, layer_shapes):
+    """The oracle against the unmodified reference's output with that backbone (oracle/make_golden_backbones.py), trunk
+    statistics to 1e-6, and the drop-in module's state-dict keys/shapes against the reference module's."""
+    import lseg_b200  # noqa: F401
+    from lseg_b200.lseg_net import LSegNet
+    from parity_util import NET_KW
+    z = np.load(os.path.join(GOLD, f"ref_{tag}.npz"))
+    labels = [str(s) for s in z["small_labels"]]
+    x = synth.make_image(2, 64, 96, seed=2064)
+    sd = state_dict(0, backbone)
+    out, st = O.lseg_forward(x, synth.tokenize(labels), sd, return_stages=True, backbone=backbone)
+    ref = torch.from_numpy(z["small_logits"])
+    assert out.shape == ref.shape == (2, 5, 64, 96)
+    assert rel_err(out, ref) < 5e-3  # two executions of the fp16 text tower (measured 3.0e-3 at max|logit| ~ 0.3)
+    assert torch.equal(st["taps"][3][0, 0], torch.from_numpy(z["small_tap3_row0"]))
+    for i in range(4):
+        for name, t in (("taps", st["taps"][i]), ("layers", st["layers"][i])):
+            got = np.array([t.mean().item(), t.std().item(), t.abs().max().item()])
+            assert np.allclose(got, z[f"small_{name}_stats"][i], rtol=1e-6, atol=1e-7), (name, i)
+    assert [tuple(l.shape[1:]) for l in st["layers"]] == layer_shapes
+    want = json.load(open(os.path.join(GOLD, f"state_dict_keys_{tag}.json")))
+    net = LSegNet(labels=["a", "b"], **{**NET_KW, "backbone": backbone})
+    assert {k: list(v.shape) for k, v in net.state_dict().items()} == want
+    net.load_state_dict(sd)
+    assert net.out_c == st["text_features"].shape[1]
+    with pytest.raises(AssertionError):  # lseg_blocks.py:53-55 failure mode for backbones that are not built
+        LSegNet(labels=["a"], **{**NET_KW, "backbone": "clip_resnet101"})
+
+
 def test_checkpoint_load_through_parent_module():
     """Lightning's load_from_checkpoint loads `net.`-prefixed keys on the PARENT module; torch then recurses with
     _load_from_state_dict and never calls a child's load_state_dict override. strict=True must still accept real-checkpoint
