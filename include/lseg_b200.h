@@ -132,6 +132,10 @@ int lseg_l2norm_scale(const float* x, void* y, long long M, int C, float logit_s
 int lseg_l2norm_f16(const void* x, void* y, int M, int C, void* stream);
 /* fp16 logits [planes,H,W] -> fp32 [planes,2H,2W], bilinear align_corners=True (k20; lseg_net.py:203). */
 int lseg_upsample2x_nchw(const void* x, float* y, long long planes, int H, int W, void* stream);
+/* The same values bit for bit from a kernel built to run BESIDE the trunk of the next step on a side stream (no shared
+ * memory, 128 threads x <= 32 registers, streaming stores): the gathering rank of the multi-GPU logits gather expands all
+ * shards with it (lang-seg_b200/parallel.py). Slower than lseg_upsample2x_nchw when it has the GPU to itself. */
+int lseg_upsample2x_nchw_bg(const void* x, float* y, long long planes, int H, int W, void* stream);
 /* same from fp32 planes (after the arch_option 1 / 2 head blocks) */
 int lseg_upsample2x_nchw_f32(const float* x, float* y, long long planes, int H, int W, void* stream);
 /* Interpolate (lseg_blocks.py:113-147) fused with torch.max(., 1)[1]: lr fp16 [B,K,H,W] -> mask int64 [B,2H,2W]

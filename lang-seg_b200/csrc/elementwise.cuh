@@ -463,6 +463,60 @@ static inline int launch_upsample2x_nchw(const TIn* x, float* y, long long plane
 }
 
 // ------------------------------------------------------------------------------------------
+// "Background" variant of the logits upsample for the multi-GPU gather (lang-seg_b200/parallel.py::LogitsGather): the
+// gathering rank expands every shard's fp16 low-res logits to fp32 on a side stream while its NEXT step's trunk runs.
+// The trunk's GEMM / attention CTAs own all of an SM's shared memory and all but ~4 K of its registers, so a kernel
+// that is to run BESIDE them (instead of serialising with them, which is what upsample2x_nchw_kernel does) must use no
+// shared memory and <= 32 registers x 128 threads: source values are read straight from global memory (the fp16 source
+// is 1/8 of the bytes and L1/L2-resident), 8 scalar loads + one streaming 16 B store per 4 outputs. It does not need
+// HBM peak: 8.85 GB (N = 8) within one 8.4 ms step is 1.05 TB/s. Same lerp2 sequence as upsample2x_nchw_kernel ->
+// bit-identical values. grid (ceil(Ho / kBgRows), planes), 128 threads: a block walks kBgRows output rows, a thread
+// owns 4 consecutive output columns per 512-column pass.
+// ------------------------------------------------------------------------------------------
+constexpr int kBgRows = 16;
+__global__ void __launch_bounds__(128, 16) upsample2x_nchw_bg_kernel(const __half* __restrict__ x, float* __restrict__ y,
+                                                                     int H, int W) {
+  const int Ho = 2 * H, Wo = 2 * W;
+  const float sh = (Ho > 1) ? static_cast<float>(H - 1) / (Ho - 1) : 0.f;
+  const float sw = (Wo > 1) ? static_cast<float>(W - 1) / (Wo - 1) : 0.f;
+  const long long pl = blockIdx.y;
+  const __half* plane = x + pl * H * W;
+  float* oplane = y + pl * Ho * Wo;
+  const int oy_end = min(Ho, static_cast<int>(blockIdx.x + 1) * kBgRows);
+  for (int oy = blockIdx.x * kBgRows; oy < oy_end; ++oy) {
+    const float fy = sh * oy;
+    const int y0 = static_cast<int>(fy);
+    const int y1 = min(y0 + 1, H - 1);
+    const float ly = fy - y0, hy = 1.f - ly;
+    const __half* r0 = plane + y0 * W;
+    const __half* r1 = plane + y1 * W;
+    for (int ox = threadIdx.x * 4; ox < Wo; ox += 512) {
+      float o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float fx = sw * (ox + k);
+        const int xi = static_cast<int>(fx);
+        const float lxk = fx - xi;
+        const int xa = min(xi, W - 1), xb = min(xa + 1, W - 1);
+        const float va = lerp2(hy, __half2float(__ldg(r0 + xa)), ly, __half2float(__ldg(r1 + xa)));
+        const float vb = lerp2(hy, __half2float(__ldg(r0 + xb)), ly, __half2float(__ldg(r1 + xb)));
+        o[k] = lerp2(1.f - lxk, va, lxk, vb);
+      }
+      __stcs(reinterpret_cast<float4*>(oplane + static_cast<long long>(oy) * Wo + ox), make_float4(o[0], o[1], o[2], o[3]));
+    }
+  }
+}
+static inline int launch_upsample2x_nchw_bg(const __half* x, float* y, long long planes, int H, int W, cudaStream_t s) {
+  if (W % 2 != 0 || planes > 65535 || planes <= 0) {
+    set_error("upsample2x_nchw_bg: needs W %% 2 == 0, 0 < planes <= 65535 (W=%d planes=%lld)", W, planes);
+    return -1;
+  }
+  const dim3 grid((2 * H + kBgRows - 1) / kBgRows, static_cast<unsigned>(planes));
+  upsample2x_nchw_bg_kernel<<<grid, 128, 0, s>>>(x, y, H, W);
+  LSEG_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------
 // Fused scratch.output_conv + class argmax: the callers of LSeg.forward only ever take
 // torch.max(logits, 1)[1] (lseg_app.py:357-360, test_lseg.py:397, test_lseg_zs.py:301). This kernel interpolates the
 // fp16 low-resolution logits [B, K, H, W] exactly like upsample2x_nchw_kernel (same lerp2 sequence, so the values are

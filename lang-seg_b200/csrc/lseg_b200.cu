@@ -783,6 +783,11 @@ int lseg_upsample2x_nchw(const void* x, float* y, long long planes, int H, int W
   return launch_upsample2x_nchw(static_cast<const __half*>(x), y, planes, H, W, static_cast<cudaStream_t>(stream));
 }
 
+int lseg_upsample2x_nchw_bg(const void* x, float* y, long long planes, int H, int W, void* stream) {
+  if (ensure_init()) return -1;
+  return launch_upsample2x_nchw_bg(static_cast<const __half*>(x), y, planes, H, W, static_cast<cudaStream_t>(stream));
+}
+
 int lseg_upsample2x_nchw_f32(const float* x, float* y, long long planes, int H, int W, void* stream) {
   if (ensure_init()) return -1;
   if ((2 * W) % 4 != 0) {

@@ -224,10 +224,12 @@ def l2norm_f16(x):
     return y
 
 
-def upsample2x_nchw(x):
+def upsample2x_nchw(x, background=False):
+    """background=True: the shared-memory-free kernel of the multi-GPU gather (same values bit for bit)."""
     B, K, H, W = x.shape
     y = torch.empty((B, K, 2 * H, 2 * W), dtype=torch.float32, device=x.device)
-    check(load().lseg_upsample2x_nchw(_ptr(x, torch.float16), _ptr(y), B * K, H, W, _stream()))
+    fn = load().lseg_upsample2x_nchw_bg if background else load().lseg_upsample2x_nchw
+    check(fn(_ptr(x, torch.float16), _ptr(y), B * K, H, W, _stream()))
     return y
 
 

@@ -86,8 +86,11 @@ class LogitsGather:
     available; also what the gloo CPU tests exercise).
     """
 
-    def __init__(self, engine, B, K, H, W, root=0, mode="p2p_copy", group=None, timeout_ms=30000, materialize=True):
+    def __init__(self, engine, B, K, H, W, root=0, mode="p2p_copy", group=None, timeout_ms=30000, materialize=True,
+                 background=True):
         self.engine, self.B, self.K, self.H, self.W = engine, B, K, H, W
+        self.background = background
+        self.repeat = 1  # tools/gather_check.py --root-repeat: emulate the expansion load of a larger world
         # materialize=False: root keeps the gathered fp16 low-res logits (`lowres()`), the exact information content of
         # the step, and does not expand them to fp32 — what a consumer that takes the argmax / a crop would want
         self.materialize = materialize
@@ -259,9 +262,15 @@ class LogitsGather:
         if not self.materialize:
             return
         lib = _lib.load()
-        _lib.check(lib.lseg_upsample2x_nchw(C.c_void_p(lr_ptr), C.c_void_p(self.out.data_ptr()),
-                                            self.world * self.B * self.K, self.h2, self.w2,
-                                            C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        # the shared-memory-free kernel: runs beside the next step's trunk instead of serialising with it
+        fn = lib.lseg_upsample2x_nchw_bg if self.background else lib.lseg_upsample2x_nchw
+        per = max(1, 65535 // (self.B * self.K))  # images per launch (grid.y limit)
+        for r0 in [r for _ in range(self.repeat) for r in range(0, self.world, per)]:
+            n = min(per, self.world - r0) * self.B * self.K
+            off = r0 * self.B * self.K
+            _lib.check(fn(C.c_void_p(lr_ptr + 2 * off * self.h2 * self.w2),
+                          C.c_void_p(self.out.data_ptr() + 4 * off * self.H * self.W), n, self.h2, self.w2,
+                          C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
 
     def sync(self):
         """Make the current stream wait for everything this object has enqueued on its side stream."""

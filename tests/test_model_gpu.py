@@ -297,6 +297,7 @@ def test_other_backbone_forward_vs_oracle(tag, B, H, W, K):
         c, lh, lw = lay.shape[1], lay.shape[2], lay.shape[3]
         got_l = eng.debug_tensor(f"layer{k}", (B, lh, lw, cfg["stored"][k]), torch.float16).permute(0, 3, 1, 2).float()
         d[f"layer{k}"] = rel_err(got_l[:, :c], lay)
+        d[f"layer{k}_tol"] = logit_tolerance(lay, STAGE_TOL)  # stored in fp16: the stage tolerance + one quantum
         d[f"layer{k}_pad_max"] = float(got_l[:, c:].abs().max()) if cfg["stored"][k] > c else 0.0
     p1 = eng.debug_tensor("path1", (B, H // 2, W // 2, 256), torch.float16)
     d["path1"] = rel_err(p1.permute(0, 3, 1, 2), st["path_1"])
@@ -312,7 +313,7 @@ def test_other_backbone_forward_vs_oracle(tag, B, H, W, K):
     _report(f"{tag}_forward_B{B}_{H}x{W}_K{K}", d)
     assert torch.isfinite(got).all()
     for k in range(4):
-        assert d[f"tap{k}"] <= STAGE_TOL and d[f"layer{k}"] <= STAGE_TOL, d
+        assert d[f"tap{k}"] <= STAGE_TOL and d[f"layer{k}"] <= d[f"layer{k}_tol"], d
         assert d[f"layer{k}_pad_max"] == 0.0, d  # the channel pad (96 -> 128) carries zero weights: exactly zero
     assert d["path1"] <= STAGE_TOL, d
     assert d["logits_teacher_forced"] <= d["logit_tol_tf"], d

@@ -297,6 +297,8 @@ def test_upsample_argmax_matches_logits(ops, B, K, H, W):
     assert torch.equal(m, up.argmax(1)) or torch.equal(up.gather(1, m[:, None]), up.max(1, keepdim=True)[0])
     # first-maximum rule (what torch.max returns on CPU)
     assert torch.equal(m.cpu(), torch.max(up.cpu(), 1)[1])
+    # the shared-memory-free kernel of the multi-GPU gather: the same values bit for bit
+    assert torch.equal(ops.upsample2x_nchw(lg, background=True), up)
 
 
 @pytest.mark.parametrize("mode,act,in_f16", [(1, "lrelu", True), (1, "none", False), (2, "tanh", True), (2, "relu", False)])

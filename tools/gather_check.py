@@ -25,6 +25,9 @@ def main():
     ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--size", type=int, default=480)
     ap.add_argument("--labels", type=int, default=150)
+    ap.add_argument("--root-repeat", type=int, default=1,
+                    help="experiment: rank 0 expands the gathered shards this many times per step (at world 2, 4 = the "
+                         "fp32 expansion load of world 8)")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -44,13 +47,23 @@ def main():
     xs = [torch.randn(B, 3, S, S, generator=torch.Generator().manual_seed(100 * rank + i)).clamp_(-1, 1).to(dev)
           for i in range(3)]
     res = {}
-    for mode in ("p2p_copy", "p2p_store", "nccl"):
-        g = LogitsGather(eng, B, K, S, S, root=0, mode=mode)
+    # (mode, background kernel for rank 0's fp32 expansion, trunk on a high-priority stream, materialise fp32)
+    variants = [("p2p_copy", "p2p_copy", True, False, True), ("p2p_copy_fg", "p2p_copy", False, False, True),
+                ("p2p_copy_hp", "p2p_copy", True, True, True), ("p2p_copy_lowres", "p2p_copy", True, False, False),
+                ("p2p_store", "p2p_store", True, False, True), ("nccl", "nccl", True, False, True)]
+    lo, hi = torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, "priority_range") else (0, -1)
+    hp_stream = torch.cuda.Stream(device=dev, priority=hi)
+    for name, mode, background, high_prio, materialize in variants:
+        g = LogitsGather(eng, B, K, S, S, root=0, mode=mode, background=background, materialize=materialize)
+        g.repeat = args.root_repeat
+        trunk = hp_stream if high_prio else torch.cuda.current_stream(dev)
+        torch.cuda.synchronize()
         ok = True
-        for i in range(5):  # correctness over several steps (slot reuse), different inputs per step
+        for i in range(5 if materialize else 0):  # correctness over several steps (slot reuse), different inputs per step
             x = xs[i % 3]
-            full = g.forward(x, text)
-            g.sync()
+            with torch.cuda.stream(trunk):
+                full = g.forward(x, text)
+                g.sync()
             torch.cuda.synchronize()
             own = eng.forward(x, text, K)
             ref = torch.empty((world * B, K, S, S), dtype=torch.float32, device=dev) if rank == 0 else None
@@ -63,22 +76,25 @@ def main():
                 del ref, lst
             del own
         # timing: pipelined steps
-        for _ in range(3):
-            g.forward(xs[0], text)
-        g.sync()
+        with torch.cuda.stream(trunk):
+            for _ in range(3):
+                g.forward(xs[0], text)
+            g.sync()
         dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(args.steps):
-            g.forward(xs[i % 3], text)
-        g.sync()
-        e1.record()
+        with torch.cuda.stream(trunk):
+            e0.record()
+            for i in range(args.steps):
+                g.forward(xs[i % 3], text)
+            g.sync()
+            e1.record()
         torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         wd = ops.read_watchdog()
-        res[mode] = {"ran_as": g.mode, "fallback": g.fallback_reason, "bit_identical": ok if rank == 0 else None,
+        res[name] = {"ran_as": g.mode, "background": background, "trunk_high_priority": high_prio,
+                     "materialize": materialize, "root_repeat": args.root_repeat, "fallback": g.fallback_reason, "bit_identical": ok if rank == 0 else None,
                      "ms_per_step": float(t.item()), "img_per_s": world * B / float(t.item()) * 1e3, "watchdog": wd[0]}
         g.close()
         dist.barrier()

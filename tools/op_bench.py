@@ -103,6 +103,27 @@ def bench_ln():
           "gbs_b2b": byts / b2b / 1e3, "frac_hbm_b2b": byts / b2b / 1e3 / 6564.2})
 
 
+def bench_upsample():
+    """fp32 logits expansion: the shared-memory kernel of the step and the background kernel of the multi-GPU gather."""
+    B, K, H, W = 8, 150, 240, 240
+    nb = 3
+    xs = [torch.randn((B, K, H, W), device="cuda").half() for _ in range(nb)]
+    byts = B * K * H * W * (2 + 16)
+    lib = ops.load()
+    import ctypes as C
+    for name, fn in (("upsample2x_nchw", lib.lseg_upsample2x_nchw), ("upsample2x_nchw_bg", lib.lseg_upsample2x_nchw_bg)):
+        outs = [torch.empty((B, K, 2 * H, 2 * W), device="cuda") for _ in range(nb)]
+
+        def f(i, fn=fn):
+            ops.check(fn(C.c_void_p(xs[i % nb].data_ptr()), C.c_void_p(outs[i % nb].data_ptr()), B * K, H, W,
+                         C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        med, mn = time_launches(f, nb, iters=20, warmup=4)
+        b2b = time_back_to_back(f, nb, iters=20, warmup=4)
+        emit({"op": name, "case": "8x150x240x240 fp16 -> 480x480 fp32", "median_us": med, "min_us": mn, "b2b_us": b2b,
+              "gbs_b2b": byts / b2b / 1e3, "frac_hbm_b2b": byts / b2b / 1e3 / 6564.2})
+        del outs
+
+
 def bench_gemm():
     M = 8 * 901
     cases = [("qkv", 3072, 1024, "f16"), ("proj", 1024, 1024, "add"), ("fc1", 4096, 1024, "gelu"), ("fc2", 1024, 4096, "add")]
@@ -130,10 +151,12 @@ def bench_gemm():
 
 
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["mhsa", "ln", "gemm"]
+    what = sys.argv[1:] or ["mhsa", "ln", "gemm", "up"]
     if "mhsa" in what:
         bench_mhsa()
     if "ln" in what:
         bench_ln()
     if "gemm" in what:
         bench_gemm()
+    if "up" in what:
+        bench_upsample()
