@@ -303,6 +303,86 @@ static inline int launch_upsample2x_nhwc(const __half* x, __half* y, int B, int 
 }
 
 // ------------------------------------------------------------------------------------------
+// bilinear x2, align_corners=True, NHWC fp32 -> NHWC fp32 | fp16, C = 256: the fusion blocks' upsample applied AFTER
+// out_conv (lseg_blocks.py:352-356 runs interpolate, then the 1x1 out_conv; both are linear per pixel and the
+// interpolation weights sum to one, so conv-then-interpolate is the same map with a quarter of the conv's pixels, and —
+// with the conv result kept in fp32 — one fp16 rounding less than interpolating an fp16 tensor first).
+// A warp owns 4 consecutive output pixels of one output row (lane = 4 channels, two passes of 128): the <= 4 source
+// pixels x 2 rows they touch are loaded once (8 x 16 B per lane in flight), each output picks its pair by a
+// warp-uniform offset. `add` (nullable, fp32, output shape) is summed into the result: the engine passes the next
+// fusion block's other input so that its residual conv needs one skip operand instead of two.
+// grid (ceil(Wo/32), Ho, B), 256 threads.
+// ------------------------------------------------------------------------------------------
+template <typename TOut>
+__global__ void __launch_bounds__(256, 3) upsample2x_nhwc256_f32_kernel(const float* __restrict__ x, TOut* __restrict__ y,
+                                                                        const float* __restrict__ add, int H, int W) {
+  griddep_launch_dependents();
+  griddep_wait();
+  constexpr int C = 256;
+  const int Ho = 2 * H, Wo = 2 * W;
+  const int oy = blockIdx.y, b = blockIdx.z;
+  const int lane = threadIdx.x & 31;
+  const int ox0 = blockIdx.x * 32 + (threadIdx.x >> 5) * 4;
+  if (ox0 >= Wo) return;
+  const float sh = (Ho > 1) ? static_cast<float>(H - 1) / (Ho - 1) : 0.f;
+  const float sw = (Wo > 1) ? static_cast<float>(W - 1) / (Wo - 1) : 0.f;
+  const float fy = sh * oy;
+  const int y0 = static_cast<int>(fy);
+  const int y1 = min(y0 + 1, H - 1);
+  const float ly = fy - y0, hy = 1.f - ly;
+  const int xs = static_cast<int>(sw * ox0);  // first source column; the 4 outputs use columns xs .. xs+3
+  const float* base = x + static_cast<long long>(b) * H * W * C;
+  const long long opix = (static_cast<long long>(b) * Ho + oy) * Wo + ox0;
+  TOut* dst = y + opix * C;
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {  // two passes of 128 channels: a lane holds 4 channels, loads are 512 B per warp
+    const int ch = p * 128 + lane * 4;
+    const float* row0 = base + static_cast<long long>(y0) * W * C + ch;
+    const float* row1 = base + static_cast<long long>(y1) * W * C + ch;
+    float4 q0[4], q1[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long off = static_cast<long long>(min(xs + j, W - 1)) * C;
+      q0[j] = *reinterpret_cast<const float4*>(row0 + off);
+      q1[j] = *reinterpret_cast<const float4*>(row1 + off);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (ox0 + k >= Wo) break;  // warp-uniform
+      const float fx = sw * (ox0 + k);
+      const int x0 = static_cast<int>(fx);
+      const float lx = fx - x0, hx = 1.f - lx;
+      const int d = x0 - xs;  // 0..2, warp-uniform
+      float4 a0 = q0[0], a1 = q0[1], b0 = q1[0], b1 = q1[1];
+      if (d == 1) { a0 = q0[1]; a1 = q0[2]; b0 = q1[1]; b1 = q1[2]; }
+      if (d == 2) { a0 = q0[2]; a1 = q0[3]; b0 = q1[2]; b1 = q1[3]; }
+      float4 o;
+      o.x = hy * (hx * a0.x + lx * a1.x) + ly * (hx * b0.x + lx * b1.x);
+      o.y = hy * (hx * a0.y + lx * a1.y) + ly * (hx * b0.y + lx * b1.y);
+      o.z = hy * (hx * a0.z + lx * a1.z) + ly * (hx * b0.z + lx * b1.z);
+      o.w = hy * (hx * a0.w + lx * a1.w) + ly * (hx * b0.w + lx * b1.w);
+      if (add) {  // the next block's skip term folded in here: xs[0] + xs[1] of lseg_blocks.py:345-347 (uniform branch)
+        const float4 r = *reinterpret_cast<const float4*>(add + (opix + k) * C + ch);
+        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+      }
+      if constexpr (sizeof(TOut) == 4) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + static_cast<long long>(k) * C + ch) = o;
+      } else {
+        __half2 h[2] = {__floats2half2_rn(o.x, o.y), __floats2half2_rn(o.z, o.w)};
+        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(dst) + static_cast<long long>(k) * C + ch) =
+            *reinterpret_cast<uint2*>(h);
+      }
+    }
+  }
+}
+template <typename TOut>
+static inline int launch_upsample2x_nhwc256_f32(const float* x, TOut* y, const float* add, int B, int H, int W,
+                                                cudaStream_t s) {
+  launch_pdl(upsample2x_nhwc256_f32_kernel<TOut>, dim3((2 * W + 31) / 32, 2 * H, B), dim3(256), 0, s, x, y, add, H, W);
+  LSEG_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------
 // pixel-feature normalisation (modules/models/lseg_net.py:191,194): row / ||row||_2 in fp32, cast to
 // fp16, then multiply by logit_scale in fp16 (the reference's `logit_scale * image_features.half()`
 // rounds the product to fp16 before the matmul). One warp per row of C=512.
@@ -368,6 +448,7 @@ __device__ __forceinline__ float lerp2(float w0, float a, float w1, float b) { r
 // stores (512 B contiguous per warp instruction). The horizontal taps/weights live in registers and are
 // reused for all of the warp's rows. grid (ceil(Ho / (8 warps * kUpRows)), planes), W % 8 == 0, W <= 512.
 // ------------------------------------------------------------------------------------------
+static int g_upsample_split = getenv("LSEG_UPSAMPLE_SPLIT") ? atoi(getenv("LSEG_UPSAMPLE_SPLIT")) : 0;
 constexpr int kUpRows = 4;      // output rows per warp
 constexpr int kUpMaxW = 512;    // widest source row (smem line)
 // 8 consecutive source values as fp32 (TIn = __half: one 16-byte load; float: two)
@@ -386,7 +467,8 @@ __device__ __forceinline__ void load8_f32(const float* p, float (&o)[8]) {
   o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
 }
 // TIn = __half: the fp16 matmul result (arch_option 0); float: the output of the arch_option 1/2 head blocks
-template <bool STREAM, typename TIn = __half>  // STREAM: st.global.cs stores (A/B switch LSEG_UPSAMPLE_CS=1; default plain stores)
+// SPLIT: smem line stored split by column parity (A/B switch lseg_debug_upsample_layout / LSEG_UPSAMPLE_SPLIT)
+template <bool STREAM, typename TIn = __half, bool SPLIT = false>  // STREAM: st.global.cs stores (LSEG_UPSAMPLE_CS=1)
 __global__ void upsample2x_nchw_kernel(const TIn* __restrict__ x, float* __restrict__ y, int H, int W) {
   griddep_launch_dependents();
   griddep_wait();
@@ -419,8 +501,13 @@ __global__ void upsample2x_nchw_kernel(const TIn* __restrict__ x, float* __restr
       // de-interleaved line: even source columns in v[0..), odd ones in v[kUpMaxW/2..). The horizontal pass of a
       // lane reads columns ~2*xq + const, i.e. a stride of two words across the warp: interleaved that is a 2-way bank
       // conflict on every LDS (the kernel is LSU-bound), split by parity it is one conflict-free wavefront
-      reinterpret_cast<float4*>(v)[c] = make_float4(o[0], o[2], o[4], o[6]);
-      reinterpret_cast<float4*>(v + kUpMaxW / 2)[c] = make_float4(o[1], o[3], o[5], o[7]);
+      if (SPLIT) {
+        reinterpret_cast<float4*>(v)[c] = make_float4(o[0], o[2], o[4], o[6]);
+        reinterpret_cast<float4*>(v + kUpMaxW / 2)[c] = make_float4(o[1], o[3], o[5], o[7]);
+      } else {
+        reinterpret_cast<float4*>(v)[2 * c] = make_float4(o[0], o[1], o[2], o[3]);
+        reinterpret_cast<float4*>(v)[2 * c + 1] = make_float4(o[4], o[5], o[6], o[7]);
+      }
     }
     __syncwarp();
     float* orow = oplane + static_cast<long long>(oy) * Wo;
@@ -436,7 +523,10 @@ __global__ void upsample2x_nchw_kernel(const TIn* __restrict__ x, float* __restr
           const int xi = static_cast<int>(fx);
           const float lxk = fx - xi;
           const int xa = min(xi, W - 1), xb = min(xa + 1, W - 1);
-          o[k] = lerp2(1.f - lxk, v[(xa & 1) * (kUpMaxW / 2) + (xa >> 1)], lxk, v[(xb & 1) * (kUpMaxW / 2) + (xb >> 1)]);
+          if (SPLIT)
+            o[k] = lerp2(1.f - lxk, v[(xa & 1) * (kUpMaxW / 2) + (xa >> 1)], lxk, v[(xb & 1) * (kUpMaxW / 2) + (xb >> 1)]);
+          else
+            o[k] = lerp2(1.f - lxk, v[xa], lxk, v[xb]);
         }
         if (STREAM)
           __stcs(reinterpret_cast<float4*>(orow + xq * 4), make_float4(o[0], o[1], o[2], o[3]));
@@ -456,9 +546,11 @@ static inline int launch_upsample2x_nchw(const TIn* x, float* y, long long plane
   static const bool stream_stores = getenv("LSEG_UPSAMPLE_CS") != nullptr;
   const dim3 grid((2 * H + rows_per_block - 1) / rows_per_block, static_cast<unsigned>(planes));
   if (stream_stores)
-    launch_pdl(upsample2x_nchw_kernel<true, TIn>, grid, dim3(256), 0, s, x, y, H, W);
+    launch_pdl(upsample2x_nchw_kernel<true, TIn, false>, grid, dim3(256), 0, s, x, y, H, W);
+  else if (g_upsample_split)
+    launch_pdl(upsample2x_nchw_kernel<false, TIn, true>, grid, dim3(256), 0, s, x, y, H, W);
   else
-    launch_pdl(upsample2x_nchw_kernel<false, TIn>, grid, dim3(256), 0, s, x, y, H, W);
+    launch_pdl(upsample2x_nchw_kernel<false, TIn, false>, grid, dim3(256), 0, s, x, y, H, W);
   LSEG_LAUNCH_CHECK();
 }
 

@@ -476,7 +476,7 @@ static int build_image_plan(lseg_engine* eng, int B, int H, int W, cudaStream_t 
   }
 
   // ---- fusion decoder (lseg_blocks.py:337-358; lseg_net.py:176-179) ----
-  const float* path_prev = nullptr;  // fp32 NHWC output of the previous refinenet (same res as rn[k])
+  const float* path_prev = nullptr;  // fp32 NHWC: output of the previous refinenet + rn_f32[k] (same res as rn[k])
   __half* path1_f16 = nullptr;
   for (int k = 3; k >= 0; --k) {
     const int h = lh[k], ww = lw[k];
@@ -488,29 +488,40 @@ static int build_image_plan(lseg_engine* eng, int B, int H, int W, cudaStream_t 
     if (path_prev) {  // output = xs[0] + resConfUnit1(xs[1])
       LSEG_ALLOC(sum_f32, float, px * 256);
       LSEG_ALLOC(sum_relu, __half, px * 256);
-      if (add_rcu(steps, w.rcu1[k], rn_relu[k], rn_f32[k], path_prev, tmp, B, h, ww, sum_f32, nullptr, sum_relu))
+      // path_prev already holds xs[0] + xs[1] (previous block's output + this level's layer_rn, summed by the
+      // interpolation kernel below): the residual conv adds ONE fp32 operand instead of two
+      if (add_rcu(steps, w.rcu1[k], rn_relu[k], path_prev, nullptr, tmp, B, h, ww, sum_f32, nullptr, sum_relu))
         return -1;
       rcu2_in_relu = sum_relu;
       rcu2_in_f32 = sum_f32;
     }
     if (add_rcu(steps, w.rcu2[k], rcu2_in_relu, rcu2_in_f32, nullptr, tmp, B, h, ww, nullptr, r2, nullptr)) return -1;
-    LSEG_ALLOC(up, __half, px * 4 * 256);
-    steps.push_back([=](const CallCtx&, cudaStream_t s) {
-      return launch_upsample2x_nhwc(r2, up, B, h, ww, 256, s);
-    });
-    GemmEpi e = epi_none();
-    e.bias = w.out_conv[k].b;
-    e.ldc = 256;
+    // lseg_blocks.py:352-356: interpolate(x2, align_corners) then out_conv (1x1). Run in the other order — the 1x1 conv
+    // on the low-res tensor (a quarter of the pixels), result kept in fp32, then ONE interpolation pass that writes
+    // the block's output (fp32 for the next block's skip add, fp16 for head1): the same linear map (the interpolation
+    // weights sum to one, so the bias commutes too), 3/4 of the conv's FLOPs and the fp16 hi-res intermediate gone.
+    LSEG_ALLOC(oc_low, float, px * 256);
+    {
+      GemmEpi e = epi_none();
+      e.bias = w.out_conv[k].b;
+      e.out_f32 = oc_low;
+      e.ldc = 256;
+      if (add_gemm(steps, r2, 256, (int)px, (int)px, w.out_conv[k], e)) return -1;
+    }
     if (k > 0) {
       LSEG_ALLOC(pth, float, px * 4 * 256);
-      e.out_f32 = pth;
+      const float* next_rn = rn_f32[k - 1];  // the next block's other input, same shape as pth
+      steps.push_back([=](const CallCtx&, cudaStream_t s) {
+        return launch_upsample2x_nhwc256_f32<float>(oc_low, pth, next_rn, B, h, ww, s);
+      });
       path_prev = pth;
     } else {
       LSEG_ALLOC(pth16, __half, px * 4 * 256);
-      e.out_f16 = pth16;
+      steps.push_back([=](const CallCtx&, cudaStream_t s) {
+        return launch_upsample2x_nhwc256_f32<__half>(oc_low, pth16, nullptr, B, h, ww, s);
+      });
       path1_f16 = pth16;
     }
-    if (add_gemm(steps, up, 256, (int)(px * 4), (int)(px * 4), w.out_conv[k], e)) return -1;
   }
   plan->debug["path1"] = path1_f16;
 

@@ -753,6 +753,19 @@ int lseg_upsample2x_nhwc(const void* x, void* y, int B, int H, int W, int C, voi
                                 static_cast<cudaStream_t>(stream));
 }
 
+int lseg_upsample2x_nhwc_f32(const float* x, void* y, const float* add, int B, int H, int W, int C, int out_f16,
+                             void* stream) {
+  if (ensure_init()) return -1;
+  if (C != 256) {
+    set_error("upsample2x_nhwc_f32: C=%d (the decoder width, 256)", C);
+    return -1;
+  }
+  if (out_f16)
+    return launch_upsample2x_nhwc256_f32<__half>(x, static_cast<__half*>(y), nullptr, B, H, W,
+                                                 static_cast<cudaStream_t>(stream));
+  return launch_upsample2x_nhwc256_f32<float>(x, static_cast<float*>(y), add, B, H, W, static_cast<cudaStream_t>(stream));
+}
+
 int lseg_l2norm_scale(const float* x, void* y, long long M, int C, float logit_scale, void* stream) {
   if (ensure_init()) return -1;
   if (C % 128 != 0 || C > 512) {
@@ -781,6 +794,12 @@ int lseg_upsample2x_nchw(const void* x, float* y, long long planes, int H, int W
     return -1;
   }
   return launch_upsample2x_nchw(static_cast<const __half*>(x), y, planes, H, W, static_cast<cudaStream_t>(stream));
+}
+
+int lseg_debug_upsample_layout(int split) {
+  const int old = g_upsample_split;
+  g_upsample_split = split ? 1 : 0;
+  return old;
 }
 
 int lseg_upsample2x_nchw_bg(const void* x, float* y, long long planes, int H, int W, void* stream) {

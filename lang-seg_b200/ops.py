@@ -203,10 +203,15 @@ def im2col_3x3_s2(x):
     return a
 
 
-def upsample2x_nhwc(x):
+def upsample2x_nhwc(x, out_dtype=torch.float16, add=None):
+    """fp16 NHWC -> fp16; fp32 NHWC (C = 256) -> fp32 or fp16 (the decoder's conv-then-interpolate order)."""
     B, H, W, Cc = x.shape
-    y = torch.empty((B, 2 * H, 2 * W, Cc), dtype=torch.float16, device=x.device)
-    check(load().lseg_upsample2x_nhwc(_ptr(x, torch.float16), _ptr(y), B, H, W, Cc, _stream()))
+    y = torch.empty((B, 2 * H, 2 * W, Cc), dtype=out_dtype, device=x.device)
+    if x.dtype == torch.float32:
+        check(load().lseg_upsample2x_nhwc_f32(_ptr(x, torch.float32), _ptr(y), _ptr(add, torch.float32) if add is not None
+                                              else None, B, H, W, Cc, int(out_dtype == torch.float16), _stream()))
+    else:
+        check(load().lseg_upsample2x_nhwc(_ptr(x, torch.float16), _ptr(y), B, H, W, Cc, _stream()))
     return y
 
 

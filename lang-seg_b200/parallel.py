@@ -87,7 +87,7 @@ class LogitsGather:
     """
 
     def __init__(self, engine, B, K, H, W, root=0, mode="p2p_copy", group=None, timeout_ms=30000, materialize=True,
-                 background=True):
+                 background=False):
         self.engine, self.B, self.K, self.H, self.W = engine, B, K, H, W
         self.background = background
         self.repeat = 1  # tools/gather_check.py --root-repeat: emulate the expansion load of a larger world
@@ -262,7 +262,8 @@ class LogitsGather:
         if not self.materialize:
             return
         lib = _lib.load()
-        # the shared-memory-free kernel: runs beside the next step's trunk instead of serialising with it
+        # background=True: the shared-memory-free kernel meant to run beside the next step's trunk (measured: it does
+        # not — see DESIGN.md section 6 — so the default is the faster shared-memory kernel)
         fn = lib.lseg_upsample2x_nchw_bg if self.background else lib.lseg_upsample2x_nchw
         per = max(1, 65535 // (self.B * self.K))  # images per launch (grid.y limit)
         for r0 in [r for _ in range(self.repeat) for r in range(0, self.world, per)]:

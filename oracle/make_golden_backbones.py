@@ -75,6 +75,7 @@ def make(TAG, BACKBONE):
             out["k150_logits_lattice"] = ref[:, :, ::8, ::8].numpy()
             out["k150_argmax"] = ref.argmax(1).to(torch.uint8).numpy()
             out["k150_margin_f16"] = (top2[:, 0] - top2[:, 1]).half().numpy()
+        out[f"{tag}_floor"] = np.array(e2)  # the reference's two executions of its fp16 text tower, in the logits
         out[f"{tag}_taps_stats"] = np.stack([_stats(cap[f"tap{i}"]) for i in range(4)])
         out[f"{tag}_layers_stats"] = np.stack([_stats(cap[f"layer{i}"]) for i in range(4)])
         out[f"{tag}_path1_stats"] = _stats(cap["path1"])

@@ -331,7 +331,12 @@ def test_other_backbone_against_reference_golden(tag):
     x = synth.make_image(2, 64, 96, seed=2064)
     got = net_o(x.cuda(), synth.tokenize(labels)).cpu()
     ref = torch.from_numpy(g["small_logits"])
-    d = {"small_logits": rel_err(got, ref), "small_tol": logit_tolerance(ref, FULL_LOGIT_REL)}
+    # logits tolerance = TEXT_FLOOR_FACTOR x what the reference's own two executions of the fp16 text tower (the module
+    # behind this fixture vs the oracle's recipe) differ by in THESE logits, recorded in the fixture, + one fp16 quantum;
+    # never below the default backbone's FULL_LOGIT_REL
+    rel_small = max(FULL_LOGIT_REL, TEXT_FLOOR_FACTOR * float(g["small_floor"]))
+    rel_k150 = max(FULL_LOGIT_REL, TEXT_FLOOR_FACTOR * float(g["k150_floor"]))
+    d = {"small_logits": rel_err(got, ref), "small_tol": logit_tolerance(ref, rel_small), "k150_floor": float(g["k150_floor"])}
     rep = argmax_report(got, ref, margin_eps(ref))
     x = synth.make_image(1, 480, 480, seed=1480)
     got = net_o(x.cuda(), synth.tokenize(synth.ade20k_labels())).cpu()
@@ -346,8 +351,42 @@ def test_other_backbone_against_reference_golden(tag):
     d["margin_eps"] = eps
     _report(f"{tag}_reference_golden", d)
     assert d["small_logits"] <= d["small_tol"] and rep["ok"], (d, rep)
-    assert d["k150_lattice"] <= logit_tolerance(lat, FULL_LOGIT_REL), d
+    assert d["k150_lattice"] <= logit_tolerance(lat, rel_k150), d
     assert d["k150_mismatch"] == 0 or d["k150_worst_mismatch_margin"] < eps, d
+
+
+def test_forward_on_side_streams(net):
+    """Everything a forward enqueues goes to the CALLER's current stream (no implicit legacy-stream work): issued on a
+    non-default stream — default and highest priority — while another stream keeps the GPU busy, it returns the bits of
+    the default-stream forward. Also the low-res entry point of the multi-GPU gather."""
+    from lseg_b200 import ops
+    tokens = synth.tokenize(synth.ade20k_labels()[:19])
+    x = synth.make_image(3, 160, 224, seed=5).cuda()
+    eng = net._engine_for(torch.device("cuda"))
+    text = net._text_features(eng, tokens)
+    ref = eng.forward(x, text, 19).clone()
+    ref_lr = eng.forward_lowres(x, text, 19).clone()
+    assert torch.equal(ops.upsample2x_nchw(ref_lr), ref)
+    torch.cuda.synchronize()
+    noise_stream = torch.cuda.Stream()
+    junk = torch.randn(4096, 4096, device="cuda")
+    prios = [0, -1]
+    if hasattr(torch.cuda.Stream, "priority_range"):
+        prios.append(torch.cuda.Stream.priority_range()[1])
+    for prio in prios:
+        s = torch.cuda.Stream(priority=prio)
+        with torch.cuda.stream(noise_stream):
+            for _ in range(20):
+                junk = junk @ junk * 1e-4
+        with torch.cuda.stream(s):
+            out = eng.forward(x, text, 19)
+            lr = eng.forward_lowres(x, text, 19)
+            out2 = eng.forward(x, text, 19)
+        s.synchronize()
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref), prio
+        assert torch.equal(lr, ref_lr), prio
+        assert torch.equal(out2, ref), prio
 
 
 def test_against_reference_golden(net):

@@ -270,6 +270,13 @@ def test_im2col_upsample_norms(ops):
     y = ops.upsample2x_nhwc(x)
     refu = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="bilinear", align_corners=True)
     _close(y, refu.permute(0, 2, 3, 1), 1e-3, "upsample nhwc")
+    for shape in ((2, 15, 15, 256), (1, 30, 41, 256), (3, 7, 60, 256)):  # fp32 input (after out_conv), odd widths
+        xf = _rand(shape, 27, 2.0, torch.float32)
+        want = F.interpolate(xf.permute(0, 3, 1, 2), scale_factor=2, mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
+        _close(ops.upsample2x_nhwc(xf, torch.float32), want, 2e-6, "upsample nhwc fp32 -> fp32")
+        _close(ops.upsample2x_nhwc(xf, torch.float16), want, 1e-3, "upsample nhwc fp32 -> fp16")
+        skip = _rand(tuple(want.shape), 26, 1.0, torch.float32)
+        _close(ops.upsample2x_nhwc(xf, torch.float32, add=skip), want + skip, 2e-6, "upsample nhwc fp32 + skip")
     lg = _rand((2, 5, 24, 40), 28, 3.0)
     up = ops.upsample2x_nchw(lg)
     _close(up, F.interpolate(lg.float(), scale_factor=2, mode="bilinear", align_corners=True), 1e-6, "upsample nchw")

@@ -111,7 +111,10 @@ def bench_upsample():
     byts = B * K * H * W * (2 + 16)
     lib = ops.load()
     import ctypes as C
-    for name, fn in (("upsample2x_nchw", lib.lseg_upsample2x_nchw), ("upsample2x_nchw_bg", lib.lseg_upsample2x_nchw_bg)):
+    for name, fn, split in (("upsample2x_nchw interleaved line", lib.lseg_upsample2x_nchw, 0),
+                            ("upsample2x_nchw parity-split line", lib.lseg_upsample2x_nchw, 1),
+                            ("upsample2x_nchw_bg", lib.lseg_upsample2x_nchw_bg, 0)):
+        lib.lseg_debug_upsample_layout(split)
         outs = [torch.empty((B, K, 2 * H, 2 * W), device="cuda") for _ in range(nb)]
 
         def f(i, fn=fn):
@@ -122,6 +125,7 @@ def bench_upsample():
         emit({"op": name, "case": "8x150x240x240 fp16 -> 480x480 fp32", "median_us": med, "min_us": mn, "b2b_us": b2b,
               "gbs_b2b": byts / b2b / 1e3, "frac_hbm_b2b": byts / b2b / 1e3 / 6564.2})
         del outs
+    lib.lseg_debug_upsample_layout(0)
 
 
 def bench_gemm():
