@@ -126,12 +126,13 @@ int lseg_readout_split(const float* tap, void* tok, void* cls, int B, int T, int
 int lseg_im2col_3x3_s2(const void* x, void* a, int B, int H, int W, int C, void* stream);
 /* bilinear x2 align_corners=True, NHWC fp16 (k16; lseg_blocks.py:352-354). */
 int lseg_upsample2x_nhwc(const void* x, void* y, int B, int H, int W, int C, void* stream);
-/* The same interpolation of an fp32 NHWC tensor with C = 256 into fp32 (out_f16 = 0) or fp16 (out_f16 = 1): the fusion
- * blocks' upsample as the engine runs it, AFTER the 1x1 out_conv (lseg_blocks.py:352-356 — the two are linear per pixel
- * and commute; conv first touches a quarter of the pixels). add (nullable, fp32 [B,2H,2W,C], fp32 output only) is summed
- * into the result: xs[0] + ... of the next block (lseg_blocks.py:345-347). */
-int lseg_upsample2x_nhwc_f32(const float* x, void* y, const float* add, int B, int H, int W, int C, int out_f16,
-                             void* stream);
+/* The same interpolation for the decoder width C = 256 as the engine runs it, AFTER the 1x1 out_conv
+ * (lseg_blocks.py:352-356 — the two are linear per pixel and commute; conv first touches a quarter of the pixels):
+ * x fp16 (in_f16 = 1, the engine's choice) or fp32 NHWC [B,H,W,256] -> y fp16 (out_f16 = 1) or fp32 [B,2H,2W,256].
+ * add (nullable, fp32, output shape, fp32 output only) is summed into the result: xs[0] + ... of the next block
+ * (lseg_blocks.py:345-347). */
+int lseg_upsample2x_nhwc256(const void* x, int in_f16, void* y, int out_f16, const float* add, int B, int H, int W,
+                            void* stream);
 /* rows fp32 [M,C] -> half(row/||row||) * logit_scale in fp16 (k19 prologue; lseg_net.py:191,194). */
 int lseg_l2norm_scale(const float* x, void* y, long long M, int C, float logit_scale, void* stream);
 /* text rows fp16 [M,C] -> row/||row|| in fp16 (lseg_net.py:192). */

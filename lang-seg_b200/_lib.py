@@ -77,7 +77,7 @@ class Weights(C.Structure):
 SYMBOLS = [
     "lseg_last_error", "lseg_abi_version", "lseg_read_watchdog",
     "lseg_gemm", "lseg_mhsa", "lseg_mhsa_variant", "lseg_text_attn", "lseg_mhsa_trace", "lseg_debug_gemm_trace", "lseg_set_deterministic", "lseg_layernorm", "lseg_patchify", "lseg_pos_resize", "lseg_assemble_tokens",
-    "lseg_readout_split", "lseg_im2col_3x3_s2", "lseg_upsample2x_nhwc", "lseg_upsample2x_nhwc_f32", "lseg_l2norm_scale", "lseg_l2norm_f16",
+    "lseg_readout_split", "lseg_im2col_3x3_s2", "lseg_upsample2x_nhwc", "lseg_upsample2x_nhwc256", "lseg_l2norm_scale", "lseg_l2norm_f16",
     "lseg_upsample2x_nchw", "lseg_debug_upsample_layout", "lseg_upsample2x_nchw_bg", "lseg_upsample2x_nchw_f32", "lseg_head_block", "lseg_upsample2x_argmax", "lseg_forward_argmax", "lseg_text_embed", "lseg_text_eot_gather",
     "lseg_create", "lseg_destroy", "lseg_encode_text", "lseg_forward", "lseg_forward_lowres", "lseg_debug_buffer",
     "lseg_last_launch_count", "lseg_forward_profiled",
@@ -131,8 +131,8 @@ def load(build_if_missing=True):
     lib.lseg_readout_split.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.lseg_im2col_3x3_s2.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.lseg_upsample2x_nhwc.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
-    lib.lseg_upsample2x_nhwc_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                             C.c_void_p]
+    lib.lseg_upsample2x_nhwc256.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                            C.c_void_p]
     lib.lseg_l2norm_scale.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_void_p]
     lib.lseg_l2norm_f16.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.lseg_upsample2x_nchw.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p]

@@ -145,6 +145,19 @@ namespace lseg {
     return -1;                                                                              \
   }
 
+// Arena of the plan under construction: split-K GEMMs (gemm_plan -> ws_bytes) take their partial-sum workspace from it.
+static thread_local Arena* t_plan_arena = nullptr;
+static int plan_workspace(GemmPlan* plan) {
+  if (!plan->ws_bytes) return 0;
+  float* ws = t_plan_arena ? static_cast<float*>(t_plan_arena->alloc(plan->ws_bytes)) : nullptr;
+  if (!ws) {
+    set_error("split-K workspace allocation of %zu bytes failed", plan->ws_bytes);
+    return -1;
+  }
+  gemm_set_workspace(plan, ws);
+  return 0;
+}
+
 static GemmEpi epi_none() {
   GemmEpi e;
   memset(&e, 0, sizeof(e));
@@ -166,7 +179,7 @@ static int add_gemm(std::vector<Step>& steps, const __half* a, long long lda, in
   d.K = lin.in;
   d.e = e;
   GemmPlan plan;
-  if (gemm_plan(d, &plan)) return -1;
+  if (gemm_plan(d, &plan) || plan_workspace(&plan)) return -1;
   steps.emplace_back([plan](const CallCtx&, cudaStream_t s) { return gemm_run(plan, s); }, KIND_GEMM,
                      2.0 * M * lin.out * lin.in);
   return 0;
@@ -191,7 +204,7 @@ static int add_conv3x3(std::vector<Step>& steps, const __half* a, int B, int H, 
   d.pad = 1;
   d.e = e;
   GemmPlan plan;
-  if (gemm_plan(d, &plan)) return -1;
+  if (gemm_plan(d, &plan) || plan_workspace(&plan)) return -1;
   steps.emplace_back([plan](const CallCtx&, cudaStream_t s) { return gemm_run(plan, s); }, KIND_GEMM,
                      2.0 * B * H * W * lin.out * 9.0 * C);
   return 0;
@@ -253,6 +266,7 @@ static int build_image_plan(lseg_engine* eng, int B, int H, int W, cudaStream_t 
   plan->W = W;
   plan->epoch = g_plan_epoch;
   Arena& arena = plan->arena;
+  t_plan_arena = &arena;
   std::vector<Step>& steps = plan->steps;
   // backbone geometry (lseg_vit.py:442-522 _make_pretrained_clip_vitl16_384 / _vitb32_384): token width, depth, heads,
   // patch size and the per-level reassemble recipe come with the weights
@@ -497,14 +511,15 @@ static int build_image_plan(lseg_engine* eng, int B, int H, int W, cudaStream_t 
     }
     if (add_rcu(steps, w.rcu2[k], rcu2_in_relu, rcu2_in_f32, nullptr, tmp, B, h, ww, nullptr, r2, nullptr)) return -1;
     // lseg_blocks.py:352-356: interpolate(x2, align_corners) then out_conv (1x1). Run in the other order — the 1x1 conv
-    // on the low-res tensor (a quarter of the pixels), result kept in fp32, then ONE interpolation pass that writes
-    // the block's output (fp32 for the next block's skip add, fp16 for head1): the same linear map (the interpolation
-    // weights sum to one, so the bias commutes too), 3/4 of the conv's FLOPs and the fp16 hi-res intermediate gone.
-    LSEG_ALLOC(oc_low, float, px * 256);
+    // on the low-res tensor (a quarter of the pixels), then ONE interpolation pass that writes the block's output
+    // (fp32 for the next block's skip add, with that block's other input already summed in; fp16 for head1): the
+    // same linear map (the interpolation weights sum to one, so the bias commutes too), 3/4 of the conv's FLOPs and
+    // the hi-res fp16 intermediate gone; one fp16 rounding (of the low-res conv result) as before (of the hi-res one).
+    LSEG_ALLOC(oc_low, __half, px * 256);
     {
       GemmEpi e = epi_none();
       e.bias = w.out_conv[k].b;
-      e.out_f32 = oc_low;
+      e.out_f16 = oc_low;  // fp16 TMA-store epilogue (the register-direct fp32 one measured 66 us at level 1)
       e.ldc = 256;
       if (add_gemm(steps, r2, 256, (int)px, (int)px, w.out_conv[k], e)) return -1;
     }
@@ -512,13 +527,13 @@ static int build_image_plan(lseg_engine* eng, int B, int H, int W, cudaStream_t 
       LSEG_ALLOC(pth, float, px * 4 * 256);
       const float* next_rn = rn_f32[k - 1];  // the next block's other input, same shape as pth
       steps.push_back([=](const CallCtx&, cudaStream_t s) {
-        return launch_upsample2x_nhwc256_f32<float>(oc_low, pth, next_rn, B, h, ww, s);
+        return launch_upsample2x_nhwc256_f16<float>(oc_low, pth, next_rn, B, h, ww, s);
       });
       path_prev = pth;
     } else {
       LSEG_ALLOC(pth16, __half, px * 4 * 256);
       steps.push_back([=](const CallCtx&, cudaStream_t s) {
-        return launch_upsample2x_nhwc256_f32<__half>(oc_low, pth16, nullptr, B, h, ww, s);
+        return launch_upsample2x_nhwc256_f16<__half>(oc_low, pth16, nullptr, B, h, ww, s);
       });
       path1_f16 = pth16;
     }
@@ -760,6 +775,7 @@ static int build_text_plan(lseg_engine* eng, int K) {
   std::unique_ptr<TextPlan> plan(new TextPlan());
   plan->K = K;
   Arena& arena = plan->arena;
+  t_plan_arena = &arena;
   const int L = 77, Wd = w.text_width, OC = w.out_c, theads = w.text_heads;
   const long long M = static_cast<long long>(K) * L;
   const int kpad = ((K + 127) / 128) * 128;

@@ -92,6 +92,9 @@ struct GemmParams {
   int tiles_h, tiles_w;
   int num_m_tiles, num_n_tiles;
   int split_k;   // EPI_TMA_ADD only: balance (tile, k-chunk) units over the CTA pairs instead of whole tiles
+  int split_fixed;       // EPI_DIRECT, >= 2: every tile's K loop is cut into this many equal segments, each a work unit of
+  long long split_rows;  //   its own; segment s stores its RAW fp32 partial at row (s * split_rows + row) of out_f32 and
+                         //   splitk_reduce_kernel sums the segments in index order (deterministic) and applies the epilogue
   unsigned long long* trace;  // debug timeline ([2 pairs][12 warps][512] of clock64 << 8 | tag), normally nullptr
   int probe;  // measurement only (tools/gemm_probe.py; results are garbage when non-zero):
               //   1 = skip epilogue work, 2 = skip TMA loads, 4 = skip MMA issue   (CTA-pair kernel)
@@ -343,10 +346,12 @@ constexpr int kEpiStageBytes = 2 * 4096;  // per epilogue warp: two 32-row x 128
 template <int EPI, bool SINGLE_BUF = false, typename WaitFn>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t t_row, int n_base, int ncols,
                                                    int m_tile, int r, WaitFn wait_accumulator, uint8_t* stage_buf,
-                                                   int& store_groups, GemmTrace& tr, bool first_k = true) {
+                                                   int& store_groups, GemmTrace& tr, bool first_k = true,
+                                                   long long row_shift = 0) {
   const GemmEpi& e = p.e;
   long long grow;
   const bool valid = gemm_row_map(p, m_tile, r, grow);
+  if constexpr (EPI == EPI_DIRECT) grow += row_shift;  // split_fixed: this segment's plane of the partial-sum workspace
   if constexpr (EPI == EPI_DIRECT) {
     // The fp32 residual of chunk c+1 is requested before chunk c is processed, and that of chunk 0 before the
     // accumulator is even ready, so the residual read latency overlaps the main loop / the previous chunk.
@@ -576,7 +581,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((Gemm2Cfg<BN, EPI, E
     int tile_next, tile_step, num_tiles, k_iters;
     long long unit, unit_end;
     bool split;
+    int fixed, seg;
     __device__ bool next(int& tile, int& k0, int& k1) {
+      if (fixed > 1) {  // units = (tile, segment), dealt round-robin
+        if (tile_next >= num_tiles * fixed) return false;
+        tile = tile_next / fixed;
+        seg = tile_next - tile * fixed;
+        tile_next += tile_step;
+        k0 = static_cast<int>(static_cast<long long>(seg) * k_iters / fixed);
+        k1 = static_cast<int>(static_cast<long long>(seg + 1) * k_iters / fixed);
+        return true;
+      }
       if (!split) {
         if (tile_next >= num_tiles) return false;
         tile = tile_next;
@@ -601,6 +616,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((Gemm2Cfg<BN, EPI, E
     sc.num_tiles = num_tiles;
     sc.k_iters = p.k_iters;
     sc.split = (EPI == EPI_TMA_ADD) && p.split_k;
+    sc.fixed = (EPI == EPI_DIRECT) ? p.split_fixed : 0;
+    sc.seg = 0;
     const long long units = static_cast<long long>(num_tiles) * p.k_iters;
     // boundaries on multiples of 4 k-chunks: no sliver segments whose epilogue would cost more than their MMAs
     sc.unit = ((units * pair / num_pairs) + 3) & ~3ll;
@@ -732,7 +749,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((Gemm2Cfg<BN, EPI, E
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + col0;
       gemm_epilogue_tile<EPI, Cfg::kEpiWarps == 16>(p, t_row, n_tile * BN + col0, ncols, m_tile, r,
                               [&]() { mbar_wait(&tmem_full[acc], acc_phase, 24); }, stage_buf, store_groups, tr,
-                              k_begin == 0);
+                              k_begin == 0, static_cast<long long>(sc.seg) * p.split_rows);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster_relaxed(&tmem_empty[acc], 0);  // leader CTA's barrier: 2 CTAs x 8 warps
@@ -748,6 +765,64 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((Gemm2Cfg<BN, EPI, E
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc_2cta(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Deterministic split-K, second half: out = epilogue(sum_s partial[s]) for the GEMMs whose tile count leaves most of
+// the CTA pairs idle (3x3 convs on the 15x15 / 30x30 decoder levels: 8 and 29 pair tiles on 74 pairs, K up to 9216).
+// ws fp32 [S][M][N] (N == ldc of the partials); one thread = 4 consecutive columns of one row, segments summed in index
+// order. Epilogue = the row-major subset of gemm_epilogue_math / gemm_epilogue_store: scale, bias (per column), act, two
+// fp32 residuals, fp32 / fp16 / relu-fp16 outputs with the FINAL row stride e.ldc.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, int S, long long M, int N,
+                                                            GemmEpi e) {
+  griddep_launch_dependents();
+  griddep_wait();
+  const int n4 = N >> 2;
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= M * n4) return;
+  const long long row = i / n4;
+  const int col = static_cast<int>(i - row * n4) * 4;
+  const long long plane = M * static_cast<long long>(N);
+  const float* src = ws + row * N + col;
+  float4 a = *reinterpret_cast<const float4*>(src);
+  for (int s = 1; s < S; ++s) {
+    const float4 q = *reinterpret_cast<const float4*>(src + s * plane);
+    a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
+  }
+  if (e.scale) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(e.scale + col));
+    a.x *= q.x; a.y *= q.y; a.z *= q.z; a.w *= q.w;
+  }
+  if (e.bias) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+    a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
+  }
+  if (e.act == ACT_GELU) {
+    a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w);
+  } else if (e.act == ACT_QUICKGELU) {
+    a.x = quick_gelu(a.x); a.y = quick_gelu(a.y); a.z = quick_gelu(a.z); a.w = quick_gelu(a.w);
+  } else if (e.act == ACT_RELU) {
+    a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+  }
+  const long long off = row * e.ldc + col;
+  if (e.res_f32) {
+    const float4 q = *reinterpret_cast<const float4*>(e.res_f32 + off);
+    a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
+  }
+  if (e.res2_f32) {
+    const float4 q = *reinterpret_cast<const float4*>(e.res2_f32 + off);
+    a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
+  }
+  if (e.out_f32) *reinterpret_cast<float4*>(e.out_f32 + off) = a;
+  if (e.out_f16) {
+    __half2 h[2] = {__floats2half2_rn(a.x, a.y), __floats2half2_rn(a.z, a.w)};
+    *reinterpret_cast<uint2*>(e.out_f16 + off) = *reinterpret_cast<uint2*>(h);
+  }
+  if (e.out_f16_relu) {
+    __half2 h[2] = {__floats2half2_rn(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f)), __floats2half2_rn(fmaxf(a.z, 0.f), fmaxf(a.w, 0.f))};
+    *reinterpret_cast<uint2*>(e.out_f16_relu + off) = *reinterpret_cast<uint2*>(h);
   }
 }
 

@@ -206,7 +206,30 @@ struct GemmPlan {
   int ew16;     // 1: 16 epilogue warps (short-K / GELU fp16 TMA-store GEMMs)
   int two_cta;  // 1: CTA-pair kernel (tcgen05 cta_group::2), 0: single-CTA kernel
   int epi;      // GemmEpiMode (CTA-pair kernel)
+  // deterministic split-K (gemm_tc.cuh splitk_reduce_kernel): p.split_fixed segments per tile write raw partials to a
+  // workspace the CALLER provides (gemm_set_workspace) before gemm_run; final_epi is the epilogue the reduce applies
+  size_t ws_bytes;
+  GemmEpi final_epi;
 };
+
+// Split the K loop when whole tiles leave at least half of the CTA pairs idle (decoder convs on the 15x15 / 30x30
+// levels, layer3_rn / layer4_rn, the stride-2 reassemble conv): segments = pairs / tiles, at least 4 k-chunks each.
+static int gemm_pick_split(const GemmDesc& d, const GemmParams& p, int pair_tiles, int max_pairs) {
+  static const int mode = getenv("LSEG_SPLITK_FIXED") ? atoi(getenv("LSEG_SPLITK_FIXED")) : -1;  // 0 off, >1 forced, -1 auto
+  if (mode == 0 || !g_gemm_two_cta) return 0;
+  const GemmEpi& e = d.e;
+  const bool plain_epi = e.store == STORE_ROWMAJOR && e.bias_group_rows == 0 && !e.out_row_sumsq && !e.res_f16 &&
+                         !e.row_sumsq && (d.N % 8 == 0) && (e.out_f32 || e.out_f16 || e.out_f16_relu);
+  if (!plain_epi || !(d.conv || d.K >= 4096)) return 0;
+  if (pair_tiles * 2 > max_pairs) return 0;
+  int s = max_pairs / pair_tiles;
+  if (mode > 1) s = mode;
+  if (s > p.k_iters / 4) s = p.k_iters / 4;
+  if (s > 16) s = 16;
+  return s >= 2 ? s : 0;
+}
+
+static void gemm_set_workspace(GemmPlan* plan, float* ws) { plan->p.e.out_f32 = ws; }
 
 static int gemm_plan(const GemmDesc& d, GemmPlan* plan) {
   if (ensure_init()) return -1;
@@ -284,6 +307,30 @@ static int gemm_plan(const GemmDesc& d, GemmPlan* plan) {
   // convs feeding the next conv, head1, text in_proj / c_fc)
   plan->epi = EPI_DIRECT;
   plan->ew16 = 0;
+  plan->ws_bytes = 0;
+  {
+    const int pair_tiles = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
+    const int split = gemm_pick_split(d, p, pair_tiles, g_num_sms / 2);
+    if (split) {
+      plan->final_epi = d.e;
+      p.split_fixed = split;
+      p.split_rows = d.M;
+      p.e = GemmEpi{};
+      memset(&p.e, 0, sizeof(p.e));
+      p.e.store = STORE_ROWMAJOR;
+      p.e.ldc = d.N;
+      p.e.row_scale = 1.f;
+      plan->ws_bytes = sizeof(float) * static_cast<size_t>(split) * d.M * d.N;
+      const int units = pair_tiles * split;
+      const int max_pairs = g_num_sms / 2;
+      plan->grid = 2 * (units < max_pairs ? units : max_pairs);
+      if (d.e.store == STORE_ROWMAJOR && (d.e.ldc % 8 != 0)) {
+        set_error("gemm: ldc must be a multiple of 8");
+        return -1;
+      }
+      return 0;
+    }
+  }
   {
     const GemmEpi& e = p.e;
     static const bool disabled = getenv("LSEG_GEMM_NO_TMA_STORE") != nullptr;
@@ -338,8 +385,25 @@ static int gemm_plan(const GemmDesc& d, GemmPlan* plan) {
   return 0;
 }
 
+static int gemm_run_kernel(const GemmPlan& plan, cudaStream_t stream);
 static int gemm_run(const GemmPlan& plan, cudaStream_t stream) {
   if (plan.grid <= 0) return 0;
+  if (plan.p.split_fixed > 1) {
+    if (!plan.p.e.out_f32) {
+      set_error("gemm: split-K plan without a workspace (gemm_set_workspace)");
+      return -1;
+    }
+    if (gemm_run_kernel(plan, stream)) return -1;
+    const long long quads = static_cast<long long>(plan.p.M) * (plan.p.N / 4);
+    launch_pdl(splitk_reduce_kernel, dim3(static_cast<unsigned>((quads + 255) / 256)), dim3(256), 0, stream,
+               static_cast<const float*>(plan.p.e.out_f32), plan.p.split_fixed, static_cast<long long>(plan.p.M), plan.p.N,
+               plan.final_epi);
+    LSEG_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
+  return gemm_run_kernel(plan, stream);
+}
+static int gemm_run_kernel(const GemmPlan& plan, cudaStream_t stream) {
   {
 #define LSEG_LAUNCH_TC2(BN_, EPI_) \
   launch_pdl(gemm_tc2_kernel<BN_, EPI_>, dim3(plan.grid), dim3(Gemm2Cfg<BN_, EPI_>::kThreads), Gemm2Cfg<BN_, EPI_>::kSmemBytes, stream, plan.p)
@@ -513,6 +577,27 @@ int lseg_gemm(const lseg_gemm_args* a, void* stream) {
   fill_epi(a, &d.e);
   GemmPlan plan;
   if (gemm_plan(d, &plan)) return -1;
+  if (plan.ws_bytes) {  // stage-op call: a per-device scratch that only grows (the engine plans own theirs)
+    static std::mutex mu;
+    static float* scratch[64] = {nullptr};
+    static size_t cap[64] = {0};
+    int dev = 0;
+    LSEG_CHECK_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev < 0 || dev >= 64) {
+      set_error("lseg_gemm: device index %d", dev);
+      return -1;
+    }
+    if (cap[dev] < plan.ws_bytes) {
+      LSEG_CHECK_CUDA(cudaDeviceSynchronize());
+      if (scratch[dev]) cudaFree(scratch[dev]);
+      scratch[dev] = nullptr;
+      cap[dev] = 0;
+      LSEG_CHECK_CUDA(cudaMalloc(&scratch[dev], plan.ws_bytes));
+      cap[dev] = plan.ws_bytes;
+    }
+    gemm_set_workspace(&plan, scratch[dev]);
+  }
   return gemm_run(plan, static_cast<cudaStream_t>(stream));
 }
 
@@ -753,17 +838,20 @@ int lseg_upsample2x_nhwc(const void* x, void* y, int B, int H, int W, int C, voi
                                 static_cast<cudaStream_t>(stream));
 }
 
-int lseg_upsample2x_nhwc_f32(const float* x, void* y, const float* add, int B, int H, int W, int C, int out_f16,
-                             void* stream) {
+int lseg_upsample2x_nhwc256(const void* x, int in_f16, void* y, int out_f16, const float* add, int B, int H, int W,
+                            void* stream) {
   if (ensure_init()) return -1;
-  if (C != 256) {
-    set_error("upsample2x_nhwc_f32: C=%d (the decoder width, 256)", C);
+  if (add && out_f16) {
+    set_error("upsample2x_nhwc256: the skip operand goes with an fp32 output");
     return -1;
   }
-  if (out_f16)
-    return launch_upsample2x_nhwc256_f32<__half>(x, static_cast<__half*>(y), nullptr, B, H, W,
-                                                 static_cast<cudaStream_t>(stream));
-  return launch_upsample2x_nhwc256_f32<float>(x, static_cast<float*>(y), add, B, H, W, static_cast<cudaStream_t>(stream));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (in_f16) {
+    if (out_f16) return launch_upsample2x_nhwc256_f16<__half>(static_cast<const __half*>(x), static_cast<__half*>(y), nullptr, B, H, W, s);
+    return launch_upsample2x_nhwc256_f16<float>(static_cast<const __half*>(x), static_cast<float*>(y), add, B, H, W, s);
+  }
+  if (out_f16) return launch_upsample2x_nhwc256_f32<__half>(static_cast<const float*>(x), static_cast<__half*>(y), nullptr, B, H, W, s);
+  return launch_upsample2x_nhwc256_f32<float>(static_cast<const float*>(x), static_cast<float*>(y), add, B, H, W, s);
 }
 
 int lseg_l2norm_scale(const float* x, void* y, long long M, int C, float logit_scale, void* stream) {

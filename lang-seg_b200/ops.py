@@ -203,13 +203,18 @@ def im2col_3x3_s2(x):
     return a
 
 
-def upsample2x_nhwc(x, out_dtype=torch.float16, add=None):
-    """fp16 NHWC -> fp16; fp32 NHWC (C = 256) -> fp32 or fp16 (the decoder's conv-then-interpolate order)."""
+def upsample2x_nhwc(x, out_dtype=torch.float16, add=None, decoder=False):
+    """bilinear x2 align_corners=True over NHWC. decoder=False: the generic fp16 -> fp16 kernel (any C);
+    decoder=True (or fp32 input / fp32 output / add): the C = 256 kernels of the fusion blocks — fp16 | fp32 source,
+    fp16 | fp32 result, optional fp32 skip operand summed in."""
     B, H, W, Cc = x.shape
     y = torch.empty((B, 2 * H, 2 * W, Cc), dtype=out_dtype, device=x.device)
-    if x.dtype == torch.float32:
-        check(load().lseg_upsample2x_nhwc_f32(_ptr(x, torch.float32), _ptr(y), _ptr(add, torch.float32) if add is not None
-                                              else None, B, H, W, Cc, int(out_dtype == torch.float16), _stream()))
+    if decoder or x.dtype == torch.float32 or out_dtype == torch.float32 or add is not None:
+        if Cc != 256:
+            raise ValueError("the decoder interpolation kernels are built for C = 256")
+        check(load().lseg_upsample2x_nhwc256(_ptr(x), int(x.dtype == torch.float16), _ptr(y),
+                                             int(out_dtype == torch.float16),
+                                             _ptr(add, torch.float32) if add is not None else None, B, H, W, _stream()))
     else:
         check(load().lseg_upsample2x_nhwc(_ptr(x, torch.float16), _ptr(y), B, H, W, Cc, _stream()))
     return y

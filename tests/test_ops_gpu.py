@@ -126,6 +126,39 @@ def test_conv3x3(ops, B, H, W, Cin, Cout):
     _close(relu16, ref.clamp_min(0), 1e-3, "conv3x3 relu copy")
 
 
+@pytest.mark.parametrize("B,H,W,Cin", [(8, 15, 15, 256), (8, 30, 30, 256), (8, 15, 15, 1024), (1, 30, 30, 1024)])
+def test_conv3x3_split_k_epilogues(ops, B, H, W, Cin):
+    """Low-resolution decoder convs run as deterministic split-K (raw fp32 partials + splitk_reduce_kernel): the reduce
+    applies the whole RCU epilogue — folded-BN scale / shift, ReLU, two fp32 residuals, fp32 + fp16 + relu-fp16 outputs —
+    and two runs give the same bits."""
+    Cout = 256
+    x = _rand((B, H, W, Cin), 52)
+    wt = _rand((Cout, Cin, 3, 3), 53, 0.03)
+    scale = _rand((Cout,), 54, 0.2, torch.float32) + 1.0
+    shift = _rand((Cout,), 55, 0.3, torch.float32)
+    r1 = _rand((B, H, W, Cout), 56, 1.0, torch.float32)
+    r2 = _rand((B, H, W, Cout), 57, 1.0, torch.float32)
+    conv = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), padding=1).permute(0, 2, 3, 1)
+    wp = ops.pad_rows(wt.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous())
+    # conv1 of an RCU: relu(bn(conv)) -> fp16
+    t16 = torch.zeros((B, H, W, Cout), dtype=torch.float16, device="cuda")
+    ops.gemm(x, wp, Cout, conv=(3, 1), scale=scale, bias=shift, act=ops.ACT_RELU, out_f16=t16, ldc=Cout)
+    _close(t16, (conv * scale + shift).clamp_min(0), 1e-3, "split-K conv + bn + relu")
+    # conv2 of an RCU: bn(conv) + x + skip -> fp32, fp16, relu-fp16
+    o32 = torch.zeros((B, H, W, Cout), dtype=torch.float32, device="cuda")
+    o16 = torch.zeros((B, H, W, Cout), dtype=torch.float16, device="cuda")
+    orl = torch.zeros((B, H, W, Cout), dtype=torch.float16, device="cuda")
+    ops.gemm(x, wp, Cout, conv=(3, 1), scale=scale, bias=shift, res_f32=r1, res2_f32=r2, out_f32=o32, out_f16=o16,
+             out_f16_relu=orl, ldc=Cout)
+    ref = conv * scale + shift + r1 + r2
+    _close(o32, ref, 3e-4, "split-K conv + residuals fp32")
+    _close(o16, ref, 1e-3, "split-K conv + residuals fp16")
+    _close(orl, ref.clamp_min(0), 1e-3, "split-K conv + residuals relu fp16")
+    again = torch.zeros_like(o32)
+    ops.gemm(x, wp, Cout, conv=(3, 1), scale=scale, bias=shift, res_f32=r1, res2_f32=r2, out_f32=again, ldc=Cout)
+    assert torch.equal(again, o32), "split-K reduction is not deterministic"
+
+
 @pytest.mark.parametrize("s,cin,cout,g", [(4, 256, 256, 30), (2, 512, 512, 6)])
 def test_deconv_depth_to_space(ops, s, cin, cout, g):
     B = 2
@@ -277,6 +310,11 @@ def test_im2col_upsample_norms(ops):
         _close(ops.upsample2x_nhwc(xf, torch.float16), want, 1e-3, "upsample nhwc fp32 -> fp16")
         skip = _rand(tuple(want.shape), 26, 1.0, torch.float32)
         _close(ops.upsample2x_nhwc(xf, torch.float32, add=skip), want + skip, 2e-6, "upsample nhwc fp32 + skip")
+        xh = xf.half()  # the engine's variant: fp16 source (low-res out_conv result)
+        wanth = F.interpolate(xh.float().permute(0, 3, 1, 2), scale_factor=2, mode="bilinear",
+                              align_corners=True).permute(0, 2, 3, 1)
+        _close(ops.upsample2x_nhwc(xh, torch.float32, add=skip), wanth + skip, 2e-6, "upsample nhwc fp16 -> fp32 + skip")
+        _close(ops.upsample2x_nhwc(xh, torch.float16, decoder=True), wanth, 1e-3, "upsample nhwc fp16 -> fp16 (decoder)")
     lg = _rand((2, 5, 24, 40), 28, 3.0)
     up = ops.upsample2x_nchw(lg)
     _close(up, F.interpolate(lg.float(), scale_factor=2, mode="bilinear", align_corners=True), 1e-6, "upsample nchw")
