@@ -322,10 +322,15 @@ def main():
     value, total_ms = compute_value, compute_ms
     if dist is not None:
         del out
-        def run_gather(materialize):
+        def run_gather(materialize, root_batch=None):
             g = LogitsGather(eng, B, K, S, S, root=0, mode=args.gather, materialize=materialize)
+            xg = x
+            if root_batch is not None and g.mode.startswith("p2p"):
+                g.root_batch = root_batch
+                if rank == 0:
+                    xg = x[:root_batch].contiguous()
             for _ in range(W):
-                g.forward(x, text)
+                g.forward(xg, text)
             g.sync()
             barrier()
             smp = ClockSampler(local_rank)
@@ -335,12 +340,33 @@ def main():
             t0 = time.perf_counter()
             e0.record()
             for i in range(Ksteps):
-                full = g.forward(x, text)
+                full = g.forward(xg, text)
             g.sync()
             e1.record()
             barrier()
             wall = time.perf_counter() - t0
             return g, full, max_over_ranks(e0.elapsed_time(e1)), wall, smp.summary()
+
+        # Load-balanced variant: rank 0 also expands every shard to fp32 (t_up per image, serialised with its trunk), so it
+        # computes fewer images itself: the largest root batch whose step fits the other ranks' (which skip the expansion).
+        t_up = 0.0285 * (K * S * S) / (150.0 * 480 * 480)             # ms per image, measured (profiles/r02_upsample*)
+        t_img = max(1e-3, compute_ms / Ksteps / B - t_up)              # ms per image of the trunk
+        root_batch = B
+        while root_batch > 1 and root_batch * t_img + (root_batch + (world - 1) * B) * t_up > B * t_img:
+            root_batch -= 1
+        if os.environ.get("LSEG_BENCH_ROOT_BATCH"):  # exercise the path at small N
+            root_batch = max(1, min(B, int(os.environ["LSEG_BENCH_ROOT_BATCH"])))
+        balanced = None
+        if root_batch < B and args.gather.startswith("p2p"):
+            gb, _, bal_ms, _, _ = run_gather(True, root_batch)
+            n_img = (world - 1) * B + root_batch
+            if gb.mode.startswith("p2p"):
+                balanced = {"value": n_img * Ksteps / (bal_ms / 1e3), "ms_per_step": bal_ms / Ksteps,
+                            "images_per_step": n_img, "root_batch": root_batch,
+                            "what": "same gather, rank 0 computes root_batch images instead of %d because it alone expands "
+                                    "all shards to fp32; the other ranks keep %d (NOT the configuration of `value`)" % (B, B)}
+            gb.close()
+            del gb
 
         g0, _, lowres_ms, _, _ = run_gather(False)   # exchange only: root keeps the fp16 low-res logits of all shards
         g0.close()
@@ -364,6 +390,7 @@ def main():
                                                "shards' fp16 low-res logits resident on rank 0 (the difference to `value` is "
                                                "rank 0 writing N*B*K*H*W*4 bytes of fp32 logits per step, which cannot "
                                                "overlap kernels that own every SM's shared memory)"},
+                       "balanced": balanced,
                        "compute_only": {"value": compute_value, "ms_per_step": compute_ms / Ksteps,
                                         "what": "the same K steps without the gather (round-1 definition of value)"}}
         g.close()

@@ -288,6 +288,11 @@ void lseg_destroy(lseg_engine* e);
  * tokens int64 [K,77] -> text fp16 [rows_padded(K), 512], rows >= K zeroed; rows_padded = ceil(K/128)*128. */
 int lseg_encode_text(lseg_engine* e, const int64_t* tokens, int K, void* text_out, void* stream);
 
+/* Stream contract of every lseg_engine call: all work is enqueued on `stream` (nothing on the legacy default stream, no
+ * host synchronisation once the launch plan of a batch shape exists). An engine owns ONE set of activation buffers per
+ * cached shape, so calls on the same engine must be ordered — same stream, or event-ordered across streams; two forwards
+ * in flight on two streams corrupt each other. Independent concurrency = one engine per stream / thread (weights shared by
+ * pointer: the descriptor only borrows them). */
 /* LSeg.forward after tokenisation (lseg_net.py:166-205).
  * x fp32 NCHW [B,3,H,W] (H, W multiples of 32) -> out fp32 NCHW [B,K,H,W].
  * text fp16 [rows_padded(K),512] shared by all images (text_image_stride = 0), or one K-row block per

@@ -220,12 +220,19 @@ static int gemm_pick_split(const GemmDesc& d, const GemmParams& p, int pair_tile
   const GemmEpi& e = d.e;
   const bool plain_epi = e.store == STORE_ROWMAJOR && e.bias_group_rows == 0 && !e.out_row_sumsq && !e.res_f16 &&
                          !e.row_sumsq && (d.N % 8 == 0) && (e.out_f32 || e.out_f16 || e.out_f16_relu);
-  if (!plain_epi || !(d.conv || d.K >= 4096)) return 0;
+  // implicit-GEMM convs and the im2col'ed stride-2 reassemble conv (K = 9216); never the in-place residual GEMMs of the
+  // trunk (their reduce-add epilogue and 224-wide tiles are a different plan)
+  const bool inplace = e.res_f32 && e.res_f32 == e.out_f32;
+  if (!plain_epi || inplace || !(d.conv || d.K >= 8192)) return 0;
   if (pair_tiles * 2 > max_pairs) return 0;
   int s = max_pairs / pair_tiles;
   if (mode > 1) s = mode;
   if (s > p.k_iters / 4) s = p.k_iters / 4;
   if (s > 16) s = 16;
+  // two or three segments only pay where the unsplit GEMM would leave through the register-direct epilogue (fp32 /
+  // residual / multi-output: measured 39 -> 30 us at 30x30); a plain fp16 output keeps its TMA-store epilogue (25 -> 28 us)
+  const bool tma_f16 = e.out_f16 && !e.out_f32 && !e.out_f16_relu && !e.res_f32 && !e.res2_f32;
+  if (s < 4 && tma_f16 && mode <= 1) return 0;
   return s >= 2 ? s : 0;
 }
 

@@ -91,6 +91,10 @@ class LogitsGather:
         self.engine, self.B, self.K, self.H, self.W = engine, B, K, H, W
         self.background = background
         self.repeat = 1  # tools/gather_check.py --root-repeat: emulate the expansion load of a larger world
+        # images the gathering rank computes itself (<= B). It also expands every shard to fp32 (~29 us per image of
+        # HBM writes that cannot overlap its trunk), so with equal shards it is the slowest rank; `root_batch` < B
+        # balances that (bench.py `gather.balanced`). Its slot keeps B entries; entries >= root_batch are not written.
+        self.root_batch = B
         # materialize=False: root keeps the gathered fp16 low-res logits (`lowres()`), the exact information content of
         # the step, and does not expand them to fp32 — what a consumer that takes the argmax / a crop would want
         self.materialize = materialize
@@ -266,12 +270,21 @@ class LogitsGather:
         # not — see DESIGN.md section 6 — so the default is the faster shared-memory kernel)
         fn = lib.lseg_upsample2x_nchw_bg if self.background else lib.lseg_upsample2x_nchw
         per = max(1, 65535 // (self.B * self.K))  # images per launch (grid.y limit)
-        for r0 in [r for _ in range(self.repeat) for r in range(0, self.world, per)]:
-            n = min(per, self.world - r0) * self.B * self.K
-            off = r0 * self.B * self.K
+        cs = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+        def expand(img0, n_img):
+            off = img0 * self.K
             _lib.check(fn(C.c_void_p(lr_ptr + 2 * off * self.h2 * self.w2),
-                          C.c_void_p(self.out.data_ptr() + 4 * off * self.H * self.W), n, self.h2, self.w2,
-                          C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+                          C.c_void_p(self.out.data_ptr() + 4 * off * self.H * self.W), n_img * self.K, self.h2, self.w2, cs))
+
+        for _ in range(self.repeat):
+            if self.root_batch < self.B and self.root == 0:  # own (short) shard, then the peers' slots
+                expand(0, self.root_batch)
+                first = 1
+            else:
+                first = 0
+            for r0 in range(first, self.world, per):
+                expand(r0 * self.B, min(per, self.world - r0) * self.B)
 
     def sync(self):
         """Make the current stream wait for everything this object has enqueued on its side stream."""

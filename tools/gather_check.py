@@ -75,6 +75,7 @@ def main():
                 ok = ok and bool(torch.equal(full, ref))
                 del ref, lst
             del own
+            torch.cuda.synchronize()  # the plain forward above shares the engine's buffers with the next gather step
         # timing: pipelined steps
         with torch.cuda.stream(trunk):
             for _ in range(3):
