@@ -212,20 +212,22 @@ struct GemmPlan {
   GemmEpi final_epi;
 };
 
-// Split the K loop when whole tiles leave at least half of the CTA pairs idle (decoder convs on the 15x15 / 30x30
-// levels, layer3_rn / layer4_rn, the stride-2 reassemble conv): segments = pairs / tiles, at least 4 k-chunks each.
-static int gemm_pick_split(const GemmDesc& d, const GemmParams& p, int pair_tiles, int max_pairs) {
+// Split the K loop of the implicit-GEMM convs whose tile count leaves most CTA pairs idle (3x3 convs on the 15x15 / 30x30
+// decoder levels, layer3_rn / layer4_rn). The segment count is a function of the PER-IMAGE geometry only — it is sized
+// for a batch of kSplitRefBatch images whatever the actual batch — so the summation order, and with it every bit of the
+// result, is the same for batch 1 and batch 64 (the evaluator's batched and one-by-one runs must agree exactly).
+constexpr int kSplitRefBatch = 8;
+static int gemm_pick_split(const GemmDesc& d, const GemmParams& p, int n_tiles, int max_pairs) {
   static const int mode = getenv("LSEG_SPLITK_FIXED") ? atoi(getenv("LSEG_SPLITK_FIXED")) : -1;  // 0 off, >1 forced, -1 auto
-  if (mode == 0 || !g_gemm_two_cta) return 0;
+  if (mode == 0 || !g_gemm_two_cta || !d.conv) return 0;
   const GemmEpi& e = d.e;
   const bool plain_epi = e.store == STORE_ROWMAJOR && e.bias_group_rows == 0 && !e.out_row_sumsq && !e.res_f16 &&
                          !e.row_sumsq && (d.N % 8 == 0) && (e.out_f32 || e.out_f16 || e.out_f16_relu);
-  // implicit-GEMM convs and the im2col'ed stride-2 reassemble conv (K = 9216); never the in-place residual GEMMs of the
-  // trunk (their reduce-add epilogue and 224-wide tiles are a different plan)
   const bool inplace = e.res_f32 && e.res_f32 == e.out_f32;
-  if (!plain_epi || inplace || !(d.conv || d.K >= 8192)) return 0;
-  if (pair_tiles * 2 > max_pairs) return 0;
-  int s = max_pairs / pair_tiles;
+  if (!plain_epi || inplace) return 0;
+  const int ref_pair_tiles = ((kSplitRefBatch * p.tiles_h * p.tiles_w + 1) / 2) * n_tiles;
+  if (ref_pair_tiles * 2 > max_pairs) return 0;
+  int s = max_pairs / ref_pair_tiles;
   if (mode > 1) s = mode;
   if (s > p.k_iters / 4) s = p.k_iters / 4;
   if (s > 16) s = 16;
@@ -317,7 +319,7 @@ static int gemm_plan(const GemmDesc& d, GemmPlan* plan) {
   plan->ws_bytes = 0;
   {
     const int pair_tiles = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
-    const int split = gemm_pick_split(d, p, pair_tiles, g_num_sms / 2);
+    const int split = gemm_pick_split(d, p, p.num_n_tiles, g_num_sms / 2);
     if (split) {
       plan->final_epi = d.e;
       p.split_fixed = split;

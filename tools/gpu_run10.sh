@@ -3,7 +3,7 @@
 cd "${GRAFT_REPO_ROOT:-.}"
 mkdir -p gpurun_out
 rm -f gpurun_out/parity.jsonl
-timeout 2700 python -m pytest tests -m gpu -q -x > gpurun_out/pytest10.log 2>&1
+timeout 2700 python -m pytest tests -m gpu -q > gpurun_out/pytest10.log 2>&1
 echo "pytest exit $?"; tail -8 gpurun_out/pytest10.log | cut -c1-400
 run() {  # name, env...
   name=$1; shift
@@ -16,5 +16,5 @@ print('$name', d['value'], d['ms_per_step'], d['roofline']['frac'], d['step_brea
 }
 run split X=1
 run nosplit LSEG_SPLITK_FIXED=0
-run split2 X=1
-run nosplit2 LSEG_SPLITK_FIXED=0
+
+
