@@ -514,26 +514,42 @@ static int build_image_plan(lseg_engine* eng, int B, int H, int W, cudaStream_t 
     // on the low-res tensor (a quarter of the pixels), then ONE interpolation pass that writes the block's output
     // (fp32 for the next block's skip add, with that block's other input already summed in; fp16 for head1): the
     // same linear map (the interpolation weights sum to one, so the bias commutes too), 3/4 of the conv's FLOPs and
-    // the hi-res fp16 intermediate gone; one fp16 rounding (of the low-res conv result) as before (of the hi-res one).
-    LSEG_ALLOC(oc_low, __half, px * 256);
+    // the hi-res fp16 intermediate gone.
+    // The low-res conv result stays in fp32 by default (one fp16 rounding less than interpolating an fp16 tensor; path_1
+    // measured 0.7e-3 against the oracle, 1.05e-3 with an fp16 intermediate). LSEG_OUTCONV_F16 = bit mask of levels
+    // (bit k = refinenet k+1) whose result leaves through the 2.4x faster fp16 TMA-store epilogue instead (A/B).
+    static const int f16_mask = getenv("LSEG_OUTCONV_F16") ? atoi(getenv("LSEG_OUTCONV_F16")) : 0;
+    const bool low_f16 = (f16_mask >> k) & 1;
+    __half* oc16 = nullptr;
+    float* oc32 = nullptr;
     {
       GemmEpi e = epi_none();
       e.bias = w.out_conv[k].b;
-      e.out_f16 = oc_low;  // fp16 TMA-store epilogue (the register-direct fp32 one measured 66 us at level 1)
       e.ldc = 256;
+      if (low_f16) {
+        LSEG_ALLOC(t16, __half, px * 256);
+        oc16 = t16;
+        e.out_f16 = t16;
+      } else {
+        LSEG_ALLOC(t32, float, px * 256);
+        oc32 = t32;
+        e.out_f32 = t32;
+      }
       if (add_gemm(steps, r2, 256, (int)px, (int)px, w.out_conv[k], e)) return -1;
     }
     if (k > 0) {
       LSEG_ALLOC(pth, float, px * 4 * 256);
       const float* next_rn = rn_f32[k - 1];  // the next block's other input, same shape as pth
       steps.push_back([=](const CallCtx&, cudaStream_t s) {
-        return launch_upsample2x_nhwc256_f16<float>(oc_low, pth, next_rn, B, h, ww, s);
+        return low_f16 ? launch_upsample2x_nhwc256_f16<float>(oc16, pth, next_rn, B, h, ww, s)
+                       : launch_upsample2x_nhwc256_f32<float>(oc32, pth, next_rn, B, h, ww, s);
       });
       path_prev = pth;
     } else {
       LSEG_ALLOC(pth16, __half, px * 4 * 256);
       steps.push_back([=](const CallCtx&, cudaStream_t s) {
-        return launch_upsample2x_nhwc256_f16<__half>(oc_low, pth16, nullptr, B, h, ww, s);
+        return low_f16 ? launch_upsample2x_nhwc256_f16<__half>(oc16, pth16, nullptr, B, h, ww, s)
+                       : launch_upsample2x_nhwc256_f32<__half>(oc32, pth16, nullptr, B, h, ww, s);
       });
       path1_f16 = pth16;
     }

@@ -313,12 +313,19 @@ __device__ __forceinline__ void gemm_epilogue_store(const GemmEpi& e, int N, flo
   } else {  // STORE_NCHW_T : out[(b*K + n)*P + p], fp16 (lanes = consecutive pixels -> coalesced)
     const int b = static_cast<int>(grow / e.nchw_p);
     const int pix = static_cast<int>(grow - static_cast<long long>(b) * e.nchw_p);
-    const int c_lo = e.nchw_group > 0 ? b * e.nchw_group : 0;  // first column of this row's image block
-    __half* op = e.out_f16 + (static_cast<long long>(b) * e.nchw_k + (n0 - c_lo)) * e.nchw_p + pix;
+    if (e.nchw_group == 0) {  // one label set for all images: the chunk's columns are channels n0 .. n0+31
+      __half* op = e.out_f16 + (static_cast<long long>(b) * e.nchw_k + n0) * e.nchw_p + pix;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const int ch = n0 + i - c_lo;
-      if (ch >= 0 && ch < e.nchw_k && n0 + i < N) op[static_cast<long long>(i) * e.nchw_p] = __float2half_rn(f[i]);
+      for (int i = 0; i < 32; ++i)
+        if (n0 + i < e.nchw_k) op[static_cast<long long>(i) * e.nchw_p] = __float2half_rn(f[i]);
+    } else {  // per-image column blocks (zero-shot path): keep the columns of this row's image block only
+      const int c_lo = b * e.nchw_group;
+      __half* op = e.out_f16 + (static_cast<long long>(b) * e.nchw_k + (n0 - c_lo)) * e.nchw_p + pix;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int ch = n0 + i - c_lo;
+        if (ch >= 0 && ch < e.nchw_k && n0 + i < N) op[static_cast<long long>(i) * e.nchw_p] = __float2half_rn(f[i]);
+      }
     }
   }
 }
