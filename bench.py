@@ -234,6 +234,9 @@ def main():
     ap.add_argument("--backbone", default="clip_vitl16_384",
                     choices=["clip_vitl16_384", "clipRN50x16_vitl16_384", "clip_vitb32_384"],
                     help="BASELINE.json's metric is quoted on the default; the others are extra lines (config.backbone)")
+    ap.add_argument("--gather-sidestream", action="store_true",
+                    help="rank 0 expands step s on a side stream during step s+1 instead of on its main stream after it "
+                         "(LogitsGather pipelined=False; measured slower, kept for A/B)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-eval", action="store_true", help="skip the multi-scale evaluator line (SURVEY 8(f) row 1)")
@@ -323,7 +326,8 @@ def main():
     if dist is not None:
         del out
         def run_gather(materialize, root_batch=None):
-            g = LogitsGather(eng, B, K, S, S, root=0, mode=args.gather, materialize=materialize)
+            g = LogitsGather(eng, B, K, S, S, root=0, mode=args.gather, materialize=materialize,
+                             pipelined=not args.gather_sidestream)
             xg = x
             if root_batch is not None and g.mode.startswith("p2p"):
                 g.root_batch = root_batch
@@ -331,7 +335,7 @@ def main():
                     xg = x[:root_batch].contiguous()
             for _ in range(W):
                 g.forward(xg, text)
-            g.sync()
+            g.flush()
             barrier()
             smp = ClockSampler(local_rank)
             smp.start()
@@ -340,8 +344,8 @@ def main():
             t0 = time.perf_counter()
             e0.record()
             for i in range(Ksteps):
-                full = g.forward(xg, text)
-            g.sync()
+                g.forward(xg, text)
+            full = g.flush()  # pipelined gather: the expansion of the last step; side-stream gather: its drain
             e1.record()
             barrier()
             wall = time.perf_counter() - t0
@@ -384,7 +388,11 @@ def main():
                        "root_shard_bit_identical_to_plain_forward": check,
                        "what": "fp16 low-res logits (the reference's fp16 matmul result, 1/8 of the fp32 bytes it determines) "
                                "pushed into rank 0's buffer over NVLink by the copy engines, release/acquire flags, rank 0 "
-                               "upsamples all shards to fp32 [N*B,K,H,W] on a side stream (overlaps the next step)",
+                               "expands all shards to fp32 [N*B,K,H,W] (x2 upsample, bit-identical to each rank's own); "
+                               + ("on a side stream during its next step" if args.gather_sidestream else
+                                  "pipelined: step s-1 is expanded on its main stream after its forward of step s, the last "
+                                  "step inside the timed region too"),
+                       "pipelined": not args.gather_sidestream,
                        "lowres_only": {"value": world * B * Ksteps / (lowres_ms / 1e3), "ms_per_step": lowres_ms / Ksteps,
                                        "what": "the same steps with the exchange but without rank 0's fp32 expansion: all "
                                                "shards' fp16 low-res logits resident on rank 0 (the difference to `value` is "

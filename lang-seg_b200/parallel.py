@@ -87,9 +87,16 @@ class LogitsGather:
     """
 
     def __init__(self, engine, B, K, H, W, root=0, mode="p2p_copy", group=None, timeout_ms=30000, materialize=True,
-                 background=False):
+                 background=False, pipelined=False):
         self.engine, self.B, self.K, self.H, self.W = engine, B, K, H, W
         self.background = background
+        # pipelined=True (p2p modes): the gathering rank expands step s-1 on its MAIN stream right after its own forward of
+        # step s, instead of expanding step s on a side stream while the trunk of step s+1 runs. The expansion cannot
+        # overlap the trunk anyway (it needs the SMs the trunk's CTAs fill); interleaved with it, it costs more than its
+        # own time (N = 8: 11.0 ms/step against 8.4 + 1.8), and the data of step s-1 has long arrived, so nothing waits.
+        # forward() then returns the gathered logits of the PREVIOUS step (None at the first call); flush() the last.
+        self.pipelined = pipelined and mode.startswith("p2p")
+        self._expanded = 0
         self.repeat = 1  # tools/gather_check.py --root-repeat: emulate the expansion load of a larger world
         # images the gathering rank computes itself (<= B). It also expands every shard to fp32 (~29 us per image of
         # HBM writes that cannot overlap its trunk), so with equal shards it is the slowest rank; `root_batch` < B
@@ -240,6 +247,10 @@ class LogitsGather:
             return None
         # root
         eng.forward_lowres(x, text, self.K, text_image_stride, logits_lr=self._slot(self.base, par, self.root))
+        if self.pipelined:
+            if s > 1 and self._expanded < s - 1:
+                return self._expand_on(cur, s - 1)
+            return self.out if s > 1 else None
         ready = torch.cuda.Event()
         ready.record(cur)
         with torch.cuda.stream(self.comm):
@@ -257,6 +268,30 @@ class LogitsGather:
             ev = torch.cuda.Event()
             ev.record(self.comm)
         self.done[par] = ev
+        return self.out
+
+    def _expand_on(self, stream, t):
+        """root, pipelined mode: expand the gathered shards of step t on `stream` (the caller's current stream)."""
+        import ctypes as C
+        from . import _lib
+        lib, st = self.lib, C.c_void_p(stream.cuda_stream)
+        peers = [r for r in range(self.world) if r != self.root]
+        if self.root == 0:
+            _lib.check(lib.lseg_p2p_wait(C.c_void_p(self.base + 8), self.world - 1, 1, t, self.timeout_ms, st))
+        else:
+            for r in peers:
+                _lib.check(lib.lseg_p2p_wait(C.c_void_p(self.base + 8 * r), 1, 1, t, self.timeout_ms, st))
+        self._upsample(self._slot(self.base, t & 1, 0))
+        for r in peers:
+            _lib.check(lib.lseg_p2p_signal(C.c_void_p(self.peer_bases[r] + 8 * _CONSUMED), t, st))
+        self._expanded = t
+        return self.out
+
+    def flush(self):
+        """pipelined mode: expand the last step (root) and return the gathered logits; otherwise just sync()."""
+        if self.pipelined and self.rank == self.root and self.mode != "single" and self._expanded < self.step:
+            self._expand_on(torch.cuda.current_stream(self.device), self.step)
+        self.sync()
         return self.out
 
     def _upsample(self, lr_ptr):

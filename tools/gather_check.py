@@ -48,13 +48,16 @@ def main():
           for i in range(3)]
     res = {}
     # (mode, background kernel for rank 0's fp32 expansion, trunk on a high-priority stream, materialise fp32)
-    variants = [("p2p_copy", "p2p_copy", True, False, True), ("p2p_copy_fg", "p2p_copy", False, False, True),
-                ("p2p_copy_hp", "p2p_copy", True, True, True), ("p2p_copy_lowres", "p2p_copy", True, False, False),
-                ("p2p_store", "p2p_store", True, False, True), ("nccl", "nccl", True, False, True)]
+    variants = [("p2p_copy", "p2p_copy", False, False, True), ("p2p_copy_pipelined", "p2p_copy", False, False, True),
+                ("p2p_copy_bg", "p2p_copy", True, False, True),
+                ("p2p_copy_hp", "p2p_copy", False, True, True), ("p2p_copy_lowres", "p2p_copy", False, False, False),
+                ("p2p_store", "p2p_store", False, False, True), ("p2p_store_pipelined", "p2p_store", False, False, True),
+                ("nccl", "nccl", False, False, True)]
     lo, hi = torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, "priority_range") else (0, -1)
     hp_stream = torch.cuda.Stream(device=dev, priority=hi)
     for name, mode, background, high_prio, materialize in variants:
-        g = LogitsGather(eng, B, K, S, S, root=0, mode=mode, background=background, materialize=materialize)
+        g = LogitsGather(eng, B, K, S, S, root=0, mode=mode, background=background, materialize=materialize,
+                         pipelined=name.endswith("_pipelined"))
         g.repeat = args.root_repeat
         trunk = hp_stream if high_prio else torch.cuda.current_stream(dev)
         torch.cuda.synchronize()
@@ -62,8 +65,8 @@ def main():
         for i in range(5 if materialize else 0):  # correctness over several steps (slot reuse), different inputs per step
             x = xs[i % 3]
             with torch.cuda.stream(trunk):
-                full = g.forward(x, text)
-                g.sync()
+                g.forward(x, text)
+                full = g.flush()
             torch.cuda.synchronize()
             own = eng.forward(x, text, K)
             ref = torch.empty((world * B, K, S, S), dtype=torch.float32, device=dev) if rank == 0 else None
@@ -80,7 +83,7 @@ def main():
         with torch.cuda.stream(trunk):
             for _ in range(3):
                 g.forward(xs[0], text)
-            g.sync()
+            g.flush()
         dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -88,7 +91,7 @@ def main():
             e0.record()
             for i in range(args.steps):
                 g.forward(xs[i % 3], text)
-            g.sync()
+            g.flush()
             e1.record()
         torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=dev)

@@ -10,7 +10,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --
   --log-file gpurun_out/launches_${R}.csv $BENCH > gpurun_out/ncu_launches_${R}.log 2>&1
 # (2) DRAM traffic of every GEMM / attention launch (algorithmic-vs-actual bytes for roofline.traffic)
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
-  -k regex:'gemm_tc|mhsa' -c 1500 --csv --log-file gpurun_out/traffic_${R}.csv $BENCH > gpurun_out/ncu_traffic_${R}.log 2>&1
+  -k regex:'gemm_tc2|mhsa' -c 1500 --csv --log-file gpurun_out/traffic_${R}.csv $BENCH > gpurun_out/ncu_traffic_${R}.log 2>&1
 # (3) full-set captures: 8 consecutive GEMM launches inside the ViT trunk of a warm forward, one attention launch
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tc2 --launch-skip 200 -c 8 \
   -f -o gpurun_out/prof_gemm_${R} $BENCH > gpurun_out/ncu_gemm_${R}.log 2>&1
@@ -18,6 +18,9 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:mhsa
   -f -o gpurun_out/prof_mhsa_${R} $BENCH > gpurun_out/ncu_mhsa_${R}.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:upsample2x_nchw --launch-skip 2 -c 1 \
   -f -o gpurun_out/prof_upsample_${R} $BENCH > gpurun_out/ncu_upsample_${R}.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:layernorm --launch-skip 20 -c 1 \
+# the ViT instance (fp32 residual stream, C = 1024); the text tower's <__half, 512> launches come first and are skipped by name
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'layernorm_kernel<float' --launch-skip 20 -c 1 \
   -f -o gpurun_out/prof_ln_${R} $BENCH > gpurun_out/ncu_ln_${R}.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'splitk_reduce|upsample2x_nhwc256' --launch-skip 14 -c 4 \
+  -f -o gpurun_out/prof_decoder_${R} $BENCH > gpurun_out/ncu_decoder_${R}.log 2>&1
 ls -la gpurun_out | tail -12

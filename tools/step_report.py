@@ -4,7 +4,11 @@ no PDL overlap between launches, ~10-15 us of event overhead on the short ones):
 the engine's plan (lang-seg_b200/csrc/engine.cuh build_image_plan, clip_vitl16_384) and writes a markdown table grouped by
 shape — the per-shape GEMM table of profiles/.
 
-  python tools/step_report.py gpurun_out/profile.json [B] > profiles/r02_gemm_shapes.md
+  python tools/step_report.py gpurun_out/profile.json [gpurun_out/traffic.csv] > profiles/r02_gemm_shapes.md
+
+With the ncu capture of `--metrics dram__bytes_read.sum,dram__bytes_write.sum -k regex:'gemm_tc2|mhsa'` of the same command
+(tools/profile_run.sh step 2) the table gains the measured DRAM MB per launch (cold L2 under ncu) next to the algorithmic
+MB (operands + weights + outputs, B = 8 at 480x480).
 """
 import json
 import sys
@@ -42,26 +46,91 @@ def labels():
     return out
 
 
+def algorithmic_mb(name, B=8):
+    """operand + weight + output (+ residual) bytes of one launch, MB; None where not tabulated"""
+    M = B * 901
+    f16, f32 = 2, 4
+    t = None
+    if name.startswith("QKV"):
+        t = M * 1024 * f16 + 3072 * 1024 * f16 + M * 3072 * f16
+    elif name.startswith("proj"):
+        t = M * 1024 * f16 + 1024 * 1024 * f16 + 2 * M * 1024 * f32
+    elif name.startswith("fc1"):
+        t = M * 1024 * f16 + 4096 * 1024 * f16 + M * 4096 * f16
+    elif name.startswith("fc2"):
+        t = M * 4096 * f16 + 4096 * 1024 * f16 + 2 * M * 1024 * f32
+    elif name == "MHSA":
+        t = M * 3072 * f16 + M * 1024 * f16
+    elif name.startswith("head1"):
+        px = B * 240 * 240
+        t = px * 256 * f16 + 512 * 256 * f16 + px * 512 * f16 + px * 16 * f32
+    elif name.startswith("pixel x text"):
+        px = B * 240 * 240
+        t = px * 512 * f16 + px * 16 * f32 + 256 * 512 * f16 + px * 150 * f16
+    elif "3x3" in name or "rcu" in name:
+        res = int(name.rsplit("@", 1)[1])
+        px = B * res * res
+        cin = 256
+        for c in (512, 1024):
+            if f"{c}->" in name:
+                cin = c
+        t = px * cin * f16 + 256 * 9 * cin * f16
+        if "layer" in name:
+            t += px * 256 * (f32 + f16)
+        elif "conv1" in name:
+            t += px * 256 * f16
+        elif "fp32+relu" in name:
+            t += px * 256 * (f32 + f32 + f16)
+        else:
+            t += px * 256 * (f32 + f16)
+    return None if t is None else t / 1e6
+
+
+def read_traffic(path, n_expected):
+    import csv
+    with open(path) as f:
+        lines = [l for l in f if not l.startswith("==")]
+    per = OrderedDict()
+    for r in csv.DictReader(lines):
+        d = per.setdefault(r["ID"], {"name": r["Kernel Name"]})
+        d[r["Metric Name"]] = float(r["Metric Value"].replace(",", ""))
+    rows = [d for d in per.values() if "gemm_tc2" in d["name"] or "mhsa" in d["name"]]
+    rows = rows[-n_expected:]
+    return [(d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)) / 1e6 for d in rows]
+
+
 def main():
     prof = json.load(open(sys.argv[1]))
     lab = labels()
     if len(lab) != len(prof):
         print(f"<!-- label count {len(lab)} != launches {len(prof)}: plan changed, labels dropped -->")
         lab = [KINDS.get(e["kind"], "?") for e in prof]
+    n_tc = sum(1 for e in prof if e["kind"] in (1, 2))
+    dram = read_traffic(sys.argv[2], n_tc) if len(sys.argv) > 2 else None
+    if dram is not None and len(dram) != n_tc:
+        print(f"<!-- traffic capture has {len(dram)} GEMM/MHSA launches, the step {n_tc}: DRAM column dropped -->")
+        dram = None
     groups = OrderedDict()
+    it = iter(dram) if dram else None
     for name, e in zip(lab, prof):
-        g = groups.setdefault(name, {"n": 0, "ms": 0.0, "gf": 0.0, "kind": e["kind"]})
+        g = groups.setdefault(name, {"n": 0, "ms": 0.0, "gf": 0.0, "kind": e["kind"], "dram": 0.0, "nd": 0})
         g["n"] += 1
         g["ms"] += e["ms"]
         g["gf"] += e["gflop"]
+        if it is not None and e["kind"] in (1, 2):
+            g["dram"] += next(it)
+            g["nd"] += 1
     total = sum(e["ms"] for e in prof)
-    print("| launch | count | avg µs | GFLOP each | TFLOP/s | share of the event-timed sum |")
-    print("|---|---:|---:|---:|---:|---:|")
+    print("| launch | count | avg µs | GFLOP each | TFLOP/s | algorithmic MB | DRAM MB (ncu, cold L2) | share of the event-timed sum |")
+    print("|---|---:|---:|---:|---:|---:|---:|---:|")
     for name, g in groups.items():
         us = g["ms"] / g["n"] * 1e3
         gf = g["gf"] / g["n"]
         tf = f"{g['gf'] / g['ms']:.0f}" if g["gf"] > 0.5 else "–"
-        print(f"| {name} | {g['n']} | {us:.1f} | {gf:.2f} | {tf} | {100 * g['ms'] / total:.1f} % |")
+        alg = algorithmic_mb(name)
+        alg = f"{alg:.1f}" if alg is not None else "–"
+        dr = f"{g['dram'] / g['nd']:.1f}" if g["nd"] else "–"
+        print(f"| {name} | {g['n']} | {us:.1f} | {gf:.2f} | {tf} | {alg} | {dr} | {100 * g['ms'] / total:.1f} % |")
     print(f"\nsum of the event-timed launches: {total:.3f} ms ({len(prof)} launches); the step itself (launches overlapped by "
           "programmatic dependent launch, no events in between) is what `bench.py` reports as ms_per_step.")
     fam = {}
