@@ -18,8 +18,8 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:mhsa
   -f -o gpurun_out/prof_mhsa_${R} $BENCH > gpurun_out/ncu_mhsa_${R}.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:upsample2x_nchw --launch-skip 2 -c 1 \
   -f -o gpurun_out/prof_upsample_${R} $BENCH > gpurun_out/ncu_upsample_${R}.log 2>&1
-# the ViT instance (fp32 residual stream, C = 1024); the text tower's <__half, 512> launches come first and are skipped by name
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'layernorm_kernel<float' --launch-skip 20 -c 1 \
+# the ViT instance (fp32 residual stream, C = 1024): match the demangled name, the text tower's <__half, 512> launches come first
+timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'layernorm_kernel<float' --launch-skip 20 -c 1 \
   -f -o gpurun_out/prof_ln_${R} $BENCH > gpurun_out/ncu_ln_${R}.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'splitk_reduce|upsample2x_nhwc256' --launch-skip 14 -c 4 \
   -f -o gpurun_out/prof_decoder_${R} $BENCH > gpurun_out/ncu_decoder_${R}.log 2>&1

@@ -67,7 +67,7 @@ def algorithmic_mb(name, B=8):
     elif name.startswith("pixel x text"):
         px = B * 240 * 240
         t = px * 512 * f16 + px * 16 * f32 + 256 * 512 * f16 + px * 150 * f16
-    elif "3x3" in name or "rcu" in name:
+    elif "@" in name and ("3x3" in name or "rcu" in name):
         res = int(name.rsplit("@", 1)[1])
         px = B * res * res
         cin = 256
