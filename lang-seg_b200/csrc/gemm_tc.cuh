@@ -313,20 +313,17 @@ __device__ __forceinline__ void gemm_epilogue_store(const GemmEpi& e, int N, flo
   } else {  // STORE_NCHW_T : out[(b*K + n)*P + p], fp16 (lanes = consecutive pixels -> coalesced)
     const int b = static_cast<int>(grow / e.nchw_p);
     const int pix = static_cast<int>(grow - static_cast<long long>(b) * e.nchw_p);
-    if (e.nchw_group == 0) {  // one label set for all images: the chunk's columns are channels n0 .. n0+31
-      __half* op = e.out_f16 + (static_cast<long long>(b) * e.nchw_k + n0) * e.nchw_p + pix;
+    // One label set for all images (nchw_group == 0): the chunk's columns n0 .. n0+31 are channels n0 .. n0+31.
+    // Per-image column blocks (zero-shot path): a row of image b keeps columns [b*group, b*group + nchw_k) as channels
+    // 0 .. nchw_k-1. Both are "store element i of the chunk iff lo <= i < hi" on a pointer shifted by the block start —
+    // two scalar bounds per chunk, no per-element index arithmetic (a separate branch for the grouped case spilled).
+    const int c_lo = b * e.nchw_group;  // 0 when nchw_group == 0
+    const int lo = max(0, c_lo - n0);
+    const int hi = min(min(32, c_lo + e.nchw_k - n0), N - n0);
+    __half* op = e.out_f16 + (static_cast<long long>(b) * e.nchw_k + (n0 - c_lo)) * e.nchw_p + pix;
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (n0 + i < e.nchw_k) op[static_cast<long long>(i) * e.nchw_p] = __float2half_rn(f[i]);
-    } else {  // per-image column blocks (zero-shot path): keep the columns of this row's image block only
-      const int c_lo = b * e.nchw_group;
-      __half* op = e.out_f16 + (static_cast<long long>(b) * e.nchw_k + (n0 - c_lo)) * e.nchw_p + pix;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int ch = n0 + i - c_lo;
-        if (ch >= 0 && ch < e.nchw_k && n0 + i < N) op[static_cast<long long>(i) * e.nchw_p] = __float2half_rn(f[i]);
-      }
-    }
+    for (int i = 0; i < 32; ++i)
+      if (i >= lo && i < hi) op[static_cast<long long>(i) * e.nchw_p] = __float2half_rn(f[i]);
   }
 }
 
@@ -354,11 +351,12 @@ template <int EPI, bool SINGLE_BUF = false, typename WaitFn>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t t_row, int n_base, int ncols,
                                                    int m_tile, int r, WaitFn wait_accumulator, uint8_t* stage_buf,
                                                    int& store_groups, GemmTrace& tr, bool first_k = true,
-                                                   long long row_shift = 0) {
+                                                   int split_seg = 0) {
   const GemmEpi& e = p.e;
   long long grow;
   const bool valid = gemm_row_map(p, m_tile, r, grow);
-  if constexpr (EPI == EPI_DIRECT) grow += row_shift;  // split_fixed: this segment's plane of the partial-sum workspace
+  // split_fixed: this segment's plane of the partial-sum workspace (split_rows is 0 otherwise)
+  if constexpr (EPI == EPI_DIRECT) grow += split_seg * p.split_rows;
   if constexpr (EPI == EPI_DIRECT) {
     // The fp32 residual of chunk c+1 is requested before chunk c is processed, and that of chunk 0 before the
     // accumulator is even ready, so the residual read latency overlaps the main loop / the previous chunk.
@@ -756,7 +754,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((Gemm2Cfg<BN, EPI, E
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + col0;
       gemm_epilogue_tile<EPI, Cfg::kEpiWarps == 16>(p, t_row, n_tile * BN + col0, ncols, m_tile, r,
                               [&]() { mbar_wait(&tmem_full[acc], acc_phase, 24); }, stage_buf, store_groups, tr,
-                              k_begin == 0, static_cast<long long>(sc.seg) * p.split_rows);
+                              k_begin == 0, sc.seg);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster_relaxed(&tmem_empty[acc], 0);  // leader CTA's barrier: 2 CTAs x 8 warps
