@@ -314,7 +314,7 @@ static inline int launch_upsample2x_nhwc(const __half* x, __half* y, int B, int 
 // grid (ceil(Wo/32), Ho, B), 256 threads.
 // ------------------------------------------------------------------------------------------
 template <typename TOut>
-__global__ void __launch_bounds__(256, 3) upsample2x_nhwc256_f32_kernel(const float* __restrict__ x, TOut* __restrict__ y,
+__global__ void __launch_bounds__(256, 2) upsample2x_nhwc256_f32_kernel(const float* __restrict__ x, TOut* __restrict__ y,
                                                                         const float* __restrict__ add, int H, int W) {
   griddep_launch_dependents();
   griddep_wait();

@@ -533,9 +533,13 @@ struct Gemm2Cfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + kStageOutBytes + 1024 + 256;
 };
 
-template <int BN, int EPI, int EW = 8>
+// FIXED_SPLIT: the deterministic split-K schedule (GemmParams::split_fixed) is its own instantiation — its index
+// arithmetic costs the other kernels their uniform-datapath code (UISETP 254 -> 97, BSSY/BSYNC pairs appear) when it is
+// merely present as a runtime branch.
+template <int BN, int EPI, int EW = 8, bool FIXED_SPLIT = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((Gemm2Cfg<BN, EPI, EW>::kThreads), 1)
     gemm_tc2_kernel(const __grid_constant__ GemmParams p) {
+  static_assert(!FIXED_SPLIT || EPI == EPI_DIRECT, "split-K partials leave through the register-direct epilogue");
   using Cfg = Gemm2Cfg<BN, EPI, EW>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -588,13 +592,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((Gemm2Cfg<BN, EPI, E
     bool split;
     int fixed, seg;
     __device__ bool next(int& tile, int& k0, int& k1) {
-      if (fixed > 1) {  // units = (tile, segment), dealt round-robin
+      if constexpr (FIXED_SPLIT) {  // units = (tile, segment), dealt round-robin; 32-bit arithmetic (seg < 16)
         if (tile_next >= num_tiles * fixed) return false;
         tile = tile_next / fixed;
         seg = tile_next - tile * fixed;
         tile_next += tile_step;
-        k0 = static_cast<int>(static_cast<long long>(seg) * k_iters / fixed);
-        k1 = static_cast<int>(static_cast<long long>(seg + 1) * k_iters / fixed);
+        k0 = seg * k_iters / fixed;
+        k1 = (seg + 1) * k_iters / fixed;
         return true;
       }
       if (!split) {
@@ -621,7 +625,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((Gemm2Cfg<BN, EPI, E
     sc.num_tiles = num_tiles;
     sc.k_iters = p.k_iters;
     sc.split = (EPI == EPI_TMA_ADD) && p.split_k;
-    sc.fixed = (EPI == EPI_DIRECT) ? p.split_fixed : 0;
+    sc.fixed = FIXED_SPLIT ? p.split_fixed : 0;
     sc.seg = 0;
     const long long units = static_cast<long long>(num_tiles) * p.k_iters;
     // boundaries on multiples of 4 k-chunks: no sliver segments whose epilogue would cost more than their MMAs
@@ -754,7 +758,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((Gemm2Cfg<BN, EPI, E
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + col0;
       gemm_epilogue_tile<EPI, Cfg::kEpiWarps == 16>(p, t_row, n_tile * BN + col0, ncols, m_tile, r,
                               [&]() { mbar_wait(&tmem_full[acc], acc_phase, 24); }, stage_buf, store_groups, tr,
-                              k_begin == 0, sc.seg);
+                              k_begin == 0, FIXED_SPLIT ? sc.seg : 0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster_relaxed(&tmem_empty[acc], 0);  // leader CTA's barrier: 2 CTAs x 8 warps

@@ -103,6 +103,10 @@ static int init_device(int dev) {
   LSEG_SET_SMEM_TC2(128, EPI_TMA_ADD);
   LSEG_SET_SMEM_TC2(224, EPI_TMA_ADD);
 #undef LSEG_SET_SMEM_TC2
+  cudaFuncSetAttribute(gemm_tc2_kernel<256, EPI_DIRECT, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       Gemm2Cfg<256, EPI_DIRECT>::kSmemBytes);
+  cudaFuncSetAttribute(gemm_tc2_kernel<128, EPI_DIRECT, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       Gemm2Cfg<128, EPI_DIRECT>::kSmemBytes);
   cudaFuncSetAttribute(gemm_tc2_kernel<256, EPI_TMA_F16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        Gemm2Cfg<256, EPI_TMA_F16, 16>::kSmemBytes);
 #define LSEG_M2_ATTR(K)                                                                       \
@@ -422,6 +426,9 @@ static int gemm_run_kernel(const GemmPlan& plan, cudaStream_t stream) {
                    Gemm2Cfg<256, EPI_TMA_F16, 16>::kSmemBytes, stream, plan.p);
       else if (plan.epi == EPI_TMA_F16) LSEG_LAUNCH_TC2(256, EPI_TMA_F16);
       else if (plan.epi == EPI_TMA_ADD) LSEG_LAUNCH_TC2(256, EPI_TMA_ADD);
+      else if (plan.p.split_fixed > 1)
+        launch_pdl(gemm_tc2_kernel<256, EPI_DIRECT, 8, true>, dim3(plan.grid), dim3(Gemm2Cfg<256, EPI_DIRECT>::kThreads),
+                   Gemm2Cfg<256, EPI_DIRECT>::kSmemBytes, stream, plan.p);
       else LSEG_LAUNCH_TC2(256, EPI_DIRECT);
     } else if (plan.bn == 224) {
       if (plan.epi != EPI_TMA_ADD) {
@@ -432,6 +439,9 @@ static int gemm_run_kernel(const GemmPlan& plan, cudaStream_t stream) {
     } else {
       if (plan.epi == EPI_TMA_F16) LSEG_LAUNCH_TC2(128, EPI_TMA_F16);
       else if (plan.epi == EPI_TMA_ADD) LSEG_LAUNCH_TC2(128, EPI_TMA_ADD);
+      else if (plan.p.split_fixed > 1)
+        launch_pdl(gemm_tc2_kernel<128, EPI_DIRECT, 8, true>, dim3(plan.grid), dim3(Gemm2Cfg<128, EPI_DIRECT>::kThreads),
+                   Gemm2Cfg<128, EPI_DIRECT>::kSmemBytes, stream, plan.p);
       else LSEG_LAUNCH_TC2(128, EPI_DIRECT);
     }
 #undef LSEG_LAUNCH_TC2
