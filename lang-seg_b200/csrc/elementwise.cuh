@@ -313,8 +313,9 @@ static inline int launch_upsample2x_nhwc(const __half* x, __half* y, int B, int 
 // fusion block's other input so that its residual conv needs one skip operand instead of two.
 // grid (ceil(Wo/32), Ho, B), 256 threads.
 // ------------------------------------------------------------------------------------------
+// (256, 3): 80 registers with a 16-24 B spill measured FASTER than spill-free at 2 blocks / SM (121 vs 144 us at level 1)
 template <typename TOut>
-__global__ void __launch_bounds__(256, 2) upsample2x_nhwc256_f32_kernel(const float* __restrict__ x, TOut* __restrict__ y,
+__global__ void __launch_bounds__(256, 3) upsample2x_nhwc256_f32_kernel(const float* __restrict__ x, TOut* __restrict__ y,
                                                                         const float* __restrict__ add, int H, int W) {
   griddep_launch_dependents();
   griddep_wait();
