@@ -214,7 +214,10 @@ __device__ __forceinline__ void gemm_epilogue_math(const GemmEpi& e, int N, cons
   }
 }
 
-// EPI_DIRECT store part, straight from registers (thread <-> row)
+// EPI_DIRECT store part, straight from registers (thread <-> row). GROUPED: STORE_NCHW_T with per-image column blocks
+// (zero-shot path) — a compile-time variant: as a runtime case it costs the common kernel 4 registers and 128
+// instructions (the one-label-set instantiation is instruction-for-instruction the round-1 kernel again).
+template <bool GROUPED = false>
 __device__ __forceinline__ void gemm_epilogue_store(const GemmEpi& e, int N, float (&f)[32], const float4 (&res)[8],
                                                     bool has_res, long long grow, int n0) {
   const int nvalid = min(32, N - n0);
@@ -313,17 +316,22 @@ __device__ __forceinline__ void gemm_epilogue_store(const GemmEpi& e, int N, flo
   } else {  // STORE_NCHW_T : out[(b*K + n)*P + p], fp16 (lanes = consecutive pixels -> coalesced)
     const int b = static_cast<int>(grow / e.nchw_p);
     const int pix = static_cast<int>(grow - static_cast<long long>(b) * e.nchw_p);
-    // One label set for all images (nchw_group == 0): the chunk's columns n0 .. n0+31 are channels n0 .. n0+31.
-    // Per-image column blocks (zero-shot path): a row of image b keeps columns [b*group, b*group + nchw_k) as channels
-    // 0 .. nchw_k-1. Both are "store element i of the chunk iff lo <= i < hi" on a pointer shifted by the block start —
-    // two scalar bounds per chunk, no per-element index arithmetic (a separate branch for the grouped case spilled).
-    const int c_lo = b * e.nchw_group;  // 0 when nchw_group == 0
-    const int lo = max(0, c_lo - n0);
-    const int hi = min(min(32, c_lo + e.nchw_k - n0), N - n0);
-    __half* op = e.out_f16 + (static_cast<long long>(b) * e.nchw_k + (n0 - c_lo)) * e.nchw_p + pix;
+    if constexpr (!GROUPED) {  // one label set for all images: the chunk's columns are channels n0 .. n0+31
+      __half* op = e.out_f16 + (static_cast<long long>(b) * e.nchw_k + n0) * e.nchw_p + pix;
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (i >= lo && i < hi) op[static_cast<long long>(i) * e.nchw_p] = __float2half_rn(f[i]);
+      for (int i = 0; i < 32; ++i)
+        if (n0 + i < e.nchw_k) op[static_cast<long long>(i) * e.nchw_p] = __float2half_rn(f[i]);
+    } else {
+      // per-image column blocks: a row of image b keeps columns [b*group, b*group + nchw_k) as channels 0 .. nchw_k-1:
+      // "store element i of the chunk iff lo <= i < hi" on a pointer shifted by the block start
+      const int c_lo = b * e.nchw_group;
+      const int lo = max(0, c_lo - n0);
+      const int hi = min(min(32, c_lo + e.nchw_k - n0), N - n0);
+      __half* op = e.out_f16 + (static_cast<long long>(b) * e.nchw_k + (n0 - c_lo)) * e.nchw_p + pix;
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i >= lo && i < hi) op[static_cast<long long>(i) * e.nchw_p] = __float2half_rn(f[i]);
+    }
   }
 }
 
@@ -347,7 +355,7 @@ constexpr int kEpiStageBytes = 2 * 4096;  // per epilogue warp: two 32-row x 128
 // Epilogue of one 128 x (ncols) accumulator slab for one warp (r = quarter*32 + lane = this thread's row).
 // SINGLE_BUF: one 4 KB staging tile per warp instead of two (16-epilogue-warp configuration, where a warp emits one
 // store group per tile and the previous tile's bulk store has long finished reading the buffer).
-template <int EPI, bool SINGLE_BUF = false, typename WaitFn>
+template <int EPI, bool SINGLE_BUF = false, bool GROUPED = false, typename WaitFn>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t t_row, int n_base, int ncols,
                                                    int m_tile, int r, WaitFn wait_accumulator, uint8_t* stage_buf,
                                                    int& store_groups, GemmTrace& tr, bool first_k = true,
@@ -406,7 +414,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] *= row_mul;
         }
-        gemm_epilogue_store(e, p.N, f, rcur, has_res, grow, n0);
+        gemm_epilogue_store<GROUPED>(e, p.N, f, rcur, has_res, grow, n0);
       }
     }
   } else {
@@ -536,10 +544,11 @@ struct Gemm2Cfg {
 // FIXED_SPLIT: the deterministic split-K schedule (GemmParams::split_fixed) is its own instantiation — its index
 // arithmetic costs the other kernels their uniform-datapath code (UISETP 254 -> 97, BSSY/BSYNC pairs appear) when it is
 // merely present as a runtime branch.
-template <int BN, int EPI, int EW = 8, bool FIXED_SPLIT = false>
+template <int BN, int EPI, int EW = 8, bool FIXED_SPLIT = false, bool GROUPED = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((Gemm2Cfg<BN, EPI, EW>::kThreads), 1)
     gemm_tc2_kernel(const __grid_constant__ GemmParams p) {
   static_assert(!FIXED_SPLIT || EPI == EPI_DIRECT, "split-K partials leave through the register-direct epilogue");
+  static_assert(!GROUPED || (EPI == EPI_DIRECT && !FIXED_SPLIT), "per-image column blocks: NCHW-T store, register-direct");
   using Cfg = Gemm2Cfg<BN, EPI, EW>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -756,7 +765,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((Gemm2Cfg<BN, EPI, E
       const int m_tile = (tile % m_pairs) * 2 + static_cast<int>(rank);
       const int n_tile = tile / m_pairs;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + col0;
-      gemm_epilogue_tile<EPI, Cfg::kEpiWarps == 16>(p, t_row, n_tile * BN + col0, ncols, m_tile, r,
+      gemm_epilogue_tile<EPI, Cfg::kEpiWarps == 16, GROUPED>(p, t_row, n_tile * BN + col0, ncols, m_tile, r,
                               [&]() { mbar_wait(&tmem_full[acc], acc_phase, 24); }, stage_buf, store_groups, tr,
                               k_begin == 0, FIXED_SPLIT ? sc.seg : 0);
       tc_fence_before();

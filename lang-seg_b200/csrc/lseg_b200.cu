@@ -107,6 +107,10 @@ static int init_device(int dev) {
                        Gemm2Cfg<256, EPI_DIRECT>::kSmemBytes);
   cudaFuncSetAttribute(gemm_tc2_kernel<128, EPI_DIRECT, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        Gemm2Cfg<128, EPI_DIRECT>::kSmemBytes);
+  cudaFuncSetAttribute(gemm_tc2_kernel<256, EPI_DIRECT, 8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       Gemm2Cfg<256, EPI_DIRECT>::kSmemBytes);
+  cudaFuncSetAttribute(gemm_tc2_kernel<128, EPI_DIRECT, 8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       Gemm2Cfg<128, EPI_DIRECT>::kSmemBytes);
   cudaFuncSetAttribute(gemm_tc2_kernel<256, EPI_TMA_F16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        Gemm2Cfg<256, EPI_TMA_F16, 16>::kSmemBytes);
 #define LSEG_M2_ATTR(K)                                                                       \
@@ -429,6 +433,9 @@ static int gemm_run_kernel(const GemmPlan& plan, cudaStream_t stream) {
       else if (plan.p.split_fixed > 1)
         launch_pdl(gemm_tc2_kernel<256, EPI_DIRECT, 8, true>, dim3(plan.grid), dim3(Gemm2Cfg<256, EPI_DIRECT>::kThreads),
                    Gemm2Cfg<256, EPI_DIRECT>::kSmemBytes, stream, plan.p);
+      else if (plan.p.e.store == STORE_NCHW_T && plan.p.e.nchw_group > 0)
+        launch_pdl(gemm_tc2_kernel<256, EPI_DIRECT, 8, false, true>, dim3(plan.grid),
+                   dim3(Gemm2Cfg<256, EPI_DIRECT>::kThreads), Gemm2Cfg<256, EPI_DIRECT>::kSmemBytes, stream, plan.p);
       else LSEG_LAUNCH_TC2(256, EPI_DIRECT);
     } else if (plan.bn == 224) {
       if (plan.epi != EPI_TMA_ADD) {
@@ -442,6 +449,9 @@ static int gemm_run_kernel(const GemmPlan& plan, cudaStream_t stream) {
       else if (plan.p.split_fixed > 1)
         launch_pdl(gemm_tc2_kernel<128, EPI_DIRECT, 8, true>, dim3(plan.grid), dim3(Gemm2Cfg<128, EPI_DIRECT>::kThreads),
                    Gemm2Cfg<128, EPI_DIRECT>::kSmemBytes, stream, plan.p);
+      else if (plan.p.e.store == STORE_NCHW_T && plan.p.e.nchw_group > 0)
+        launch_pdl(gemm_tc2_kernel<128, EPI_DIRECT, 8, false, true>, dim3(plan.grid),
+                   dim3(Gemm2Cfg<128, EPI_DIRECT>::kThreads), Gemm2Cfg<128, EPI_DIRECT>::kSmemBytes, stream, plan.p);
       else LSEG_LAUNCH_TC2(128, EPI_DIRECT);
     }
 #undef LSEG_LAUNCH_TC2
