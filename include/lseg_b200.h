@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LSEG_B200_ABI_VERSION 3
+#define LSEG_B200_ABI_VERSION 4
 
 /* ---- error / info ------------------------------------------------------------------------------ */
 const char* lseg_last_error(void);
@@ -79,6 +79,8 @@ typedef struct lseg_gemm_args {
   int row_sumsq_parts;
   float row_scale;
   float* out_row_sumsq;
+  int relu_after_res;   /* 1: ReLU after the fp32 residual add, on every output (torchvision Bottleneck: relu(bn3(conv3(..)) +
+                         * identity), the ResNet-101 zero-shot trunk lseg_net_zs.py:307-310); row-major store, needs res_f32 */
 } lseg_gemm_args;
 int lseg_gemm(const lseg_gemm_args* args, void* stream);
 
@@ -124,6 +126,12 @@ int lseg_assemble_tokens(const float* patch, const float* cls, const float* pos,
 int lseg_readout_split(const float* tap, void* tok, void* cls, int B, int T, int D, void* stream);
 /* NHWC fp16 [B,H,W,C] -> im2col rows for the 3x3 stride-2 pad-1 conv (k13; lseg_vit.py:516-522). */
 int lseg_im2col_3x3_s2(const void* x, void* a, int B, int H, int W, int C, void* stream);
+/* ResNet-101 trunk glue (lseg_net_zs.py:307-310, torchvision resnet101): rows of the 7x7 stride-2 pad-3 stem conv
+ * (x fp32 NCHW [B,3,H,W] -> fp16 [B*(H/2)*(W/2), 192], column c*49 + ky*7 + kx, zero beyond 147); MaxPool2d(3, 2, 1) and
+ * the pixel subsampling of a 1x1 stride-2 conv on NHWC fp16 [B,H,W,C] -> [B,H/2,W/2,C]. */
+int lseg_stem_im2col(const float* x, void* a, int B, int H, int W, void* stream);
+int lseg_maxpool3x3s2_nhwc(const void* x, void* y, int B, int H, int W, int C, void* stream);
+int lseg_subsample2_nhwc(const void* x, void* y, int B, int H, int W, int C, void* stream);
 /* bilinear x2 align_corners=True, NHWC fp16 (k16; lseg_blocks.py:352-354). */
 int lseg_upsample2x_nhwc(const void* x, void* y, int B, int H, int W, int C, void* stream);
 /* The same interpolation for the decoder width C = 256 as the engine runs it, AFTER the 1x1 out_conv
@@ -230,8 +238,15 @@ typedef struct lseg_text_block_w {         /* CLIP ResidualAttentionBlock (Appen
   lseg_linear_w in_proj, out_proj, c_fc, c_proj;
 } lseg_text_block_w;
 
+typedef struct lseg_bottleneck_w {         /* torchvision Bottleneck v1.5, BatchNorm (eval, eps 1e-5) folded to scale/shift */
+  lseg_linear_w conv1, conv2, conv3, down; /* 1x1 [w, cin] | 3x3 [w, 9*w] tap-major | 1x1 [4w, w] | 1x1 [4w, cin], w NULL if absent */
+  const float *bn1_scale, *bn1_shift, *bn2_scale, *bn2_shift, *bn3_scale, *bn3_shift, *bnd_scale, *bnd_shift;
+  int stride;                              /* of conv2 and of the downsample conv: 1 | 2 */
+} lseg_bottleneck_w;
+
 #define LSEG_VIT_DEPTH 24
 #define LSEG_TEXT_DEPTH 12
+#define LSEG_RESNET_BLOCKS 33              /* resnet101: 3 + 4 + 23 + 3 */
 
 typedef struct lseg_weights {
   /* image trunk: a timm VisionTransformer driven by forward_flex (lseg_vit.py:166-201). The geometry travels with
@@ -276,6 +291,14 @@ typedef struct lseg_weights {
   int head_act;                            /* LSEG_HEAD_ACT_* of kwargs["activation"] */
   float head_block_w[9];                   /* scratch.head_block.depthwise.depthwise.weight [1,1,3,3] */
   float head_block_b;                      /* ... .bias [1] */
+  /* image trunk selector: 0 = ViT (everything above "decoder"), 1 = ResNet-101 (backbone "clip_resnet101" of the
+   * zero-shot model LSegRNNetZS, lseg_net_zs.py:240-339: pretrained.layer1..4 = torchvision resnet101 stages feed
+   * scratch.layerN_rn directly; post_channels = {256, 512, 1024, 2048}; the ViT / reassemble fields are ignored) */
+  int trunk;
+  lseg_linear_w rn_stem;                   /* conv1 7x7 s2 p3 as [64, 192]: column c*49 + ky*7 + kx, zero beyond 147 */
+  const float *rn_stem_scale, *rn_stem_shift;
+  int rn_layers[4];                        /* blocks per stage: 3, 4, 23, 3 */
+  lseg_bottleneck_w rn_blocks[LSEG_RESNET_BLOCKS];
 } lseg_weights;
 
 typedef struct lseg_engine lseg_engine;

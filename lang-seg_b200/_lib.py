@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "liblseg_b200.so")
 
 VIT_DEPTH = 24
 TEXT_DEPTH = 12
-ABI_VERSION = 3  # == LSEG_B200_ABI_VERSION of include/lseg_b200.h; the struct mirrors below follow that layout
+ABI_VERSION = 4  # == LSEG_B200_ABI_VERSION of include/lseg_b200.h; the struct mirrors below follow that layout
 
 ACT_NONE, ACT_GELU, ACT_QUICKGELU, ACT_RELU = 0, 1, 2, 3
 HEAD_ACT = {"none": 0, "relu": 1, "lrelu": 2, "tanh": 3}
@@ -32,7 +32,7 @@ class GemmArgs(C.Structure):
         ("d2s_s", C.c_int), ("d2s_cout", C.c_int), ("d2s_h", C.c_int), ("d2s_w", C.c_int),
         ("nchw_p", C.c_int), ("nchw_k", C.c_int), ("nchw_group", C.c_int),
         ("row_sumsq", C.c_void_p), ("row_sumsq_parts", C.c_int), ("row_scale", C.c_float),
-        ("out_row_sumsq", C.c_void_p),
+        ("out_row_sumsq", C.c_void_p), ("relu_after_res", C.c_int),
     ]
 
 
@@ -56,6 +56,16 @@ class TextBlockW(C.Structure):
                 ("in_proj", LinearW), ("out_proj", LinearW), ("c_fc", LinearW), ("c_proj", LinearW)]
 
 
+class BottleneckW(C.Structure):
+    _fields_ = [("conv1", LinearW), ("conv2", LinearW), ("conv3", LinearW), ("down", LinearW),
+                ("bn1_scale", C.c_void_p), ("bn1_shift", C.c_void_p), ("bn2_scale", C.c_void_p), ("bn2_shift", C.c_void_p),
+                ("bn3_scale", C.c_void_p), ("bn3_shift", C.c_void_p), ("bnd_scale", C.c_void_p), ("bnd_shift", C.c_void_p),
+                ("stride", C.c_int)]
+
+
+RESNET_BLOCKS = 33
+
+
 class Weights(C.Structure):
     _fields_ = [
         ("vit_dim", C.c_int), ("vit_depth", C.c_int), ("vit_heads", C.c_int), ("patch_size", C.c_int),
@@ -70,6 +80,8 @@ class Weights(C.Structure):
         ("lnf_g", C.c_void_p), ("lnf_b", C.c_void_p), ("text_proj", LinearW),
         ("arch_option", C.c_int), ("block_depth", C.c_int), ("head_act", C.c_int),
         ("head_block_w", C.c_float * 9), ("head_block_b", C.c_float),
+        ("trunk", C.c_int), ("rn_stem", LinearW), ("rn_stem_scale", C.c_void_p), ("rn_stem_shift", C.c_void_p),
+        ("rn_layers", C.c_int * 4), ("rn_blocks", BottleneckW * RESNET_BLOCKS),
     ]
 
 
@@ -77,7 +89,7 @@ class Weights(C.Structure):
 SYMBOLS = [
     "lseg_last_error", "lseg_abi_version", "lseg_read_watchdog",
     "lseg_gemm", "lseg_mhsa", "lseg_mhsa_variant", "lseg_text_attn", "lseg_mhsa_trace", "lseg_debug_gemm_trace", "lseg_set_deterministic", "lseg_layernorm", "lseg_patchify", "lseg_pos_resize", "lseg_assemble_tokens",
-    "lseg_readout_split", "lseg_im2col_3x3_s2", "lseg_upsample2x_nhwc", "lseg_upsample2x_nhwc256", "lseg_l2norm_scale", "lseg_l2norm_f16",
+    "lseg_readout_split", "lseg_im2col_3x3_s2", "lseg_stem_im2col", "lseg_maxpool3x3s2_nhwc", "lseg_subsample2_nhwc", "lseg_upsample2x_nhwc", "lseg_upsample2x_nhwc256", "lseg_l2norm_scale", "lseg_l2norm_f16",
     "lseg_upsample2x_nchw", "lseg_debug_upsample_layout", "lseg_upsample2x_nchw_bg", "lseg_upsample2x_nchw_f32", "lseg_head_block", "lseg_upsample2x_argmax", "lseg_forward_argmax", "lseg_text_embed", "lseg_text_eot_gather",
     "lseg_create", "lseg_destroy", "lseg_encode_text", "lseg_forward", "lseg_forward_lowres", "lseg_debug_buffer",
     "lseg_last_launch_count", "lseg_forward_profiled",
@@ -130,6 +142,9 @@ def load(build_if_missing=True):
                                          C.c_void_p]
     lib.lseg_readout_split.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.lseg_im2col_3x3_s2.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.lseg_stem_im2col.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.lseg_maxpool3x3s2_nhwc.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.lseg_subsample2_nhwc.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.lseg_upsample2x_nhwc.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.lseg_upsample2x_nhwc256.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                             C.c_void_p]

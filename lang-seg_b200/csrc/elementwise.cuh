@@ -238,6 +238,107 @@ static inline int launch_im2col_3x3_s2(const __half* x, __half* a, int B, int H,
 }
 
 // ------------------------------------------------------------------------------------------
+// ResNet-101 trunk of the zero-shot model (lseg_net_zs.py:307-310; torchvision resnet101 split by
+// _make_resnet_backbone, lseg_blocks_zs.py:109-119). Three glue kernels around the GEMMs:
+//   stem_im2col   x fp32 NCHW [B,3,H,W] -> rows fp16 [B*(H/2)*(W/2), 192] of the 7x7 stride-2 pad-3 stem conv; column
+//                 c*49 + ky*7 + kx (the flattening of conv1.weight [64,3,7,7]), columns 147..191 zero (K = 3 chunks of 64)
+//   maxpool3x3s2  NHWC fp16 [B,Hi,Wi,C] -> [B,Hi/2,Wi/2,C], kernel 3 stride 2 pad 1 (padding never wins: -inf)
+//   subsample2    NHWC fp16 [B,Hi,Wi,C] -> [B,Hi/2,Wi/2,C], pixel (2y, 2x): the A operand of a 1x1 stride-2 conv
+// ------------------------------------------------------------------------------------------
+constexpr int kStemK = 192;
+__global__ void __launch_bounds__(192) stem_im2col_kernel(const float* __restrict__ x, __half* __restrict__ a, int H, int W) {
+  griddep_launch_dependents();
+  griddep_wait();
+  const int Ho = H / 2, Wo = W / 2;
+  const long long pix = blockIdx.x;  // b*Ho*Wo + oy*Wo + ox
+  const int ox = static_cast<int>(pix % Wo);
+  const int oy = static_cast<int>((pix / Wo) % Ho);
+  const int b = static_cast<int>(pix / (static_cast<long long>(Wo) * Ho));
+  const int t = threadIdx.x;
+  float v = 0.f;
+  if (t < 147) {
+    const int c = t / 49, r = t - c * 49;
+    const int ky = r / 7, kx = r - ky * 7;
+    const int iy = 2 * oy - 3 + ky, ix = 2 * ox - 3 + kx;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[((static_cast<long long>(b) * 3 + c) * H + iy) * W + ix];
+  }
+  a[pix * kStemK + t] = __float2half_rn(v);
+}
+static inline int launch_stem_im2col(const float* x, __half* a, int B, int H, int W, cudaStream_t s) {
+  if (H % 2 || W % 2) {
+    set_error("stem_im2col: H=%d, W=%d must be even", H, W);
+    return -1;
+  }
+  launch_pdl(stem_im2col_kernel, dim3(static_cast<unsigned>(static_cast<long long>(B) * (H / 2) * (W / 2))), dim3(192), 0, s,
+             x, a, H, W);
+  LSEG_LAUNCH_CHECK();
+}
+
+__global__ void __launch_bounds__(256) maxpool3x3s2_nhwc_kernel(const __half* __restrict__ x, __half* __restrict__ y, int Hi,
+                                                                int Wi, int C) {
+  griddep_launch_dependents();
+  griddep_wait();
+  const int Ho = Hi / 2, Wo = Wi / 2, c8 = C / 8;
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(gridDim.y) * Ho * Wo * c8;
+  (void)total;
+  const int b = blockIdx.y;
+  if (i >= static_cast<long long>(Ho) * Wo * c8) return;
+  const int c = static_cast<int>(i % c8);
+  const int ox = static_cast<int>((i / c8) % Wo);
+  const int oy = static_cast<int>(i / (static_cast<long long>(c8) * Wo));
+  __half2 m[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) m[k] = __float2half2_rn(-INFINITY);
+  for (int dy = 0; dy < 3; ++dy) {
+    const int iy = 2 * oy - 1 + dy;
+    if (iy < 0 || iy >= Hi) continue;
+    for (int dx = 0; dx < 3; ++dx) {
+      const int ix = 2 * ox - 1 + dx;
+      if (ix < 0 || ix >= Wi) continue;
+      const uint4 q = reinterpret_cast<const uint4*>(x + ((static_cast<long long>(b) * Hi + iy) * Wi + ix) * C)[c];
+      const __half2* qh = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) m[k] = __hmax2(m[k], qh[k]);
+    }
+  }
+  reinterpret_cast<uint4*>(y + ((static_cast<long long>(b) * Ho + oy) * Wo + ox) * C)[c] = *reinterpret_cast<uint4*>(m);
+}
+static inline int launch_maxpool3x3s2_nhwc(const __half* x, __half* y, int B, int Hi, int Wi, int C, cudaStream_t s) {
+  if (C % 8 || Hi % 2 || Wi % 2) {
+    set_error("maxpool3x3s2: C %% 8 == 0 and even H, W (C=%d H=%d W=%d)", C, Hi, Wi);
+    return -1;
+  }
+  const long long n = static_cast<long long>(Hi / 2) * (Wi / 2) * (C / 8);
+  launch_pdl(maxpool3x3s2_nhwc_kernel, dim3(static_cast<unsigned>((n + 255) / 256), B), dim3(256), 0, s, x, y, Hi, Wi, C);
+  LSEG_LAUNCH_CHECK();
+}
+
+__global__ void __launch_bounds__(256) subsample2_nhwc_kernel(const __half* __restrict__ x, __half* __restrict__ y, int Hi, int Wi,
+                                                              int C) {
+  griddep_launch_dependents();
+  griddep_wait();
+  const int Ho = Hi / 2, Wo = Wi / 2, c8 = C / 8;
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const int b = blockIdx.y;
+  if (i >= static_cast<long long>(Ho) * Wo * c8) return;
+  const int c = static_cast<int>(i % c8);
+  const int ox = static_cast<int>((i / c8) % Wo);
+  const int oy = static_cast<int>(i / (static_cast<long long>(c8) * Wo));
+  reinterpret_cast<uint4*>(y + ((static_cast<long long>(b) * Ho + oy) * Wo + ox) * C)[c] =
+      reinterpret_cast<const uint4*>(x + ((static_cast<long long>(b) * Hi + 2 * oy) * Wi + 2 * ox) * C)[c];
+}
+static inline int launch_subsample2_nhwc(const __half* x, __half* y, int B, int Hi, int Wi, int C, cudaStream_t s) {
+  if (C % 8 || Hi % 2 || Wi % 2) {
+    set_error("subsample2: C %% 8 == 0 and even H, W (C=%d H=%d W=%d)", C, Hi, Wi);
+    return -1;
+  }
+  const long long n = static_cast<long long>(Hi / 2) * (Wi / 2) * (C / 8);
+  launch_pdl(subsample2_nhwc_kernel, dim3(static_cast<unsigned>((n + 255) / 256), B), dim3(256), 0, s, x, y, Hi, Wi, C);
+  LSEG_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------
 // bilinear x2, align_corners=True, NHWC fp16 -> NHWC fp16 (fusion blocks, lseg_blocks.py:352-354).
 // src = dst * (in-1)/(out-1), computed like ATen (float scale, float product).
 // grid (ceil(Wo/32), Ho, B), 256 threads: a warp produces 4 consecutive output pixels (32 channel groups of 8 per

@@ -258,15 +258,12 @@ static int get_pos_embed(lseg_engine* eng, int gh, int gw, cudaStream_t stream, 
   return 0;
 }
 
-static int build_image_plan(lseg_engine* eng, int B, int H, int W, cudaStream_t stream) {
+// ViT trunk + readout + reassemble: fills layer_in[k] (NHWC fp16 inputs of scratch.layerN_rn), their stored channel
+// counts and sizes.
+static int build_vit_trunk(lseg_engine* eng, ImagePlan* plan, int B, int H, int W, cudaStream_t stream,
+                           __half* (&layer_in)[4], int (&c_post)[4], int (&lh)[4], int (&lw)[4]) {
   const lseg_weights& w = eng->w;
-  std::unique_ptr<ImagePlan> plan(new ImagePlan());
-  plan->B = B;
-  plan->H = H;
-  plan->W = W;
-  plan->epoch = g_plan_epoch;
   Arena& arena = plan->arena;
-  t_plan_arena = &arena;
   std::vector<Step>& steps = plan->steps;
   // backbone geometry (lseg_vit.py:442-522 _make_pretrained_clip_vitl16_384 / _vitb32_384): token width, depth, heads,
   // patch size and the per-level reassemble recipe come with the weights
@@ -381,7 +378,6 @@ static int build_image_plan(lseg_engine* eng, int B, int H, int W, cudaStream_t 
   // Level k: 1x1 conv D -> post_channels[k], then ConvTranspose (k = s, stride s), nothing, or a 3x3 stride-2 conv
   // (lseg_vit.py:465-520 for ViT-L/16: x4, x2, -, /2; 531-586 for ViT-B/32: x8, x4, x2, -). post_channels are the
   // STORED widths: reference counts rounded up to a multiple of 64 with zero weights in the pad (96 -> 128).
-  int c_post[4], lh[4], lw[4];
   for (int k = 0; k < 4; ++k) {
     c_post[k] = w.post_channels[k];
     const int r = w.post_resample[k];
@@ -404,7 +400,6 @@ static int build_image_plan(lseg_engine* eng, int B, int H, int W, cudaStream_t 
   LSEG_CHECK_CUDA(cudaMemsetAsync(cls16, 0, sizeof(__half) * (size_t)cls_rows * D, stream));
   LSEG_ALLOC(clsb, float, (size_t)B * D);
   LSEG_ALLOC(ro, __half, BT * D);
-  __half* layer_in[4];  // NHWC fp16 inputs of scratch.layerN_rn
   for (int k = 0; k < 4; ++k) {
     const float* tap = taps[k];
     steps.push_back([=](const CallCtx&, cudaStream_t s) {
@@ -467,6 +462,152 @@ static int build_image_plan(lseg_engine* eng, int B, int H, int W, cudaStream_t 
     }
   }
 
+  return 0;
+}
+
+// ResNet-101 trunk of the zero-shot model (lseg_net_zs.py:307-310: pretrained.layer1..4 = torchvision resnet101 stages,
+// lseg_blocks_zs.py:109-119): stem 7x7 s2 (im2col + GEMM, BN + ReLU in the epilogue) -> maxpool -> 33 bottlenecks.
+// Every conv is the tcgen05 GEMM: 1x1 = plain GEMM over the NHWC pixels, 3x3 stride 1 = implicit GEMM, 3x3 stride 2 =
+// im2col rows + GEMM, 1x1 stride 2 = GEMM over the subsampled pixels; BatchNorm folded into the fp32 epilogue. The
+// residual stream is fp32 (one buffer per stage, updated in place by conv3's epilogue: relu(bn3(conv3) + identity)),
+// with an fp16 copy as the next conv's operand — the same split as the decoder's RCUs.
+static int build_resnet_trunk(lseg_engine* eng, ImagePlan* plan, int B, int H, int W, cudaStream_t stream,
+                              __half* (&layer_in)[4], int (&c_post)[4], int (&lh)[4], int (&lw)[4]) {
+  (void)stream;
+  const lseg_weights& w = eng->w;
+  Arena& arena = plan->arena;
+  std::vector<Step>& steps = plan->steps;
+  const int Hs = H / 2, Ws = W / 2;  // stem output
+  const long long R0 = static_cast<long long>(B) * Hs * Ws;
+  LSEG_ALLOC(stem_a, __half, R0 * kStemK);
+  LSEG_ALLOC(stem_o, __half, R0 * 64);
+  steps.push_back([=](const CallCtx& c, cudaStream_t s) { return launch_stem_im2col(c.x, stem_a, B, H, W, s); });
+  {
+    GemmEpi e = epi_none();
+    e.scale = w.rn_stem_scale;
+    e.bias = w.rn_stem_shift;
+    e.act = ACT_RELU;
+    e.out_f16 = stem_o;
+    e.ldc = 64;
+    if (add_gemm(steps, stem_a, kStemK, (int)R0, (int)R0, w.rn_stem, e)) return -1;
+  }
+  int h = Hs / 2, ww = Ws / 2;  // after the 3x3 stride-2 max pool
+  LSEG_ALLOC(pool_o, __half, static_cast<long long>(B) * h * ww * 64);
+  steps.push_back([=](const CallCtx&, cudaStream_t s) { return launch_maxpool3x3s2_nhwc(stem_o, pool_o, B, Hs, Ws, 64, s); });
+  const __half* x16 = pool_o;
+  int cin = 64, blk = 0;
+  for (int L = 0; L < 4; ++L) {
+    const int width = 64 << L, cout = 4 * width;
+    const int n = w.rn_layers[L];
+    if (n <= 0 || blk + n > LSEG_RESNET_BLOCKS) {
+      set_error("resnet trunk: stage %d has %d blocks", L + 1, n);
+      return -1;
+    }
+    const int stride0 = w.rn_blocks[blk].stride;
+    const int ho = h / stride0, wo = ww / stride0;
+    const long long px_in = static_cast<long long>(B) * h * ww, px = static_cast<long long>(B) * ho * wo;
+    LSEG_ALLOC(t1, __half, px_in * width);
+    LSEG_ALLOC(t2, __half, px * width);
+    LSEG_ALLOC(y32, float, px * cout);   // the stage's residual stream, updated in place
+    LSEG_ALLOC(y16a, __half, px * cout);
+    LSEG_ALLOC(y16b, __half, px * cout);
+    for (int i = 0; i < n; ++i, ++blk) {
+      const lseg_bottleneck_w& bw = w.rn_blocks[blk];
+      const int stride = (i == 0) ? stride0 : 1;
+      if (bw.stride != stride || (stride != 1 && stride != 2) || ((i == 0) != (bw.down.w != nullptr))) {
+        set_error("resnet trunk: block %d of stage %d: stride %d / downsample do not fit a torchvision Bottleneck stage", i,
+                  L + 1, bw.stride);
+        return -1;
+      }
+      const int hi = (i == 0) ? h : ho, wi = (i == 0) ? ww : wo;
+      const long long pxi = static_cast<long long>(B) * hi * wi;
+      {  // conv1 1x1 + bn1 + relu
+        GemmEpi e = epi_none();
+        e.scale = bw.bn1_scale;
+        e.bias = bw.bn1_shift;
+        e.act = ACT_RELU;
+        e.out_f16 = t1;
+        e.ldc = width;
+        if (add_gemm(steps, x16, cin, (int)pxi, (int)pxi, bw.conv1, e)) return -1;
+      }
+      {  // conv2 3x3 (stride here, torchvision v1.5) + bn2 + relu
+        GemmEpi e = epi_none();
+        e.scale = bw.bn2_scale;
+        e.bias = bw.bn2_shift;
+        e.act = ACT_RELU;
+        e.out_f16 = t2;
+        e.ldc = width;
+        if (stride == 1) {
+          if (add_conv3x3(steps, t1, B, hi, wi, width, bw.conv2, e)) return -1;
+        } else {
+          LSEG_ALLOC(a2, __half, px * 9 * width);
+          steps.push_back([=](const CallCtx&, cudaStream_t s) { return launch_im2col_3x3_s2(t1, a2, B, hi, wi, width, s); });
+          if (add_gemm(steps, a2, 9 * width, (int)px, (int)px, bw.conv2, e)) return -1;
+        }
+      }
+      if (i == 0) {  // identity = bn_d(conv_d 1x1 stride s (x)) -> the stage's fp32 stream
+        const __half* xs = x16;
+        if (stride == 2) {
+          LSEG_ALLOC(sub, __half, px * cin);
+          const __half* xin = x16;
+          steps.push_back([=](const CallCtx&, cudaStream_t s) { return launch_subsample2_nhwc(xin, sub, B, hi, wi, cin, s); });
+          xs = sub;
+        }
+        GemmEpi e = epi_none();
+        e.scale = bw.bnd_scale;
+        e.bias = bw.bnd_shift;
+        e.out_f32 = y32;
+        e.ldc = cout;
+        if (add_gemm(steps, xs, cin, (int)px, (int)px, bw.down, e)) return -1;
+      }
+      __half* y16 = (i & 1) ? y16b : y16a;
+      {  // conv3 1x1 + bn3, + identity, relu -> fp32 stream (in place) and its fp16 copy
+        GemmEpi e = epi_none();
+        e.scale = bw.bn3_scale;
+        e.bias = bw.bn3_shift;
+        e.res_f32 = y32;
+        e.out_f32 = y32;
+        e.out_f16 = y16;
+        e.relu_after_res = 1;
+        e.ldc = cout;
+        if (add_gemm(steps, t2, width, (int)px, (int)px, bw.conv3, e)) return -1;
+      }
+      x16 = y16;
+      cin = cout;
+    }
+    layer_in[L] = const_cast<__half*>(x16);
+    c_post[L] = cout;
+    lh[L] = ho;
+    lw[L] = wo;
+    h = ho;
+    ww = wo;
+  }
+  if (blk != LSEG_RESNET_BLOCKS && blk <= 0) return -1;
+  for (int k = 0; k < 3; ++k)
+    if (lh[k] != 2 * lh[k + 1] || lw[k] != 2 * lw[k + 1]) {
+      set_error("resnet trunk: stage sizes are not a x2 pyramid (H, W multiples of 32)");
+      return -1;
+    }
+  return 0;
+}
+
+static int build_image_plan(lseg_engine* eng, int B, int H, int W, cudaStream_t stream) {
+  const lseg_weights& w = eng->w;
+  std::unique_ptr<ImagePlan> plan(new ImagePlan());
+  plan->B = B;
+  plan->H = H;
+  plan->W = W;
+  plan->epoch = g_plan_epoch;
+  Arena& arena = plan->arena;
+  t_plan_arena = &arena;
+  std::vector<Step>& steps = plan->steps;
+  __half* layer_in[4];  // NHWC fp16 inputs of scratch.layerN_rn
+  int c_post[4], lh[4], lw[4];
+  if (w.trunk == 1) {
+    if (build_resnet_trunk(eng, plan.get(), B, H, W, stream, layer_in, c_post, lh, lw)) return -1;
+  } else {
+    if (build_vit_trunk(eng, plan.get(), B, H, W, stream, layer_in, c_post, lh, lw)) return -1;
+  }
   for (int k = 0; k < 4; ++k) {
     char name[12];
     snprintf(name, sizeof(name), "layer%d", k);
@@ -897,7 +1038,18 @@ int lseg_create(const lseg_weights* w, int device, lseg_engine** out) {
     set_error("lseg_create: null argument");
     return -1;
   }
-  if (w->vit_heads <= 0 || w->vit_dim != 64 * w->vit_heads || (w->vit_dim != 768 && w->vit_dim != 1024) ||
+  if (w->trunk != 0 && w->trunk != 1) {
+    set_error("lseg_create: trunk %d (0 ViT, 1 ResNet-101)", w->trunk);
+    return -1;
+  }
+  if (w->trunk == 1) {
+    int nblk = 0;
+    for (int k = 0; k < 4; ++k) nblk += w->rn_layers[k] > 0 ? w->rn_layers[k] : LSEG_RESNET_BLOCKS + 1;
+    if (nblk > LSEG_RESNET_BLOCKS || !w->rn_stem.w) {
+      set_error("lseg_create: ResNet trunk with %d blocks (at most %d) / missing stem", nblk, LSEG_RESNET_BLOCKS);
+      return -1;
+    }
+  } else if (w->vit_heads <= 0 || w->vit_dim != 64 * w->vit_heads || (w->vit_dim != 768 && w->vit_dim != 1024) ||
       w->vit_depth <= 0 || w->vit_depth > LSEG_VIT_DEPTH || (w->patch_size != 16 && w->patch_size != 32) ||
       w->pos_grid <= 0) {
     set_error("lseg_create: backbone geometry dim=%d depth=%d heads=%d patch=%d pos_grid=%d (dim = 64*heads in {768, "
@@ -911,7 +1063,7 @@ int lseg_create(const lseg_weights* w, int device, lseg_engine** out) {
               w->text_width, w->text_heads, w->out_c);
     return -1;
   }
-  for (int k = 0; k < 4; ++k)
+  for (int k = 0; k < 4 && w->trunk == 0; ++k)
     if (w->hooks[k] < 0 || w->hooks[k] >= w->vit_depth || (k && w->hooks[k] <= w->hooks[k - 1])) {
       set_error("lseg_create: hooks must be increasing block indices below depth %d", w->vit_depth);
       return -1;

@@ -76,6 +76,8 @@ struct GemmEpi {
   int row_sumsq_parts;     //   result *= row_scale * rsqrt(sum of the row's parts)
   float row_scale;
   float* out_row_sumsq;    // nullable: [rows, ceil(N/32)] partial sums of result^2 (fp32, pre-rounding)
+  int relu_after_res;      // EPI_DIRECT, row-major: ReLU applied AFTER the fp32 residual add, to every output
+                           // (torchvision Bottleneck: relu(bn3(conv3) + identity)); a compile-time kernel variant
 };
 
 struct GemmParams {
@@ -217,7 +219,8 @@ __device__ __forceinline__ void gemm_epilogue_math(const GemmEpi& e, int N, cons
 // EPI_DIRECT store part, straight from registers (thread <-> row). GROUPED: STORE_NCHW_T with per-image column blocks
 // (zero-shot path) — a compile-time variant: as a runtime case it costs the common kernel 4 registers and 128
 // instructions (the one-label-set instantiation is instruction-for-instruction the round-1 kernel again).
-template <bool GROUPED = false>
+// RELU_RES: GemmEpi::relu_after_res (ResNet bottleneck output), row-major full chunks and tails alike.
+template <bool GROUPED = false, bool RELU_RES = false>
 __device__ __forceinline__ void gemm_epilogue_store(const GemmEpi& e, int N, float (&f)[32], const float4 (&res)[8],
                                                     bool has_res, long long grow, int n0) {
   const int nvalid = min(32, N - n0);
@@ -246,6 +249,10 @@ __device__ __forceinline__ void gemm_epilogue_store(const GemmEpi& e, int N, flo
           const float4 q = rp[i];
           f[4 * i + 0] += q.x; f[4 * i + 1] += q.y; f[4 * i + 2] += q.z; f[4 * i + 3] += q.w;
         }
+      }
+      if constexpr (RELU_RES) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
       }
       if (e.out_f32) {
         float4* op = reinterpret_cast<float4*>(e.out_f32 + off);
@@ -285,6 +292,7 @@ __device__ __forceinline__ void gemm_epilogue_store(const GemmEpi& e, int N, flo
           float x = f[i];
           if (e.res_f32) x += e.res_f32[off + i];
           if (e.res2_f32) x += e.res2_f32[off + i];
+          if constexpr (RELU_RES) x = fmaxf(x, 0.f);
           if (e.out_f32) e.out_f32[off + i] = x;
           if (e.out_f16) {
             __half hx = __float2half_rn(x);
@@ -355,7 +363,7 @@ constexpr int kEpiStageBytes = 2 * 4096;  // per epilogue warp: two 32-row x 128
 // Epilogue of one 128 x (ncols) accumulator slab for one warp (r = quarter*32 + lane = this thread's row).
 // SINGLE_BUF: one 4 KB staging tile per warp instead of two (16-epilogue-warp configuration, where a warp emits one
 // store group per tile and the previous tile's bulk store has long finished reading the buffer).
-template <int EPI, bool SINGLE_BUF = false, bool GROUPED = false, typename WaitFn>
+template <int EPI, bool SINGLE_BUF = false, bool GROUPED = false, bool RELU_RES = false, typename WaitFn>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t t_row, int n_base, int ncols,
                                                    int m_tile, int r, WaitFn wait_accumulator, uint8_t* stage_buf,
                                                    int& store_groups, GemmTrace& tr, bool first_k = true,
@@ -414,7 +422,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] *= row_mul;
         }
-        gemm_epilogue_store<GROUPED>(e, p.N, f, rcur, has_res, grow, n0);
+        gemm_epilogue_store<GROUPED, RELU_RES>(e, p.N, f, rcur, has_res, grow, n0);
       }
     }
   } else {
@@ -544,9 +552,10 @@ struct Gemm2Cfg {
 // FIXED_SPLIT: the deterministic split-K schedule (GemmParams::split_fixed) is its own instantiation — its index
 // arithmetic costs the other kernels their uniform-datapath code (UISETP 254 -> 97, BSSY/BSYNC pairs appear) when it is
 // merely present as a runtime branch.
-template <int BN, int EPI, int EW = 8, bool FIXED_SPLIT = false, bool GROUPED = false>
+template <int BN, int EPI, int EW = 8, bool FIXED_SPLIT = false, bool GROUPED = false, bool RELU_RES = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((Gemm2Cfg<BN, EPI, EW>::kThreads), 1)
     gemm_tc2_kernel(const __grid_constant__ GemmParams p) {
+  static_assert(!RELU_RES || (EPI == EPI_DIRECT && !FIXED_SPLIT && !GROUPED), "relu-after-residual: plain register-direct");
   static_assert(!FIXED_SPLIT || EPI == EPI_DIRECT, "split-K partials leave through the register-direct epilogue");
   static_assert(!GROUPED || (EPI == EPI_DIRECT && !FIXED_SPLIT), "per-image column blocks: NCHW-T store, register-direct");
   using Cfg = Gemm2Cfg<BN, EPI, EW>;
@@ -765,7 +774,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((Gemm2Cfg<BN, EPI, E
       const int m_tile = (tile % m_pairs) * 2 + static_cast<int>(rank);
       const int n_tile = tile / m_pairs;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + col0;
-      gemm_epilogue_tile<EPI, Cfg::kEpiWarps == 16, GROUPED>(p, t_row, n_tile * BN + col0, ncols, m_tile, r,
+      gemm_epilogue_tile<EPI, Cfg::kEpiWarps == 16, GROUPED, RELU_RES>(p, t_row, n_tile * BN + col0, ncols, m_tile, r,
                               [&]() { mbar_wait(&tmem_full[acc], acc_phase, 24); }, stage_buf, store_groups, tr,
                               k_begin == 0, FIXED_SPLIT ? sc.seg : 0);
       tc_fence_before();
@@ -832,6 +841,9 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
   if (e.res2_f32) {
     const float4 q = *reinterpret_cast<const float4*>(e.res2_f32 + off);
     a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
+  }
+  if (e.relu_after_res) {
+    a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
   }
   if (e.out_f32) *reinterpret_cast<float4*>(e.out_f32 + off) = a;
   if (e.out_f16) {

@@ -111,6 +111,10 @@ static int init_device(int dev) {
                        Gemm2Cfg<256, EPI_DIRECT>::kSmemBytes);
   cudaFuncSetAttribute(gemm_tc2_kernel<128, EPI_DIRECT, 8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        Gemm2Cfg<128, EPI_DIRECT>::kSmemBytes);
+  cudaFuncSetAttribute(gemm_tc2_kernel<256, EPI_DIRECT, 8, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       Gemm2Cfg<256, EPI_DIRECT>::kSmemBytes);
+  cudaFuncSetAttribute(gemm_tc2_kernel<128, EPI_DIRECT, 8, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       Gemm2Cfg<128, EPI_DIRECT>::kSmemBytes);
   cudaFuncSetAttribute(gemm_tc2_kernel<256, EPI_TMA_F16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        Gemm2Cfg<256, EPI_TMA_F16, 16>::kSmemBytes);
 #define LSEG_M2_ATTR(K)                                                                       \
@@ -263,7 +267,8 @@ static int gemm_plan(const GemmDesc& d, GemmPlan* plan) {
     // 145 = 1.96 -> 2 waves of narrower tiles (-12 %). The per-element K order is unchanged, so results are identical.
     static const int add_bn = getenv("LSEG_GEMM_ADD_BN") ? atoi(getenv("LSEG_GEMM_ADD_BN")) : 0;  // 0: automatic
     const bool inplace_add = !d.conv && d.e.out_f32 && d.e.res_f32 == d.e.out_f32 && !d.e.res2_f32 && !d.e.res_f16 &&
-                             !d.e.out_f16 && !d.e.out_f16_relu && !d.e.out_row_sumsq && d.e.store == STORE_ROWMAJOR &&
+                             !d.e.out_f16 && !d.e.out_f16_relu && !d.e.out_row_sumsq && !d.e.relu_after_res &&
+                             d.e.store == STORE_ROWMAJOR &&
                              (d.N % 8 == 0) && d.N >= 64 && (d.e.ldc % 4 == 0) && g_gemm_two_cta &&
                              getenv("LSEG_GEMM_NO_TMA_STORE") == nullptr;  // == the EPI_TMA_ADD condition below
     if (inplace_add && d.N > 128) {
@@ -352,6 +357,10 @@ static int gemm_plan(const GemmDesc& d, GemmPlan* plan) {
     const GemmEpi& e = p.e;
     static const bool disabled = getenv("LSEG_GEMM_NO_TMA_STORE") != nullptr;
     const bool rowmajor = plan->two_cta && !disabled && e.store == STORE_ROWMAJOR && (d.N % 8 == 0) && d.N >= 64;
+    if (e.relu_after_res && (e.store != STORE_ROWMAJOR || !e.res_f32 || e.res_f16 || e.out_row_sumsq || !plan->two_cta)) {
+      set_error("gemm: relu_after_res needs a row-major store and an fp32 residual");
+      return -1;
+    }
     if (rowmajor && e.out_f16 && !e.out_f32 && !e.out_f16_relu && !e.res_f16 && !e.res_f32 && !e.res2_f32 &&
         (e.ldc % 8 == 0)) {
       if (d.conv) {
@@ -368,7 +377,7 @@ static int gemm_plan(const GemmDesc& d, GemmPlan* plan) {
       plan->epi = EPI_TMA_F16;
       plan->ew16 = (bn == 256 && (p.k_iters <= 8 || e.act == ACT_GELU)) ? 1 : 0;
     } else if (rowmajor && !d.conv && e.out_f32 && e.res_f32 == e.out_f32 && !e.res2_f32 && !e.res_f16 &&
-               !e.out_f16 && !e.out_f16_relu && !e.out_row_sumsq && (e.ldc % 4 == 0)) {
+               !e.out_f16 && !e.out_f16_relu && !e.out_row_sumsq && !e.relu_after_res && (e.ldc % 4 == 0)) {
       // in-place fp32 residual stream: x += A W^T + b through a bulk tensor reduce-add (x is never read)
       const uint64_t dims[2] = {(uint64_t)d.N, (uint64_t)d.M};
       const uint64_t str[1] = {(uint64_t)e.ldc * 4};
@@ -436,6 +445,9 @@ static int gemm_run_kernel(const GemmPlan& plan, cudaStream_t stream) {
       else if (plan.p.e.store == STORE_NCHW_T && plan.p.e.nchw_group > 0)
         launch_pdl(gemm_tc2_kernel<256, EPI_DIRECT, 8, false, true>, dim3(plan.grid),
                    dim3(Gemm2Cfg<256, EPI_DIRECT>::kThreads), Gemm2Cfg<256, EPI_DIRECT>::kSmemBytes, stream, plan.p);
+      else if (plan.p.e.relu_after_res)
+        launch_pdl(gemm_tc2_kernel<256, EPI_DIRECT, 8, false, false, true>, dim3(plan.grid),
+                   dim3(Gemm2Cfg<256, EPI_DIRECT>::kThreads), Gemm2Cfg<256, EPI_DIRECT>::kSmemBytes, stream, plan.p);
       else LSEG_LAUNCH_TC2(256, EPI_DIRECT);
     } else if (plan.bn == 224) {
       if (plan.epi != EPI_TMA_ADD) {
@@ -451,6 +463,9 @@ static int gemm_run_kernel(const GemmPlan& plan, cudaStream_t stream) {
                    Gemm2Cfg<128, EPI_DIRECT>::kSmemBytes, stream, plan.p);
       else if (plan.p.e.store == STORE_NCHW_T && plan.p.e.nchw_group > 0)
         launch_pdl(gemm_tc2_kernel<128, EPI_DIRECT, 8, false, true>, dim3(plan.grid),
+                   dim3(Gemm2Cfg<128, EPI_DIRECT>::kThreads), Gemm2Cfg<128, EPI_DIRECT>::kSmemBytes, stream, plan.p);
+      else if (plan.p.e.relu_after_res)
+        launch_pdl(gemm_tc2_kernel<128, EPI_DIRECT, 8, false, false, true>, dim3(plan.grid),
                    dim3(Gemm2Cfg<128, EPI_DIRECT>::kThreads), Gemm2Cfg<128, EPI_DIRECT>::kSmemBytes, stream, plan.p);
       else LSEG_LAUNCH_TC2(128, EPI_DIRECT);
     }
@@ -580,6 +595,7 @@ static void fill_epi(const lseg_gemm_args* a, GemmEpi* e) {
   e->row_sumsq_parts = a->row_sumsq_parts;
   e->row_scale = a->row_scale;
   e->out_row_sumsq = a->out_row_sumsq;
+  e->relu_after_res = a->relu_after_res;
 }
 
 int lseg_gemm(const lseg_gemm_args* a, void* stream) {
@@ -859,6 +875,23 @@ int lseg_im2col_3x3_s2(const void* x, void* a, int B, int H, int W, int C, void*
   if (ensure_init()) return -1;
   return launch_im2col_3x3_s2(static_cast<const __half*>(x), static_cast<__half*>(a), B, H, W, C,
                               static_cast<cudaStream_t>(stream));
+}
+
+int lseg_stem_im2col(const float* x, void* a, int B, int H, int W, void* stream) {
+  if (ensure_init()) return -1;
+  return launch_stem_im2col(x, static_cast<__half*>(a), B, H, W, static_cast<cudaStream_t>(stream));
+}
+
+int lseg_maxpool3x3s2_nhwc(const void* x, void* y, int B, int H, int W, int C, void* stream) {
+  if (ensure_init()) return -1;
+  return launch_maxpool3x3s2_nhwc(static_cast<const __half*>(x), static_cast<__half*>(y), B, H, W, C,
+                                  static_cast<cudaStream_t>(stream));
+}
+
+int lseg_subsample2_nhwc(const void* x, void* y, int B, int H, int W, int C, void* stream) {
+  if (ensure_init()) return -1;
+  return launch_subsample2_nhwc(static_cast<const __half*>(x), static_cast<__half*>(y), B, H, W, C,
+                                static_cast<cudaStream_t>(stream));
 }
 
 int lseg_upsample2x_nhwc(const void* x, void* y, int B, int H, int W, int C, void* stream) {

@@ -63,9 +63,43 @@ def _readout_holder(D):
     return r
 
 
+def _bottleneck_holder(inplanes, planes, downsample):
+    """torchvision.models.resnet.Bottleneck parameter names (conv1/bn1/conv2/bn2/conv3/bn3[/downsample.{0,1}])."""
+    b = nn.Module()
+    b.conv1 = nn.Conv2d(inplanes, planes, 1, bias=False)
+    b.bn1 = nn.BatchNorm2d(planes)
+    b.conv2 = nn.Conv2d(planes, planes, 3, padding=1, bias=False)
+    b.bn2 = nn.BatchNorm2d(planes)
+    b.conv3 = nn.Conv2d(planes, planes * 4, 1, bias=False)
+    b.bn3 = nn.BatchNorm2d(planes * 4)
+    if downsample:
+        b.downsample = nn.Sequential(nn.Conv2d(inplanes, planes * 4, 1, bias=False), nn.BatchNorm2d(planes * 4))
+    return b
+
+
+def _resnet_holder(cfg):
+    """pretrained.layer1..4 as _make_resnet_backbone builds them (lseg_blocks_zs.py:109-119): layer1 = Sequential(conv1,
+    bn1, relu, maxpool, resnet.layer1), layer2..4 = the torchvision stages."""
+    p = nn.Module()
+    inplanes = 64
+    for layer, (planes, n) in enumerate(zip((64, 128, 256, 512), cfg["layers"]), start=1):
+        blocks = []
+        for i in range(n):
+            blocks.append(_bottleneck_holder(inplanes, planes, i == 0))
+            inplanes = planes * 4
+        stage = nn.Sequential(*blocks)
+        if layer == 1:
+            stage = nn.Sequential(nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False), nn.BatchNorm2d(64), nn.Identity(),
+                                  nn.Identity(), stage)
+        setattr(p, f"layer{layer}", stage)
+    return p
+
+
 def _pretrained_holder(cfg):
     """act_postprocess1..4 with the reference's Sequential indices (0 readout, 3 the 1x1 conv, 4 the resampling op;
     lseg_vit.py:309-398 for ViT-B/32, :445-520 for ViT-L/16)."""
+    if cfg.get("trunk") == "resnet101":
+        return _resnet_holder(cfg)
     D = cfg["dim"]
     p = nn.Module()
     p.model = _vit_holder(cfg)
@@ -305,6 +339,10 @@ class LSegNet(_LSegBase):
         self.crop_size = crop_size
         self.scale_factor = scale_factor
         self.labels = labels
+        if BACKBONES.get(kwargs.get("backbone", "clip_vitl16_384"), {}).get("trunk") == "resnet101":
+            # lseg_blocks.py:53-55: the ViT model's _make_encoder does not know this backbone (it belongs to LSegRNNetZS)
+            print(f"Backbone '{kwargs['backbone']}' not implemented")
+            assert False
         self._init_common(**kwargs)
         self.text = tokenize(self.labels)
         if path is not None:
@@ -359,6 +397,7 @@ class LSegNetZS(_LSegBase):
         self.label_list = label_list
         self.use_pretrained = use_pretrained
         self._init_common(**kwargs)
+        self._check_backbone()
         self.texts = [tokenize(["others", name]) for name in self.label_list]  # lseg_net_zs.py:169-175
         if path is not None:
             self.load(path)
@@ -390,9 +429,32 @@ class LSegNetZS(_LSegBase):
         engine = self._engine_for(x.device)
         return engine.forward(x.float(), self._image_text(engine, class_info, x.device), 2, text_image_stride=2)
 
+    def _check_backbone(self):
+        if BACKBONES[self.backbone].get("trunk") == "resnet101":
+            # the reference keeps the two apart the same way: LSegNetZS asserts out in _make_encoder's ViT branch
+            raise ValueError("backbone 'clip_resnet101' is the trunk of LSegRNNetZS (lseg_net_zs.py:345), not LSegNetZS")
+
     @torch.no_grad()
     def predict(self, x, class_info):
         """argmax over the ['others', name] pair per pixel (test_lseg_zs.py:301), fused on the device."""
         self._check_eval()
         engine = self._engine_for(x.device)
         return engine.forward_argmax(x.float(), self._image_text(engine, class_info, x.device), 2, text_image_stride=2)
+
+
+class LSegRNNetZS(LSegNetZS):
+    """Zero-shot model on the ResNet-101 trunk (reference: lseg_net_zs.py:240-378, `LSegRN` / `LSegRNNetZS`; backbone
+    "clip_resnet101" = torchvision resnet101 + the CLIP ViT-B/32 text tower, lseg_vit_zs.py:742-748): the four ResNet stages
+    feed scratch.layerN_rn directly (lseg_net_zs.py:307-315); decoder, per-image ['others', name] head and x2 output as in
+    LSegNetZS. Same constructor and state-dict keys (pretrained.layer1.{0,1,4.*}, pretrained.layer{2,3,4}.*, scratch.*,
+    clip_pretrained.*)."""
+
+    def __init__(self, label_list, path=None, scale_factor=0.5, aux=False, use_relabeled=False, use_pretrained=True,
+                 **kwargs):
+        kwargs.setdefault("backbone", "clip_resnet101")
+        super().__init__(label_list, path=path, scale_factor=scale_factor, aux=aux, use_relabeled=use_relabeled,
+                         use_pretrained=use_pretrained, **kwargs)
+
+    def _check_backbone(self):
+        if BACKBONES[self.backbone].get("trunk") != "resnet101":
+            raise ValueError(f"LSegRNNetZS runs the ResNet trunk (backbone 'clip_resnet101'), got {self.backbone!r}")

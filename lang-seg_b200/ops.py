@@ -48,7 +48,8 @@ def read_watchdog():
 
 def gemm(a, w, N=None, *, bias=None, bias_group_rows=0, scale=None, act=ACT_NONE, res_f32=None, res2_f32=None,
          res_f16=None, out_f32=None, out_f16=None, out_f16_relu=None, ldc=None, M=None,
-         conv=None, store=STORE_ROWMAJOR, d2s=None, nchw=None, row_sumsq=None, row_scale=1.0, out_row_sumsq=None):
+         conv=None, store=STORE_ROWMAJOR, d2s=None, nchw=None, row_sumsq=None, row_scale=1.0, out_row_sumsq=None,
+         relu_after_res=False):
     """C = epi(A W^T).  a: fp16 [M,K] (or NHWC [B,H,W,C] when conv=(ksize,pad)); w: fp16 [rows>=N, Ktot]."""
     args = GemmArgs()
     args.a = _ptr(a, torch.float16)
@@ -85,6 +86,7 @@ def gemm(a, w, N=None, *, bias=None, bias_group_rows=0, scale=None, act=ACT_NONE
     args.row_sumsq_parts = int(row_sumsq.shape[1]) if row_sumsq is not None else 0
     args.row_scale = float(row_scale)
     args.out_row_sumsq = _ptr(out_row_sumsq, torch.float32)
+    args.relu_after_res = int(bool(relu_after_res))
     check(load().lseg_gemm(C.byref(args), _stream()))
 
 
@@ -201,6 +203,28 @@ def im2col_3x3_s2(x):
     a = torch.empty((B * Ho * Wo, 9 * Cc), dtype=torch.float16, device=x.device)
     check(load().lseg_im2col_3x3_s2(_ptr(x, torch.float16), _ptr(a), B, H, W, Cc, _stream()))
     return a
+
+
+def stem_im2col(x):
+    """x fp32 NCHW [B,3,H,W] -> fp16 [B*(H/2)*(W/2), 192] rows of the ResNet stem conv (7x7 s2 p3), zero beyond column 147."""
+    B, _, H, W = x.shape
+    a = torch.empty((B * (H // 2) * (W // 2), 192), dtype=torch.float16, device=x.device)
+    check(load().lseg_stem_im2col(_ptr(x, torch.float32), _ptr(a), B, H, W, _stream()))
+    return a
+
+
+def maxpool3x3s2_nhwc(x):
+    B, H, W, Cc = x.shape
+    y = torch.empty((B, H // 2, W // 2, Cc), dtype=torch.float16, device=x.device)
+    check(load().lseg_maxpool3x3s2_nhwc(_ptr(x, torch.float16), _ptr(y), B, H, W, Cc, _stream()))
+    return y
+
+
+def subsample2_nhwc(x):
+    B, H, W, Cc = x.shape
+    y = torch.empty((B, H // 2, W // 2, Cc), dtype=torch.float16, device=x.device)
+    check(load().lseg_subsample2_nhwc(_ptr(x, torch.float16), _ptr(y), B, H, W, Cc, _stream()))
+    return y
 
 
 def upsample2x_nhwc(x, out_dtype=torch.float16, add=None, decoder=False):

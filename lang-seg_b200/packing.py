@@ -40,6 +40,10 @@ BACKBONES = {
     "clip_vitb32_384": dict(dim=768, depth=12, heads=12, patch=32, hooks=(2, 5, 8, 11),
                             features=(96, 192, 384, 768), resample=(8, 4, 2, 0), timm="vit_base_patch32_384",
                             clip="ViT-B/32", text=(512, 8, 512)),
+    # zero-shot model LSegRNNetZS only (lseg_net_zs.py:240-378; lseg_blocks_zs.py:42-48, lseg_vit_zs.py:742-748): a
+    # torchvision resnet101 whose four stages feed scratch.layerN_rn directly — no ViT, no reassemble
+    "clip_resnet101": dict(trunk="resnet101", layers=(3, 4, 23, 3), features=(256, 512, 1024, 2048),
+                           clip="ViT-B/32", text=(512, 8, 512)),
 }
 
 
@@ -137,8 +141,46 @@ class PackedWeights:
             slot.b = None
 
     # -- packing -------------------------------------------------------------------------------
+    def _pack_resnet(self, sd, cfg):
+        """torchvision resnet101 under the key names of _make_resnet_backbone (lseg_blocks_zs.py:109-119): the stem is
+        pretrained.layer1.{0,1}, stage 1 pretrained.layer1.4.*, stages 2-4 pretrained.layer{2,3,4}.*."""
+        d = self.desc
+        d.trunk = 1
+        stem = sd["pretrained.layer1.0.weight"]
+        if tuple(stem.shape) != (64, 3, 7, 7):
+            raise ValueError(f"{self.backbone}: stem conv is {tuple(stem.shape)}, expected (64, 3, 7, 7)")
+        self._linear(d.rn_stem, _pad_to(stem.reshape(64, 147), 1, 192), None)
+        s, t = fold_bn(sd, "pretrained.layer1.1.")
+        d.rn_stem_scale, d.rn_stem_shift = self._f32(s), self._f32(t)
+        blk = 0
+        for layer, n in enumerate(cfg["layers"], start=1):
+            d.rn_layers[layer - 1] = n
+            for i in range(n):
+                q = f"pretrained.layer1.4.{i}." if layer == 1 else f"pretrained.layer{layer}.{i}."
+                b = d.rn_blocks[blk]
+                w1, w2, w3 = sd[q + "conv1.weight"], sd[q + "conv2.weight"], sd[q + "conv3.weight"]
+                self._linear(b.conv1, w1.reshape(w1.shape[0], w1.shape[1]), None)
+                self._linear(b.conv2, conv3x3_to_gemm(w2), None)
+                self._linear(b.conv3, w3.reshape(w3.shape[0], w3.shape[1]), None)
+                for j, slot in ((1, "bn1"), (2, "bn2"), (3, "bn3")):
+                    s, t = fold_bn(sd, f"{q}bn{j}.")
+                    setattr(b, slot + "_scale", self._f32(s))
+                    setattr(b, slot + "_shift", self._f32(t))
+                b.stride = 2 if (layer > 1 and i == 0) else 1
+                if i == 0:
+                    wd = sd[q + "downsample.0.weight"]
+                    self._linear(b.down, wd.reshape(wd.shape[0], wd.shape[1]), None)
+                    s, t = fold_bn(sd, q + "downsample.1.")
+                    b.bnd_scale, b.bnd_shift = self._f32(s), self._f32(t)
+                blk += 1
+        for k in range(4):
+            d.post_channels[k] = cfg["features"][k]
+
     def _pack(self, sd, cfg):
         d = self.desc
+        if cfg.get("trunk") == "resnet101":
+            self._pack_resnet(sd, cfg)
+            return self._pack_decoder_and_text(sd, cfg)
         p = "pretrained.model."
         D, P = cfg["dim"], cfg["patch"]
         d.vit_dim, d.vit_depth, d.vit_heads, d.patch_size = D, cfg["depth"], cfg["heads"], P
@@ -178,6 +220,10 @@ class PackedWeights:
             elif r == -2:  # Conv2d 3x3 stride 2 [cout, cin, 3, 3]
                 w = _pad_to(_pad_to(sd[q + "4.weight"], 0, cp), 1, cp)
                 self._linear(d.post_resample_w[k], conv3x3_to_gemm(w), _pad_to(sd[q + "4.bias"], 0, cp))
+        self._pack_decoder_and_text(sd, cfg)
+
+    def _pack_decoder_and_text(self, sd, cfg):
+        d = self.desc
         for k in range(4):
             self._linear(d.layer_rn[k], conv3x3_to_gemm(_pad_to(sd[f"scratch.layer{k + 1}_rn.weight"], 1,
                                                                 stored_channels(cfg["features"][k]))), None)

@@ -300,6 +300,59 @@ def lseg_forward(x, tokens, sd, text_weights=None, return_stages=False, arch_opt
     return out
 
 
+# ------------------------------------------------------------------------------------------------
+# ResNet-101 trunk of the zero-shot model LSegRNNetZS (modules/models/lseg_net_zs.py:240-339; backbone
+# "clip_resnet101": torchvision resnet101 split by _make_resnet_backbone, lseg_blocks_zs.py:109-119 /
+# lseg_vit_zs.py:742-760). Third-party arithmetic restated: torchvision 0.10 (torch 1.9.1) ResNet v1.5 — Bottleneck =
+# 1x1 -> BN -> ReLU -> 3x3 (stride on THIS conv) -> BN -> ReLU -> 1x1 -> BN, + identity (1x1 stride-s conv + BN when the
+# shape changes), ReLU; stem 7x7 s2 p3 -> BN -> ReLU -> maxpool 3x3 s2 p1; BatchNorm eval, eps 1e-5.
+# ------------------------------------------------------------------------------------------------
+RESNET101_LAYERS = (3, 4, 23, 3)
+
+
+def _rn_prefix(layer, i):
+    """state-dict prefix of block i of layer 1..4: layer1 is nn.Sequential(conv1, bn1, relu, maxpool, resnet.layer1)."""
+    return f"pretrained.layer1.4.{i}." if layer == 1 else f"pretrained.layer{layer}.{i}."
+
+
+def resnet_bottleneck(x, sd, prefix, stride):
+    out = F.relu(_bn(F.conv2d(x, sd[prefix + "conv1.weight"]), sd, prefix + "bn1."))
+    out = F.relu(_bn(F.conv2d(out, sd[prefix + "conv2.weight"], stride=stride, padding=1), sd, prefix + "bn2."))
+    out = _bn(F.conv2d(out, sd[prefix + "conv3.weight"]), sd, prefix + "bn3.")
+    if prefix + "downsample.0.weight" in sd:
+        x = _bn(F.conv2d(x, sd[prefix + "downsample.0.weight"], stride=stride), sd, prefix + "downsample.1.")
+    return F.relu(out + x)
+
+
+def resnet101_layers(x, sd):
+    """pretrained.layer1..4 of lseg_net_zs.py:307-310 -> four NCHW fp32 maps (256/512/1024/2048 channels, strides 4..32)."""
+    x = F.relu(_bn(F.conv2d(x, sd["pretrained.layer1.0.weight"], stride=2, padding=3), sd, "pretrained.layer1.1."))
+    x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+    outs = []
+    for layer, n in enumerate(RESNET101_LAYERS, start=1):
+        for i in range(n):
+            x = resnet_bottleneck(x, sd, _rn_prefix(layer, i), 2 if (layer > 1 and i == 0) else 1)
+        outs.append(x)
+    return outs
+
+
+@torch.no_grad()
+def lseg_forward_rn_zs(x, class_info, label_tokens, sd, text_weights=None, return_stages=False):
+    """LSegRN.forward (modules/models/lseg_net_zs.py:300-338): ResNet-101 layers -> the same scratch decoder and the
+    zero-shot head (one ['others', name] pair per image)."""
+    tw = text_weights if text_weights is not None else clip_text_weights_fp16(sd)
+    layers = resnet101_layers(x, sd)
+    path_1 = decoder(layers, sd)
+    outs = []
+    for i in range(x.shape[0]):
+        tf = clip_encode_text(label_tokens[int(class_info[i])], tw)
+        outs.append(correlation_head(path_1[i:i + 1], tf, sd))
+    out = output_conv(torch.cat(outs, dim=0))
+    if return_stages:
+        return out, {"layers": layers, "path_1": path_1}
+    return out
+
+
 @torch.no_grad()
 def lseg_forward_zs(x, class_info, label_tokens, sd, text_weights=None):
     """Zero-shot LSeg.forward (modules/models/lseg_net_zs.py:177-214): per-image ['others', name] pair.

@@ -53,7 +53,42 @@ BACKBONE_SHAPES = {
                                    text=(768, 768)),
     "clip_vitb32_384": dict(dim=768, depth=12, patch=32, feats=(96, 192, 384, 768), resample=(8, 4, 2, 0),
                             text=(512, 512)),
+    # zero-shot ResNet trunk (lseg_net_zs.py:240-339): no ViT, the scratch decoder takes resnet101's four stages
+    "clip_resnet101": dict(feats=(256, 512, 1024, 2048), text=(512, 512)),
 }
+
+
+def _resnet101_state(g, sd):
+    """torchvision resnet101 parameters under the key names of _make_resnet_backbone (lseg_blocks_zs.py:109-119):
+    pretrained.layer1 = Sequential(conv1, bn1, relu, maxpool, layer1), pretrained.layer2..4 = resnet.layer2..4."""
+    def bn(prefix, c):
+        sd[prefix + "weight"] = g.uniform((c,), 0.5, 1.5)
+        sd[prefix + "bias"] = g.normal((c,), 0.1)
+        sd[prefix + "running_mean"] = g.normal((c,), 0.1)
+        sd[prefix + "running_var"] = g.uniform((c,), 0.5, 1.5)
+        sd[prefix + "num_batches_tracked"] = torch.tensor(100, dtype=torch.int64)
+
+    def conv(shape):  # kaiming-normal fan_out like torchvision's ResNet init, damped so 33 blocks stay O(1)
+        fan_out = shape[0] * shape[2] * shape[3]
+        return g.normal(shape, (2.0 / fan_out) ** 0.5)
+
+    sd["pretrained.layer1.0.weight"] = conv((64, 3, 7, 7))
+    bn("pretrained.layer1.1.", 64)
+    inplanes = 64
+    for layer, (planes, n) in enumerate(zip((64, 128, 256, 512), (3, 4, 23, 3)), start=1):
+        for i in range(n):
+            p = f"pretrained.layer1.4.{i}." if layer == 1 else f"pretrained.layer{layer}.{i}."
+            sd[p + "conv1.weight"] = conv((planes, inplanes, 1, 1))
+            bn(p + "bn1.", planes)
+            sd[p + "conv2.weight"] = conv((planes, planes, 3, 3))
+            bn(p + "bn2.", planes)
+            sd[p + "conv3.weight"] = conv((planes * 4, planes, 1, 1))
+            bn(p + "bn3.", planes * 4)
+            sd[p + "bn3.weight"] *= 0.12  # keep the residual branches from multiplying the stream over 33 blocks
+            if i == 0:
+                sd[p + "downsample.0.weight"] = conv((planes * 4, inplanes, 1, 1))
+                bn(p + "downsample.1.", planes * 4)
+            inplanes = planes * 4
 
 
 def make_state_dict(seed=0, with_clip_visual_stub=False, head_block=False, backbone="clip_vitl16_384"):
@@ -62,6 +97,9 @@ def make_state_dict(seed=0, with_clip_visual_stub=False, head_block=False, backb
     g = _Gen(seed)
     sd = {}
     shp = BACKBONE_SHAPES[backbone]
+    if backbone == "clip_resnet101":
+        _resnet101_state(g, sd)
+        return _decoder_and_text_state(g, sd, shp, with_clip_visual_stub, head_block)
     D, P, depth = shp["dim"], shp["patch"], shp["depth"]
     p = "pretrained.model."
     sd[p + "cls_token"] = g.normal((1, 1, D), 0.02)
@@ -99,6 +137,11 @@ def make_state_dict(seed=0, with_clip_visual_stub=False, head_block=False, backb
         elif r == -2:
             sd[q + "weight"] = g.kaiming((c, c, 3, 3))
             sd[q + "bias"] = g.uniform((c,), -0.01, 0.01)
+    return _decoder_and_text_state(g, sd, shp, with_clip_visual_stub, head_block)
+
+
+def _decoder_and_text_state(g, sd, shp, with_clip_visual_stub, head_block):
+    feats = list(shp["feats"])
     for k in range(4):
         sd[f"scratch.layer{k + 1}_rn.weight"] = g.kaiming((256, feats[k], 3, 3))
     for k in range(1, 5):

@@ -30,7 +30,7 @@ def test_header_symbols_exported(lib):
     missing = [s for s in declared if not hasattr(lib, s)]
     assert not missing, f"declared in include/lseg_b200.h but not exported: {missing}"
     assert sorted(_lib.SYMBOLS) == declared, "ctypes binding list out of sync with the header"
-    assert lib.lseg_abi_version() == _lib.ABI_VERSION == 3
+    assert lib.lseg_abi_version() == _lib.ABI_VERSION == 4
 
 
 def test_no_torch_types_in_signatures():

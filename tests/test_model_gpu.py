@@ -389,6 +389,82 @@ def test_forward_on_side_streams(net):
         assert torch.equal(out2, ref), prio
 
 
+# ------------------------------------------------------------------------------------------------
+# LSegRNNetZS: the zero-shot model on the ResNet-101 trunk (lseg_net_zs.py:240-378, backbone "clip_resnet101")
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def net_rn():
+    import lseg_b200  # noqa: F401
+    from lseg_b200.lseg_net import LSegRNNetZS
+    names = [line.strip() for line in open(os.path.join(GOLD, "fewshot_pascal.txt")) if line.strip()]
+    n = LSegRNNetZS(label_list=names, features=256, arch_option=0, block_depth=0, activation="lrelu")
+    n.load_state_dict(state_dict(0, "clip_resnet101"))
+    return n.cuda().eval()
+
+
+@pytest.mark.parametrize("B,H,W", [(3, 96, 128), (1, 480, 480), (8, 480, 480)])
+def test_rn101_zs_forward_vs_oracle(net_rn, B, H, W):
+    """ResNet stages (the fp16 operands of scratch.layerN_rn), path_1 and the zero-shot logits against the oracle; the
+    stages and path_1 are stored in fp16: stage tolerance + one quantum. CPU emulation of the engine's rounding points
+    (fp16 conv operands, fp32 residual stream) puts the stages at 0.6-0.7e-3."""
+    from oracle import lseg_oracle as O
+    sd = state_dict(0, "clip_resnet101")
+    texts = [synth.tokenize(["others", n]) for n in net_rn.label_list]
+    x = synth.make_image(B, H, W, seed=B * 1000 + H + 101)
+    class_info = torch.tensor([(3 + 5 * i) % len(texts) for i in range(B)])
+    ref, st = O.lseg_forward_rn_zs(x, class_info, texts, sd, return_stages=True)
+    got = net_rn(x.cuda(), class_info)
+    eng = net_rn._engine_for(torch.device("cuda"))
+    d = {"launches": eng.last_launch_count()}
+    for k in range(4):
+        lay = st["layers"][k]
+        c, lh, lw = lay.shape[1], lay.shape[2], lay.shape[3]
+        got_l = eng.debug_tensor(f"layer{k}", (B, lh, lw, c), torch.float16).permute(0, 3, 1, 2).float()
+        d[f"layer{k}"] = rel_err(got_l, lay)
+        d[f"layer{k}_tol"] = logit_tolerance(lay, STAGE_TOL)
+    p1 = eng.debug_tensor("path1", (B, H // 2, W // 2, 256), torch.float16)
+    d["path1"] = rel_err(p1.permute(0, 3, 1, 2), st["path_1"])
+    d["path1_tol"] = logit_tolerance(st["path_1"], STAGE_TOL)
+    d["logits"] = rel_err(got, ref)
+    d["logit_tol_full"] = logit_tolerance(ref, FULL_LOGIT_REL)
+    full = argmax_report(got, ref, margin_eps(ref))
+    d.update(full)
+    _report(f"rn101_zs_forward_B{B}_{H}x{W}", d)
+    assert got.shape == (B, 2, H, W) and torch.isfinite(got).all()
+    for k in range(4):
+        assert d[f"layer{k}"] <= d[f"layer{k}_tol"], d
+    assert d["path1"] <= d["path1_tol"], d
+    assert d["logits"] <= d["logit_tol_full"], d
+    assert full["ok"], d
+    assert torch.equal(net_rn.predict(x.cuda(), class_info), torch.max(got, 1)[1])
+
+
+def test_rn101_zs_against_reference_golden(net_rn):
+    """Outputs of the UNMODIFIED reference LSegRNNetZS (oracle/make_golden_rn.py)."""
+    g = np.load(os.path.join(GOLD, "ref_rn101.npz"))
+    x = synth.make_image(3, 96, 128, seed=77)
+    got = net_rn(x.cuda(), torch.from_numpy(g["small_class_info"])).cpu()
+    ref = torch.from_numpy(g["small_logits"])
+    rel_small = max(FULL_LOGIT_REL, TEXT_FLOOR_FACTOR * float(g["small_floor"]))
+    d = {"small_logits": rel_err(got, ref), "small_tol": logit_tolerance(ref, rel_small)}
+    rep = argmax_report(got, ref, margin_eps(ref))
+    x = synth.make_image(2, 480, 480, seed=1480)
+    got = net_rn(x.cuda(), torch.from_numpy(g["s480_class_info"])).cpu()
+    lat = torch.from_numpy(g["s480_logits_lattice"])
+    rel_480 = max(FULL_LOGIT_REL, TEXT_FLOOR_FACTOR * float(g["s480_floor"]))
+    d["s480_lattice"] = rel_err(got[:, :, ::4, ::4], lat)
+    mask = torch.from_numpy(g["s480_argmax"].astype(np.int64))
+    margin = torch.from_numpy(g["s480_margin_f16"].astype(np.float32))
+    mism = got.argmax(1) != mask
+    eps = MARGIN_QUANTA_FULL * fp16_quantum(lat.abs().max())
+    d["s480_mismatch"] = int(mism.sum())
+    d["s480_worst_mismatch_margin"] = float(margin[mism].max()) if d["s480_mismatch"] else 0.0
+    _report("rn101_reference_golden", d)
+    assert d["small_logits"] <= d["small_tol"] and rep["ok"], (d, rep)
+    assert d["s480_lattice"] <= logit_tolerance(lat, rel_480), d
+    assert d["s480_mismatch"] == 0 or d["s480_worst_mismatch_margin"] < eps, d
+
+
 def test_against_reference_golden(net):
     """The committed outputs of the UNMODIFIED reference modules (oracle/make_golden.py) at 480x480, K=150 and K=2:
     logits on the stride-8 lattice, full argmax mask, margins."""

@@ -159,6 +159,61 @@ def test_conv3x3_split_k_epilogues(ops, B, H, W, Cin):
     assert torch.equal(again, o32), "split-K reduction is not deterministic"
 
 
+def test_resnet_glue_and_bottleneck_epilogue(ops):
+    """The ResNet-101 trunk's pieces against torch: stem rows (7x7 s2 p3 im2col + GEMM + folded BN + ReLU), max pool,
+    1x1 stride-2 subsampling, 3x3 stride-2 conv, and the bottleneck's closing GEMM relu(bn3(conv3) + identity) with the
+    fp32 stream updated in place."""
+    B, H, W = 2, 64, 96
+    x = _rand((B, 3, H, W), 71, 1.0, torch.float32)
+    wt = _rand((64, 3, 7, 7), 72, 0.05)
+    scale = _rand((64,), 73, 0.2, torch.float32) + 1.0
+    shift = _rand((64,), 74, 0.3, torch.float32)
+    a = ops.stem_im2col(x)
+    assert a.shape == (B * (H // 2) * (W // 2), 192) and float(a[:, 147:].abs().max()) == 0.0
+    wp = torch.zeros((128, 192), dtype=torch.float16, device="cuda")
+    wp[:64, :147] = wt.reshape(64, 147)
+    stem = torch.zeros((a.shape[0], 64), dtype=torch.float16, device="cuda")
+    ops.gemm(a, wp, 64, scale=scale, bias=shift, act=ops.ACT_RELU, out_f16=stem)
+    ref = F.relu(F.conv2d(x.half().float(), wt.float(), stride=2, padding=3) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    _close(stem.view(B, H // 2, W // 2, 64), ref.permute(0, 2, 3, 1), 1e-3, "stem conv")
+    # stage-1 shapes: K = 64 (a single 64-wide K chunk) and N = 64 (half of the narrowest tile)
+    w1 = _rand((64, 64), 82, 0.1)
+    o1 = torch.zeros((stem.shape[0], 64), dtype=torch.float16, device="cuda")
+    ops.gemm(stem, ops.pad_rows(w1), 64, scale=scale, bias=shift, act=ops.ACT_RELU, out_f16=o1)
+    _close(o1, F.relu((stem.float() @ w1.float().t()) * scale + shift), 1e-3, "1x1 conv K=64 N=64")
+    c64 = torch.zeros((B, H // 2, W // 2, 64), dtype=torch.float16, device="cuda")
+    w64 = _rand((64, 64, 3, 3), 83, 0.05)
+    ops.gemm(stem.view(B, H // 2, W // 2, 64), ops.pad_rows(w64.permute(0, 2, 3, 1).reshape(64, 9 * 64).contiguous()), 64,
+             conv=(3, 1), out_f16=c64, ldc=64)
+    _close(c64, F.conv2d(stem.view(B, H // 2, W // 2, 64).float().permute(0, 3, 1, 2), w64.float(), padding=1).permute(0, 2, 3, 1),
+           1e-3, "3x3 conv C=64 N=64")
+    pooled = ops.maxpool3x3s2_nhwc(stem.view(B, H // 2, W // 2, 64))
+    want = F.max_pool2d(stem.view(B, H // 2, W // 2, 64).float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+    assert torch.equal(pooled.float(), want)
+    t = _rand((B, 16, 24, 128), 75)
+    assert torch.equal(ops.subsample2_nhwc(t), t[:, ::2, ::2].contiguous())
+    # 3x3 stride-2 conv = im2col rows + GEMM
+    w2 = _rand((128, 128, 3, 3), 76, 0.03)
+    rows = ops.im2col_3x3_s2(t)
+    o2 = torch.zeros((rows.shape[0], 128), dtype=torch.float16, device="cuda")
+    ops.gemm(rows, ops.pad_rows(w2.permute(0, 2, 3, 1).reshape(128, 9 * 128).contiguous()), 128, out_f16=o2)
+    _close(o2.view(B, 8, 12, 128), F.conv2d(t.float().permute(0, 3, 1, 2), w2.float(), stride=2, padding=1).permute(0, 2, 3, 1),
+           1e-3, "3x3 stride-2 conv")
+    # closing GEMM of a bottleneck: in-place fp32 stream + fp16 copy, ReLU after the residual add
+    M, K, N = B * 8 * 12 * 4, 128, 512
+    t2 = _rand((M, K), 77)
+    w3 = _rand((N, K), 78, 0.05)
+    s3 = _rand((N,), 79, 0.2, torch.float32) + 1.0
+    b3 = _rand((N,), 80, 0.3, torch.float32)
+    stream = _rand((M, N), 81, 1.0, torch.float32)
+    want = F.relu((t2.float() @ w3.float().t()) * s3 + b3 + stream)
+    y16 = torch.zeros((M, N), dtype=torch.float16, device="cuda")
+    ops.gemm(t2, ops.pad_rows(w3), N, scale=s3, bias=b3, res_f32=stream, out_f32=stream, out_f16=y16, relu_after_res=True)
+    _close(stream, want, 3e-4, "bottleneck output fp32 (in place)")
+    _close(y16, want, 1e-3, "bottleneck output fp16")
+    assert float(stream.min()) >= 0.0
+
+
 @pytest.mark.parametrize("s,cin,cout,g", [(4, 256, 256, 30), (2, 512, 512, 6)])
 def test_deconv_depth_to_space(ops, s, cin, cout, g):
     B = 2

@@ -247,6 +247,37 @@ def test_other_backbone_golden_and_key_contract(tag, backbone, layer_shapes):
         LSegNet(labels=["a"], **{**NET_KW, "backbone": "clip_resnet101"})
 
 
+def test_rn101_zero_shot_golden_and_key_contract():
+    """LSegRNNetZS (ResNet-101 trunk, lseg_net_zs.py:240-378): the oracle against the unmodified reference's output
+    (oracle/make_golden_rn.py), stage statistics to 1e-6, and the drop-in module's state-dict keys/shapes."""
+    import lseg_b200  # noqa: F401
+    from lseg_b200.lseg_net import LSegNetZS, LSegRNNetZS
+    z = np.load(os.path.join(GOLD, "ref_rn101.npz"))
+    names = [line.strip() for line in open(os.path.join(GOLD, "fewshot_pascal.txt")) if line.strip()]
+    texts = [synth.tokenize(["others", n]) for n in names]
+    sd = state_dict(0, "clip_resnet101")
+    x = synth.make_image(3, 96, 128, seed=77)
+    out, st = O.lseg_forward_rn_zs(x, torch.from_numpy(z["small_class_info"]), texts, sd, return_stages=True)
+    ref = torch.from_numpy(z["small_logits"])
+    assert out.shape == ref.shape == (3, 2, 96, 128)
+    assert rel_err(out, ref) < 1.5 * float(z["small_floor"]) + 1e-3  # two executions of the fp16 text tower
+    assert [tuple(l.shape[1:]) for l in st["layers"]] == [(256, 24, 32), (512, 12, 16), (1024, 6, 8), (2048, 3, 4)]
+    for k in range(4):
+        t = st["layers"][k]
+        got = np.array([t.mean().item(), t.std().item(), t.abs().max().item()])
+        assert np.allclose(got, z["small_layers_stats"][k], rtol=1e-6, atol=1e-7), k
+    want = json.load(open(os.path.join(GOLD, "state_dict_keys_rn101.json")))
+    net = LSegRNNetZS(label_list=names, features=256, arch_option=0, block_depth=0, activation="lrelu")
+    assert {k: list(v.shape) for k, v in net.state_dict().items()} == want
+    net.load_state_dict(sd)
+    assert net.backbone == "clip_resnet101" and len(net.texts) == len(names) and net.texts[0].shape == (2, 77)
+    with pytest.raises(ValueError):  # the two zero-shot classes keep their trunks apart, like the reference's
+        LSegNetZS(label_list=names, backbone="clip_resnet101", features=256, arch_option=0, block_depth=0, activation="lrelu")
+    with pytest.raises(ValueError):
+        LSegRNNetZS(label_list=names, backbone="clip_vitl16_384", features=256, arch_option=0, block_depth=0,
+                    activation="lrelu")
+
+
 def test_checkpoint_load_through_parent_module():
     """Lightning's load_from_checkpoint loads `net.`-prefixed keys on the PARENT module; torch then recurses with
     _load_from_state_dict and never calls a child's load_state_dict override. strict=True must still accept real-checkpoint
