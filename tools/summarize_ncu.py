@@ -2,6 +2,7 @@
 """Turn ncu outputs brought back in gpurun_out/ into the small text summaries committed under profiles/.
 
   python tools/summarize_ncu.py launches gpurun_out/launches_r1.csv  > profiles/r01_launches.md
+  python tools/summarize_ncu.py launches gpurun_out/rn_launches.csv stem_im2col > profiles/r02_rn101_launches.md
   python tools/summarize_ncu.py full     gpurun_out/prof_gemm.ncu-rep > profiles/r01_gemm_full.md
 """
 import collections
@@ -31,10 +32,18 @@ METRICS = [
 ]
 
 
-def launches(path):
+def launches(path, marker=None):
+    """marker: a kernel-name substring that starts a step (e.g. stem_im2col, patchify) — only the launches between its
+    last two occurrences (ONE whole step, without the one-off weight packing / text tower of the process) are listed."""
     with open(path) as f:
         lines = [l for l in f if not l.startswith("==")]
     rows = list(csv.DictReader(lines))
+    if marker:
+        at = [i for i, r in enumerate(rows) if marker in r["Kernel Name"]]
+        if len(at) < 2:
+            raise SystemExit(f"marker {marker!r} occurs {len(at)} times, need 2")
+        rows = rows[at[-2]:at[-1]]
+        print(f"one step = the launches between the last two `{marker}` launches of the capture\n")
     agg = collections.OrderedDict()
     for r in rows:
         name = r["Kernel Name"].split("(")[0][:70]
@@ -100,4 +109,4 @@ def traffic(path):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])
