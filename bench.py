@@ -186,13 +186,29 @@ def run_reference(args, cfg):
         "impl": "reference", "metric": METRIC, "value": r["rate"], "unit": "images/sec", "n_gpus": args.gpus,
         "steps": steps, "warmup": args.warmup, "ms_per_step": r["sec"] * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "fp32 trunk / fp16 text+corr", "data": "synthetic",
-        "config": dict(cfg["config"], sample=sample),
+        "config": line_config(cfg, args, int(os.environ.get("WORLD_SIZE", "1"))),
         "cpu_baseline": {"value": r["rate"], "unit": "images/sec", "cores": r["cores"], "kind": r["kind"], "sample": sample,
                          "value_text_cached": r["rate_text_cached"], "text_tower_sec_per_call": r["text_sec"]},
         "e2e": {"value": r["rate"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def line_config(cfg, args, world):
+    """The `config` object of the JSON line — the SAME dict in both arms (`--impl b200` and `--impl reference` describe one
+    workload; what differs between the arms is said per arm inside the values, and the reference arm's bounded sample is
+    in its `cpu_baseline.sample`)."""
+    par = f"B200 arm: dp{world}, batch shard per rank, no collective on the image path"
+    if world > 1:
+        par += f"; all shards' logits gathered on rank 0 inside the timed step ({args.gather})"
+    par += "; reference arm: the host cores of rank 0"
+    return dict(cfg["config"], backbone=args.backbone, global_batch=cfg["batch"] * world, parallelism=par,
+                weights="random init of the architecture",
+                text_features="B200 arm: cached per label set; reference arm: re-run on every call as the reference does "
+                              "(cpu_baseline.value_text_cached = the same run with the text tower subtracted)",
+                l2="B200 arm, N=1: 256 MiB flush (untimed) between timed steps; N>1: back-to-back steps, per-step working "
+                   "set ~3.7 GB >> 126 MB L2")
 
 
 def make_config(args):
@@ -546,17 +562,11 @@ def main():
                                       f"fp16 text tower re-run per call as the reference does"}
 
     if rank == 0:
-        par = f"dp{world}: batch shard per rank, no collective on the image path"
-        if world > 1:
-            par += f"; logits gathered on rank 0 inside the timed step ({gather_info['mode']})"
         line = {
             "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": Ksteps, "warmup": W,
             "ms_per_step": total_ms / Ksteps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "fp16 operands, fp32 accumulate (fp32 residual stream)", "data": "synthetic",
-            "config": dict(cfg["config"], backbone=args.backbone, global_batch=B * world, parallelism=par,
-                           weights="random init of the architecture", text_features="cached per label set",
-                           l2="N=1: 256 MiB flush (untimed) between timed steps; N>1: back-to-back steps, per-step "
-                              "working set ~3.7 GB >> 126 MB L2"),
+            "config": line_config(cfg, args, world),
             "wall_s": t_wall, "clocks": clocks, "gpu_launches": launches_per_step * Ksteps,
             "launches_per_step": launches_per_step,
             "roofline": roofline, "roofline_mhsa": mhsa_roof, "step_breakdown_ms": breakdown,
